@@ -1,0 +1,117 @@
+/*
+ * jpegdec_b200.h -- batch / device-resident extension of the JPEGDEC C API and the
+ * thin host->CUDA FFI underneath it.  Plain C ABI: pointers and sizes only.
+ *
+ * Why it exists: the reference's hot path -- DecodeJPEG (src/jpeg.inl:4946-5357)
+ * driving JPEGDecodeMCU (:2090-2274), JPEGIDCT (:2278-2798), JPEGPutMCU* (:2799-4868)
+ * and JPEGDither (:4871-4940) -- decodes one image per call on one core.  A B200 needs
+ * ~10^5 independent restart segments in flight, so the throughput path takes a *batch*
+ * of images per call.  JPEG_decode() (include/JPEGDEC.h) is this API with n = 1 plus
+ * the reference's callback / framebuffer semantics replayed on the host.
+ *
+ * Per stage, which reference function it replaces:
+ *   jdk_prescan        <- JPEGFilter marker handling (:1431-1540) + restart bookkeeping (:5337-5348)
+ *   jdk_entropy        <- JPEGDecodeMCU (:2090-2274) incl. the 64-bit window behaviour
+ *   jdk_stitch/_patch  <- cross-segment window phase of the same function
+ *   jdk_idct_color_*   <- JPEGIDCT + DC-only shortcut (:5146-5154) + JPEGPutMCU22/11/Gray/8BitGray
+ *   jdk_scaled_*       <- the 1/4 and 1/8 paths of the above (:2305-2326, :3323-3396, :3627-3748)
+ *   jdk_dither         <- JPEGDither (:4871-4940)
+ */
+#ifndef JPEGDEC_B200_H
+#define JPEGDEC_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct JPEGB200_CTX JPEGB200_CTX;     /* one per (process, GPU) */
+typedef struct JPEGB200_BATCH JPEGB200_BATCH; /* one decode job: n images, one pixel type / option set */
+
+/* batch flags */
+#define JPEGB200_OUT_DEVICE 1   /* output pointers are device pointers (pixels stay in HBM) */
+#define JPEGB200_IN_DEVICE 2    /* compressed bytes already live in device memory (one blob) */
+#define JPEGB200_TIGHT_ROWS 4   /* (default) write only valid rows/columns: out is out_w x out_h */
+
+/* stage indices for JPEGB200_batchGetTimings (milliseconds, CUDA events on the batch stream) */
+enum {
+    JPEGB200_T_H2D = 0,
+    JPEGB200_T_PRESCAN,
+    JPEGB200_T_ENTROPY,
+    JPEGB200_T_STITCH,
+    JPEGB200_T_IDCT,
+    JPEGB200_T_DITHER,
+    JPEGB200_T_D2H,
+    JPEGB200_T_TOTAL,
+    JPEGB200_NUM_TIMINGS
+};
+
+/* counters for JPEGB200_batchGetCounters */
+enum {
+    JPEGB200_C_LAUNCHES = 0,   /* kernels launched by the last batchDecode */
+    JPEGB200_C_SEGMENTS,
+    JPEGB200_C_BLOCKS,
+    JPEGB200_C_EVENTS,         /* window-truncation events found (reference quirk) */
+    JPEGB200_C_COMPRESSED_BYTES,
+    JPEGB200_C_OUTPUT_BYTES,
+    JPEGB200_C_RECORD_BYTES,   /* coefficient-record bytes actually written */
+    JPEGB200_C_H2D_BYTES,
+    JPEGB200_C_D2H_BYTES,
+    JPEGB200_NUM_COUNTERS
+};
+
+/* ---- context ---- */
+JPEGB200_CTX *JPEGB200_create(int device, int arith_mode);
+void JPEGB200_destroy(JPEGB200_CTX *ctx);
+const char *JPEGB200_lastErrorString(JPEGB200_CTX *ctx);
+int JPEGB200_deviceCount(void);
+void *JPEGB200_hostAlloc(size_t bytes);   /* pinned host memory for inputs/outputs */
+void JPEGB200_hostFree(void *p);
+
+/* ---- batch job ---- */
+/* Parses the n headers on the host (no GPU work).  datas[i]/sizes[i]: JPEG files in host memory
+ * (or, with JPEGB200_IN_DEVICE, offsets are taken relative to `datas[0]` inside one device blob whose
+ * host mirror is given for parsing -- see batchSetDeviceInput).  pixel_type / options as in JPEGDEC.h. */
+JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes,
+                                     int n, int pixel_type, int options);
+void JPEGB200_batchDestroy(JPEGB200_BATCH *b);
+int JPEGB200_batchCount(JPEGB200_BATCH *b);
+/* per-image facts after batchCreate: status is JPEG_SUCCESS or the open() error the reference would give */
+int JPEGB200_batchImageInfo(JPEGB200_BATCH *b, int i, int32_t *width, int32_t *height, int32_t *subsample,
+                            int32_t *out_w, int32_t *out_h, int32_t *status);
+/* bytes needed for a tightly packed output of image i (out_h rows of out_pitch bytes) */
+int64_t JPEGB200_batchOutputBytes(JPEGB200_BATCH *b, int i, int64_t *pitch_bytes);
+/* Destination for image i.  Device pointer if the batch is decoded with JPEGB200_OUT_DEVICE, else host
+ * (pinned recommended).  pitch_bytes = 0 -> tight. */
+int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int64_t pitch_bytes);
+/* Let the library own a device output arena (tight images back to back, 256-B aligned). */
+int JPEGB200_batchAllocDeviceOutput(JPEGB200_BATCH *b);
+int JPEGB200_batchGetDeviceOutput(JPEGB200_BATCH *b, int i, void **devptr, int64_t *pitch_bytes);
+/* dither needs no extra buffers from the caller: packed rows are written to the output. */
+
+int JPEGB200_batchUpload(JPEGB200_BATCH *b);            /* H2D: compressed bytes + descriptors (async) */
+int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags); /* kernel launches (async) */
+int JPEGB200_batchDownload(JPEGB200_BATCH *b);          /* D2H of pixels for host outputs (async) */
+int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status /* n entries, may be NULL */);
+int JPEGB200_batchGetTimings(JPEGB200_BATCH *b, float *ms /* JPEGB200_NUM_TIMINGS */);
+int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters /* JPEGB200_NUM_COUNTERS */);
+void *JPEGB200_batchStream(JPEGB200_BATCH *b);          /* cudaStream_t the job runs on */
+
+/* One-call convenience: create + upload + decode + (download) + wait + destroy.
+ * outs[i]: destination (host, or device with JPEGB200_OUT_DEVICE); pitches may be NULL (tight). */
+int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
+                         int pixel_type, int options, void *const *outs, const int64_t *pitches,
+                         int flags, int32_t *status);
+
+/* ---- shared-table blob (multi-GPU: rank 0 exports, NCCL broadcast, other ranks import) ---- */
+#define JPEGB200_TABLE_BLOB_BYTES (6400 * 2 + 3 * 64 * 2 + 16)
+int JPEGB200_exportTables(const uint8_t *jpeg, int size, uint8_t *blob /* JPEGB200_TABLE_BLOB_BYTES */);
+int JPEGB200_setSharedTables(JPEGB200_CTX *ctx, const uint8_t *blob);
+int JPEGB200_sharedTableHits(JPEGB200_CTX *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPEGDEC_B200_H */

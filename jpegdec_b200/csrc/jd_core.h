@@ -1,0 +1,557 @@
+/*
+ * jd_core.h -- per-thread building blocks of the sm_100a kernels.
+ *
+ * Everything here is `__host__ __device__` so that the *same* code the CUDA
+ * kernels execute per thread can also be stepped sequentially by the host-side
+ * kernel simulator in tests/hostsim/ (test infrastructure) and diffed against
+ * the compiled reference where no GPU exists.  Nothing in the shipped library
+ * calls these on the CPU: the product path is the kernels in jd_kernels.cu.
+ *
+ * Semantics follow bitbank2/JPEGDEC src/jpeg.inl (cited per function); the code
+ * is organised for a GPU thread, not translated from the reference.
+ */
+#ifndef JD_CORE_H
+#define JD_CORE_H
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define JD_HD __host__ __device__ __forceinline__
+#else
+#define JD_HD static inline
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* Device-side Huffman LUT set (one per distinct DHT set).                     */
+/* Entry = (code_len << 8) | symbol ; 0 = invalid code.                        */
+/*   DC table t: JD_LUT_DC(t) .. +1152 : idx = w16 >= 0xF800 ? 1024 + ((w16>>4)&0x7F) : w16>>6 */
+/*   AC table t: JD_LUT_AC(t) .. +2048 : idx = w16 >= 0xFC00 ? 1024 + (w16 & 0x3FF)  : w16>>6 */
+/* The two-level split mirrors the code classes the reference accepts          */
+/* (src/jpeg.inl:1093-1178 DC: <=6 bits or 5 leading ones; :1182-1273 AC: <=10 */
+/* bits or 6 leading ones) so every file the reference opens is decodable.     */
+/* ------------------------------------------------------------------------- */
+#define JD_LUT_DC_SIZE 1152
+#define JD_LUT_AC_SIZE 2048
+#define JD_LUT_DC(t) ((t) * JD_LUT_DC_SIZE)
+#define JD_LUT_AC(t) (2 * JD_LUT_DC_SIZE + (t) * JD_LUT_AC_SIZE)
+#define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE) /* 6400 u16 = 12800 B */
+
+/* Block header written by the entropy kernel, read by the IDCT kernels (8 B). */
+/*   bits  0..31 : index of the block's first AC record in the record array     */
+/*   bits 32..47 : DC coefficient (int16, = (short)predictor, jpeg.inl:2163)    */
+/*   bits 48..55 : number of AC records (0..63)                                 */
+/* AC record (u16): (run << 12) | (value & 0xFFF); value==0 only for ZRL.       */
+typedef unsigned long long jd_u64;
+
+JD_HD jd_u64 jd_pack_hdr(uint32_t rec_index, int dc, uint32_t nrec)
+{
+    return (jd_u64)rec_index | ((jd_u64)(uint16_t)(int16_t)dc << 32) | ((jd_u64)(nrec & 0xFF) << 48);
+}
+
+/* de-zigzag: zigzag index k -> natural (row-major) index (ITU T.81 Figure 5). */
+#define JD_DEZIGZAG_INIT { \
+    0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, \
+    12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, \
+    35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, \
+    58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 }
+
+/* ------------------------------------------------------------------------- */
+/* Bit-window phase tracking (reference quirk).                  */
+/*                                                                             */
+/* The reference keeps a 64-bit window loaded at byte pBuf and a bit offset     */
+/* `off`; it reloads (pBuf += off>>3; off &= 7) only when off > 47, and only at  */
+/* fixed points (jpeg.inl:2110 block entry, :2149 before DC extra bits, :2225    */
+/* top of AC loop, :2259 after AC extra bits).  AC extra bits are taken from     */
+/* `ulBits << off` with no reload (:2249-2252), so if off + S > 64 the low       */
+/* off+S-64 bits read as zero.  `off` at a restart-segment start depends on the  */
+/* previous segment (6 possibilities), so each segment decoder tracks all six    */
+/* candidates.  With P = true bit position and j = (P>>3) - pBuf (whole bytes   */
+/* consumed inside the window) we have off = 8*j + (P&7): a reload happens iff   */
+/* j >= 6 and sets j = 0.  The six j values live in six nibbles of one word.     */
+/* ------------------------------------------------------------------------- */
+#define JD_JW_INIT 0x543210u
+#define JD_JW_ONES 0x111111u
+
+JD_HD uint32_t jd_jw_ckpt(uint32_t jw)
+{
+    uint32_t t = (jw + 0x222222u) & 0x888888u; /* bit3 of nibble set <=> j >= 6 */
+    uint32_t m = t | (t - (t >> 3));           /* 0xF in those nibbles */
+    return jw & ~m;
+}
+
+/* Truncation event: one stored AC value that some start-phase candidates read truncated. */
+typedef struct {
+    uint32_t rec_index; /* global index of the AC record to patch */
+    uint32_t seg;       /* global segment index */
+    uint32_t j1;        /* candidate nibbles (j after the code length was added) */
+    uint16_t field;     /* the S raw extra bits */
+    uint8_t s;          /* SSSS */
+    uint8_t p7;         /* (P + len) & 7 */
+} JDEvent;
+
+/* value the reference would store for candidate nibble jc (jpeg.inl:2249-2252) */
+JD_HD int jd_event_value(const JDEvent *e, uint32_t jc)
+{
+    int lost = 8 * (int)jc + e->p7 + e->s - 64;
+    uint32_t f = e->field;
+    if (lost > 0) {
+        if (lost >= e->s) f = 0; else f &= ~((1u << lost) - 1u);
+    }
+    int v = (int)f;
+    if (!(e->field >> (e->s - 1))) v -= (1 << e->s) - 1; /* sign from the first extra bit (always inside the window) */
+    return v;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Per-segment entropy decode (one GPU thread).                                 */
+/* Reference semantics: JPEGDecodeMCU src/jpeg.inl:2090-2274 driven by          */
+/* DecodeJPEG :5128-5348 (block order, DC predictor reset and byte alignment    */
+/* at restart), input un-stuffed the way JPEGFilter :1431-1540 does.            */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t *data;  /* compressed batch buffer */
+    uint32_t start;       /* first byte of this segment */
+    uint32_t end;         /* end of this image's file data (exclusive) */
+    uint32_t nmcu;        /* MCUs in this segment */
+    uint32_t bpm;         /* blocks per MCU */
+    uint32_t ncomp;       /* 1 or 3 */
+    uint32_t tsel;        /* per component c: bit (2c) = DC table, bit (2c+1) = AC table */
+    uint32_t rec_index0;  /* global index of this segment's first record */
+    uint32_t rec_cap;     /* record capacity of this segment */
+    uint32_t seg;         /* global segment index (for events) */
+} JDSegIn;
+
+typedef struct {
+    uint32_t jmap;   /* six nibbles: window phase at segment end (after byte alignment) per start candidate */
+    int32_t err_mcu; /* -1 ok, else local MCU index where decoding failed */
+    uint32_t nrec;
+} JDSegOut;
+
+/* status codes written per segment */
+#define JD_SEG_OK 0
+#define JD_SEG_BADCODE 1
+#define JD_SEG_OVERFLOW 2
+#define JD_SEG_BADSIZE 3   /* SSSS > 11 in an AC symbol: not baseline */
+#define JD_SEG_MISSING 4   /* restart marker not found */
+
+#ifdef __CUDACC__
+#define JD_LD8(p) (*(p))
+#else
+#define JD_LD8(p) (*(p))
+#endif
+
+template <typename EventSink>
+JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
+                             jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
+                             EventSink &sink, JDSegOut &out)
+{
+    const uint8_t *data = in.data;
+    uint32_t pos = in.start;
+    const uint32_t end = in.end;
+    jd_u64 bb = 0;      /* bit buffer, MSB first */
+    int nb = 0;         /* valid bits in bb */
+    bool eos = false;   /* hit a marker / end of data: feed zeros */
+
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    uint32_t jw = JD_JW_INIT;
+    int P = 0, Pb = 0;  /* bits consumed in this segment, and P>>3 */
+    uint32_t nrec_total = 0;
+    int err = -1;
+    bool last_was_eob = true;
+
+    const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
+    uint32_t nblk_total = in.nmcu * in.bpm;
+    uint32_t blk_in_mcu = 0;
+    uint32_t comp = 0;
+
+    for (uint32_t b = 0; b < nblk_total; b++) {
+        /* component of this block: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
+        comp = (blk_in_mcu < nluma) ? 0u : (blk_in_mcu - nluma + 1u);
+        const uint32_t dcsel = (in.tsel >> (2 * comp)) & 1u;
+        const uint32_t acsel = (in.tsel >> (2 * comp + 1)) & 1u;
+        const uint16_t *tdc = lut + JD_LUT_DC(dcsel);
+        const uint16_t *tac = lut + JD_LUT_AC(acsel);
+        uint32_t k = 0;            /* zigzag index: 0 = DC pending */
+        uint32_t nrec = 0;
+        uint32_t rec0 = nrec_total;
+        int dcval = 0;
+        bool done = false;
+        while (!done) {
+            /* ---- refill: keep >= 32 valid bits ---- */
+            if (nb <= 32) {
+                bool fast = false;
+                if (!eos && ((pos & 3u) == 0u) && pos + 4u <= end) {
+                    uint32_t w = *(const uint32_t *)(data + pos);
+                    /* any 0xFF byte?  haszero(~w) */
+                    if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0u) {
+#ifdef __CUDA_ARCH__
+                        w = __byte_perm(w, 0, 0x0123);
+#else
+                        w = __builtin_bswap32(w);
+#endif
+                        bb |= (jd_u64)w << (32 - nb);
+                        nb += 32;
+                        pos += 4;
+                        fast = true;
+                    }
+                }
+                if (!fast) {
+                    /* byte path: FF00 -> FF; FFxx (xx != 0) = marker: segment data ends */
+                    for (int i = 0; i < 4 && nb <= 56; i++) {
+                        uint32_t c = 0;
+                        if (!eos && pos < end) {
+                            c = JD_LD8(data + pos);
+                            pos++;
+                            if (c == 0xFFu) {
+                                uint32_t c2 = (pos < end) ? JD_LD8(data + pos) : 0xD9u;
+                                if (c2 == 0u) pos++;
+                                else { eos = true; pos--; c = 0; }
+                            }
+                        } else {
+                            eos = true;
+                        }
+                        bb |= (jd_u64)c << (56 - nb);
+                        nb += 8;
+                        if ((pos & 3u) == 0u && !eos && nb > 32) break; /* re-aligned: go back to word loads */
+                    }
+                }
+            }
+            /* ---- window checkpoint (R1 at block entry / R3 at AC loop top; also the previous R4) ---- */
+            jw = jd_jw_ckpt(jw);
+            /* ---- code lookup ---- */
+            const uint32_t w16 = (uint32_t)(bb >> 48);
+            const bool isdc = (k == 0);
+            const uint16_t *t = isdc ? tdc : tac;
+            const uint32_t thr = isdc ? 0xF800u : 0xFC00u;
+            const uint32_t sh = isdc ? 4u : 0u;
+            const uint32_t msk = isdc ? 0x7Fu : 0x3FFu;
+            const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
+            const uint32_t e = t[idx];
+            if (e == 0u) { err = JD_SEG_BADCODE; break; }
+            const int len = (int)(e >> 8);
+            const uint32_t rs = e & 0xFFu;
+            const int s = (int)(rs & 15u);
+            bb <<= len;
+            uint32_t field = 0;
+            int v = 0;
+            if (s) {
+                field = (uint32_t)(bb >> (64 - s));
+                v = (int)field;
+                if (!(field >> (s - 1))) v -= (1 << s) - 1;
+                bb <<= s;
+            }
+            nb -= len + s;
+            if (isdc) {
+                /* DC: jpeg.inl:2128-2165.  Window reload R2 (:2149) only when the LUT has no
+                 * precomputed difference, i.e. not (SSSS != 0 && len + SSSS <= 6) (:1132). */
+                P += len;
+                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+                if (s != 0 && len + s > 6) jw = jd_jw_ckpt(jw);
+                P += s;
+                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+                int *pp = (comp == 0) ? &pred0 : (comp == 1 ? &pred1 : &pred2);
+                *pp += v;
+                dcval = *pp;
+                k = 1;
+                last_was_eob = false;
+            } else if (rs == 0u) {
+                /* EOB (:2241-2244): leaves without the trailing window check */
+                P += len;
+                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+                done = true;
+                last_was_eob = true;
+            } else {
+                k += rs >> 4;
+                if (s && k < 64u) {
+                    if (s > 11) { err = JD_SEG_BADSIZE; break; }
+                    if (len + s >= 18) {
+                        /* possible truncated read for some start phases */
+                        const int P1 = P + len;
+                        const uint32_t j1 = jw + (uint32_t)((P1 >> 3) - Pb) * JD_JW_ONES;
+                        const int p7 = P1 & 7;
+                        if (((j1 + 0x222222u) & 0x888888u) != 0u) {
+                            bool any = false;
+                            for (int c = 0; c < 6; c++) {
+                                int jc = (int)((j1 >> (4 * c)) & 15u);
+                                if (8 * jc + p7 + s > 64) any = true;
+                            }
+                            if (any) {
+                                JDEvent ev;
+                                ev.rec_index = in.rec_index0 + nrec_total;
+                                ev.seg = in.seg;
+                                ev.j1 = j1;
+                                ev.field = (uint16_t)field;
+                                ev.s = (uint8_t)s;
+                                ev.p7 = (uint8_t)p7;
+                                sink.push(ev);
+                            }
+                        }
+                    }
+                }
+                if (k < 64u) {
+                    /* one record per AC symbol (ZRL has value 0); symbols past 63 are dropped (:2247 pZig<pEnd2) */
+                    if (nrec_total >= in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
+                    rec[nrec_total] = (uint16_t)(((rs >> 4) << 12) | ((uint32_t)v & 0xFFFu));
+                    nrec_total++;
+                    nrec++;
+                }
+                k++;
+                P += len + s;
+                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+                last_was_eob = false;
+                if (k >= 64u) done = true;
+            }
+        }
+        if (err >= 0) { out.err_mcu = (int32_t)(b / in.bpm); break; }
+        blk_hdr[b] = jd_pack_hdr(in.rec_index0 + rec0, dcval, nrec);
+        if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
+    }
+    if (err < 0) {
+        out.err_mcu = -1;
+        /* end of restart interval (jpeg.inl:5337-5347): R4 already happened unless the last
+         * block ended with EOB; then the bit offset is rounded up to a byte without a reload. */
+        if (!last_was_eob) jw = jd_jw_ckpt(jw);
+        if (P & 7) jw += JD_JW_ONES;
+    } else {
+        out.err_mcu = (out.err_mcu & 0x0FFFFFFF) | (err << 28);
+    }
+    out.jmap = jw;
+    out.nrec = nrec_total;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Dequant + IDCT arithmetic (reference JPEGIDCT src/jpeg.inl:2278-2798).       */
+/* ------------------------------------------------------------------------- */
+
+/* clamp table of the reference: ucRangeTable[(v>>5) & 0x3ff] (jpeg.inl:159-222) as arithmetic:
+ * s = sign-extended low 10 bits of (v>>5); result = clamp(s + 128, 0, 255). */
+JD_HD uint32_t jd_range(int v)
+{
+    int s = (int)((uint32_t)v << 17) >> 22; /* bits 5..14 of v, sign-extended from bit 14 */
+    s += 128;
+    s = s < 0 ? 0 : s;
+    s = s > 255 ? 255 : s;
+    return (uint32_t)s;
+}
+
+/* mulhi of the SSE2 build: _mm_mulhi_epi16(_mm_slli_epi16(x,2), K) with x taken mod 2^16.
+ * (int16)(x<<2) << 16 == x << 18 in 32-bit wrap arithmetic, so the whole thing is a 32x32
+ * high multiply of (x << 18) by K. */
+JD_HD int jd_mh2(int x, int K)
+{
+#ifdef __CUDA_ARCH__
+    return __mulhi((int)((uint32_t)x << 18), K);
+#else
+    return (int)(((int64_t)(int32_t)((uint32_t)x << 18) * (int64_t)K) >> 32);
+#endif
+}
+
+#define JD_K0414 (1697 * 4)
+#define JD_K1414 (5793 * 4)
+#define JD_K1847 (7568 * 4)
+#define JD_K2613 (10703 * 2)
+#define JD_K1082 (4433 * 4)
+
+/* Column pass, SSE2-build arithmetic (jpeg.inl:2327-2440).  d[r] = coefficient * quant for
+ * rows 0..7 of one column (any 32-bit value congruent mod 2^16 to the int16 lane); every
+ * result is only meaningful mod 2^16 -- the caller stores (int16).  rows47_empty selects the
+ * reduced variant the reference takes when flag 0x2000 is clear (:2330-2367). */
+JD_HD void jd_col_sse16(const int d[8], bool rows47_empty, int o[8])
+{
+    int T0, T1, T2, T3, T4, T5, T6, T7;
+    if (rows47_empty) {
+        const int d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+        int t12 = jd_mh2(d2, JD_K0414);
+        T0 = d0 + d2; T3 = d0 - d2; T1 = d0 + t12; T2 = d0 - t12;
+        T7 = d1 + d3;
+        int t11 = jd_mh2(d1 - d3, JD_K1414);
+        int z5 = jd_mh2(d1 - d3, JD_K1847);
+        t12 = 2 * jd_mh2(d3, JD_K2613) + z5;
+        T6 = t12 - T7;
+        T5 = t11 - T6;
+        T4 = (jd_mh2(d1, JD_K1082) - z5) + T5;
+    } else {
+        int t10 = d[0] + d[4], t11 = d[0] - d[4];
+        int t13 = d[2] + d[6];
+        int t12 = jd_mh2(d[2] - d[6], JD_K1414) - t13;
+        T0 = t10 + t13; T3 = t10 - t13; T1 = t11 + t12; T2 = t11 - t12;
+        int z13 = d[5] + d[3], z10 = d[5] - d[3];
+        int z11 = d[1] + d[7], z12 = d[1] - d[7];
+        T7 = z11 + z13;
+        t11 = jd_mh2(z11 - z13, JD_K1414);
+        int z5 = jd_mh2(z10 + z12, JD_K1847);
+        t12 = 2 * jd_mh2(z10, -JD_K2613) + z5;
+        T6 = t12 - T7;
+        T5 = t11 - T6;
+        T4 = (jd_mh2(z12, JD_K1082) - z5) + T5;
+    }
+    o[0] = T0 + T7; o[1] = T1 + T6; o[2] = T2 + T5; o[3] = T3 - T4;
+    o[4] = T3 + T4; o[5] = T2 - T5; o[6] = T1 - T6; o[7] = T0 - T7;
+}
+
+/* Column pass, -DNO_SIMD build arithmetic (jpeg.inl:2555-2678).  m[r] = raw coefficient
+ * (int16 value), q[r] = prescaled quant (signed short).  Processing an all-zero column gives
+ * zeros, so the reference's per-column skip (:2558) needs no special case. */
+JD_HD void jd_col_scalar(const int m[8], const int q[8], bool rows47_empty, int o[8])
+{
+    int tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, tmp7, tmp10, tmp11, tmp12, tmp13, z5, z10, z11, z12, z13;
+    if (rows47_empty) {
+        tmp10 = m[0] * q[0];
+        tmp1 = m[2] * q[2];
+        tmp12 = (tmp1 * 106) >> 8;
+        tmp0 = tmp10 + tmp1; tmp3 = tmp10 - tmp1; tmp1 = tmp10 + tmp12; tmp2 = tmp10 - tmp12;
+        tmp4 = m[1] * q[1];
+        if (m[3] != 0) {
+            tmp5 = m[3] * q[3];
+            tmp7 = tmp4 + tmp5;
+            tmp11 = ((tmp4 - tmp5) * 362) >> 8;
+            z5 = ((tmp4 - tmp5) * 473) >> 8;
+            tmp12 = ((-tmp5 * -669) >> 8) + z5;
+            tmp6 = tmp12 - tmp7;
+            tmp5 = tmp11 - tmp6;
+            tmp10 = ((tmp4 * 277) >> 8) - z5;
+            tmp4 = tmp10 + tmp5;
+        } else { /* not equal to the general formula (:2586-2592) */
+            tmp7 = tmp4;
+            tmp5 = (145 * tmp4) >> 8;
+            tmp6 = (217 * tmp4) >> 8;
+            tmp4 = (-51 * tmp4) >> 8;
+        }
+    } else {
+        tmp0 = m[0] * q[0];
+        tmp2 = m[4] * q[4];
+        tmp10 = tmp0 + tmp2; tmp11 = tmp0 - tmp2;
+        tmp1 = m[2] * q[2];
+        tmp3 = m[6] * q[6];
+        tmp13 = tmp1 + tmp3;
+        tmp12 = (((tmp1 - tmp3) * 362) >> 8) - tmp13;
+        tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp11 + tmp12; tmp2 = tmp11 - tmp12;
+        tmp5 = m[3] * q[3];
+        tmp6 = m[5] * q[5];
+        z13 = tmp6 + tmp5; z10 = tmp6 - tmp5;
+        tmp4 = m[1] * q[1];
+        tmp7 = m[7] * q[7];
+        z11 = tmp4 + tmp7; z12 = tmp4 - tmp7;
+        tmp7 = z11 + z13;
+        tmp11 = ((z11 - z13) * 362) >> 8;
+        z5 = ((z10 + z12) * 473) >> 8;
+        tmp12 = ((z10 * -669) >> 8) + z5;
+        tmp6 = tmp12 - tmp7;
+        tmp5 = tmp11 - tmp6;
+        tmp10 = ((z12 * 277) >> 8) - z5;
+        tmp4 = tmp10 + tmp5;
+    }
+    o[0] = tmp0 + tmp7; o[1] = tmp1 + tmp6; o[2] = tmp2 + tmp5; o[3] = tmp3 - tmp4;
+    o[4] = tmp3 + tmp4; o[5] = tmp2 - tmp5; o[6] = tmp1 - tmp6; o[7] = tmp0 - tmp7;
+}
+
+/* Row pass (both builds, jpeg.inl:2681-2797).  p[c] = int16 column results of one row
+ * (sign-extended); colmask = low byte of the block's u16MCUFlags.  Writes 8 pixel bytes. */
+JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])
+{
+    int tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, tmp7;
+    if ((colmask & 0xf0u) == 0u) {
+        if ((colmask & 0xfcu) == 0u) { /* 1-2 columns: approximation (:2688-2697) */
+            tmp0 = tmp1 = tmp2 = tmp3 = p[0];
+            tmp7 = p[1];
+            tmp6 = (tmp7 * 217) >> 8;
+            tmp5 = (tmp7 * 145) >> 8;
+            tmp4 = -((tmp7 * 51) >> 8);
+        } else {
+            int tmp10 = p[0], tmp13 = p[2];
+            int tmp12 = (tmp13 * 106) >> 8;
+            tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp10 + tmp12; tmp2 = tmp10 - tmp12;
+            int z13 = p[3], z11 = p[1];
+            tmp7 = z11 + z13;
+            int tmp11 = ((z11 - z13) * 362) >> 8;
+            int z5 = ((z11 - z13) * 473) >> 8;
+            tmp10 = ((z11 * 277) >> 8) - z5;
+            tmp12 = ((z13 * 669) >> 8) + z5;
+            tmp6 = tmp12 - tmp7;
+            tmp5 = tmp11 - tmp6;
+            tmp4 = tmp10 + tmp5;
+        }
+    } else {
+        int tmp10 = p[0] + p[4], tmp11 = p[0] - p[4];
+        int tmp13 = p[2] + p[6];
+        int tmp12 = (((p[2] - p[6]) * 362) >> 8) - tmp13;
+        tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp11 + tmp12; tmp2 = tmp11 - tmp12;
+        int z13 = p[5] + p[3], z10 = p[5] - p[3];
+        int z11 = p[1] + p[7], z12 = p[1] - p[7];
+        tmp7 = z11 + z13;
+        tmp11 = ((z11 - z13) * 362) >> 8;
+        int z5 = ((z10 + z12) * 473) >> 8;
+        tmp10 = ((z12 * 277) >> 8) - z5;
+        tmp12 = ((z10 * -669) >> 8) + z5;
+        tmp6 = tmp12 - tmp7;
+        tmp5 = tmp11 - tmp6;
+        tmp4 = tmp10 + tmp5;
+    }
+    o[0] = jd_range(tmp0 + tmp7); o[1] = jd_range(tmp1 + tmp6);
+    o[2] = jd_range(tmp2 + tmp5); o[3] = jd_range(tmp3 - tmp4);
+    o[4] = jd_range(tmp3 + tmp4); o[5] = jd_range(tmp2 - tmp5);
+    o[6] = jd_range(tmp1 - tmp6); o[7] = jd_range(tmp0 - tmp7);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Colour conversion (reference JPEGPixel* src/jpeg.inl:3101-3278 for the       */
+/* scalar build and all scaled paths; SSE2 full-size paths :3409-3517,          */
+/* :4006-4308).                                                                 */
+/* ------------------------------------------------------------------------- */
+
+JD_HD int jd_clamp255(int v) { v = v < 0 ? 0 : v; return v > 255 ? 255 : v; }
+
+/* scalar: Y12 = luma << 12 (or sum of 4 << 10 at half scale).  Returns B,G,R *unclamped*. */
+JD_HD void jd_ycc_scalar(int Y12, int Cb, int Cr, int *R, int *G, int *B)
+{
+    int cb = Cb - 128, cr = Cr - 128;
+    *B = (7258 * cb + Y12) >> 12;
+    *G = (-1409 * cb - 2925 * cr + Y12) >> 12;
+    *R = (5742 * cr + Y12) >> 12;
+}
+
+/* usRangeTableR/G/B (jpeg.inl:262-555): index v & 0x3ff; [0,255] -> v; [256,511] -> 255; [512,1023] -> 0 */
+JD_HD uint32_t jd_rt(int v)
+{
+    v &= 0x3ff;
+    return (uint32_t)(v < 256 ? v : (v < 512 ? 255 : 0));
+}
+
+JD_HD uint32_t jd_rgb565_scalar(int Y12, int Cb, int Cr)
+{
+    int R, G, B;
+    jd_ycc_scalar(Y12, Cb, Cr, &R, &G, &B);
+    return ((jd_rt(R) >> 3) << 11) | ((jd_rt(G) >> 2) << 5) | (jd_rt(B) >> 3);
+}
+
+/* JPEGPixelRGB (jpeg.inl:3152-3176): clamp to [0,255]; bytes R,G,B,A in memory */
+JD_HD uint32_t jd_rgb8888_scalar(int Y12, int Cb, int Cr)
+{
+    int R, G, B;
+    jd_ycc_scalar(Y12, Cb, Cr, &R, &G, &B);
+    return 0xFF000000u | ((uint32_t)jd_clamp255(B) << 16) | ((uint32_t)jd_clamp255(G) << 8) | (uint32_t)jd_clamp255(R);
+}
+
+/* SSE2 build: chroma terms (shared by the pixels that use this chroma sample).
+ * c16 = (C-128)<<8 as int16; MH(c16,K) = (c16*K)>>16. */
+JD_HD void jd_chroma_sse(int Cb, int Cr, int *tr, int *tg, int *tb)
+{
+    int cb16 = (Cb - 128) * 256, cr16 = (Cr - 128) * 256;
+    *tr = (cr16 * 5742) >> 16;
+    *tg = ((cr16 * -2925) >> 16) + ((cb16 * -1409) >> 16);
+    *tb = (cb16 * 7258) >> 16;
+}
+
+JD_HD void jd_rgb_sse(int Y, int tr, int tg, int tb, int *R, int *G, int *B)
+{
+    int Y4 = Y << 4;
+    *R = jd_clamp255((Y4 + tr) >> 4);
+    *G = jd_clamp255((Y4 + tg) >> 4);
+    *B = jd_clamp255((Y4 + tb) >> 4);
+}
+
+JD_HD uint32_t jd_gray565(uint32_t g) { return ((g >> 3) << 11) | ((g >> 2) << 5) | (g >> 3); }
+
+JD_HD uint32_t jd_bswap16(uint32_t v) { return ((v >> 8) | (v << 8)) & 0xFFFFu; }
+
+#endif /* JD_CORE_H */

@@ -1,0 +1,283 @@
+/*
+ * tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE: a sequential stepper for the per-thread
+ * code of the CUDA kernels (jpegdec_b200/csrc/jd_core.h) plus the host parser/table code
+ * (jd_host.c).  It lets the CPU-only test tier prove, against the compiled reference
+ * (oracle/_ref), that the exact arithmetic / bit-reader / window-phase logic the kernels run
+ * is bit-exact -- where no GPU exists.  It is NOT part of libjpegdec_b200.so and nothing in
+ * the product calls it.
+ *
+ * Stages mirror the GPU pipeline (jd_device.cu): prescan -> per-segment entropy decode ->
+ * phase stitch + patch -> per-block dequant/IDCT -> pixel assembly.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../jpegdec_b200/csrc/jd_core.h"
+#include "../../jpegdec_b200/csrc/jd_internal.h"
+
+struct VecSink {
+    std::vector<JDEvent> ev;
+    void push(const JDEvent &e) { ev.push_back(e); }
+};
+
+static const uint8_t kDezigzag[64] = JD_DEZIGZAG_INIT;
+
+struct Planes {
+    int sshift;          /* 0 full / half (block bytes are full 8x8), 2 quarter, 3 eighth */
+    int bs;              /* block-byte edge: 8, 2 or 1 */
+    int yw, yh, cw, ch;  /* plane sizes in block-bytes */
+    std::vector<uint8_t> Y, Cb, Cr;
+};
+
+extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int options, int arith,
+                              uint8_t *out, int out_pitch, int *out_w, int *out_h, int *n_events,
+                              int *err)
+{
+    JDInfo info;
+    int start = 0;
+    if (!jd_parse_header(data, size, 0, &info)) { *err = info.error; return -1; }
+    if (options & JPEG_EXIF_THUMBNAIL) {
+        if (info.thumb_data == 0 || info.thumb_w == 0) { *err = JPEG_INVALID_PARAMETER; return 0; }
+        start = info.thumb_data;
+        if (!jd_parse_header(data, size, start, &info)) { *err = info.error; return 0; }
+    }
+    if (info.mode != 0xC0 || !info.tables_ok) { *err = JPEG_UNSUPPORTED_FEATURE; return 0; }
+    *err = 0;
+    std::vector<uint16_t> lut(JD_LUT_ENTRIES);
+    jd_build_lut(&info, lut.data());
+    int16_t quant[3 * 64];
+    jd_build_quant(&info, quant);
+
+    int sshift = 0;
+    if (options & JPEG_SCALE_HALF) sshift = 1;
+    else if (options & JPEG_SCALE_QUARTER) sshift = 2;
+    else if (options & JPEG_SCALE_EIGHTH) sshift = 3;
+    if ((options & JPEG_LUMA_ONLY) && pixel_type < EIGHT_BIT_GRAYSCALE) pixel_type = EIGHT_BIT_GRAYSCALE;
+
+    /* ---- prescan: restart segments ---- */
+    const int total_mcus = info.mcus_x * info.mcus_y;
+    const int mps = info.restart_interval ? info.restart_interval : total_mcus;
+    const int nseg = (total_mcus + mps - 1) / mps;
+    std::vector<uint32_t> seg_start(nseg, 0xFFFFFFFFu);
+    seg_start[0] = (uint32_t)info.scan_offset;
+    {
+        int k = 1;
+        for (int i = info.scan_offset; i + 1 < size && k < nseg; i++) {
+            if (data[i] == 0xFF && data[i + 1] >= 0xD0 && data[i + 1] <= 0xD7) { seg_start[k++] = (uint32_t)(i + 2); i++; }
+        }
+    }
+    /* compressed buffer padded + aligned like the device buffer */
+    std::vector<uint32_t> padded((size + 64) / 4 + 16, 0);
+    memcpy(padded.data(), data, (size_t)size);
+    const uint8_t *cdata = (const uint8_t *)padded.data();
+
+    const int nblk = total_mcus * info.bpm;
+    std::vector<jd_u64> hdr(nblk, 0);
+    std::vector<uint16_t> rec((size_t)size * 4 + 1024, 0);
+    std::vector<uint32_t> jmap(nseg, 0);
+    VecSink sink;
+    int bad = 0;
+    for (int sgi = 0; sgi < nseg; sgi++) {
+        JDSegIn in;
+        in.data = cdata;
+        in.start = seg_start[sgi];
+        in.end = (uint32_t)size;
+        int m0 = sgi * mps;
+        in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
+        in.bpm = (uint32_t)info.bpm;
+        in.ncomp = (uint32_t)info.ncomp;
+        in.tsel = (uint32_t)info.tsel;
+        if (in.start == 0xFFFFFFFFu) { bad = 1; break; }
+        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset);
+        in.rec_cap = 4u * ((sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu ? seg_start[sgi + 1] : (uint32_t)size) - in.start) + 64u;
+        in.seg = (uint32_t)sgi;
+        JDSegOut so;
+        jd_decode_segment(in, lut.data(), hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        jmap[sgi] = so.jmap;
+        if (so.err_mcu >= 0) { bad = 1; break; }
+    }
+    if (bad) { *err = JPEG_DECODE_ERROR; }
+    /* ---- stitch: true window phase at each segment start, then patch ---- */
+    std::vector<uint32_t> phase(nseg, 0);
+    {
+        uint32_t c = 0;
+        for (int sgi = 0; sgi < nseg; sgi++) {
+            phase[sgi] = c;
+            uint32_t j = (jmap[sgi] >> (4 * c)) & 15u;
+            c = (j >= 6) ? 0 : j;
+        }
+    }
+    int nev = 0;
+    for (size_t i = 0; i < sink.ev.size(); i++) {
+        const JDEvent &e = sink.ev[i];
+        uint32_t jc = (e.j1 >> (4 * phase[e.seg])) & 15u;
+        if (8 * (int)jc + e.p7 + e.s > 64) {
+            int v = jd_event_value(&e, jc);
+            rec[e.rec_index] = (uint16_t)((rec[e.rec_index] & 0xF000u) | ((uint32_t)v & 0xFFFu));
+            nev++;
+        }
+    }
+    if (n_events) *n_events = nev;
+
+    /* ---- per-block dequant + IDCT into block-byte planes ---- */
+    Planes pl;
+    pl.sshift = sshift;
+    pl.bs = (sshift >= 2) ? (8 >> sshift) : 8;
+    const int hs = info.mcu_w / 8, vs = info.mcu_h / 8;
+    pl.yw = info.mcus_x * hs * pl.bs; pl.yh = info.mcus_y * vs * pl.bs;
+    pl.cw = info.mcus_x * pl.bs; pl.ch = info.mcus_y * pl.bs;
+    pl.Y.assign((size_t)pl.yw * pl.yh, 0);
+    if (info.ncomp == 3) { pl.Cb.assign((size_t)pl.cw * pl.ch, 0); pl.Cr.assign((size_t)pl.cw * pl.ch, 0); }
+    const int nluma = (info.ncomp == 3) ? info.bpm - 2 : info.bpm;
+    for (int m = 0; m < total_mcus; m++) {
+        int mx = m % info.mcus_x, my = m / info.mcus_x;
+        for (int b = 0; b < info.bpm; b++) {
+            int comp = (b < nluma) ? 0 : (b - nluma + 1);
+            const int16_t *q = quant + comp * 64;
+            jd_u64 h = hdr[(size_t)m * info.bpm + b];
+            uint32_t ri = (uint32_t)h;
+            int dc = (int16_t)(uint16_t)(h >> 32);
+            int nrec = (int)((h >> 48) & 0xFF);
+            int16_t tile[64];
+            memset(tile, 0, sizeof(tile));
+            tile[0] = (int16_t)dc;
+            uint32_t flags = 0;
+            int k = 1;
+            const int limit = (sshift >= 2) ? 5 : 64;
+            for (int i = 0; i < nrec; i++) {
+                uint32_t r = rec[ri + i];
+                k += (int)(r >> 12);
+                int v = (int)(r << 20) >> 20;
+                if (v != 0 && k < limit) {
+                    int n = kDezigzag[k];
+                    tile[n] = (int16_t)v;
+                    flags |= 1u << (n & 7);
+                    flags |= (uint32_t)n << 8;
+                }
+                k++;
+            }
+            uint8_t px[64];
+            if (sshift == 3 || flags == 0) {
+                uint8_t c = (uint8_t)jd_range(dc * (int)q[0]);
+                memset(px, c, 64);
+            } else if (sshift == 2) {
+                int t4 = tile[0] * q[0], t5 = tile[8] * q[8];
+                int t0 = t4 + t5, t2 = t4 - t5;
+                t4 = tile[1] * q[1]; t5 = tile[9] * q[9];
+                int t1 = t4 + t5, t3 = t4 - t5;
+                px[0] = (uint8_t)jd_range(t0 + t1); px[1] = (uint8_t)jd_range(t0 - t1);
+                px[2] = (uint8_t)jd_range(t2 + t3); px[3] = (uint8_t)jd_range(t2 - t3);
+            } else {
+                int16_t col[64];
+                const bool r47 = (flags & 0x2000u) == 0;
+                for (int c = 0; c < 8; c++) {
+                    int o[8];
+                    if (arith == JPEG_ARITH_SSE2) {
+                        int d[8];
+                        for (int r = 0; r < 8; r++) d[r] = tile[r * 8 + c] * q[r * 8 + c];
+                        jd_col_sse16(d, r47, o);
+                    } else {
+                        int mm[8], qq[8];
+                        for (int r = 0; r < 8; r++) { mm[r] = tile[r * 8 + c]; qq[r] = q[r * 8 + c]; }
+                        jd_col_scalar(mm, qq, r47, o);
+                    }
+                    for (int r = 0; r < 8; r++) col[r * 8 + c] = (int16_t)o[r];
+                }
+                for (int r = 0; r < 8; r++) {
+                    int p[8];
+                    uint32_t o[8];
+                    for (int c = 0; c < 8; c++) p[c] = col[r * 8 + c];
+                    jd_row(p, flags & 0xFFu, o);
+                    for (int c = 0; c < 8; c++) px[r * 8 + c] = (uint8_t)o[c];
+                }
+            }
+            /* store block bytes: full 8x8, or 2x2 (bytes 0..3 row-major) / 1 */
+            uint8_t *plane; int pw, bx, by;
+            if (comp == 0) {
+                plane = pl.Y.data(); pw = pl.yw;
+                int lx = (hs == 2) ? (b & 1) : 0;
+                int ly = (hs == 2 && vs == 2) ? (b >> 1) : ((vs == 2 && hs == 1) ? b : 0);
+                bx = mx * hs + lx; by = my * vs + ly;
+            } else {
+                plane = (comp == 1) ? pl.Cb.data() : pl.Cr.data(); pw = pl.cw;
+                bx = mx; by = my;
+            }
+            for (int y = 0; y < pl.bs; y++)
+                for (int x = 0; x < pl.bs; x++)
+                    plane[(size_t)(by * pl.bs + y) * pw + bx * pl.bs + x] = px[y * pl.bs + x];
+        }
+    }
+
+    /* ---- pixel assembly ---- */
+    const int ow = (info.width + (1 << sshift) - 1) >> sshift, oh = (info.height + (1 << sshift) - 1) >> sshift;
+    *out_w = ow; *out_h = oh;
+    const bool sse_full = (arith == JPEG_ARITH_SSE2) && sshift == 0 && (info.subsample == 0x22 || info.subsample == 0x11);
+    for (int oy = 0; oy < oh; oy++) {
+        uint8_t *row = out + (size_t)oy * out_pitch;
+        for (int ox = 0; ox < ow; ox++) {
+            int Y, Y12, Cb = 128, Cr = 128;
+            if (sshift == 1) {
+                const uint8_t *yp = &pl.Y[(size_t)(2 * oy) * pl.yw + 2 * ox];
+                int sum = yp[0] + yp[1] + yp[pl.yw] + yp[pl.yw + 1];
+                Y = (sum + 2) >> 2;   /* gray paths */
+                Y12 = sum << 10;      /* colour paths: no rounding */
+                if (info.ncomp == 3) {
+                    if (hs == 2 && vs == 2) { Cb = pl.Cb[(size_t)oy * pl.cw + ox]; Cr = pl.Cr[(size_t)oy * pl.cw + ox]; }
+                    else if (hs == 1 && vs == 1) {
+                        const uint8_t *a = &pl.Cb[(size_t)(2 * oy) * pl.cw + 2 * ox], *b2 = &pl.Cr[(size_t)(2 * oy) * pl.cw + 2 * ox];
+                        Cb = (a[0] + a[1] + a[pl.cw] + a[pl.cw + 1] + 2) >> 2;
+                        Cr = (b2[0] + b2[1] + b2[pl.cw] + b2[pl.cw + 1] + 2) >> 2;
+                    } else if (hs == 2) { /* 4:2:2: chroma full height, half width: average 2 rows */
+                        Cb = (pl.Cb[(size_t)(2 * oy) * pl.cw + ox] + pl.Cb[(size_t)(2 * oy + 1) * pl.cw + ox] + 1) >> 1;
+                        Cr = (pl.Cr[(size_t)(2 * oy) * pl.cw + ox] + pl.Cr[(size_t)(2 * oy + 1) * pl.cw + ox] + 1) >> 1;
+                    } else { /* 4:4:0 */
+                        Cb = (pl.Cb[(size_t)oy * pl.cw + 2 * ox] + pl.Cb[(size_t)oy * pl.cw + 2 * ox + 1] + 1) >> 1;
+                        Cr = (pl.Cr[(size_t)oy * pl.cw + 2 * ox] + pl.Cr[(size_t)oy * pl.cw + 2 * ox + 1] + 1) >> 1;
+                    }
+                }
+            } else {
+                Y = pl.Y[(size_t)oy * pl.yw + ox];
+                Y12 = Y << 12;
+                if (info.ncomp == 3) {
+                    Cb = pl.Cb[(size_t)(oy / vs) * pl.cw + ox / hs];
+                    Cr = pl.Cr[(size_t)(oy / vs) * pl.cw + ox / hs];
+                }
+            }
+            if (pixel_type >= EIGHT_BIT_GRAYSCALE) {
+                row[ox] = (uint8_t)Y;
+            } else if (info.ncomp == 1) {
+                uint32_t v = jd_gray565((uint32_t)Y);
+                if (pixel_type != RGB565_LITTLE_ENDIAN) v = jd_bswap16(v);
+                ((uint16_t *)row)[ox] = (uint16_t)v;
+            } else if (sse_full) {
+                int tr, tg, tb, R, G, B;
+                jd_chroma_sse(Cb, Cr, &tr, &tg, &tb);
+                jd_rgb_sse(Y, tr, tg, tb, &R, &G, &B);
+                if (pixel_type == RGB8888) ((uint32_t *)row)[ox] = 0xFF000000u | ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B;
+                else ((uint16_t *)row)[ox] = (uint16_t)(((R >> 3) << 11) | ((G >> 2) << 5) | (B >> 3));
+            } else {
+                if (pixel_type == RGB8888) ((uint32_t *)row)[ox] = jd_rgb8888_scalar(Y12, Cb, Cr);
+                else {
+                    uint32_t v = jd_rgb565_scalar(Y12, Cb, Cr);
+                    if (pixel_type == RGB565_BIG_ENDIAN) v = jd_bswap16(v);
+                    ((uint16_t *)row)[ox] = (uint16_t)v;
+                }
+            }
+        }
+    }
+    return bad ? 0 : 1;
+}
+
+/* open()-level behaviour for conformance tests */
+extern "C" int hostsim_open(const uint8_t *data, int size, int *w, int *h, int *subsample, int *err,
+                            int *has_thumb, int *tw, int *th, int *orientation, int *bpp)
+{
+    JDInfo info;
+    int rc = jd_parse_header(data, size, 0, &info);
+    *w = info.width; *h = info.height; *subsample = info.subsample; *err = info.error;
+    *has_thumb = info.has_thumb; *tw = info.thumb_w; *th = info.thumb_h; *orientation = info.orientation;
+    *bpp = info.bpp;
+    return rc;
+}
