@@ -124,6 +124,7 @@ typedef struct {
 typedef struct {
     uint32_t jmap;   /* six nibbles: window phase at segment end (after byte alignment) per start candidate */
     int32_t err_mcu; /* -1 ok, else local MCU index where decoding failed */
+    uint32_t status; /* JD_SEG_* */
     uint32_t nrec;
 } JDSegOut;
 
@@ -302,18 +303,22 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                 if (k >= 64u) done = true;
             }
         }
-        if (err >= 0) { out.err_mcu = (int32_t)(b / in.bpm); break; }
+        if (err >= 0) {
+            /* undecodable from here: later stages must still find well-formed (empty) headers */
+            out.err_mcu = (int32_t)(b / in.bpm);
+            for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0);
+            break;
+        }
         blk_hdr[b] = jd_pack_hdr(in.rec_index0 + rec0, dcval, nrec);
         if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
     }
+    out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
     if (err < 0) {
         out.err_mcu = -1;
         /* end of restart interval (jpeg.inl:5337-5347): R4 already happened unless the last
          * block ended with EOB; then the bit offset is rounded up to a byte without a reload. */
         if (!last_was_eob) jw = jd_jw_ckpt(jw);
         if (P & 7) jw += JD_JW_ONES;
-    } else {
-        out.err_mcu = (out.err_mcu & 0x0FFFFFFF) | (err << 28);
     }
     out.jmap = jw;
     out.nrec = nrec_total;

@@ -1,0 +1,758 @@
+/*
+ * jd_device.cu -- batch decode pipeline on one B200: buffers, uploads, kernel launches,
+ * CUDA-event stage timings, downloads.  Exposes the JPEGB200_* C ABI (include/jpegdec_b200.h).
+ * There is no CPU fallback anywhere in this file: if CUDA is unavailable every entry point fails.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <new>
+
+#include "jd_kernels.cuh"
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx_err(), 256, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return 0;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+static char g_err[256];
+
+struct JPEGB200_CTX {
+    int device;
+    int arith;
+    char err[256];
+    bool has_shared;
+    uint64_t shared_hash;
+    uint16_t shared_lut[JD_LUT_ENTRIES];
+    int shared_hits;
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        if (count <= n && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct JPEGB200_BATCH {
+    JPEGB200_CTX *ctx;
+    int n;
+    int pixel_type, options, sshift, ptclass, dither_bits;
+    bool gray_out;
+    bool padded; /* write the whole MCU-aligned frame (single-image API: callbacks deliver whole MCUs) */
+    cudaStream_t stream;
+    std::vector<JDInfo> infos;
+    std::vector<int32_t> parse_status;
+    std::vector<const uint8_t *> datas;
+    std::vector<int32_t> sizes;
+    std::vector<JDImageDesc> descs;
+    std::vector<int16_t> quant;
+    std::vector<uint16_t> luts;
+    std::vector<uint32_t> work, cta_lut, seg_img;
+    std::vector<uint64_t> comp_off; /* offset of each file in the device blob */
+    std::vector<void *> outs;
+    std::vector<int64_t> pitches;
+    std::vector<uint8_t> errinit;   /* dither: initial error line per image (reference quirk) */
+    size_t comp_total, out_total, gray_total;
+    uint32_t nseg, nlut;
+    uint64_t nblk;
+    bool contiguous_in;
+    bool uploaded, out_device, arena_owned;
+    DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
+    DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
+    DevBuf<uint32_t> d_err_off;
+    std::vector<JDImageDesc> descs_dl; /* descriptors read back (status, err_mcu) */
+    DevBuf<JDImageDesc> d_descs;
+    DevBuf<int16_t> d_quant;
+    DevBuf<uint16_t> d_luts, d_rec;
+    DevBuf<uint32_t> d_work, d_cta_lut, d_seg_img, d_seg_start, d_seg_jmap, d_seg_status, d_seg_nrec, d_seg_phase, d_counters;
+    DevBuf<jd_u64> d_blk_hdr;
+    DevBuf<JDEvent> d_events;
+    std::vector<uint64_t> arena_off; /* per-image offset inside d_out */
+    cudaEvent_t ev[JPEGB200_NUM_TIMINGS + 2];
+    bool have_ev;
+    float ms[JPEGB200_NUM_TIMINGS];
+    int64_t counters[JPEGB200_NUM_COUNTERS];
+    uint32_t h_counters[4];
+};
+
+static char *ctx_err() { return g_err; }
+
+#define JD_EVENT_CAP (1u << 20)
+
+extern "C" int JPEGB200_deviceCount(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" JPEGB200_CTX *JPEGB200_create(int device, int arith_mode)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (%d devices)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed", device); return nullptr; }
+    /* make sure the sm_100a kernel image is loadable on this GPU */
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, jdk_prescan);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "kernel image not loadable on device %d: %s (built for sm_100a only)", device, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    JPEGB200_CTX *c = new (std::nothrow) JPEGB200_CTX();
+    if (!c) return nullptr;
+    c->device = device;
+    c->arith = arith_mode ? JPEG_ARITH_SCALAR : JPEG_ARITH_SSE2;
+    c->err[0] = 0;
+    c->has_shared = false;
+    c->shared_hits = 0;
+    return c;
+}
+
+extern "C" void JPEGB200_destroy(JPEGB200_CTX *ctx) { delete ctx; }
+
+extern "C" const char *JPEGB200_lastErrorString(JPEGB200_CTX *) { return g_err; }
+
+extern "C" void *JPEGB200_hostAlloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void JPEGB200_hostFree(void *p) { if (p) cudaFreeHost(p); }
+
+/* ---- shared table blob ---- */
+extern "C" int JPEGB200_exportTables(const uint8_t *jpeg, int size, uint8_t *blob)
+{
+    JDInfo *info = new JDInfo();
+    int rc = jd_parse_header(jpeg, size, 0, info);
+    if (rc) {
+        uint64_t h = jd_tables_hash(info);
+        memcpy(blob, &h, 8);
+        memset(blob + 8, 0, 8);
+        jd_build_lut(info, (uint16_t *)(blob + 16));
+        jd_build_quant(info, (int16_t *)(blob + 16 + JD_LUT_ENTRIES * 2));
+    }
+    delete info;
+    return rc;
+}
+
+extern "C" int JPEGB200_setSharedTables(JPEGB200_CTX *ctx, const uint8_t *blob)
+{
+    if (!ctx) return 0;
+    memcpy(&ctx->shared_hash, blob, 8);
+    memcpy(ctx->shared_lut, blob + 16, JD_LUT_ENTRIES * 2);
+    ctx->has_shared = true;
+    ctx->shared_hits = 0;
+    return 1;
+}
+
+extern "C" int JPEGB200_sharedTableHits(JPEGB200_CTX *ctx) { return ctx ? ctx->shared_hits : 0; }
+
+/* ---- batch ---- */
+static int bytes_per_pixel_class(int ptclass) { return ptclass == JD_PT_565 ? 2 : (ptclass == JD_PT_8888 ? 4 : 1); }
+
+extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes,
+                                                int n, int pixel_type, int options)
+{
+    if (!ctx || n <= 0 || pixel_type < 0 || pixel_type >= INVALID_PIXEL_TYPE) { snprintf(g_err, sizeof(g_err), "invalid parameter"); return nullptr; }
+    JPEGB200_BATCH *b = new (std::nothrow) JPEGB200_BATCH();
+    if (!b) return nullptr;
+    b->ctx = ctx;
+    b->n = n;
+    if ((options & JPEG_LUMA_ONLY) && pixel_type < EIGHT_BIT_GRAYSCALE) pixel_type = EIGHT_BIT_GRAYSCALE; /* jpeg.inl:4991 */
+    b->pixel_type = pixel_type;
+    b->padded = (options & 0x10000) != 0; /* JPEGB200_OPT_PADDED (internal, jd_api.c) */
+    b->options = options;
+    b->sshift = (options & JPEG_SCALE_HALF) ? 1 : (options & JPEG_SCALE_QUARTER) ? 2 : (options & JPEG_SCALE_EIGHTH) ? 3 : 0;
+    b->gray_out = pixel_type >= EIGHT_BIT_GRAYSCALE;
+    b->ptclass = (pixel_type == RGB8888) ? JD_PT_8888 : (b->gray_out ? JD_PT_GRAY : JD_PT_565);
+    b->dither_bits = (pixel_type == FOUR_BIT_DITHERED) ? 4 : (pixel_type == TWO_BIT_DITHERED) ? 2 : (pixel_type == ONE_BIT_DITHERED) ? 1 : 0;
+    b->stream = nullptr;
+    b->uploaded = false; b->out_device = false; b->arena_owned = false; b->have_ev = false;
+    memset(b->ms, 0, sizeof(b->ms));
+    memset(b->counters, 0, sizeof(b->counters));
+    b->infos.resize(n);
+    b->parse_status.assign(n, JPEG_SUCCESS);
+    b->datas.assign(datas, datas + n);
+    b->sizes.assign(sizes, sizes + n);
+    b->descs.resize(n);
+    b->quant.assign((size_t)n * 192, 0);
+    b->outs.assign(n, nullptr);
+    b->pitches.assign(n, 0);
+    b->comp_off.assign(n, 0);
+    b->arena_off.assign(n, 0);
+
+    /* input layout: one span if the files already sit back to back in host memory */
+    bool contig = true;
+    for (int i = 1; i < n && contig; i++) {
+        const uint8_t *prev_end = datas[i - 1] + sizes[i - 1];
+        if (datas[i] < prev_end || (size_t)(datas[i] - prev_end) > 4096) contig = false;
+    }
+    b->contiguous_in = contig;
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        if (contig) off = (size_t)(datas[i] - datas[0]);
+        b->comp_off[i] = off;
+        if (!contig) off += ((size_t)sizes[i] + 15) & ~(size_t)15;
+    }
+    b->comp_total = contig ? (size_t)(datas[n - 1] + sizes[n - 1] - datas[0]) : off;
+    if (b->comp_total >= (1ull << 30)) {
+        snprintf(g_err, sizeof(g_err), "batch holds %zu compressed bytes; limit is 1 GiB per batch (split it)", b->comp_total);
+        delete b;
+        return nullptr;
+    }
+
+    std::vector<uint64_t> lut_hash;
+    uint32_t seg = 0;
+    uint64_t blk = 0;
+    size_t out_total = 0, gray_total = 0;
+    for (int i = 0; i < n; i++) {
+        JDInfo &inf = b->infos[i];
+        JDImageDesc &d = b->descs[i];
+        memset(&d, 0, sizeof(d));
+        int ok = jd_parse_header(datas[i], sizes[i], 0, &inf);
+        int st = ok ? JPEG_SUCCESS : inf.error;
+        if (ok && (options & JPEG_EXIF_THUMBNAIL)) {
+            if (inf.thumb_data == 0 || inf.thumb_w == 0) { ok = 0; st = JPEG_INVALID_PARAMETER; }
+            else { ok = jd_parse_header(datas[i], sizes[i], inf.thumb_data, &inf); if (!ok) st = inf.error; }
+        }
+        if (ok && inf.mode != 0xC0) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; } /* progressive thumbnails: out of scope */
+        if (ok && !inf.tables_ok) { ok = 0; st = JPEG_DECODE_ERROR; }           /* jpeg.inl:2166 */
+        if (ok && inf.ncomp == 1 && pixel_type == RGB8888) { ok = 0; st = JPEG_INVALID_PARAMETER; }
+        b->parse_status[i] = st;
+        if (!ok) { /* keep a harmless empty descriptor */
+            d.nseg = 0; d.seg_base = seg; d.blk_base = (uint32_t)blk; d.status = (uint32_t)st;
+            continue;
+        }
+        jd_build_quant(&inf, &b->quant[(size_t)i * 192]);
+        /* Huffman LUT set: dedupe on the raw DHT content */
+        uint64_t h = jd_tables_hash(&inf);
+        uint32_t li = 0;
+        for (; li < lut_hash.size(); li++) if (lut_hash[li] == h) break;
+        if (li == lut_hash.size()) {
+            lut_hash.push_back(h);
+            b->luts.resize((size_t)(li + 1) * JD_LUT_ENTRIES);
+            if (ctx->has_shared && ctx->shared_hash == h) { memcpy(&b->luts[(size_t)li * JD_LUT_ENTRIES], ctx->shared_lut, JD_LUT_ENTRIES * 2); ctx->shared_hits++; }
+            else jd_build_lut(&inf, &b->luts[(size_t)li * JD_LUT_ENTRIES]);
+        } else if (ctx->has_shared && ctx->shared_hash == h) ctx->shared_hits++;
+        const uint32_t total_mcus = (uint32_t)inf.mcus_x * inf.mcus_y;
+        const uint32_t mps = inf.restart_interval ? (uint32_t)inf.restart_interval : total_mcus;
+        d.scan_off = (uint32_t)(b->comp_off[i] + inf.scan_offset);
+        d.scan_end = (uint32_t)(b->comp_off[i] + sizes[i]);
+        d.width = (uint16_t)inf.width; d.height = (uint16_t)inf.height;
+        d.mcus_x = (uint16_t)inf.mcus_x; d.mcus_y = (uint16_t)inf.mcus_y;
+        d.subsample = (uint8_t)inf.subsample; d.ncomp = (uint8_t)inf.ncomp; d.bpm = (uint8_t)inf.bpm; d.tsel = (uint8_t)inf.tsel;
+        d.mcus_per_seg = mps;
+        d.nseg = (total_mcus + mps - 1) / mps;
+        d.seg_base = seg;
+        d.blk_base = (uint32_t)blk;
+        d.lutset = li;
+        const int s = b->sshift;
+        d.out_w = (uint32_t)((inf.width + (1 << s) - 1) >> s);
+        d.out_h = (uint32_t)((inf.height + (1 << s) - 1) >> s);
+        if (b->padded) {
+            d.out_w = (uint32_t)inf.mcus_x * (uint32_t)(inf.mcu_w >> s);
+            d.out_h = (uint32_t)inf.mcus_y * (uint32_t)(inf.mcu_h >> s);
+        }
+        size_t pitch;
+        if (b->dither_bits) {
+            const uint32_t pw = (uint32_t)inf.mcus_x * (uint32_t)(inf.mcu_w >> s);
+            pitch = ((size_t)pw * b->dither_bits + 7) / 8;
+            gray_total += (((size_t)pw * (size_t)inf.mcus_y * (size_t)(inf.mcu_h >> s)) + 255) & ~(size_t)255;
+        } else pitch = (size_t)d.out_w * bytes_per_pixel_class(b->ptclass);
+        d.out_pitch = (uint32_t)pitch;
+        b->pitches[i] = (int64_t)pitch;
+        b->arena_off[i] = out_total;
+        out_total += (pitch * d.out_h + 255) & ~(size_t)255;
+        seg += d.nseg;
+        blk += (uint64_t)total_mcus * inf.bpm;
+        if (blk >= (1ull << 32)) { snprintf(g_err, sizeof(g_err), "batch too large (block count)"); delete b; return nullptr; }
+    }
+    b->nseg = seg; b->nblk = blk; b->nlut = (uint32_t)lut_hash.size();
+    b->out_total = out_total; b->gray_total = gray_total;
+    /* work list: CTAs of 128 segments sharing one LUT set */
+    b->seg_img.resize(seg ? seg : 1);
+    for (uint32_t li = 0; li < (b->nlut ? b->nlut : 1); li++) {
+        for (int i = 0; i < n; i++) {
+            const JDImageDesc &d = b->descs[i];
+            if (d.nseg == 0 || b->parse_status[i] != JPEG_SUCCESS || d.lutset != li) continue;
+            for (uint32_t s2 = 0; s2 < d.nseg; s2++) { b->seg_img[d.seg_base + s2] = (uint32_t)i; b->work.push_back(d.seg_base + s2); }
+        }
+        while (b->work.size() % JD_ENTROPY_THREADS) b->work.push_back(JD_NONE);
+        while (b->cta_lut.size() < b->work.size() / JD_ENTROPY_THREADS) b->cta_lut.push_back(li);
+    }
+    return b;
+}
+
+extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    b->d_comp.release(); if (b->arena_owned) b->d_out.release(); b->d_gray.release(); b->d_errline.release();
+    b->d_gray_off.release(); b->d_err_off.release();
+    b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
+    b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
+    b->d_seg_jmap.release(); b->d_seg_status.release(); b->d_seg_nrec.release(); b->d_seg_phase.release();
+    b->d_counters.release(); b->d_blk_hdr.release(); b->d_events.release();
+    if (b->have_ev) for (auto &e : b->ev) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+extern "C" int JPEGB200_batchCount(JPEGB200_BATCH *b) { return b ? b->n : 0; }
+
+extern "C" int JPEGB200_batchImageInfo(JPEGB200_BATCH *b, int i, int32_t *width, int32_t *height, int32_t *subsample,
+                                       int32_t *out_w, int32_t *out_h, int32_t *status)
+{
+    if (!b || i < 0 || i >= b->n) return 0;
+    const JDInfo &inf = b->infos[i];
+    if (width) *width = inf.width;
+    if (height) *height = inf.height;
+    if (subsample) *subsample = inf.subsample;
+    if (out_w) *out_w = (int32_t)b->descs[i].out_w;
+    if (out_h) *out_h = (int32_t)b->descs[i].out_h;
+    if (status) *status = b->parse_status[i];
+    return 1;
+}
+
+extern "C" int64_t JPEGB200_batchOutputBytes(JPEGB200_BATCH *b, int i, int64_t *pitch_bytes)
+{
+    if (!b || i < 0 || i >= b->n) return 0;
+    if (pitch_bytes) *pitch_bytes = (int64_t)b->descs[i].out_pitch;
+    return (int64_t)b->descs[i].out_pitch * b->descs[i].out_h;
+}
+
+extern "C" int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int64_t pitch_bytes)
+{
+    if (!b || i < 0 || i >= b->n) return 0;
+    b->outs[i] = out;
+    if (pitch_bytes > 0) b->pitches[i] = pitch_bytes;
+    return 1;
+}
+
+static int batch_stream(JPEGB200_BATCH *b)
+{
+    CK(cudaSetDevice(b->ctx->device));
+    if (!b->stream) CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    if (!b->have_ev) {
+        for (auto &e : b->ev) CK(cudaEventCreate(&e));
+        b->have_ev = true;
+    }
+    return 1;
+}
+
+extern "C" void *JPEGB200_batchStream(JPEGB200_BATCH *b) { if (!b || !batch_stream(b)) return nullptr; return (void *)b->stream; }
+
+extern "C" int JPEGB200_batchAllocDeviceOutput(JPEGB200_BATCH *b)
+{
+    if (!b) return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(b->d_out.alloc(b->out_total + 256));
+    b->arena_owned = true;
+    return 1;
+}
+
+extern "C" int JPEGB200_batchGetDeviceOutput(JPEGB200_BATCH *b, int i, void **devptr, int64_t *pitch_bytes)
+{
+    if (!b || i < 0 || i >= b->n || !b->d_out.p) return 0;
+    if (devptr) *devptr = b->d_out.p + b->arena_off[i];
+    if (pitch_bytes) *pitch_bytes = (int64_t)b->descs[i].out_pitch;
+    return 1;
+}
+
+extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
+{
+    if (!b) return 0;
+    if (!batch_stream(b)) return 0;
+    const int n = b->n;
+    CK(b->d_comp.alloc(b->comp_total + 256));
+    CK(b->d_descs.alloc(n));
+    CK(b->d_quant.alloc((size_t)n * 192));
+    CK(b->d_luts.alloc(b->luts.size() ? b->luts.size() : 1));
+    CK(b->d_work.alloc(b->work.size() ? b->work.size() : 1));
+    CK(b->d_cta_lut.alloc(b->cta_lut.size() ? b->cta_lut.size() : 1));
+    CK(b->d_seg_img.alloc(b->seg_img.size()));
+    const size_t ns = b->nseg ? b->nseg : 1;
+    CK(b->d_seg_start.alloc(ns + 1)); CK(b->d_seg_jmap.alloc(ns)); CK(b->d_seg_status.alloc(ns));
+    CK(b->d_seg_nrec.alloc(ns)); CK(b->d_seg_phase.alloc(ns));
+    CK(b->d_counters.alloc(4));
+    CK(b->d_blk_hdr.alloc(b->nblk ? b->nblk : 1));
+    CK(b->d_rec.alloc(4 * b->comp_total + 1024));
+    CK(b->d_events.alloc(JD_EVENT_CAP));
+    cudaStream_t st = b->stream;
+    CK(cudaEventRecord(b->ev[0], st));
+    /* zero the tail padding so word loads past the last file read zeros */
+    CK(cudaMemsetAsync(b->d_comp.p + b->comp_total, 0, 256, st));
+    if (b->contiguous_in) {
+        CK(cudaMemcpyAsync(b->d_comp.p, b->datas[0], b->comp_total, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int i = 0; i < n; i++)
+            CK(cudaMemcpyAsync(b->d_comp.p + b->comp_off[i], b->datas[i], (size_t)b->sizes[i], cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(b->d_descs.p, b->descs.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_quant.p, b->quant.data(), sizeof(int16_t) * 192 * n, cudaMemcpyHostToDevice, st));
+    if (b->luts.size()) CK(cudaMemcpyAsync(b->d_luts.p, b->luts.data(), b->luts.size() * 2, cudaMemcpyHostToDevice, st));
+    if (b->work.size()) CK(cudaMemcpyAsync(b->d_work.p, b->work.data(), b->work.size() * 4, cudaMemcpyHostToDevice, st));
+    if (b->cta_lut.size()) CK(cudaMemcpyAsync(b->d_cta_lut.p, b->cta_lut.data(), b->cta_lut.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_seg_img.p, b->seg_img.data(), b->seg_img.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(b->ev[1], st));
+    b->uploaded = true;
+    b->counters[JPEGB200_C_H2D_BYTES] = (int64_t)(b->comp_total + sizeof(JDImageDesc) * n + 384 * (size_t)n + b->luts.size() * 2 +
+                                                  b->work.size() * 4 + b->cta_lut.size() * 4 + b->seg_img.size() * 4);
+    return 1;
+}
+
+/* ---- IDCT kernel dispatch ---- */
+template <int HS, int VS, int NC, int MPB, int PT>
+static void launch_idct_pt(const JDIdctArgs &a, dim3 grid, int arith, bool half, cudaStream_t st)
+{
+    using G = JDGeo<HS, VS, NC, MPB>;
+    if (arith == JPEG_ARITH_SSE2) {
+        if (half) jdk_idct_color<HS, VS, NC, MPB, PT, JPEG_ARITH_SSE2, true><<<grid, G::THREADS, 0, st>>>(a);
+        else jdk_idct_color<HS, VS, NC, MPB, PT, JPEG_ARITH_SSE2, false><<<grid, G::THREADS, 0, st>>>(a);
+    } else {
+        if (half) jdk_idct_color<HS, VS, NC, MPB, PT, JPEG_ARITH_SCALAR, true><<<grid, G::THREADS, 0, st>>>(a);
+        else jdk_idct_color<HS, VS, NC, MPB, PT, JPEG_ARITH_SCALAR, false><<<grid, G::THREADS, 0, st>>>(a);
+    }
+}
+
+template <int HS, int VS, int MPB3, int MPB1>
+static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, int ncomp, int ptclass,
+                           int arith, bool half, cudaStream_t st)
+{
+    if (ptclass == JD_PT_GRAY) {
+        dim3 grid(((mcus_x + MPB1 - 1) / MPB1) * mcus_y, nimg);
+        launch_idct_pt<HS, VS, 1, MPB1, JD_PT_GRAY>(a, grid, arith, half, st);
+    } else if (ncomp == 1) {
+        if (HS != 1 || VS != 1 || ptclass != JD_PT_565) return 0;
+        dim3 grid(((mcus_x + MPB1 - 1) / MPB1) * mcus_y, nimg);
+        launch_idct_pt<1, 1, 1, MPB1, JD_PT_565>(a, grid, arith, half, st);
+    } else {
+        dim3 grid(((mcus_x + MPB3 - 1) / MPB3) * mcus_y, nimg);
+        if (ptclass == JD_PT_565) launch_idct_pt<HS, VS, 3, MPB3, JD_PT_565>(a, grid, arith, half, st);
+        else launch_idct_pt<HS, VS, 3, MPB3, JD_PT_8888>(a, grid, arith, half, st);
+    }
+    return 1;
+}
+
+__global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
+                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift);
+
+extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
+{
+    if (!b) return 0;
+    if (!b->uploaded) { snprintf(g_err, sizeof(g_err), "batchDecode before batchUpload"); return 0; }
+    if (!batch_stream(b)) return 0;
+    cudaStream_t st = b->stream;
+    const int n = b->n;
+    b->out_device = (flags & JPEGB200_OUT_DEVICE) != 0;
+    int launches = 0;
+    /* output placement */
+    bool user_dev_out = false;
+    if (b->out_device && !b->arena_owned) {
+        user_dev_out = true;
+        for (int i = 0; i < n; i++) if (!b->outs[i] && b->parse_status[i] == JPEG_SUCCESS) user_dev_out = false;
+    }
+    uint8_t *out_base = nullptr;
+    if (user_dev_out) {
+        /* user device pointers: offsets relative to the lowest pointer */
+        uintptr_t lo = ~(uintptr_t)0;
+        for (int i = 0; i < n; i++) if (b->outs[i] && (uintptr_t)b->outs[i] < lo) lo = (uintptr_t)b->outs[i];
+        out_base = (uint8_t *)lo;
+        for (int i = 0; i < n; i++) {
+            b->descs[i].out_off = b->outs[i] ? (uint64_t)((uintptr_t)b->outs[i] - lo) : 0;
+            b->descs[i].out_pitch = (uint32_t)b->pitches[i];
+        }
+    } else {
+        if (!b->d_out.p) { CK(b->d_out.alloc(b->out_total + 256)); b->arena_owned = true; }
+        out_base = b->d_out.p;
+        for (int i = 0; i < n; i++) b->descs[i].out_off = b->arena_off[i];
+    }
+    /* dither: the IDCT stage writes an MCU-aligned 8-bit image first */
+    std::vector<uint64_t> gray_off;
+    std::vector<uint32_t> err_off;
+    std::vector<JDImageDesc> descs_stage = b->descs;
+    if (b->dither_bits) {
+        CK(b->d_gray.alloc(b->gray_total + 256));
+        size_t go = 0, eo = 0;
+        gray_off.resize(2 * (size_t)n); err_off.resize(n);
+        b->errinit.clear();
+        for (int i = 0; i < n; i++) {
+            const JDInfo &inf = b->infos[i];
+            gray_off[i] = go; err_off[i] = (uint32_t)eo;
+            gray_off[(size_t)n + i] = b->descs[i].out_off;
+            if (b->parse_status[i] != JPEG_SUCCESS) continue;
+            const uint32_t pw = (uint32_t)inf.mcus_x * (uint32_t)(inf.mcu_w >> b->sshift);
+            const uint32_t ph = (uint32_t)inf.mcus_y * (uint32_t)(inf.mcu_h >> b->sshift);
+            descs_stage[i].out_off = go;
+            descs_stage[i].out_pitch = pw;
+            go += (((size_t)pw * ph) + 255) & ~(size_t)255;
+            /* initial error line = the reference's DHT scratch bytes (they share usPixels, jpeg.inl:843 / :4881) */
+            const size_t el = ((size_t)pw + 16 + 15) & ~(size_t)15;
+            b->errinit.resize(eo + el, 0);
+            const size_t cp = el < JD_HUFFVALS_BYTES ? el : JD_HUFFVALS_BYTES;
+            memcpy(&b->errinit[eo], inf.p.huffvals, cp);
+            eo += el;
+        }
+        CK(b->d_errline.alloc(eo + 16));
+        CK(cudaMemcpyAsync(b->d_errline.p, b->errinit.data(), eo, cudaMemcpyHostToDevice, st));
+        CK(b->d_gray_off.alloc(2 * (size_t)n)); CK(b->d_err_off.alloc(n));
+        /* pageable sources: the runtime stages them before returning, so the vectors may go out of scope */
+        CK(cudaMemcpyAsync(b->d_gray_off.p, gray_off.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_err_off.p, err_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(b->d_descs.p, descs_stage.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(b->d_counters.p, 0, 16, st));
+
+    CK(cudaEventRecord(b->ev[2], st));
+    jdk_prescan<<<n, 256, 0, st>>>(b->d_comp.p, b->d_descs.p, b->d_seg_start.p);
+    launches++;
+    CK(cudaEventRecord(b->ev[3], st));
+    if (!b->work.empty()) {
+        JDEntropyArgs ea;
+        ea.data = b->d_comp.p; ea.imgs = b->d_descs.p; ea.luts = b->d_luts.p; ea.work = b->d_work.p; ea.cta_lut = b->d_cta_lut.p;
+        ea.seg_img = b->d_seg_img.p; ea.seg_start = b->d_seg_start.p; ea.blk_hdr = b->d_blk_hdr.p; ea.rec = b->d_rec.p;
+        ea.rec_total = (uint32_t)(4 * b->comp_total + 1024);
+        ea.seg_jmap = b->d_seg_jmap.p; ea.seg_status = b->d_seg_status.p; ea.seg_nrec = b->d_seg_nrec.p;
+        ea.events = b->d_events.p; ea.event_count = b->d_counters.p; ea.event_cap = JD_EVENT_CAP;
+        ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0;
+        jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
+        launches++;
+    }
+    CK(cudaEventRecord(b->ev[4], st));
+    jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p);
+    jdk_patch<<<32, 256, 0, st>>>(b->d_events.p, b->d_counters.p, JD_EVENT_CAP, b->d_seg_phase.p, b->d_rec.p, b->d_counters.p + 1);
+    launches += 2;
+    CK(cudaEventRecord(b->ev[5], st));
+    /* IDCT + colour: one launch per run of images with the same geometry class */
+    const bool half = b->sshift == 1;
+    uint8_t *stage_out = b->dither_bits ? b->d_gray.p : out_base;
+    for (int i0 = 0; i0 < n;) {
+        if (b->parse_status[i0] != JPEG_SUCCESS) { i0++; continue; }
+        const JDInfo &f = b->infos[i0];
+        int i1 = i0 + 1;
+        uint32_t max_mx = f.mcus_x, max_my = f.mcus_y;
+        while (i1 < n && i1 - i0 < 65535 && b->parse_status[i1] == JPEG_SUCCESS && b->infos[i1].subsample == f.subsample &&
+               b->infos[i1].ncomp == f.ncomp) {
+            if ((uint32_t)b->infos[i1].mcus_x > max_mx) max_mx = b->infos[i1].mcus_x;
+            if ((uint32_t)b->infos[i1].mcus_y > max_my) max_my = b->infos[i1].mcus_y;
+            i1++;
+        }
+        const uint32_t nimg = (uint32_t)(i1 - i0);
+        if (b->sshift >= 2) {
+            JDScaledArgs sa;
+            sa.imgs = b->d_descs.p; sa.blk_hdr = b->d_blk_hdr.p; sa.rec = b->d_rec.p; sa.quant = b->d_quant.p;
+            sa.out = stage_out; sa.img0 = (uint32_t)i0; sa.pixel_type = (uint32_t)b->pixel_type; sa.eighth = (b->sshift == 3);
+            sa.padded = (b->dither_bits || b->padded) ? 1u : 0u;
+            dim3 grid((max_mx * max_my + 127) / 128, nimg);
+            jdk_scaled<<<grid, 128, 0, st>>>(sa);
+        } else {
+            JDIdctArgs ia;
+            ia.imgs = b->d_descs.p; ia.blk_hdr = b->d_blk_hdr.p; ia.rec = b->d_rec.p; ia.quant = b->d_quant.p;
+            ia.out = stage_out; ia.img0 = (uint32_t)i0;
+            ia.big_endian = (f.ncomp == 1) ? (b->pixel_type != RGB565_LITTLE_ENDIAN) : (b->pixel_type == RGB565_BIG_ENDIAN);
+            ia.padded = (b->dither_bits || b->padded) ? 1u : 0u;
+            int ok = 0;
+            const int ar = b->ctx->arith;
+            switch (f.subsample) {
+                case 0x00: case 0x11: ok = launch_idct_geo<1, 1, 16, 32>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;
+                case 0x21: ok = launch_idct_geo<2, 1, 8, 16>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;
+                case 0x12: ok = launch_idct_geo<1, 2, 8, 16>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;
+                case 0x22: ok = launch_idct_geo<2, 2, 8, 8>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;
+            }
+            if (!ok) { snprintf(g_err, sizeof(g_err), "no kernel for subsample 0x%02x / pixel type %d", f.subsample, b->pixel_type); return 0; }
+        }
+        launches++;
+        i0 = i1;
+    }
+    CK(cudaEventRecord(b->ev[6], st));
+    if (b->dither_bits) {
+        jdk_dither<<<(n + 31) / 32, 32, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p, b->d_err_off.p,
+                                                  out_base, (uint32_t)b->dither_bits, (uint32_t)b->sshift);
+        launches++;
+    }
+    CK(cudaEventRecord(b->ev[7], st));
+    CK(cudaGetLastError());
+    b->counters[JPEGB200_C_LAUNCHES] = launches;
+    b->counters[JPEGB200_C_SEGMENTS] = b->nseg;
+    b->counters[JPEGB200_C_BLOCKS] = (int64_t)b->nblk;
+    b->counters[JPEGB200_C_COMPRESSED_BYTES] = (int64_t)b->comp_total;
+    int64_t ob = 0;
+    for (int i = 0; i < n; i++) if (b->parse_status[i] == JPEG_SUCCESS) ob += (int64_t)b->pitches[i] * b->descs[i].out_h;
+    b->counters[JPEGB200_C_OUTPUT_BYTES] = ob;
+    return 1;
+}
+
+extern "C" int JPEGB200_batchDownload(JPEGB200_BATCH *b)
+{
+    if (!b || !b->stream) return 0;
+    cudaStream_t st = b->stream;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaEventRecord(b->ev[8], st));
+    int64_t bytes = 0;
+    if (!b->out_device) {
+        const int n = b->n;
+        /* one copy when the user's buffers mirror the arena layout, else one 2-D copy per image */
+        bool mirror = true;
+        for (int i = 0; i < n && mirror; i++) {
+            if (b->parse_status[i] != JPEG_SUCCESS) continue;
+            if (!b->outs[i] || !b->outs[0]) { mirror = false; break; }
+            if ((uint8_t *)b->outs[i] - (uint8_t *)b->outs[0] != (ptrdiff_t)b->arena_off[i]) mirror = false;
+            if (b->pitches[i] != (int64_t)b->descs[i].out_pitch) mirror = false;
+        }
+        if (mirror && b->parse_status[0] == JPEG_SUCCESS) {
+            size_t span = b->arena_off[n - 1] + (size_t)b->descs[n - 1].out_pitch * b->descs[n - 1].out_h;
+            CK(cudaMemcpyAsync(b->outs[0], b->d_out.p, span, cudaMemcpyDeviceToHost, st));
+            bytes = (int64_t)span;
+        } else {
+            for (int i = 0; i < n; i++) {
+                if (b->parse_status[i] != JPEG_SUCCESS || !b->outs[i]) continue;
+                const JDImageDesc &d = b->descs[i];
+                CK(cudaMemcpy2DAsync(b->outs[i], (size_t)b->pitches[i], b->d_out.p + b->arena_off[i], d.out_pitch, d.out_pitch, d.out_h,
+                                     cudaMemcpyDeviceToHost, st));
+                bytes += (int64_t)d.out_pitch * d.out_h;
+            }
+        }
+    }
+    b->descs_dl.resize(b->n);
+    CK(cudaMemcpyAsync(b->descs_dl.data(), b->d_descs.p, sizeof(JDImageDesc) * b->n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    bytes += (int64_t)sizeof(JDImageDesc) * b->n + 16;
+    CK(cudaEventRecord(b->ev[9], st));
+    b->counters[JPEGB200_C_D2H_BYTES] = bytes;
+    return 1;
+}
+
+extern "C" int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status)
+{
+    if (!b || !b->stream) return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaGetLastError());
+    int all_ok = 1;
+    for (int i = 0; i < b->n; i++) {
+        int st = b->parse_status[i];
+        if (st == JPEG_SUCCESS && (int)b->descs_dl.size() == b->n && b->descs_dl[i].status != 0) st = JPEG_DECODE_ERROR; /* jpeg.inl:5354 */
+        if (status) status[i] = st;
+        if (st != JPEG_SUCCESS) all_ok = 0;
+    }
+    b->counters[JPEGB200_C_EVENTS] = b->h_counters[1];
+    float t;
+    auto el = [&](int a, int c) { t = 0; cudaEventElapsedTime(&t, b->ev[a], b->ev[c]); return t; };
+    b->ms[JPEGB200_T_H2D] = el(0, 1);
+    b->ms[JPEGB200_T_PRESCAN] = el(2, 3);
+    b->ms[JPEGB200_T_ENTROPY] = el(3, 4);
+    b->ms[JPEGB200_T_STITCH] = el(4, 5);
+    b->ms[JPEGB200_T_IDCT] = el(5, 6);
+    b->ms[JPEGB200_T_DITHER] = el(6, 7);
+    b->ms[JPEGB200_T_D2H] = el(8, 9);
+    b->ms[JPEGB200_T_TOTAL] = el(2, 7);
+    cudaGetLastError();
+    return all_ok ? 1 : 2;
+}
+
+extern "C" int JPEGB200_batchErrMcu(JPEGB200_BATCH *b, int i)
+{
+    if (!b || i < 0 || i >= b->n) return -1;
+    if ((int)b->descs_dl.size() != b->n) return -1;
+    return b->descs_dl[i].status ? (int)b->descs_dl[i].err_mcu : -1;
+}
+
+extern "C" int JPEGB200_batchGetTimings(JPEGB200_BATCH *b, float *ms)
+{
+    if (!b) return 0;
+    memcpy(ms, b->ms, sizeof(b->ms));
+    return 1;
+}
+
+extern "C" int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters)
+{
+    if (!b) return 0;
+    memcpy(counters, b->counters, sizeof(b->counters));
+    return 1;
+}
+
+extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
+                                    int pixel_type, int options, void *const *outs, const int64_t *pitches,
+                                    int flags, int32_t *status)
+{
+    JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas, sizes, n, pixel_type, options);
+    if (!b) return 0;
+    for (int i = 0; i < n; i++) JPEGB200_batchSetOutput(b, i, outs ? outs[i] : nullptr, pitches ? pitches[i] : 0);
+    int rc = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, flags) && JPEGB200_batchDownload(b);
+    if (rc) rc = JPEGB200_batchWait(b, status);
+    JPEGB200_batchDestroy(b);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Floyd-Steinberg dither (reference JPEGDither src/jpeg.inl:4871-4940).                    */
+/* First version: one thread per image, rows in order; the uint8 error line persists across */
+/* MCU rows and starts from the reference's DHT scratch bytes (see batchDecode).            */
+/* ------------------------------------------------------------------------------------ */
+__global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
+                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nimg) return;
+    const JDImageDesc &im = imgs[i];
+    if (im.nseg == 0) return;
+    const uint32_t hs = (im.subsample >> 4) ? (im.subsample >> 4) : 1, vs = (im.subsample & 15) ? (im.subsample & 15) : 1;
+    const uint32_t mcu_h = (vs * 8) >> sshift;
+    const uint32_t W = (uint32_t)im.mcus_x * ((hs * 8) >> sshift); /* padded width = pitch of the gray stage */
+    const uint32_t rows = im.out_h;                                /* rows the caller sees */
+    const uint8_t *src = gray + gray_off[i];
+    uint8_t *errors = errlines + err_off[i];
+    const uint32_t dpitch = (W * bits + 7) / 8;
+    const uint32_t mask = (bits == 4) ? 0xF0u : (bits == 2 ? 0xC0u : 0x80u);
+    const uint32_t xmask = (bits == 4) ? 1u : (bits == 2 ? 3u : 7u);
+    uint8_t *o = out + gray_off[nimg + i]; /* packed-output offsets follow the gray-stage offsets */
+    for (uint32_t y = 0; y < rows; y++) {
+        if ((y % mcu_h) == 0) { errors[0] = errors[1] = errors[2] = 0; }
+        const uint8_t *p = src + (size_t)y * W;
+        uint8_t *d = o + (size_t)y * dpitch;
+        uint8_t *pe = errors + 1;
+        int lFErr = 0;
+        uint32_t cOut = 0;
+        for (uint32_t x = 0; x < W; x++) {
+            int cNew = (int)p[x] + lFErr;
+            if (cNew > 255) cNew = 255;
+            cOut = ((cOut << bits) | ((uint32_t)cNew >> (8 - bits))) & 0xFFu;
+            if ((x & xmask) == xmask) { *d++ = (uint8_t)cOut; cOut = 0; }
+            const int v = cNew - (cNew & (int)mask);
+            const int h = v >> 1;
+            const int e1 = (7 * h) >> 3, e2 = h - e1, e3 = (5 * h) >> 3, e4 = h - e3;
+            lFErr = e1 + pe[1];
+            pe[1] = (uint8_t)e2;
+            pe[0] = (uint8_t)(pe[0] + e3);
+            pe[-1] = (uint8_t)(pe[-1] + e4);
+            pe++;
+        }
+    }
+}

@@ -1,0 +1,568 @@
+/*
+ * jd_kernels.cuh -- hand-written sm_100a kernels of the decode pipeline.
+ *
+ *   jdk_prescan     one CTA per image: finds RSTn markers, writes per-segment byte offsets
+ *   jdk_entropy     one thread per restart segment: Huffman decode in registers, LUTs in
+ *                   shared memory, writes compact coefficient records + per-block headers
+ *   jdk_stitch      one thread per image: resolves the reference's bit-window phase across
+ *                   segments and folds per-segment status into the image status
+ *   jdk_patch       one thread per truncation event: rewrites the affected record
+ *   jdk_idct_color  fused record-expand + dequant + 8x8 integer IDCT + colour conversion,
+ *                   8 lanes per block, coefficient tiles and pixel planes staged in shared
+ *                   memory, 128-bit coalesced scanline stores
+ *   jdk_scaled      1/4 and 1/8 decode (DC / 2x2 butterfly), one thread per MCU
+ *   jdk_dither      Floyd-Steinberg 1/2/4-bpp, one warp-lane per image row wavefront
+ *
+ * No tensor cores: this is integer, byte-granular, HBM-bound work.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "jd_core.h"
+#include "jd_internal.h"
+
+#define JD_NONE 0xFFFFFFFFu
+#define JD_ENTROPY_THREADS 128
+
+__constant__ uint8_t c_dezigzag[64] = JD_DEZIGZAG_INIT;
+
+/* ------------------------------------------------------------------------------------ */
+/* prescan                                                                                */
+/* ------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(256) jdk_prescan(const uint8_t *__restrict__ data, const JDImageDesc *__restrict__ imgs,
+                                                    uint32_t *__restrict__ seg_start)
+{
+    const JDImageDesc &im = imgs[blockIdx.x];
+    const uint32_t nseg = im.nseg, base = im.seg_base;
+    const uint32_t tid = threadIdx.x;
+    __shared__ uint32_t s_wtot[2][8];
+    if (tid == 0) seg_start[base] = im.scan_off;
+    for (uint32_t i = 1 + tid; i < nseg; i += 256) seg_start[base + i] = JD_NONE;
+    if (nseg <= 1) return;
+    __syncthreads();
+    const uint32_t lo = im.scan_off, hi = im.scan_end;
+    uint32_t found = 0; /* markers found so far (block-uniform) */
+    int buf = 0;
+    for (uint32_t p0 = lo & ~15u; p0 < hi && found + 1 < nseg; p0 += 256 * 16) {
+        const uint32_t p = p0 + tid * 16;
+        uint32_t m = 0;
+        if (p < hi) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(data + p);
+            const uint32_t nxt = (p + 16 < hi) ? data[p + 16] : 0u;
+            const uint32_t w[5] = {v.x, v.y, v.z, v.w, nxt};
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t b0 = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+                const uint32_t b1 = (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFFu;
+                if (b0 == 0xFFu && (b1 & 0xF8u) == 0xD0u && p + i >= lo && p + i + 1 < hi) m |= 1u << i;
+            }
+        }
+        if (!__syncthreads_or(m != 0)) continue;
+        /* block-wide exclusive scan of popc(m) */
+        const uint32_t cnt = __popc(m);
+        uint32_t x = cnt;
+        const uint32_t lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) s_wtot[buf][wid] = x;
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; w2++) { uint32_t t = s_wtot[buf][w2]; if ((uint32_t)w2 < wid) wbase += t; tot += t; }
+        uint32_t k = found + wbase + x - cnt; /* index of this thread's first marker */
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            if (k + 1 < nseg) seg_start[base + k + 1] = p + bit + 2;
+            k++;
+        }
+        found += tot;
+        buf ^= 1;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* entropy decode                                                                         */
+/* ------------------------------------------------------------------------------------ */
+struct JDEventSinkDev {
+    JDEvent *events;
+    uint32_t *count;
+    uint32_t cap;
+    __device__ __forceinline__ void push(const JDEvent &e)
+    {
+        uint32_t i = atomicAdd(count, 1u);
+        if (i < cap) events[i] = e;
+    }
+};
+
+struct JDEntropyArgs {
+    const uint8_t *data;          /* compressed batch buffer (4-byte aligned base) */
+    const JDImageDesc *imgs;
+    const uint16_t *luts;         /* lut sets, JD_LUT_ENTRIES each */
+    const uint32_t *work;         /* padded work list: global segment index or JD_NONE */
+    const uint32_t *cta_lut;      /* LUT set per CTA */
+    const uint32_t *seg_img;      /* image of each segment */
+    const uint32_t *seg_start;    /* from prescan */
+    jd_u64 *blk_hdr;
+    uint16_t *rec;
+    uint32_t rec_total;           /* capacity of rec */
+    uint32_t *seg_jmap;
+    uint32_t *seg_status;         /* 0 ok, else (code << 28) | local err mcu */
+    uint32_t *seg_nrec;
+    JDEvent *events;
+    uint32_t *event_count;
+    uint32_t event_cap;
+    uint32_t nwork;
+    uint32_t data_base;           /* byte offset subtracted when sizing the record area */
+};
+
+__global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
+{
+    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
+    if (wi >= a.nwork) return;
+    const uint32_t seg = a.work[wi];
+    if (seg == JD_NONE) return;
+    const JDImageDesc &im = a.imgs[a.seg_img[seg]];
+    const uint32_t sl = seg - im.seg_base; /* local segment index */
+    const uint32_t total_mcus = (uint32_t)im.mcus_x * im.mcus_y;
+    const uint32_t m0 = sl * im.mcus_per_seg;
+    JDSegIn in;
+    in.data = a.data;
+    in.start = a.seg_start[seg];
+    in.end = im.scan_end;
+    in.nmcu = (m0 + im.mcus_per_seg <= total_mcus) ? im.mcus_per_seg : total_mcus - m0;
+    in.bpm = im.bpm;
+    in.ncomp = im.ncomp;
+    in.tsel = im.tsel;
+    in.seg = seg;
+    jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
+    JDSegOut so;
+    if (in.start == JD_NONE) {
+        /* restart marker missing: everything from here on is undecodable */
+        for (uint32_t b = 0; b < in.nmcu * in.bpm; b++) hdr[b] = 0ull;
+        a.seg_jmap[seg] = JD_JW_INIT;
+        a.seg_status[seg] = ((uint32_t)JD_SEG_MISSING << 28);
+        a.seg_nrec[seg] = 0;
+        return;
+    }
+    /* record area: 4 records per compressed byte of this segment (+64), located at 4x the
+     * segment's byte offset so no prefix sum over segments is needed */
+    const uint32_t next = (sl + 1 < im.nseg) ? a.seg_start[seg + 1] : JD_NONE;
+    const uint32_t seg_end = (next != JD_NONE) ? next : im.scan_end;
+    in.rec_index0 = 4u * (in.start - a.data_base) ;
+    uint32_t cap = 4u * (seg_end > in.start ? seg_end - in.start : 0u) ;
+    if ((uint64_t)in.rec_index0 + cap > a.rec_total) cap = (in.rec_index0 < a.rec_total) ? a.rec_total - in.rec_index0 : 0u;
+    in.rec_cap = cap;
+    JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
+    jd_decode_segment(in, s_lut, hdr, a.rec + in.rec_index0, sink, so);
+    a.seg_jmap[seg] = so.jmap;
+    a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
+    a.seg_nrec[seg] = so.nrec;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* stitch + patch                                                                          */
+/* ------------------------------------------------------------------------------------ */
+__global__ void jdk_stitch(JDImageDesc *imgs, uint32_t nimg, const uint32_t *__restrict__ seg_jmap,
+                           const uint32_t *__restrict__ seg_status, uint32_t *__restrict__ seg_phase)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nimg) return;
+    JDImageDesc &im = imgs[i];
+    uint32_t c = 0, status = 0, err_mcu = 0;
+    for (uint32_t s = 0; s < im.nseg; s++) {
+        const uint32_t g = im.seg_base + s;
+        seg_phase[g] = c;
+        const uint32_t j = (seg_jmap[g] >> (4 * c)) & 15u;
+        c = (j >= 6u) ? 0u : j;
+        const uint32_t st = seg_status[g];
+        if (st != 0u && status == 0u) { status = st >> 28; err_mcu = s * im.mcus_per_seg + (st & 0x0FFFFFFFu); }
+    }
+    im.status = status;
+    im.err_mcu = err_mcu;
+}
+
+__global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__restrict__ event_count, uint32_t cap,
+                          const uint32_t *__restrict__ seg_phase, uint16_t *__restrict__ rec, uint32_t *__restrict__ applied)
+{
+    uint32_t n = *event_count;
+    if (n > cap) n = cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const JDEvent e = events[i];
+        const uint32_t jc = (e.j1 >> (4 * seg_phase[e.seg])) & 15u;
+        if (8 * (int)jc + e.p7 + e.s > 64) {
+            const int v = jd_event_value(&e, jc);
+            rec[e.rec_index] = (uint16_t)((rec[e.rec_index] & 0xF000u) | ((uint32_t)v & 0xFFFu));
+            atomicAdd(applied, 1u);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* fused expand + dequant + IDCT + colour                                                  */
+/* ------------------------------------------------------------------------------------ */
+#define JD_PT_565 0
+#define JD_PT_8888 1
+#define JD_PT_GRAY 2
+
+struct JDIdctArgs {
+    const JDImageDesc *imgs;
+    const jd_u64 *blk_hdr;
+    const uint16_t *rec;
+    const int16_t *quant;   /* [img][3][64] natural order */
+    uint8_t *out;           /* output base */
+    uint32_t img0;          /* first image of this launch (blockIdx.y offset) */
+    uint32_t big_endian;    /* RGB565_BIG_ENDIAN requested */
+    uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate) */
+};
+
+template <int HS, int VS, int NC, int MPB>
+struct JDGeo {
+    static constexpr int BPMEFF = HS * VS + (NC == 3 ? 2 : 0);
+    static constexpr int NB = MPB * BPMEFF;
+    static constexpr int THREADS = NB * 8;
+    static constexpr int WCTA = MPB * HS * 8;
+    static constexpr int HCTA = VS * 8;
+    static constexpr int YSTRIDE = WCTA + 8;
+    static constexpr int CSTRIDE = MPB * 8 + 8;
+    static constexpr int TSTRIDE = 72; /* halfwords per coefficient tile (64 + pad: bank spread) */
+};
+
+__device__ __forceinline__ void jd_unpack8(const uint4 v, int m[8])
+{
+    m[0] = (int)(short)(v.x & 0xFFFF); m[1] = (int)v.x >> 16;
+    m[2] = (int)(short)(v.y & 0xFFFF); m[3] = (int)v.y >> 16;
+    m[4] = (int)(short)(v.z & 0xFFFF); m[5] = (int)v.z >> 16;
+    m[6] = (int)(short)(v.w & 0xFFFF); m[7] = (int)v.w >> 16;
+}
+
+template <int HS, int VS, int NC, int MPB, int PT, int ARITH, bool HALF>
+__global__ void __launch_bounds__(JDGeo<HS, VS, NC, MPB>::THREADS)
+jdk_idct_color(const JDIdctArgs a)
+{
+    using G = JDGeo<HS, VS, NC, MPB>;
+    __shared__ __align__(16) int16_t s_tile[G::NB * G::TSTRIDE];
+    __shared__ __align__(16) int16_t s_q[NC * 64];           /* transposed: [comp][c*8 + r] */
+    __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
+    __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
+    __shared__ uint8_t s_dz[64];
+
+    const uint32_t img_i = a.img0 + blockIdx.y;
+    const JDImageDesc &im = a.imgs[img_i];
+    const uint32_t strips = (im.mcus_x + MPB - 1) / MPB;
+    if (blockIdx.x >= strips * im.mcus_y) return;
+    const uint32_t my = blockIdx.x / strips, strip = blockIdx.x - my * strips;
+    const uint32_t tid = threadIdx.x;
+
+    if (tid < 64) s_dz[tid] = c_dezigzag[tid];
+    for (uint32_t i = tid; i < NC * 64; i += G::THREADS) {
+        const uint32_t comp = i >> 6, n = i & 63;
+        s_q[comp * 64 + (n & 7) * 8 + (n >> 3)] = a.quant[(size_t)img_i * 192 + comp * 64 + n];
+    }
+    __syncthreads();
+
+    /* ---- phase A: expand this block's records into a column-major coefficient tile ---- */
+    const uint32_t gb = tid >> 3, c = tid & 7;           /* block within CTA, lane within block */
+    const uint32_t ml = gb / G::BPMEFF, blk = gb - ml * G::BPMEFF;
+    const uint32_t mx = strip * MPB + ml;
+    const bool active = mx < im.mcus_x;
+    const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
+    /* position of the block in the coded stream: luma blocks first, chroma after all luma */
+    const uint32_t sblk = (comp == 0) ? blk : (uint32_t)(HS * VS) + comp - 1u;
+    jd_u64 h = 0;
+    if (active) h = a.blk_hdr[im.blk_base + ((size_t)my * im.mcus_x + mx) * im.bpm + sblk];
+    const uint32_t ri = (uint32_t)h;
+    const int dc = (int)(short)(uint16_t)(h >> 32);
+    const uint32_t nrec = (uint32_t)(h >> 48) & 0xFFu;
+    int16_t *tile = s_tile + gb * G::TSTRIDE;
+    const uint32_t gmask = 0xFFu << (tid & 24u); /* the 8 lanes of this block */
+    *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    uint32_t fl = 0;
+    {
+        const uint32_t maxn = __reduce_max_sync(0xffffffffu, nrec);
+        uint32_t kcarry = 0;
+        for (uint32_t b0 = 0; b0 < maxn; b0 += 8) {
+            const uint32_t i = b0 + c;
+            const bool have = i < nrec;
+            const uint32_t r = have ? (uint32_t)__ldg(a.rec + ri + i) : 0u;
+            uint32_t x = have ? (r >> 12) + 1u : 0u;
+            uint32_t y;
+            y = __shfl_up_sync(0xffffffffu, x, 1, 8); if (c >= 1) x += y;
+            y = __shfl_up_sync(0xffffffffu, x, 2, 8); if (c >= 2) x += y;
+            y = __shfl_up_sync(0xffffffffu, x, 4, 8); if (c >= 4) x += y;
+            const uint32_t k = kcarry + x;
+            const int v = (int)(r << 20) >> 20;
+            if (have && v != 0 && k < 64u) {
+                const uint32_t n = s_dz[k];
+                tile[(n & 7u) * 8u + (n >> 3)] = (int16_t)v;
+                fl |= (1u << (n & 7u)) | ((n & 32u) << 8);
+            }
+            kcarry += __shfl_sync(0xffffffffu, x, 7, 8);
+        }
+    }
+    fl |= __shfl_xor_sync(0xffffffffu, fl, 1);
+    fl |= __shfl_xor_sync(0xffffffffu, fl, 2);
+    fl |= __shfl_xor_sync(0xffffffffu, fl, 4);
+    __syncwarp();
+
+    /* ---- phase B: dequant + column pass (lane = column), row pass (lane = row) ---- */
+    uint32_t px0, px1; /* 8 output bytes of row `c` of this block */
+    const int16_t *q = s_q + comp * 64;
+    if (fl == 0u) {
+        /* no stored AC coefficient: the reference's DC-only fill (jpeg.inl:5146-5154) */
+        const uint32_t v = jd_range(dc * (int)q[0]);
+        px0 = px1 = v * 0x01010101u;
+    } else {
+        int m[8], qq[8], o[8];
+        jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
+        jd_unpack8(*reinterpret_cast<const uint4 *>(q + c * 8), qq);
+        if (c == 0) m[0] = dc;
+        const bool r47 = (fl & 0x2000u) == 0u;
+        if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) m[r] *= qq[r];
+            jd_col_sse16(m, r47, o);
+        } else {
+            jd_col_scalar(m, qq, r47, o);
+        }
+        __syncwarp(gmask); /* fl is uniform inside a block's 8 lanes, not across the warp */
+#pragma unroll
+        for (int r = 0; r < 8; r++) tile[r * 8 + c] = (int16_t)o[r];
+        __syncwarp(gmask);
+        int p[8];
+        uint32_t ob[8];
+        jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), p);
+        jd_row(p, fl & 0xFFu, ob);
+        px0 = ob[0] | (ob[1] << 8) | (ob[2] << 16) | (ob[3] << 24);
+        px1 = ob[4] | (ob[5] << 8) | (ob[6] << 16) | (ob[7] << 24);
+    }
+    /* stage the pixel bytes */
+    if (comp == 0) {
+        const uint32_t lx = (HS == 2) ? (blk & 1u) : 0u;
+        const uint32_t ly = (HS == 2 && VS == 2) ? (blk >> 1) : ((VS == 2) ? blk : 0u);
+        *reinterpret_cast<uint2 *>(s_y + (ly * 8 + c) * G::YSTRIDE + (ml * HS + lx) * 8) = make_uint2(px0, px1);
+    } else {
+        *reinterpret_cast<uint2 *>(s_c + ((comp - 1) * 8 + c) * G::CSTRIDE + ml * 8) = make_uint2(px0, px1);
+    }
+    __syncthreads();
+
+    /* ---- phase C: colour conversion + coalesced scanline stores ---- */
+    const uint8_t *s_cb = s_c, *s_cr = s_c + 8 * G::CSTRIDE;
+    const uint32_t W = a.padded ? (uint32_t)im.mcus_x * HS * 8 : (uint32_t)im.width;
+    const uint32_t H = a.padded ? (uint32_t)im.mcus_y * VS * 8 : (uint32_t)im.height;
+    uint8_t *outbase = a.out + im.out_off;
+    const uint32_t pitch = im.out_pitch;
+    constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
+
+    if (!HALF) {
+        constexpr int IPR = G::WCTA / 8; /* 8-pixel items per row */
+        for (uint32_t it = tid; it < (uint32_t)(IPR * G::HCTA); it += G::THREADS) {
+            const uint32_t row = it / IPR, xg = it - row * IPR;
+            const uint32_t gy = my * G::HCTA + row, gx = strip * G::WCTA + xg * 8;
+            if (gy >= H || gx >= W) continue;
+            const uint2 yy = *reinterpret_cast<const uint2 *>(s_y + row * G::YSTRIDE + xg * 8);
+            uint32_t pix[8]; /* 565: 8 x u16 in low halves; 8888: 8 x u32; gray: bytes */
+            if (PT == JD_PT_GRAY) {
+                /* handled below with yy directly */
+            } else if (NC == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
+                    uint32_t v = jd_gray565(Y);
+                    if (a.big_endian) v = jd_bswap16(v);
+                    pix[i] = v;
+                }
+            } else {
+                const uint32_t crow = row / VS;
+                if (ARITH == JPEG_ARITH_SSE2 && (HS == VS)) {
+                    /* SSE2 build, full-size 4:4:4 / 4:2:0 (jpeg.inl:3409-3517, :4006-4308): B,G,R,A; LE only */
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
+                        const uint32_t cx = (xg * 8 + i) / HS;
+                        int tr, tg, tb, R, Gc, B;
+                        jd_chroma_sse(s_cb[crow * G::CSTRIDE + cx], s_cr[crow * G::CSTRIDE + cx], &tr, &tg, &tb);
+                        jd_rgb_sse((int)Y, tr, tg, tb, &R, &Gc, &B);
+                        if (PT == JD_PT_8888) pix[i] = 0xFF000000u | ((uint32_t)R << 16) | ((uint32_t)Gc << 8) | (uint32_t)B;
+                        else pix[i] = ((uint32_t)(R >> 3) << 11) | ((uint32_t)(Gc >> 2) << 5) | (uint32_t)(B >> 3);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
+                        const uint32_t cx = (xg * 8 + i) / HS;
+                        const int Cb = s_cb[crow * G::CSTRIDE + cx], Cr = s_cr[crow * G::CSTRIDE + cx];
+                        if (PT == JD_PT_8888) pix[i] = jd_rgb8888_scalar((int)Y << 12, Cb, Cr);
+                        else {
+                            uint32_t v = jd_rgb565_scalar((int)Y << 12, Cb, Cr);
+                            if (a.big_endian) v = jd_bswap16(v);
+                            pix[i] = v;
+                        }
+                    }
+                }
+            }
+            uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
+            const bool full = gx + 8 <= W;
+            if (PT == JD_PT_GRAY) {
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0)) *reinterpret_cast<uint2 *>(dst) = yy;
+                else for (uint32_t i = 0; i < 8 && gx + i < W; i++) dst[i] = (uint8_t)(((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu);
+            } else if (PT == JD_PT_565) {
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pix[0] | (pix[1] << 16), pix[2] | (pix[3] << 16),
+                                                                  pix[4] | (pix[5] << 16), pix[6] | (pix[7] << 16));
+                } else {
+                    for (uint32_t i = 0; i < 8 && gx + i < W; i++) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)pix[i];
+                }
+            } else {
+                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pix[0], pix[1], pix[2], pix[3]);
+                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pix[4], pix[5], pix[6], pix[7]);
+                } else {
+                    for (uint32_t i = 0; i < 8 && gx + i < W; i++) reinterpret_cast<uint32_t *>(dst)[i] = pix[i];
+                }
+            }
+        }
+    } else {
+        /* 1/2 scale: 2x2 luma sums; scalar colour code in both builds (jpeg.inl:3297-3322, :3577-3626) */
+        const uint32_t OW = (W + 1) >> 1, OH = (H + 1) >> 1;
+        constexpr int OWC = G::WCTA / 2, OHC = G::HCTA / 2;
+        for (uint32_t it = tid; it < (uint32_t)(OWC * OHC); it += G::THREADS) {
+            const uint32_t oy = it / OWC, ox = it - oy * OWC;
+            const uint32_t gy = my * OHC + oy, gx = strip * OWC + ox;
+            if (gy >= OH || gx >= OW) continue;
+            const uint8_t *yp = s_y + (2 * oy) * G::YSTRIDE + 2 * ox;
+            const int sum = yp[0] + yp[1] + yp[G::YSTRIDE] + yp[G::YSTRIDE + 1];
+            uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
+            if (PT == JD_PT_GRAY) {
+                *dst = (uint8_t)((sum + 2) >> 2);
+            } else if (NC == 1) {
+                uint32_t v = jd_gray565((uint32_t)((sum + 2) >> 2));
+                if (a.big_endian) v = jd_bswap16(v);
+                *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+            } else {
+                int Cb, Cr;
+                if (HS == 2 && VS == 2) {
+                    Cb = s_cb[oy * G::CSTRIDE + ox]; Cr = s_cr[oy * G::CSTRIDE + ox];
+                } else if (HS == 1 && VS == 1) {
+                    const uint8_t *p1 = s_cb + (2 * oy) * G::CSTRIDE + 2 * ox, *p2 = s_cr + (2 * oy) * G::CSTRIDE + 2 * ox;
+                    Cb = (p1[0] + p1[1] + p1[G::CSTRIDE] + p1[G::CSTRIDE + 1] + 2) >> 2;
+                    Cr = (p2[0] + p2[1] + p2[G::CSTRIDE] + p2[G::CSTRIDE + 1] + 2) >> 2;
+                } else if (HS == 2) {
+                    Cb = (s_cb[(2 * oy) * G::CSTRIDE + ox] + s_cb[(2 * oy + 1) * G::CSTRIDE + ox] + 1) >> 1;
+                    Cr = (s_cr[(2 * oy) * G::CSTRIDE + ox] + s_cr[(2 * oy + 1) * G::CSTRIDE + ox] + 1) >> 1;
+                } else {
+                    Cb = (s_cb[oy * G::CSTRIDE + 2 * ox] + s_cb[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
+                    Cr = (s_cr[oy * G::CSTRIDE + 2 * ox] + s_cr[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
+                }
+                if (PT == JD_PT_8888) *reinterpret_cast<uint32_t *>(dst) = jd_rgb8888_scalar(sum << 10, Cb, Cr);
+                else {
+                    uint32_t v = jd_rgb565_scalar(sum << 10, Cb, Cr);
+                    if (a.big_endian) v = jd_bswap16(v);
+                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* 1/4 and 1/8 scale: one thread per MCU                                                   */
+/* ------------------------------------------------------------------------------------ */
+struct JDScaledArgs {
+    const JDImageDesc *imgs;
+    const jd_u64 *blk_hdr;
+    const uint16_t *rec;
+    const int16_t *quant;
+    uint8_t *out;
+    uint32_t img0;
+    uint32_t pixel_type;   /* JPEGDEC.h pixel type (after LUMA_ONLY folding) */
+    uint32_t eighth;       /* 1: 1/8, 0: 1/4 */
+    uint32_t padded;
+};
+
+__device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h, const int16_t *q, bool eighth, uint32_t px[4])
+{
+    const int dc = (int)(short)(uint16_t)(h >> 32);
+    if (eighth) { px[0] = jd_range(dc * (int)q[0]); return; }
+    const uint32_t ri = (uint32_t)h, nrec = (uint32_t)(h >> 48) & 0xFFu;
+    int m1 = 0, m8 = 0, m9 = 0;
+    bool any = false;
+    uint32_t k = 1;
+    for (uint32_t i = 0; i < nrec && k < 5u; i++) {
+        const uint32_t r = a.rec[ri + i];
+        k += r >> 12;
+        const int v = (int)(r << 20) >> 20;
+        if (v != 0 && k < 5u) {
+            any = true; /* zigzag 1,2,3,4 = natural 1,8,16,9 (jpeg.inl:2117-2119) */
+            if (k == 1) m1 = v; else if (k == 2) m8 = v; else if (k == 4) m9 = v;
+        }
+        k++;
+    }
+    if (!any) { px[0] = px[1] = px[2] = px[3] = jd_range(dc * (int)q[0]); return; }
+    /* 2x2 butterfly (jpeg.inl:2305-2326) */
+    int t4 = dc * q[0], t5 = m8 * q[8];
+    const int t0 = t4 + t5, t2 = t4 - t5;
+    t4 = m1 * q[1]; t5 = m9 * q[9];
+    const int t1 = t4 + t5, t3 = t4 - t5;
+    px[0] = jd_range(t0 + t1); px[1] = jd_range(t0 - t1); px[2] = jd_range(t2 + t3); px[3] = jd_range(t2 - t3);
+}
+
+__global__ void __launch_bounds__(128) jdk_scaled(const JDScaledArgs a)
+{
+    const uint32_t img_i = a.img0 + blockIdx.y;
+    const JDImageDesc &im = a.imgs[img_i];
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= (uint32_t)im.mcus_x * im.mcus_y) return;
+    const uint32_t mx = m % im.mcus_x, my = m / im.mcus_x;
+    const uint32_t hs = (im.subsample >> 4) ? (im.subsample >> 4) : 1, vs = (im.subsample & 15) ? (im.subsample & 15) : 1;
+    const uint32_t nluma = hs * vs;
+    const bool eighth = a.eighth != 0;
+    const uint32_t bs = eighth ? 1u : 2u; /* block edge in output pixels */
+    const int16_t *q = a.quant + (size_t)img_i * 192;
+    const jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m * im.bpm;
+    uint32_t ypx[4][4], cb[4], cr[4];
+    for (uint32_t b = 0; b < nluma; b++) jd_scaled_block(a, hdr[b], q, eighth, ypx[b]);
+    const bool gray_out = a.pixel_type >= EIGHT_BIT_GRAYSCALE;
+    const bool colour = (im.ncomp == 3) && !gray_out;
+    if (colour) {
+        jd_scaled_block(a, hdr[nluma], q + 64, eighth, cb);
+        jd_scaled_block(a, hdr[nluma + 1], q + 128, eighth, cr);
+    }
+    const uint32_t shift = eighth ? 3u : 2u;
+    const uint32_t W = a.padded ? (uint32_t)im.mcus_x * hs * bs : (((uint32_t)im.width + (1u << shift) - 1u) >> shift);
+    const uint32_t H = a.padded ? (uint32_t)im.mcus_y * vs * bs : (((uint32_t)im.height + (1u << shift) - 1u) >> shift);
+    uint8_t *outbase = a.out + im.out_off;
+    const uint32_t ow = hs * bs, oh = vs * bs; /* output pixels per MCU */
+    for (uint32_t y = 0; y < oh; y++) {
+        for (uint32_t x = 0; x < ow; x++) {
+            const uint32_t gx = mx * ow + x, gy = my * oh + y;
+            if (gx >= W || gy >= H) continue;
+            const uint32_t bx = x / bs, by = y / bs;
+            const uint32_t lb = (hs == 2 && vs == 2) ? by * 2 + bx : (hs == 2 ? bx : by);
+            const uint32_t Y = ypx[lb][(y % bs) * bs + (x % bs)];
+            if (gray_out) { outbase[(size_t)gy * im.out_pitch + gx] = (uint8_t)Y; continue; }
+            uint8_t *dst = outbase + (size_t)gy * im.out_pitch;
+            if (im.ncomp == 1) {
+                uint32_t v = jd_gray565(Y);
+                if (a.pixel_type != RGB565_LITTLE_ENDIAN) v = jd_bswap16(v);
+                reinterpret_cast<uint16_t *>(dst)[gx] = (uint16_t)v;
+                continue;
+            }
+            const uint32_t ci = (y / vs) * bs + (x / hs); /* nearest chroma byte of the 2x2 (or 1) chroma block */
+            if (a.pixel_type == RGB8888) reinterpret_cast<uint32_t *>(dst)[gx] = jd_rgb8888_scalar((int)Y << 12, (int)cb[ci], (int)cr[ci]);
+            else {
+                uint32_t v = jd_rgb565_scalar((int)Y << 12, (int)cb[ci], (int)cr[ci]);
+                if (a.pixel_type == RGB565_BIG_ENDIAN) v = jd_bswap16(v);
+                reinterpret_cast<uint16_t *>(dst)[gx] = (uint16_t)v;
+            }
+        }
+    }
+}
