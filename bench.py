@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s of baseline 4:2:0 batch decode on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload hd1024|uhd]
+
+A "step" = one pass of the hot path (prescan -> entropy -> stitch -> fused IDCT+colour) over
+one batch of synthetic JPEGs.  N=1 workload = BASELINE.json configs[1]: 1024 x 1920x1080
+4:2:0 q75 -> RGB8888.  `value` = source megapixels/s with compressed inputs resident in HBM
+and pixels left in HBM; `e2e` = the same metric through the public C ABI with pinned HOST
+buffers on both sides (header parse + H2D + kernels + D2H inside the timed region).
+`--impl reference` times the unmodified reference (oracle/_ref, SSE2 build) on all host cores.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_images, w, h, quality, pixel_type_name, algorithmic bytes per source pixel for the fused kernel)
+    "hd1024": dict(n=1024, w=1920, h=1080, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3,
+                   desc="1024 x 1920x1080 4:2:0 q75 -> RGB8888 (BASELINE.json configs[1])"),
+    "uhd": dict(n=256, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2, coef_bpp=3,
+                desc="256 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
+    "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # region shorter than one sample: take the nearest sample
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_images(wl, rank, unique):
+    from tests import synth
+    jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique)
+    return jp
+
+
+def cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=3):
+    """Times the unmodified reference (oracle/_ref SSE2 build), framebuffer mode, `threads` workers."""
+    from oracle import refdrv
+    ref = refdrv.Ref("sse")
+    datas = [jpegs[i % len(jpegs)] for i in range(n_sample)]
+    rows = ((wl["h"] + 15) // 16) * 16 + 16
+    bypp = wl["bpp_out"]
+    # one framebuffer per worker slot is enough for timing (image i -> worker i % threads writes fbs[i])
+    pool = [np.empty(rows * wl["w"] * bypp + 4096, dtype=np.uint8) for _ in range(min(threads, n_sample))]
+    fbs = [pool[i % len(pool)] for i in range(n_sample)]
+    best = None
+    for _ in range(passes):
+        fails, secs = ref.decode_batch(datas, pixel_type, 0, threads, fbs)
+        if fails:
+            raise RuntimeError("reference failed on %d images" % fails)
+        best = secs if best is None else min(best, secs)
+    mp = n_sample * wl["w"] * wl["h"] / 1e6
+    return mp / best, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="hd1024")
+    ap.add_argument("--unique", type=int, default=64, help="unique synthetic images per rank (cycled to the batch size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(args.warmup, 0)
+    K = max(args.steps, 1)
+    threads = os.cpu_count() or 1
+    n_img = wl["n"]
+    mp_per_step_rank = n_img * wl["w"] * wl["h"] / 1e6
+    config = {"workload": wl["desc"], "images_per_gpu": n_img, "width": wl["w"], "height": wl["h"],
+              "quality": wl["q"], "subsampling": "4:2:0", "restart_interval": "1 MCU row",
+              "pixel_type": wl["pt"], "arith_mode": "SSE2-build parity", "parallelism": "images sharded, dp%d" % world,
+              "l2_policy": "inputs_exceed_l2 (per step: %.0f MB compressed + %.1f GB pixels >> 126 MB L2)" % (
+                  n_img * 0.29 if args.workload == "hd1024" else n_img * 1.6, n_img * wl["w"] * wl["h"] * wl["bpp_out"] / 1e9)}
+
+    import jpegdec_b200 as J
+    pixel_type = getattr(J, wl["pt"])
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import refdrv
+        if not refdrv.available("sse"):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libjpegdec_ref_sse.so not built"}))
+            return 0
+        jpegs = make_images(wl, 0, min(args.unique, 32))
+        n_sample = max(threads * 4, 128)
+        for _ in range(W):
+            cpu_reference_run(wl, jpegs, pixel_type, max(threads, 16), threads, passes=1)
+        t_total, mp_total = 0.0, 0.0
+        for _ in range(K):
+            mps, secs = cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=1)
+            t_total += secs
+            mp_total += n_sample * wl["w"] * wl["h"] / 1e6
+        v = mp_total / t_total
+        sample = "%d images per step (%d unique, cycled), framebuffer mode, openRAM..close per image" % (n_sample, len(jpegs))
+        print(json.dumps({
+            "impl": "reference", "metric": "Mpixels/sec baseline 4:2:0 decode (batch)", "value": v, "unit": "Mpixels/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_total / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 (SSE2 build)", "data": "synthetic",
+            "config": dict(config, note="reference CPU path, all host threads; each step is a bounded sample of the workload"),
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    unique = min(args.unique, n_img)
+    jpegs = make_images(wl, rank, unique)
+    ctx = J.Context(local_rank, J.JPEG_ARITH_SSE2)
+    # shared Huffman/quant table blob: rank 0 exports, NCCL broadcast, every rank imports
+    blob = torch.zeros(J.TABLE_BLOB_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        blob.copy_(torch.from_numpy(ctx.export_tables(jpegs[0])))
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    ctx.set_shared_tables(blob.cpu().numpy())
+
+    # pinned input blob: the batch's files back to back (16-byte aligned starts)
+    sizes = [len(jpegs[i % unique]) for i in range(n_img)]
+    offs, o = [], 0
+    for s in sizes:
+        offs.append(o)
+        o += (s + 15) & ~15
+    L = J.lib()
+    in_ptr = L.JPEGB200_hostAlloc(o + 64)
+    in_arr = np.ctypeslib.as_array(C.cast(in_ptr, C.POINTER(C.c_ubyte)), shape=(o + 64,))
+    in_arr[:] = 0
+    for i in range(n_img):
+        in_arr[offs[i]:offs[i] + sizes[i]] = np.frombuffer(jpegs[i % unique], dtype=np.uint8)
+    ptrs = [in_ptr + off for off in offs]
+
+    # ---- device-resident throughput (`value`) ----
+    b = J.Batch(ctx, ptrs, sizes, pixel_type, 0)
+    b.alloc_device_output()
+    b.upload()
+    b.decode(J.JPEGB200_OUT_DEVICE); b.download(); st = b.wait()
+    if any(st):
+        raise SystemExit("decode failed: %s" % st[:8])
+    for _ in range(max(W - 1, 0)):
+        b.decode(J.JPEGB200_OUT_DEVICE); b.download(); b.wait()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    t0 = time.time()
+    dev_ms, stage = 0.0, {k: 0.0 for k in J.TIMING_NAMES}
+    launches = 0
+    for _ in range(K):
+        b.decode(J.JPEGB200_OUT_DEVICE); b.download(); b.wait()
+        tm = b.timings()
+        dev_ms += tm["total"]
+        for k in stage:
+            stage[k] += tm[k]
+        launches += b.counters()["launches"]
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    cnt = b.counters()
+    ms_step = max_over_ranks(dev_ms / K)
+    wall_ms_step = max_over_ranks(1e3 * (t1 - t0) / K)
+    value = world * mp_per_step_rank / (ms_step / 1e3)
+    idct_ms = stage["idct"] / K
+    entropy_ms = stage["entropy"] / K
+    # ---- bit-exactness spot check of what was just timed (first unique images vs reference) ----
+    parity = None
+    try:
+        from oracle import refdrv
+        if refdrv.available("sse") and rank == 0:
+            ref = refdrv.Ref("sse")
+            nchk = min(4, unique)
+            outs_h, st_h, _, _ = J.decode_batch_to_host(ctx, jpegs[:nchk], pixel_type, 0)
+            okc = 0
+            for i in range(nchk):
+                rc, err, img, _ = ref.decode_cb(jpegs[i], pixel_type, 0, want_log=False)
+                okc += int(rc == 1 and st_h[i] == 0 and img.shape == outs_h[i].shape and np.array_equal(img, outs_h[i]))
+            parity = "%d/%d sampled images bit-exact vs reference (SSE2 build)" % (okc, nchk)
+    except Exception as e:  # parity is asserted in tests/; here it is informational
+        parity = "not checked: %r" % (e,)
+    table_hits = ctx.shared_table_hits()
+    b.close()
+
+    # ---- end to end through the public C ABI with host buffers (`e2e`) ----
+    e2e = None
+    if not args.no_e2e:
+        out_bytes = wl["w"] * wl["h"] * wl["bpp_out"]
+        stride = (out_bytes + 255) & ~255
+        out_ptr = L.JPEGB200_hostAlloc(stride * n_img + 256)
+        if out_ptr:
+            outs = [out_ptr + i * stride for i in range(n_img)]
+
+            def one_call():
+                bb = J.Batch(ctx, ptrs, sizes, pixel_type, 0)
+                for i in range(n_img):
+                    bb.set_output(i, outs[i], 0)
+                bb.upload(); bb.decode(0); bb.download()
+                s2 = bb.wait()
+                c2 = bb.counters()
+                bb.close()
+                return s2, c2
+            for _ in range(max(1, min(W, 2))):
+                one_call()
+            barrier()
+            t0 = time.time()
+            for _ in range(K):
+                s2, c2 = one_call()
+            barrier()
+            t1 = time.time()
+            e_ms = max_over_ranks(1e3 * (t1 - t0) / K)
+            e2e = {"value": world * mp_per_step_rank / (e_ms / 1e3), "unit": "Mpixels/s",
+                   "h2d_bytes_per_step": int(c2["h2d_bytes"]), "d2h_bytes_per_step": int(c2["d2h_bytes"]),
+                   "ms_per_step": e_ms,
+                   "note": "JPEGB200 batch C-ABI call: host parse + H2D (pinned) + kernels + D2H of all pixels (pinned) + status"}
+            L.JPEGB200_hostFree(out_ptr)
+        else:
+            e2e = {"value": None, "unit": "Mpixels/s", "note": "pinned output allocation failed"}
+    L.JPEGB200_hostFree(in_ptr)
+
+    # ---- roofline of the dominant kernel (fused IDCT + colour) ----
+    peak, peak_src = load_peaks()
+    alg_bytes = n_img * wl["w"] * wl["h"] * (wl["bpp_out"] + wl["coef_bpp"])
+    achieved = alg_bytes / (idct_ms / 1e3) / 1e9
+    out_gbs = n_img * wl["w"] * wl["h"] * wl["bpp_out"] / (idct_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "jdk_idct_color", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": idct_ms,
+                "write_only_gbs": out_gbs, "write_frac": out_gbs / peak}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle import refdrv
+            if refdrv.available("sse"):
+                n_sample = max(threads * 8, 256)
+                v, secs = cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=3)
+                v1, secs1 = cpu_reference_run(wl, jpegs, pixel_type, 32, 1, passes=2)
+                cpu = {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "reference",
+                       "sample": "%d images (%d unique cycled), best of 3, framebuffer mode, oracle/_ref SSE2 build" % (n_sample, unique),
+                       "single_thread_value": v1}
+        except Exception as e:
+            cpu = {"value": None, "unit": "Mpixels/s", "cores": threads, "kind": "reference", "sample": "failed: %r" % (e,)}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    if rank == 0:
+        line = {
+            "metric": "Mpixels/sec baseline 4:2:0 decode (batch)", "value": value, "unit": "Mpixels/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int16/int32 (u8 pixels)", "data": "synthetic (%d unique seeds per GPU cycled to %d images)" % (unique, n_img),
+            "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+            "stages_ms": {k: v / K for k, v in stage.items()}, "wall_ms_per_step": wall_ms_step,
+            "entropy_symbol_stage_ms": entropy_ms, "quirk_events_per_step": int(cnt["events"]),
+            "shared_table_hits": table_hits, "parity_spot_check": parity}
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -24,6 +24,30 @@
 
 static char g_err[256];
 
+/* Device allocations are recycled through the context: a decode job borrows buffers and hands them
+ * back on destroy, so steady-state batches do no cudaMalloc/cudaFree (both synchronise the device). */
+struct JDPool {
+    struct Slot { void *p; size_t bytes; };
+    std::vector<Slot> free_;
+    cudaError_t get(size_t bytes, void **out, size_t *got)
+    {
+        int best = -1;
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].bytes >= bytes && free_[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || free_[i].bytes < free_[best].bytes)) best = (int)i;
+        if (best >= 0) { *out = free_[best].p; *got = free_[best].bytes; free_.erase(free_.begin() + best); return cudaSuccess; }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) { /* give cached memory back to the driver and retry once */
+            cudaGetLastError();
+            drain();
+            e = cudaMalloc(out, bytes);
+        }
+        *got = bytes;
+        return e;
+    }
+    void put(void *p, size_t bytes) { free_.push_back(Slot{p, bytes}); }
+    void drain() { for (auto &s : free_) cudaFree(s.p); free_.clear(); }
+};
+
 struct JPEGB200_CTX {
     int device;
     int arith;
@@ -32,22 +56,33 @@ struct JPEGB200_CTX {
     uint64_t shared_hash;
     uint16_t shared_lut[JD_LUT_ENTRIES];
     int shared_hits;
+    JDPool pool;
 };
+
+static JDPool *g_cur_pool = nullptr; /* pool of the context whose batch is being set up (calls are serialised per context) */
 
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    size_t bytes = 0;
+    JDPool *pool = nullptr;
     cudaError_t alloc(size_t count)
     {
         if (count <= n && p) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        release();
+        pool = g_cur_pool;
+        size_t need = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+        void *q = nullptr;
+        cudaError_t e = pool ? pool->get(need, &q, &bytes) : cudaMalloc(&q, bytes = need);
+        if (e == cudaSuccess) { p = (T *)q; n = count; }
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release()
+    {
+        if (p) { if (pool) pool->put(p, bytes); else cudaFree(p); }
+        p = nullptr; n = 0; bytes = 0;
+    }
 };
 
 struct JPEGB200_BATCH {
@@ -132,7 +167,14 @@ extern "C" JPEGB200_CTX *JPEGB200_create(int device, int arith_mode)
     return c;
 }
 
-extern "C" void JPEGB200_destroy(JPEGB200_CTX *ctx) { delete ctx; }
+extern "C" void JPEGB200_destroy(JPEGB200_CTX *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->pool.drain();
+    delete ctx;
+}
 
 extern "C" const char *JPEGB200_lastErrorString(JPEGB200_CTX *) { return g_err; }
 
@@ -314,7 +356,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
-    b->d_comp.release(); if (b->arena_owned) b->d_out.release(); b->d_gray.release(); b->d_errline.release();
+    b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
@@ -358,6 +400,7 @@ extern "C" int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int6
 
 static int batch_stream(JPEGB200_BATCH *b)
 {
+    g_cur_pool = &b->ctx->pool;
     CK(cudaSetDevice(b->ctx->device));
     if (!b->stream) CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     if (!b->have_ev) {
@@ -372,6 +415,7 @@ extern "C" void *JPEGB200_batchStream(JPEGB200_BATCH *b) { if (!b || !batch_stre
 extern "C" int JPEGB200_batchAllocDeviceOutput(JPEGB200_BATCH *b)
 {
     if (!b) return 0;
+    g_cur_pool = &b->ctx->pool;
     CK(cudaSetDevice(b->ctx->device));
     CK(b->d_out.alloc(b->out_total + 256));
     b->arena_owned = true;

@@ -1,0 +1,267 @@
+"""GPU tier (-m gpu): parity of the CUDA path, called through the C ABI, against the compiled reference
+(oracle/_ref, travels with the snapshot), the C restatement and the committed digests.  Bit-exact."""
+import ctypes as C
+import hashlib
+import json
+import zlib
+
+import numpy as np
+import pytest
+
+import jpegdec_b200 as J
+from tests import common as T
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+MODES = [("sse", 0), ("scalar", 1)]
+
+
+def _ref(mode):
+    from oracle import refdrv
+    return refdrv.Ref(mode) if refdrv.available(mode) else None
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    c = {0: J.Context(0, 0), 1: J.Context(0, 1)}
+    yield c
+    for x in c.values():
+        x.close()
+
+
+def test_native_library_is_the_one_running(ctxs):
+    assert J.lib().JPEGB200_deviceCount() >= 1
+    outs, st, tim, cnt = J.decode_batch_to_host(ctxs[0], [T.image("tulips")], 0, 0)
+    assert st == [0] and cnt["launches"] >= 5 and cnt["events"] >= 7
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_fixture_batch_all_pixel_types_and_scales(ctxs, mode, arith):
+    """One mixed batch (different sizes, subsamplings, Huffman table sets, DRI / no DRI) per pixel type x scale."""
+    d = T.digests()
+    blobs = [T.image(n) for n in T.VALID]
+    ref = _ref(mode)
+    for pt, ptn in T.PTS:
+        for opt, sn in T.SCALES:
+            outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], blobs, pt, opt)
+            assert st == [0] * len(blobs)
+            for n, o, data in zip(T.VALID, outs, blobs):
+                want = d[n]["%s/%s/%s" % (mode, ptn, sn)]
+                assert list(o.shape) == want["shape"]
+                assert T.sha(o) == want["sha"], (n, mode, ptn, sn)
+                if ref is not None and n in ("tulips", "zebra"):
+                    rc, err, img, _ = ref.decode_cb(data, pt, opt, want_log=False)
+                    assert np.array_equal(o, img)
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_synthetic_formats(ctxs, mode, arith):
+    """grayscale, 4:4:4, 4:2:2, 4:4:0, odd sizes, no restart markers, high quality -- vs the C restatement
+    (itself pinned to the reference on the same cases in the CPU tier) and the live reference when present."""
+    import cv2
+    cases = {"gray": synth.synth_jpeg(640, 360, 1, 75, gray=True),
+             "s444": synth.synth_jpeg(333, 251, 2, 80, subsampling="4:4:4"),
+             "s422": synth.synth_jpeg(333, 251, 3, 80, subsampling="4:2:2"),
+             "odd420": synth.synth_jpeg(301, 203, 4, 90, restart_rows=0),
+             "q98": synth.synth_jpeg(256, 256, 5, 98),
+             "hd": synth.synth_jpeg(1920, 1080, 6, 75)}
+    ok, enc = cv2.imencode(".jpg", synth.synth_pixels(200, 150, 7),
+                           [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440])
+    cases["s440"] = enc.tobytes()
+    ref = _ref(mode)
+    for pt, ptn in T.PTS:
+        for opt, sn in T.SCALES:
+            names = [n for n in cases if not (n == "gray" and pt == 2)]
+            outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], [cases[n] for n in names], pt, opt)
+            assert st == [0] * len(names)
+            for n, o in zip(names, outs):
+                if n == "s440" and pt == 2 and opt == 4:
+                    continue  # reference bug: JPEGPutMCU12 1/4 RGB8888 writes through &pOutput (jpeg.inl:4629)
+                info = J.Batch  # noqa
+                w = {"gray": 640, "s444": 333, "s422": 333, "odd420": 301, "q98": 256, "hd": 1920, "s440": 200}[n]
+                h = {"gray": 360, "s444": 251, "s422": 251, "odd420": 203, "q98": 256, "hd": 1080, "s440": 150}[n]
+                rc, want = T.oracle_decode(cases[n], pt, opt, arith, w, h)
+                assert rc == 1 and np.array_equal(o, want), (n, mode, ptn, sn)
+                if ref is not None and n in ("hd", "s422"):
+                    rc, err, img, _ = ref.decode_cb(cases[n], pt, opt, want_log=False)
+                    assert np.array_equal(o, img), (n, mode, ptn, sn)
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_dither_batch(ctxs, mode, arith):
+    d = T.digests()
+    names = ["tulips", "zebra", "ncc1701", "sciopero"]
+    for pt, ptn in T.DITHERS:
+        outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], [T.image(n) for n in names], pt, 0)
+        assert st == [0] * len(names)
+        for n, o in zip(names, outs):
+            want = d[n]["%s/%s/full" % (mode, ptn)]
+            inf = d[n]["info"]
+            rc, w2 = T.oracle_decode(T.image(n), pt, 0, arith, inf["width"], inf["height"])
+            wb = (inf["width"] * T.bpp_of(pt) + 7) // 8
+            assert np.array_equal(o[:, :wb], w2[:o.shape[0], :wb]), (n, mode, ptn)
+
+
+def _collect(j, pt, options, x=0, y=0):
+    """decode through the draw callback; returns (rc, log, tight image assembled like oracle/ref_shim.c does)."""
+    log, blocks = [], []
+
+    def draw(d):
+        nbytes = ((d.iWidth * d.iBpp + 7) // 8) * d.iHeight
+        buf = C.string_at(d.pPixels, nbytes)
+        log.append((d.x, d.y, d.iWidth, d.iHeight, d.iWidthUsed, d.iBpp))
+        blocks.append(buf)
+        return 1
+    return draw, log, blocks
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_single_image_api_callbacks_match_reference(mode, arith):
+    """JPEG_openRAM -> setPixelType -> decode: same callback sequence (x, y, iWidth, iHeight, iWidthUsed, iBpp)
+    and same delivered pixels as the reference, incl. decode offset, JPEG_USES_DMA and setMaxOutputSize."""
+    ref = _ref(mode)
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    cases = [("sciopero", 0, 0, 10, 20, 0), ("sciopero", 2, 0, 0, 0, 0), ("sciopero", 3, 0, 0, 0, 0),
+             ("sciopero", 0, 2, 0, 0, 0), ("sciopero", 0, 4, 3, 5, 0), ("sciopero", 0, 8, 0, 0, 0),
+             ("tulips", 0, 0, 0, 0, 0), ("tulips", 0, J.JPEG_USES_DMA, 0, 0, 0), ("tulips", 0, 0, 0, 0, 3),
+             ("ncc1701", 2, 0, 0, 0, 0), ("zebra", 1, 0, 0, 0, 0), ("zebra", 0, 2, 0, 0, 0), ("lange", 3, 4, 0, 0, 0),
+             ("tulips", 0, J.JPEG_LUMA_ONLY, 0, 0, 0)]
+    for name, pt, opt, xo, yo, maxm in cases:
+        data = T.image(name)
+        rc_r, err_r, img_r, log_r = ref.decode_cb(data, pt, opt, xoff=xo, yoff=yo, max_mcus=maxm)
+        j = J.JPEGDEC()
+        draw, log, blocks = _collect(j, pt, opt)
+        assert j.openRAM(data, draw) == 1
+        j.setArithMode(arith)
+        j.setPixelType(pt)
+        if maxm:
+            j.setMaxOutputSize(maxm)
+        rc = j.decode(xo, yo, opt)
+        assert rc == rc_r == 1, (name, pt, opt, j.getLastError())
+        assert [l for l in log] == [tuple(r[:6]) for r in log_r], (name, pt, opt)
+        # assemble the tight image from the delivered blocks
+        out = np.zeros_like(img_r)
+        for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+            pitch = (w * bpp + 7) // 8
+            a = np.frombuffer(buf, dtype=np.uint8).reshape(h, pitch)
+            bw = wu * bpp // 8
+            x0 = (x - xo) * bpp // 8
+            out[y - yo:y - yo + h, x0:x0 + bw] = a[:, :bw]
+        assert np.array_equal(out, img_r), (name, pt, opt)
+        j.close()
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_single_image_api_framebuffer_crop_thumb_dither(mode, arith):
+    ref = _ref(mode)
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    # framebuffer mode, multiple-of-16 width: identical bytes (reference pitch = image width)
+    data = T.image("tulips")
+    for pt in (0, 2, 3):
+        rc_r, err_r, fb_r = ref.decode_fb(data, pt, 0)
+        j = J.JPEGDEC(); assert j.openRAM(data); j.setArithMode(arith); j.setPixelType(pt)
+        fb = np.zeros_like(fb_r); j.setFramebuffer(fb)
+        assert j.decode(0, 0, 0) == rc_r == 1
+        n = 640 * 480 * T.bpp_of(pt) // 8
+        assert np.array_equal(fb[:n], fb_r[:n])
+    # crop through callbacks (reference test 2): exactly the snapped rectangle, same pixels
+    rc_r, err_r, img_r, log_r = ref.decode_cb(data, 0, 0, crop=(50, 50, 125, 170))
+    j = J.JPEGDEC(); draw, log, blocks = _collect(j, 0, 0)
+    assert j.openRAM(data, draw); j.setArithMode(arith); j.setCropArea(50, 50, 125, 170)
+    assert j.decode(0, 0, 0) == 1
+    assert log == [tuple(r[:6]) for r in log_r]
+    out = np.zeros((176, 256), np.uint8)
+    for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(h, w * 2)
+        out[y:y + h, x * 2:(x + wu) * 2] = a[:, :wu * 2]
+    assert np.array_equal(out, img_r[:176, :256])
+    # EXIF thumbnail (reference test 10): 320x240
+    tdata = T.image("thumb_test")
+    rc_r, err_r, img_r, log_r = ref.decode_cb(tdata, 0, J.JPEG_EXIF_THUMBNAIL)
+    j = J.JPEGDEC(); draw, log, blocks = _collect(j, 0, 0)
+    assert j.openRAM(tdata, draw) and j.hasThumb() and (j.getThumbWidth(), j.getThumbHeight()) == (320, 240)
+    j.setArithMode(arith)
+    assert j.decode(0, 0, J.JPEG_EXIF_THUMBNAIL) == rc_r == 1
+    assert (j.getWidth(), j.getHeight()) == (320, 240)
+    assert log == [tuple(r[:6]) for r in log_r]
+    out = np.zeros_like(img_r)
+    for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(h, w * 2)
+        out[y:y + h, x * 2:(x + wu) * 2] = a[:, :wu * 2]
+    assert np.array_equal(out, img_r)
+    # decodeDither through the callback
+    zdata = T.image("zebra")
+    rc_r, err_r, img_r, log_r = ref.decode_dither(zdata, J.ONE_BIT_DITHERED, 0)
+    j = J.JPEGDEC(); draw, log, blocks = _collect(j, 6, 0)
+    assert j.openRAM(zdata, draw); j.setArithMode(arith); j.setPixelType(J.ONE_BIT_DITHERED)
+    dbuf = np.zeros((320 + 32) * 16, np.uint8)
+    assert j.decodeDither(dbuf, 0) == rc_r == 1
+    assert log == [tuple(r[:6]) for r in log_r]
+    out = np.zeros_like(img_r)
+    for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+        a = np.frombuffer(buf, dtype=np.uint8).reshape(h, (w + 7) // 8)
+        out[y:y + h, :(wu + 7) // 8] = a[:, :(wu + 7) // 8]
+    assert np.array_equal(out[:, :40], img_r[:, :40])
+
+
+def test_corrupt_inputs_do_not_poison_the_batch(ctxs):
+    """reference tests 4-8 + 11 (MacOS/JPEGDEC_Test/JPEGDEC_Test/main.cpp:164-216, :262-300): corrupt files
+    return 0/1 without crashing; a bad image must not disturb its neighbours in the same batch."""
+    good = T.image("tulips")
+    want = J.decode_batch_to_host(ctxs[0], [good], 0, 0)[0][0]
+    blobs = [good] + [T.image("corrupt%d" % i) for i in range(1, 6)] + [good]
+    rng = np.random.default_rng(3)
+    for k in range(12):  # entropy-segment corruption
+        b = bytearray(good)
+        for _ in range(4):
+            b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
+        blobs.append(bytes(b))
+    blobs.append(good)
+    outs, st, tim, cnt = J.decode_batch_to_host(ctxs[0], blobs, 0, 0)
+    assert all(s in range(6) for s in st)
+    d = T.digests()
+    for i in range(1, 6):
+        if not d["corrupt%d" % i]["open"]:
+            assert st[i] == d["corrupt%d" % i]["info"]["error"]
+    for i in (0, 6, len(blobs) - 1):
+        assert st[i] == 0 and np.array_equal(outs[i], want)
+
+
+def test_batch_properties_at_baseline_size(ctxs):
+    """BASELINE.json configs[1] shape: 1024 x 1920x1080 -> RGB8888.  Size-independent properties: every copy of a
+    unique image in the batch yields the same CRC as that image decoded alone; the checksum of checksums is
+    identical across two runs; a sample is bit-exact vs the C restatement."""
+    uniq = synth.synth_set(8, 1920, 1080, quality=75)
+    n = 1024
+    bufs = [np.frombuffer(uniq[i % 8], dtype=np.uint8) for i in range(n)]
+    L = J.lib()
+
+    def run():
+        b = J.Batch(ctxs[0], [x.ctypes.data for x in bufs], [len(x) for x in bufs], J.RGB8888, 0)
+        b.alloc_device_output(); b.upload(); b.decode(J.JPEGB200_OUT_DEVICE); b.download()
+        st = b.wait()
+        import torch
+        crcs = []
+        for i in range(n):
+            dp, pitch = b.device_output(i)
+            nbytes, _ = b.output_bytes(i)
+            t = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            torch.cuda.cudart().cudaMemcpy(t.data_ptr(), dp, nbytes, 3)
+            crcs.append(zlib.crc32(t.cpu().numpy().tobytes()) if i < 16 or i % 97 == 0 else None)
+        cnt = b.counters()
+        b.close()
+        return st, crcs, cnt
+    st, crcs, cnt = run()
+    assert st == [0] * n
+    alone, st1, _, _ = J.decode_batch_to_host(ctxs[0], uniq, J.RGB8888, 0)
+    base = [zlib.crc32(a.tobytes()) for a in alone]
+    for i, c in enumerate(crcs):
+        if c is not None:
+            assert c == base[i % 8], i
+    st2, crcs2, _ = run()
+    assert crcs2 == crcs
+    rc, want = T.oracle_decode(uniq[3], J.RGB8888, 0, 0, 1920, 1080)
+    assert rc == 1 and np.array_equal(alone[3], want)
+    assert cnt["segments"] == n * 68 and cnt["blocks"] == n * 8160 * 6

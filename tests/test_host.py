@@ -1,0 +1,113 @@
+"""CPU tier: host logic of the product (no compute calls): C-ABI symbols, open() conformance against the
+reference's recorded behaviour, crop snapping, table builders, loud failure without a GPU."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import jpegdec_b200 as J
+from tests import common as T
+
+
+def _declared_functions(header):
+    txt = open(os.path.join(T.ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    txt = txt.split("#ifdef __cplusplus\n} /* extern")[0] if header == "JPEGDEC.h" else txt
+    names = re.findall(r"^[A-Za-z_][A-Za-z0-9_ \*]*?\b((?:JPEG|JPEGB200)_[A-Za-z0-9_]+)\s*\(", txt, flags=re.M)
+    return sorted(set(names))
+
+
+@pytest.mark.parametrize("header", ["JPEGDEC.h", "jpegdec_b200.h"])
+def test_every_declared_symbol_is_exported(header):
+    L = C.CDLL(J.LIB_PATH)
+    names = _declared_functions(header)
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), "%s declared in include/%s but not exported" % (n, header)
+
+
+def test_open_matches_reference_behaviour():
+    d = T.digests()
+    for name, rec in d.items():
+        j = J.JPEGDEC()
+        rc = j.openRAM(T.image(name))
+        inf = rec["info"]
+        assert rc == rec["open"], name
+        if rc:
+            assert (j.getWidth(), j.getHeight(), j.getSubSample(), j.getBpp()) == (
+                inf["width"], inf["height"], inf["subsample"], inf["bpp"]), name
+            assert j.getOrientation() == inf["orientation"]
+            assert j.hasThumb() == inf["has_thumb"]
+            assert (j.getThumbWidth(), j.getThumbHeight()) == (inf["thumb_w"], inf["thumb_h"])
+            assert j.getLastError() == J.JPEG_SUCCESS
+        else:
+            assert j.getLastError() == inf["error"], name
+        j.close()
+
+
+def test_open_rejects_garbage():
+    j = J.JPEGDEC()
+    assert j.openRAM(b"\x00" * 100) == 0 and j.getLastError() == J.JPEG_INVALID_FILE      # < 256 bytes
+    assert j.openRAM(b"\x12" * 1000) == 0 and j.getLastError() == J.JPEG_INVALID_FILE     # no SOI
+    assert j.openRAM(b"\xff\xd8" + b"\xff\xc1" + b"\x00" * 600) == 0 and j.getLastError() == J.JPEG_UNSUPPORTED_FEATURE
+
+
+def test_crop_snapping_known_answer():
+    # reference test 2 (MacOS/JPEGDEC_Test/JPEGDEC_Test/main.cpp:106-137): (50,50,125,170) -> (48,48,128,176)
+    j = J.JPEGDEC()
+    assert j.openRAM(T.image("tulips"))
+    j.setCropArea(50, 50, 125, 170)
+    assert j.getCropArea() == (48, 48, 128, 176)
+    j.setCropArea(-5, -5, 10000, 10000)
+    x, y, w, h = j.getCropArea()
+    assert (x, y) == (0, 0) and w == 640 - 16 and h == 480 - 16   # the reference's clamp (jpeg.inl:719-720)
+
+
+def test_fuzzed_headers_never_crash():
+    # reference tests 11-12 (main.cpp:262-300) at the open() level: byte inversions in the first 2000 bytes
+    base = bytearray(T.image("tulips"))
+    rng = np.random.default_rng(7)
+    for i in list(range(0, 700)) + list(rng.integers(700, 2000, 300)):
+        b = bytearray(base)
+        b[i] ^= 0xFF
+        j = J.JPEGDEC()
+        rc = j.openRAM(bytes(b))
+        assert rc in (0, 1)
+        assert 0 <= j.getLastError() <= J.JPEG_ERROR_MEMORY
+
+
+def test_aan_prescale_table_from_formula():
+    L = C.CDLL(J.LIB_PATH)
+    L.jd_aan_table.restype = C.POINTER(C.c_int)
+    tab = [L.jd_aan_table()[i] for i in range(64)]
+    s = [1.0] + [math.cos(k * math.pi / 16) * math.sqrt(2) for k in range(1, 8)]
+    for r in range(8):
+        for c in range(8):
+            assert abs(tab[r * 8 + c] - 16384 * s[r] * s[c]) <= 1.0, (r, c)
+
+
+def test_decode_without_gpu_fails_loudly():
+    if J.lib().JPEGB200_deviceCount() > 0:
+        pytest.skip("a GPU is present")
+    j = J.JPEGDEC()
+    assert j.openRAM(T.image("tulips"))
+    fb = np.zeros((496, 1280), np.uint8)
+    j.setFramebuffer(fb)
+    assert j.decode(0, 0, 0) == 0
+    assert j.getLastError() == J.JPEG_ERROR_MEMORY
+    assert not fb.any()                      # nothing was computed on the CPU
+    with pytest.raises(RuntimeError):
+        J.Context()
+
+
+def test_table_blob_roundtrip_host_side():
+    blob = np.zeros(J.TABLE_BLOB_BYTES, np.uint8)
+    assert J.lib().JPEGB200_exportTables(T.image("tulips"), len(T.image("tulips")), blob.ctypes.data) == 1
+    blob2 = np.zeros(J.TABLE_BLOB_BYTES, np.uint8)
+    J.lib().JPEGB200_exportTables(T.image("croptest"), len(T.image("croptest")), blob2.ctypes.data)
+    assert blob[:8].tobytes() != b"\0" * 8
+    # standard Huffman tables in both files -> same LUT hash, different quant
+    assert (blob[:8] == blob2[:8]).all() == (blob[16:16 + 12800] == blob2[16:16 + 12800]).all()

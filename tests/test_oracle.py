@@ -1,0 +1,99 @@
+"""CPU tier: the checkers themselves.  (1) the C restatement (oracle/jpegdec_oracle.c) and the sequential
+stepper of the kernels' per-thread code (tests/hostsim) reproduce the digests the *compiled reference*
+produced for every bundled image x pixel type x scale x arithmetic build (tests/golden/digests.json, written
+by tests/golden/make_golden.py); (2) where oracle/_ref is present, they are compared with it live too."""
+import numpy as np
+import pytest
+
+from tests import common as T
+
+MODES = [("sse", 0), ("scalar", 1)]
+
+
+@pytest.mark.parametrize("name", T.VALID)
+def test_restatement_matches_reference_digests(name):
+    d = T.digests()[name]
+    data = T.image(name)
+    w, h = d["info"]["width"], d["info"]["height"]
+    for mode, arith in MODES:
+        for pt, ptn in T.PTS:
+            for opt, sn in T.SCALES:
+                want = d["%s/%s/%s" % (mode, ptn, sn)]
+                rc, out = T.oracle_decode(data, pt, opt, arith, w, h)
+                assert rc == want["rc"]
+                assert list(out.shape) == want["shape"]
+                assert T.sha(out) == want["sha"], (name, mode, ptn, sn)
+
+
+@pytest.mark.parametrize("name", T.VALID)
+def test_kernel_stepper_matches_reference_digests(name):
+    d = T.digests()[name]
+    data = T.image(name)
+    w, h = d["info"]["width"], d["info"]["height"]
+    for mode, arith in MODES:
+        for pt, ptn in T.PTS:
+            for opt, sn in T.SCALES:
+                want = d["%s/%s/%s" % (mode, ptn, sn)]
+                rc, out, nev = T.hostsim_decode(data, pt, opt, arith, w, h)
+                assert rc == want["rc"]
+                assert T.sha(out) == want["sha"], (name, mode, ptn, sn)
+
+
+def test_window_quirk_events_are_needed():
+    """tulips has 7 truncated coefficient reads; without emulating them the frame differs."""
+    data = T.image("tulips")
+    rc, out, nev = T.hostsim_decode(data, 0, 0, 0, 640, 480)
+    assert nev == 7
+    rc, out, nev = T.hostsim_decode(T.image("sciopero"), 0, 0, 0, 300, 300)
+    assert nev == 9
+
+
+def test_committed_golden_frame():
+    want = np.fromfile(T.GOLD + "/frames/tulips_sse_rgb565le_full.bin", dtype=np.uint8).reshape(480, 1280)
+    rc, out = T.oracle_decode(T.image("tulips"), 0, 0, 0, 640, 480)
+    assert rc == 1 and np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("name", ["tulips", "zebra", "ncc1701", "lange"])
+def test_dither_restatement_vs_live_reference(name):
+    from oracle import refdrv
+    if not refdrv.available("sse"):
+        pytest.skip("oracle/_ref not built here")
+    data = T.image(name)
+    inf = T.digests()[name]["info"]
+    for mode, arith in MODES:
+        ref = refdrv.Ref(mode)
+        for pt, ptn in T.DITHERS:
+            for opt in (0, 2):
+                rc, err, img, log = ref.decode_dither(data, pt, opt)
+                rc2, out = T.oracle_decode(data, pt, opt, arith, inf["width"], inf["height"])
+                s = 1 if opt else 0
+                wb = ((((inf["width"] + (1 << s) - 1) >> s) * T.bpp_of(pt)) + 7) // 8
+                assert rc == rc2 == 1
+                assert np.array_equal(out[:img.shape[0], :wb], img[:, :wb]), (name, mode, ptn, opt)
+
+
+def test_synthetic_formats_vs_live_reference():
+    """4:2:2, 4:4:4, grayscale, no-restart odd-sized 4:2:0: bundled images do not cover them."""
+    from oracle import refdrv
+    from tests import synth
+    if not refdrv.available("sse"):
+        pytest.skip("oracle/_ref not built here")
+    cases = {"gray": synth.synth_jpeg(320, 200, 1, 75, gray=True),
+             "s444": synth.synth_jpeg(173, 131, 2, 80, subsampling="4:4:4"),
+             "s422": synth.synth_jpeg(173, 131, 3, 80, subsampling="4:2:2"),
+             "odd420": synth.synth_jpeg(301, 203, 4, 90, restart_rows=0)}
+    for mode, arith in MODES:
+        ref = refdrv.Ref(mode)
+        for n, data in cases.items():
+            rc0, inf = ref.info(data)
+            for pt, ptn in T.PTS:
+                if n == "gray" and pt == 2:
+                    continue  # reference writes 16-bit pixels into a 32-bit buffer here (JPEGPutMCUGray): undefined
+                for opt, sn in T.SCALES:
+                    rc, err, img, _ = ref.decode_cb(data, pt, opt, want_log=False)
+                    rc1, o1 = T.oracle_decode(data, pt, opt, arith, inf.width, inf.height)
+                    rc2, o2, _ = T.hostsim_decode(data, pt, opt, arith, inf.width, inf.height)
+                    assert rc == rc1 == rc2 == 1
+                    assert np.array_equal(o1, img), (n, mode, ptn, sn)
+                    assert np.array_equal(o2, img), (n, mode, ptn, sn)
