@@ -89,6 +89,8 @@ int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int64_t pitch_b
 /* Let the library own a device output arena (tight images back to back, 256-B aligned). */
 int JPEGB200_batchAllocDeviceOutput(JPEGB200_BATCH *b);
 int JPEGB200_batchGetDeviceOutput(JPEGB200_BATCH *b, int i, void **devptr, int64_t *pitch_bytes);
+int JPEGB200_batchReadOutput(JPEGB200_BATCH *b, int i, void *host_dst); /* synchronous D2H of one image from the arena */
+int JPEGB200_batchErrMcu(JPEGB200_BATCH *b, int i);                      /* first undecodable MCU of image i, -1 if none */
 /* dither needs no extra buffers from the caller: packed rows are written to the output. */
 
 int JPEGB200_batchUpload(JPEGB200_BATCH *b);            /* H2D: compressed bytes + descriptors (async) */

@@ -100,6 +100,7 @@ def lib():
     L.JPEGB200_batchSetOutput.argtypes = [vp, C.c_int, vp, C.c_int64]
     L.JPEGB200_batchAllocDeviceOutput.argtypes = [vp]
     L.JPEGB200_batchGetDeviceOutput.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.JPEGB200_batchReadOutput.argtypes = [vp, C.c_int, vp]
     L.JPEGB200_batchUpload.argtypes = [vp]
     L.JPEGB200_batchDecode.argtypes = [vp, C.c_int]
     L.JPEGB200_batchDownload.argtypes = [vp]
@@ -254,6 +255,12 @@ class Batch:
         p, pitch = C.c_void_p(), C.c_int64()
         self._ck(lib().JPEGB200_batchGetDeviceOutput(self.h, i, C.byref(p), C.byref(pitch)), "batchGetDeviceOutput")
         return p.value, pitch.value
+
+    def read_output(self, i):
+        nbytes, pitch = self.output_bytes(i)
+        o = np.empty(nbytes, dtype=np.uint8)
+        self._ck(lib().JPEGB200_batchReadOutput(self.h, i, o.ctypes.data), "batchReadOutput")
+        return o.reshape(-1, pitch)
 
     def upload(self): self._ck(lib().JPEGB200_batchUpload(self.h), "batchUpload")
     def decode(self, flags=0): self._ck(lib().JPEGB200_batchDecode(self.h, flags), "batchDecode")

@@ -36,17 +36,37 @@
 #define JD_LUT_AC(t) (2 * JD_LUT_DC_SIZE + (t) * JD_LUT_AC_SIZE)
 #define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE) /* 6400 u16 = 12800 B */
 
-/* Block header written by the entropy kernel, read by the IDCT kernels (8 B). */
+/* Block header written by the entropy kernel, read by the IDCT kernels (8 B):    */
 /*   bits  0..31 : index of the block's first AC record in the record array     */
 /*   bits 32..47 : DC coefficient (int16, = (short)predictor, jpeg.inl:2163)    */
-/*   bits 48..55 : number of AC records (0..63)                                 */
-/* AC record (u16): (run << 12) | (value & 0xFFF); value==0 only for ZRL.       */
+/*   bits 48..53 : number of stored AC coefficients (0..63)                     */
+/*   bit  54     : BIG -- some magnitude needs >= 10 bits: records are pairs     */
+/*   bit  55     : a stored coefficient lies in rows 4-7 (u16MCUFlags & 0x2000)  */
+/*   bits 56..63 : occupied-column mask (low byte of u16MCUFlags, jpeg.inl:2253) */
+/* AC record (u16), normal blocks: (t << 10) | (value & 0x3FF), |value| <= 511,  */
+/*   t = position in the column-major coefficient tile = (n & 7) * 8 + (n >> 3)  */
+/*   for natural index n.  BIG blocks: two u16 per coefficient: t, then value.   */
+/* Only stored coefficients get a record (no ZRL / EOB records).                 */
 typedef unsigned long long jd_u64;
 
-JD_HD jd_u64 jd_pack_hdr(uint32_t rec_index, int dc, uint32_t nrec)
+JD_HD jd_u64 jd_pack_hdr(uint32_t rec_index, int dc, uint32_t ncoef, uint32_t big, uint32_t hi, uint32_t colmask)
 {
-    return (jd_u64)rec_index | ((jd_u64)(uint16_t)(int16_t)dc << 32) | ((jd_u64)(nrec & 0xFF) << 48);
+    return (jd_u64)rec_index | ((jd_u64)(uint16_t)(int16_t)dc << 32) | ((jd_u64)(ncoef & 63u) << 48) |
+           ((jd_u64)(big & 1u) << 54) | ((jd_u64)(hi & 1u) << 55) | ((jd_u64)(colmask & 0xFFu) << 56);
 }
+#define JD_HDR_REC(h) ((uint32_t)(h))
+#define JD_HDR_DC(h) ((int)(short)(uint16_t)((h) >> 32))
+#define JD_HDR_NCOEF(h) ((uint32_t)((h) >> 48) & 63u)
+#define JD_HDR_BIG(h) ((uint32_t)((h) >> 54) & 1u)
+#define JD_HDR_HI(h) ((uint32_t)((h) >> 55) & 1u)
+#define JD_HDR_COLMASK(h) ((uint32_t)((h) >> 56) & 0xFFu)
+
+/* zigzag index k -> tile position t (column-major: t = (n & 7) * 8 + (n >> 3), n = de-zigzag(k)) */
+#define JD_TPOS_INIT { \
+    0, 8, 1, 2, 9, 16, 24, 17, 10, 3, 4, 11, 18, 25, 32, 40, \
+    33, 26, 19, 12, 5, 6, 13, 20, 27, 34, 41, 48, 56, 49, 42, 35, \
+    28, 21, 14, 7, 15, 22, 29, 36, 43, 50, 57, 58, 51, 44, 37, 30, \
+    23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63 }
 
 /* de-zigzag: zigzag index k -> natural (row-major) index (ITU T.81 Figure 5). */
 #define JD_DEZIGZAG_INIT { \
@@ -81,13 +101,22 @@ JD_HD uint32_t jd_jw_ckpt(uint32_t jw)
 
 /* Truncation event: one stored AC value that some start-phase candidates read truncated. */
 typedef struct {
-    uint32_t rec_index; /* global index of the AC record to patch */
+    uint32_t blk;       /* global block index */
     uint32_t seg;       /* global segment index */
     uint32_t j1;        /* candidate nibbles (j after the code length was added) */
     uint16_t field;     /* the S raw extra bits */
     uint8_t s;          /* SSSS */
     uint8_t p7;         /* (P + len) & 7 */
+    uint32_t ord;       /* ordinal of the coefficient among the block's stored coefficients */
 } JDEvent;
+
+/* where the value of coefficient `ord` of a block lives, and how to rewrite it */
+JD_HD void jd_patch_record(uint16_t *rec, jd_u64 hdr, uint32_t ord, int v)
+{
+    const uint32_t ri = JD_HDR_REC(hdr);
+    if (JD_HDR_BIG(hdr)) rec[ri + 2u * ord + 1u] = (uint16_t)(int16_t)v;
+    else rec[ri + ord] = (uint16_t)((rec[ri + ord] & 0xFC00u) | ((uint32_t)v & 0x3FFu));
+}
 
 /* value the reference would store for candidate nibble jc (jpeg.inl:2249-2252) */
 JD_HD int jd_event_value(const JDEvent *e, uint32_t jc)
@@ -119,6 +148,7 @@ typedef struct {
     uint32_t rec_index0;  /* global index of this segment's first record */
     uint32_t rec_cap;     /* record capacity of this segment */
     uint32_t seg;         /* global segment index (for events) */
+    uint32_t blk0;        /* global index of this segment's first block (for events) */
 } JDSegIn;
 
 typedef struct {
@@ -143,6 +173,7 @@ typedef struct {
 
 template <typename EventSink>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
+                             const uint8_t *tpos /* JD_TPOS_INIT table, shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
                              EventSink &sink, JDSegOut &out)
 {
@@ -173,7 +204,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         const uint16_t *tdc = lut + JD_LUT_DC(dcsel);
         const uint16_t *tac = lut + JD_LUT_AC(acsel);
         uint32_t k = 0;            /* zigzag index: 0 = DC pending */
-        uint32_t nrec = 0;
+        uint32_t ncoef = 0, big = 0, colmask = 0, hi = 0;
         uint32_t rec0 = nrec_total;
         int dcval = 0;
         bool done = false;
@@ -264,6 +295,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             } else {
                 k += rs >> 4;
                 if (s && k < 64u) {
+                    /* stored coefficient (jpeg.inl:2247-2256) */
                     if (s > 11) { err = JD_SEG_BADSIZE; break; }
                     if (len + s >= 18) {
                         /* possible truncated read for some start phases */
@@ -278,23 +310,42 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                             }
                             if (any) {
                                 JDEvent ev;
-                                ev.rec_index = in.rec_index0 + nrec_total;
+                                ev.blk = in.blk0 + b;
                                 ev.seg = in.seg;
                                 ev.j1 = j1;
                                 ev.field = (uint16_t)field;
                                 ev.s = (uint8_t)s;
                                 ev.p7 = (uint8_t)p7;
+                                ev.ord = ncoef;
                                 sink.push(ev);
                             }
                         }
                     }
-                }
-                if (k < 64u) {
-                    /* one record per AC symbol (ZRL has value 0); symbols past 63 are dropped (:2247 pZig<pEnd2) */
-                    if (nrec_total >= in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
-                    rec[nrec_total] = (uint16_t)(((rs >> 4) << 12) | ((uint32_t)v & 0xFFFu));
-                    nrec_total++;
-                    nrec++;
+                    const uint32_t t = tpos[k];
+                    colmask |= 1u << (t >> 3);
+                    hi |= (t >> 2) & 1u;
+                    if (s >= 10 && !big) {
+                        /* first >=10-bit magnitude of this block: switch its records to (t, value) pairs */
+                        if (nrec_total + ncoef + 2u > in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
+                        for (uint32_t i = ncoef; i-- > 0u;) {
+                            const uint32_t r = rec[rec0 + i];
+                            rec[rec0 + 2u * i] = (uint16_t)(r >> 10);
+                            rec[rec0 + 2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
+                        }
+                        nrec_total += ncoef;
+                        big = 1;
+                    }
+                    if (big) {
+                        if (nrec_total + 2u > in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
+                        rec[nrec_total] = (uint16_t)t;
+                        rec[nrec_total + 1u] = (uint16_t)(int16_t)v;
+                        nrec_total += 2u;
+                    } else {
+                        if (nrec_total >= in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
+                        rec[nrec_total] = (uint16_t)((t << 10) | ((uint32_t)v & 0x3FFu));
+                        nrec_total++;
+                    }
+                    ncoef++;
                 }
                 k++;
                 P += len + s;
@@ -306,10 +357,10 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         if (err >= 0) {
             /* undecodable from here: later stages must still find well-formed (empty) headers */
             out.err_mcu = (int32_t)(b / in.bpm);
-            for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0);
+            for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
             break;
         }
-        blk_hdr[b] = jd_pack_hdr(in.rec_index0 + rec0, dcval, nrec);
+        blk_hdr[b] = jd_pack_hdr(in.rec_index0 + rec0, dcval, ncoef, big, hi, colmask);
         if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
     }
     out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
@@ -452,7 +503,7 @@ JD_HD void jd_col_scalar(const int m[8], const int q[8], bool rows47_empty, int 
 
 /* Row pass (both builds, jpeg.inl:2681-2797).  p[c] = int16 column results of one row
  * (sign-extended); colmask = low byte of the block's u16MCUFlags.  Writes 8 pixel bytes. */
-JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])
+JD_HD void jd_row_raw(const int p[8], uint32_t colmask, int o[8])
 {
     int tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, tmp7;
     if ((colmask & 0xf0u) == 0u) {
@@ -492,10 +543,15 @@ JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])
         tmp5 = tmp11 - tmp6;
         tmp4 = tmp10 + tmp5;
     }
-    o[0] = jd_range(tmp0 + tmp7); o[1] = jd_range(tmp1 + tmp6);
-    o[2] = jd_range(tmp2 + tmp5); o[3] = jd_range(tmp3 - tmp4);
-    o[4] = jd_range(tmp3 + tmp4); o[5] = jd_range(tmp2 - tmp5);
-    o[6] = jd_range(tmp1 - tmp6); o[7] = jd_range(tmp0 - tmp7);
+    o[0] = tmp0 + tmp7; o[1] = tmp1 + tmp6; o[2] = tmp2 + tmp5; o[3] = tmp3 - tmp4;
+    o[4] = tmp3 + tmp4; o[5] = tmp2 - tmp5; o[6] = tmp1 - tmp6; o[7] = tmp0 - tmp7;
+}
+
+JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])
+{
+    int t[8];
+    jd_row_raw(p, colmask, t);
+    for (int i = 0; i < 8; i++) o[i] = jd_range(t[i]);
 }
 
 /* ------------------------------------------------------------------------- */

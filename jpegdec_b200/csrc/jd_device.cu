@@ -291,7 +291,13 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
             d.nseg = 0; d.seg_base = seg; d.blk_base = (uint32_t)blk; d.status = (uint32_t)st;
             continue;
         }
-        jd_build_quant(&inf, &b->quant[(size_t)i * 192]);
+        {   /* kernels read quant column-major ([c * 8 + r]) so a lane's column is one 16-byte load */
+            int16_t qn[192];
+            jd_build_quant(&inf, qn);
+            int16_t *qt = &b->quant[(size_t)i * 192];
+            for (int cc = 0; cc < 3; cc++)
+                for (int nn = 0; nn < 64; nn++) qt[cc * 64 + (nn & 7) * 8 + (nn >> 3)] = qn[cc * 64 + nn];
+        }
         /* Huffman LUT set: dedupe on the raw DHT content */
         uint64_t h = jd_tables_hash(&inf);
         uint32_t li = 0;
@@ -430,6 +436,16 @@ extern "C" int JPEGB200_batchGetDeviceOutput(JPEGB200_BATCH *b, int i, void **de
     return 1;
 }
 
+/* synchronous copy of image i's pixels out of the device arena (tests / spot checks) */
+extern "C" int JPEGB200_batchReadOutput(JPEGB200_BATCH *b, int i, void *host_dst)
+{
+    if (!b || i < 0 || i >= b->n || !b->d_out.p || !host_dst) return 0;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->stream) CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(host_dst, b->d_out.p + b->arena_off[i], (size_t)b->descs[i].out_pitch * b->descs[i].out_h, cudaMemcpyDeviceToHost));
+    return 1;
+}
+
 extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
 {
     if (!b) return 0;
@@ -491,14 +507,14 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
                            int arith, bool half, cudaStream_t st)
 {
     if (ptclass == JD_PT_GRAY) {
-        dim3 grid(((mcus_x + MPB1 - 1) / MPB1) * mcus_y, nimg);
+        dim3 grid((mcus_x + MPB1 - 1) / MPB1, mcus_y, nimg);
         launch_idct_pt<HS, VS, 1, MPB1, JD_PT_GRAY>(a, grid, arith, half, st);
     } else if (ncomp == 1) {
         if (HS != 1 || VS != 1 || ptclass != JD_PT_565) return 0;
-        dim3 grid(((mcus_x + MPB1 - 1) / MPB1) * mcus_y, nimg);
+        dim3 grid((mcus_x + MPB1 - 1) / MPB1, mcus_y, nimg);
         launch_idct_pt<1, 1, 1, MPB1, JD_PT_565>(a, grid, arith, half, st);
     } else {
-        dim3 grid(((mcus_x + MPB3 - 1) / MPB3) * mcus_y, nimg);
+        dim3 grid((mcus_x + MPB3 - 1) / MPB3, mcus_y, nimg);
         if (ptclass == JD_PT_565) launch_idct_pt<HS, VS, 3, MPB3, JD_PT_565>(a, grid, arith, half, st);
         else launch_idct_pt<HS, VS, 3, MPB3, JD_PT_8888>(a, grid, arith, half, st);
     }
@@ -591,7 +607,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     }
     CK(cudaEventRecord(b->ev[4], st));
     jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p);
-    jdk_patch<<<32, 256, 0, st>>>(b->d_events.p, b->d_counters.p, JD_EVENT_CAP, b->d_seg_phase.p, b->d_rec.p, b->d_counters.p + 1);
+    jdk_patch<<<32, 256, 0, st>>>(b->d_events.p, b->d_counters.p, JD_EVENT_CAP, b->d_seg_phase.p, b->d_blk_hdr.p, b->d_rec.p, b->d_counters.p + 1);
     launches += 2;
     CK(cudaEventRecord(b->ev[5], st));
     /* IDCT + colour: one launch per run of images with the same geometry class */

@@ -24,7 +24,7 @@
 #define JD_NONE 0xFFFFFFFFu
 #define JD_ENTROPY_THREADS 128
 
-__constant__ uint8_t c_dezigzag[64] = JD_DEZIGZAG_INIT;
+__constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
 
 /* ------------------------------------------------------------------------------------ */
 /* prescan                                                                                */
@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) jdk_prescan(const uint8_t *__restrict__ d
     const uint32_t nseg = im.nseg, base = im.seg_base;
     const uint32_t tid = threadIdx.x;
     __shared__ uint32_t s_wtot[2][8];
+    if (nseg == 0) return; /* header rejected on the host: owns no segment slots */
     if (tid == 0) seg_start[base] = im.scan_off;
     for (uint32_t i = 1 + tid; i < nseg; i += 256) seg_start[base + i] = JD_NONE;
     if (nseg <= 1) return;
@@ -119,6 +120,8 @@ struct JDEntropyArgs {
 __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    __shared__ uint8_t s_tpos[64];
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = c_tpos[threadIdx.x];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -142,9 +145,10 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     in.ncomp = im.ncomp;
     in.tsel = im.tsel;
     in.seg = seg;
+    in.blk0 = im.blk_base + m0 * im.bpm;
     jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
     JDSegOut so;
-    if (in.start == JD_NONE) {
+    if (in.start == JD_NONE || in.start < im.scan_off || in.start > im.scan_end) {
         /* restart marker missing: everything from here on is undecodable */
         for (uint32_t b = 0; b < in.nmcu * in.bpm; b++) hdr[b] = 0ull;
         a.seg_jmap[seg] = JD_JW_INIT;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     if ((uint64_t)in.rec_index0 + cap > a.rec_total) cap = (in.rec_index0 < a.rec_total) ? a.rec_total - in.rec_index0 : 0u;
     in.rec_cap = cap;
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
-    jd_decode_segment(in, s_lut, hdr, a.rec + in.rec_index0, sink, so);
+    jd_decode_segment(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
     a.seg_nrec[seg] = so.nrec;
@@ -190,7 +194,8 @@ __global__ void jdk_stitch(JDImageDesc *imgs, uint32_t nimg, const uint32_t *__r
 }
 
 __global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__restrict__ event_count, uint32_t cap,
-                          const uint32_t *__restrict__ seg_phase, uint16_t *__restrict__ rec, uint32_t *__restrict__ applied)
+                          const uint32_t *__restrict__ seg_phase, const jd_u64 *__restrict__ blk_hdr, uint16_t *__restrict__ rec,
+                          uint32_t *__restrict__ applied)
 {
     uint32_t n = *event_count;
     if (n > cap) n = cap;
@@ -198,8 +203,7 @@ __global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__
         const JDEvent e = events[i];
         const uint32_t jc = (e.j1 >> (4 * seg_phase[e.seg])) & 15u;
         if (8 * (int)jc + e.p7 + e.s > 64) {
-            const int v = jd_event_value(&e, jc);
-            rec[e.rec_index] = (uint16_t)((rec[e.rec_index] & 0xF000u) | ((uint32_t)v & 0xFFFu));
+            jd_patch_record(rec, blk_hdr[e.blk], e.ord, jd_event_value(&e, jc));
             atomicAdd(applied, 1u);
         }
     }
@@ -216,11 +220,11 @@ struct JDIdctArgs {
     const JDImageDesc *imgs;
     const jd_u64 *blk_hdr;
     const uint16_t *rec;
-    const int16_t *quant;   /* [img][3][64] natural order */
+    const int16_t *quant;   /* [img][3][64], column-major per component: [c * 8 + r] */
     uint8_t *out;           /* output base */
-    uint32_t img0;          /* first image of this launch (blockIdx.y offset) */
+    uint32_t img0;          /* first image of this launch (blockIdx.z offset) */
     uint32_t big_endian;    /* RGB565_BIG_ENDIAN requested */
-    uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate) */
+    uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate / callback replay) */
 };
 
 template <int HS, int VS, int NC, int MPB>
@@ -230,7 +234,7 @@ struct JDGeo {
     static constexpr int THREADS = NB * 8;
     static constexpr int WCTA = MPB * HS * 8;
     static constexpr int HCTA = VS * 8;
-    static constexpr int YSTRIDE = WCTA + 8;
+    static constexpr int YSTRIDE = WCTA + 16; /* keeps 16-byte row alignment, spreads banks */
     static constexpr int CSTRIDE = MPB * 8 + 8;
     static constexpr int TSTRIDE = 72; /* halfwords per coefficient tile (64 + pad: bank spread) */
 };
@@ -243,89 +247,98 @@ __device__ __forceinline__ void jd_unpack8(const uint4 v, int m[8])
     m[6] = (int)(short)(v.w & 0xFFFF); m[7] = (int)v.w >> 16;
 }
 
+/* d = { c[15:0] << 16 | sat_u8(a) << 8 | sat_u8(b) } : two saturating byte packs build a clamped pixel */
+__device__ __forceinline__ uint32_t jd_pack_sat(int a, int b, uint32_t c)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t jd_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+/* SSE2-build chroma terms with the >>16 of the int16 mulhi folded: ((C-128)<<8) * K >> 16 == ((C-128) * K) >> 8 */
+__device__ __forceinline__ void jd_chroma_terms_sse(uint32_t Cb, uint32_t Cr, int &tr, int &tg, int &tb)
+{
+    tr = ((int)Cr * 5742 - 128 * 5742) >> 8;
+    tg = (((int)Cr * -2925 + 128 * 2925) >> 8) + (((int)Cb * -1409 + 128 * 1409) >> 8);
+    tb = ((int)Cb * 7258 - 128 * 7258) >> 8;
+}
+
+template <int PT>
+__device__ __forceinline__ uint32_t jd_pixel_sse(uint32_t Y, int tr, int tg, int tb)
+{
+    const int Y4 = (int)Y << 4;
+    const int R = (Y4 + tr) >> 4, G = (Y4 + tg) >> 4, B = (Y4 + tb) >> 4;
+    if (PT == JD_PT_8888) return jd_pack_sat(G, B, jd_pack_sat(255, R, 0u));          /* bytes B,G,R,A */
+    const uint32_t w = jd_pack_sat(G, B, jd_pack_sat(0, R, 0u));                      /* bytes B,G,R,0 */
+    return ((w >> 8) & 0xF800u) | ((w >> 5) & 0x07E0u) | ((w >> 3) & 0x001Fu);
+}
+
+template <int PT>
+__device__ __forceinline__ uint32_t jd_pixel_scalar(int Y12, int cb, int cr, bool big_endian)
+{
+    /* JPEGPixelLE/BE/RGB (jpeg.inl:3101-3278): cb, cr already minus 128 */
+    const int B = (7258 * cb + Y12) >> 12, G = (-1409 * cb - 2925 * cr + Y12) >> 12, R = (5742 * cr + Y12) >> 12;
+    if (PT == JD_PT_8888) return jd_pack_sat(G, R, jd_pack_sat(255, B, 0u));          /* bytes R,G,B,A */
+    uint32_t v = ((jd_rt(R) >> 3) << 11) | ((jd_rt(G) >> 2) << 5) | (jd_rt(B) >> 3);
+    if (big_endian) v = jd_bswap16(v);
+    return v;
+}
+
 template <int HS, int VS, int NC, int MPB, int PT, int ARITH, bool HALF>
 __global__ void __launch_bounds__(JDGeo<HS, VS, NC, MPB>::THREADS)
 jdk_idct_color(const JDIdctArgs a)
 {
     using G = JDGeo<HS, VS, NC, MPB>;
     __shared__ __align__(16) int16_t s_tile[G::NB * G::TSTRIDE];
-    __shared__ __align__(16) int16_t s_q[NC * 64];           /* transposed: [comp][c*8 + r] */
     __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
     __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
-    __shared__ uint8_t s_dz[64];
 
-    const uint32_t img_i = a.img0 + blockIdx.y;
+    const uint32_t img_i = a.img0 + blockIdx.z;
     const JDImageDesc &im = a.imgs[img_i];
-    const uint32_t strips = (im.mcus_x + MPB - 1) / MPB;
-    if (blockIdx.x >= strips * im.mcus_y) return;
-    const uint32_t my = blockIdx.x / strips, strip = blockIdx.x - my * strips;
+    const uint32_t strip = blockIdx.x, my = blockIdx.y;
+    if (strip * MPB >= im.mcus_x || my >= im.mcus_y) return;
     const uint32_t tid = threadIdx.x;
-
-    if (tid < 64) s_dz[tid] = c_dezigzag[tid];
-    for (uint32_t i = tid; i < NC * 64; i += G::THREADS) {
-        const uint32_t comp = i >> 6, n = i & 63;
-        s_q[comp * 64 + (n & 7) * 8 + (n >> 3)] = a.quant[(size_t)img_i * 192 + comp * 64 + n];
-    }
-    __syncthreads();
 
     /* ---- phase A: expand this block's records into a column-major coefficient tile ---- */
     const uint32_t gb = tid >> 3, c = tid & 7;           /* block within CTA, lane within block */
     const uint32_t ml = gb / G::BPMEFF, blk = gb - ml * G::BPMEFF;
     const uint32_t mx = strip * MPB + ml;
-    const bool active = mx < im.mcus_x;
     const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
-    /* position of the block in the coded stream: luma blocks first, chroma after all luma */
-    const uint32_t sblk = (comp == 0) ? blk : (uint32_t)(HS * VS) + comp - 1u;
     jd_u64 h = 0;
-    if (active) h = a.blk_hdr[im.blk_base + ((size_t)my * im.mcus_x + mx) * im.bpm + sblk];
-    const uint32_t ri = (uint32_t)h;
-    const int dc = (int)(short)(uint16_t)(h >> 32);
-    const uint32_t nrec = (uint32_t)(h >> 48) & 0xFFu;
+    if (mx < im.mcus_x) h = a.blk_hdr[im.blk_base + ((size_t)my * im.mcus_x + mx) * im.bpm + blk];
+    /* (block order inside an MCU in the stream = luma blocks, Cb, Cr = our blk numbering) */
+    const uint32_t ri = JD_HDR_REC(h);
+    const int dc = JD_HDR_DC(h);
+    const uint32_t ncoef = JD_HDR_NCOEF(h);
     int16_t *tile = s_tile + gb * G::TSTRIDE;
-    const uint32_t gmask = 0xFFu << (tid & 24u); /* the 8 lanes of this block */
-    *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
-    __syncwarp();
-    uint32_t fl = 0;
-    {
-        const uint32_t maxn = __reduce_max_sync(0xffffffffu, nrec);
-        uint32_t kcarry = 0;
-        for (uint32_t b0 = 0; b0 < maxn; b0 += 8) {
-            const uint32_t i = b0 + c;
-            const bool have = i < nrec;
-            const uint32_t r = have ? (uint32_t)__ldg(a.rec + ri + i) : 0u;
-            uint32_t x = have ? (r >> 12) + 1u : 0u;
-            uint32_t y;
-            y = __shfl_up_sync(0xffffffffu, x, 1, 8); if (c >= 1) x += y;
-            y = __shfl_up_sync(0xffffffffu, x, 2, 8); if (c >= 2) x += y;
-            y = __shfl_up_sync(0xffffffffu, x, 4, 8); if (c >= 4) x += y;
-            const uint32_t k = kcarry + x;
-            const int v = (int)(r << 20) >> 20;
-            if (have && v != 0 && k < 64u) {
-                const uint32_t n = s_dz[k];
-                tile[(n & 7u) * 8u + (n >> 3)] = (int16_t)v;
-                fl |= (1u << (n & 7u)) | ((n & 32u) << 8);
-            }
-            kcarry += __shfl_sync(0xffffffffu, x, 7, 8);
-        }
-    }
-    fl |= __shfl_xor_sync(0xffffffffu, fl, 1);
-    fl |= __shfl_xor_sync(0xffffffffu, fl, 2);
-    fl |= __shfl_xor_sync(0xffffffffu, fl, 4);
-    __syncwarp();
-
-    /* ---- phase B: dequant + column pass (lane = column), row pass (lane = row) ---- */
     uint32_t px0, px1; /* 8 output bytes of row `c` of this block */
-    const int16_t *q = s_q + comp * 64;
-    if (fl == 0u) {
-        /* no stored AC coefficient: the reference's DC-only fill (jpeg.inl:5146-5154) */
-        const uint32_t v = jd_range(dc * (int)q[0]);
-        px0 = px1 = v * 0x01010101u;
+    const int16_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
+    if (__all_sync(0xffffffffu, ncoef == 0u)) {
+        /* no stored AC coefficient in any of the warp's 4 blocks: DC-only fill (jpeg.inl:5146-5154) */
+        px0 = px1 = jd_range(dc * (int)qg[0]) * 0x01010101u;
     } else {
+        *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (!JD_HDR_BIG(h)) {
+            for (uint32_t i = c; i < ncoef; i += 8) {
+                const uint32_t r = __ldg(a.rec + ri + i);
+                tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
+            }
+        } else {
+            for (uint32_t i = c; i < ncoef; i += 8) {
+                const uint32_t t = __ldg(a.rec + ri + 2 * i) & 63u;
+                tile[t] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+            }
+        }
+        __syncwarp();
+        /* ---- phase B: dequant + column pass (lane = column), row pass (lane = row) ---- */
         int m[8], qq[8], o[8];
         jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
-        jd_unpack8(*reinterpret_cast<const uint4 *>(q + c * 8), qq);
+        jd_unpack8(__ldg(reinterpret_cast<const uint4 *>(qg + c * 8)), qq);
         if (c == 0) m[0] = dc;
-        const bool r47 = (fl & 0x2000u) == 0u;
+        const bool r47 = JD_HDR_HI(h) == 0u;
         if (ARITH == JPEG_ARITH_SSE2) {
 #pragma unroll
             for (int r = 0; r < 8; r++) m[r] *= qq[r];
@@ -333,16 +346,19 @@ jdk_idct_color(const JDIdctArgs a)
         } else {
             jd_col_scalar(m, qq, r47, o);
         }
-        __syncwarp(gmask); /* fl is uniform inside a block's 8 lanes, not across the warp */
+        __syncwarp();
 #pragma unroll
         for (int r = 0; r < 8; r++) tile[r * 8 + c] = (int16_t)o[r];
-        __syncwarp(gmask);
+        __syncwarp();
         int p[8];
         uint32_t ob[8];
         jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), p);
-        jd_row(p, fl & 0xFFu, ob);
-        px0 = ob[0] | (ob[1] << 8) | (ob[2] << 16) | (ob[3] << 24);
-        px1 = ob[4] | (ob[5] << 8) | (ob[6] << 16) | (ob[7] << 24);
+        jd_row_raw(p, JD_HDR_COLMASK(h), (int *)ob);
+        /* ucRangeTable as arithmetic + two saturating packs per 4 bytes */
+#pragma unroll
+        for (int i = 0; i < 8; i++) ob[i] = (uint32_t)((((int)ob[i] << 17) >> 22) + 128);
+        px0 = jd_pack_sat((int)ob[1], (int)ob[0], jd_pack_sat((int)ob[3], (int)ob[2], 0u));
+        px1 = jd_pack_sat((int)ob[5], (int)ob[4], jd_pack_sat((int)ob[7], (int)ob[6], 0u));
     }
     /* stage the pixel bytes */
     if (comp == 0) {
@@ -354,7 +370,7 @@ jdk_idct_color(const JDIdctArgs a)
     }
     __syncthreads();
 
-    /* ---- phase C: colour conversion + coalesced scanline stores ---- */
+    /* ---- phase C: colour conversion + coalesced 128-bit scanline stores ---- */
     const uint8_t *s_cb = s_c, *s_cr = s_c + 8 * G::CSTRIDE;
     const uint32_t W = a.padded ? (uint32_t)im.mcus_x * HS * 8 : (uint32_t)im.width;
     const uint32_t H = a.padded ? (uint32_t)im.mcus_y * VS * 8 : (uint32_t)im.height;
@@ -363,70 +379,76 @@ jdk_idct_color(const JDIdctArgs a)
     constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
 
     if (!HALF) {
-        constexpr int IPR = G::WCTA / 8; /* 8-pixel items per row */
-        for (uint32_t it = tid; it < (uint32_t)(IPR * G::HCTA); it += G::THREADS) {
-            const uint32_t row = it / IPR, xg = it - row * IPR;
-            const uint32_t gy = my * G::HCTA + row, gx = strip * G::WCTA + xg * 8;
-            if (gy >= H || gx >= W) continue;
-            const uint2 yy = *reinterpret_cast<const uint2 *>(s_y + row * G::YSTRIDE + xg * 8);
-            uint32_t pix[8]; /* 565: 8 x u16 in low halves; 8888: 8 x u32; gray: bytes */
-            if (PT == JD_PT_GRAY) {
-                /* handled below with yy directly */
-            } else if (NC == 1) {
+        /* one item = PXI pixels (one 16-byte store) in each of the VS rows that share chroma */
+        constexpr int PXI = 16 / BYPP;              /* 4 (8888), 8 (565), 16 (gray) */
+        constexpr int IPR = G::WCTA / PXI;          /* items per row */
+        constexpr int NITEM = IPR * 8;              /* x (HCTA / VS) row groups */
+        constexpr bool SSE_PATH = (ARITH == JPEG_ARITH_SSE2) && (HS == VS); /* jpeg.inl:3409-3517, :4006-4308 */
+        for (uint32_t it = tid; it < (uint32_t)NITEM; it += G::THREADS) {
+            const uint32_t rg = it / IPR, xg = it - rg * IPR;
+            const uint32_t gx = strip * G::WCTA + xg * PXI;
+            if (gx >= W) continue;
+            const bool full = (gx + PXI <= W);
+            /* chroma samples covering these PXI pixels: PXI / HS of each */
+            uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
+            if (NC == 3 && PT != JD_PT_GRAY) {
+                constexpr int NCH = PXI / HS; /* 2, 4 or 8 bytes */
+                const uint8_t *pb = s_cb + rg * G::CSTRIDE + xg * NCH, *pr = s_cr + rg * G::CSTRIDE + xg * NCH;
+                if (NCH == 2) { cbw[0] = *reinterpret_cast<const uint16_t *>(pb); crw[0] = *reinterpret_cast<const uint16_t *>(pr); }
+                else if (NCH == 4) { cbw[0] = *reinterpret_cast<const uint32_t *>(pb); crw[0] = *reinterpret_cast<const uint32_t *>(pr); }
+                else { const uint2 u = *reinterpret_cast<const uint2 *>(pb), v = *reinterpret_cast<const uint2 *>(pr); cbw[0] = u.x; cbw[1] = u.y; crw[0] = v.x; crw[1] = v.y; }
+            }
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
-                    uint32_t v = jd_gray565(Y);
-                    if (a.big_endian) v = jd_bswap16(v);
-                    pix[i] = v;
+            for (int vr = 0; vr < VS; vr++) {
+                const uint32_t row = rg * VS + vr;
+                const uint32_t gy = my * G::HCTA + row;
+                if (gy >= H) continue;
+                uint32_t yw[4];
+                {
+                    const uint8_t *py = s_y + row * G::YSTRIDE + xg * PXI;
+                    if (PXI == 4) yw[0] = *reinterpret_cast<const uint32_t *>(py);
+                    else if (PXI == 8) { const uint2 u = *reinterpret_cast<const uint2 *>(py); yw[0] = u.x; yw[1] = u.y; }
+                    else { const uint4 u = *reinterpret_cast<const uint4 *>(py); yw[0] = u.x; yw[1] = u.y; yw[2] = u.z; yw[3] = u.w; }
                 }
-            } else {
-                const uint32_t crow = row / VS;
-                if (ARITH == JPEG_ARITH_SSE2 && (HS == VS)) {
-                    /* SSE2 build, full-size 4:4:4 / 4:2:0 (jpeg.inl:3409-3517, :4006-4308): B,G,R,A; LE only */
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
-                        const uint32_t cx = (xg * 8 + i) / HS;
-                        int tr, tg, tb, R, Gc, B;
-                        jd_chroma_sse(s_cb[crow * G::CSTRIDE + cx], s_cr[crow * G::CSTRIDE + cx], &tr, &tg, &tb);
-                        jd_rgb_sse((int)Y, tr, tg, tb, &R, &Gc, &B);
-                        if (PT == JD_PT_8888) pix[i] = 0xFF000000u | ((uint32_t)R << 16) | ((uint32_t)Gc << 8) | (uint32_t)B;
-                        else pix[i] = ((uint32_t)(R >> 3) << 11) | ((uint32_t)(Gc >> 2) << 5) | (uint32_t)(B >> 3);
-                    }
+                uint32_t ow[4]; /* the 16 output bytes */
+                if (PT == JD_PT_GRAY) {
+                    ow[0] = yw[0]; ow[1] = yw[1]; ow[2] = yw[2]; ow[3] = yw[3];
                 } else {
+                    uint32_t pix[PXI];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const uint32_t Y = ((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu;
-                        const uint32_t cx = (xg * 8 + i) / HS;
-                        const int Cb = s_cb[crow * G::CSTRIDE + cx], Cr = s_cr[crow * G::CSTRIDE + cx];
-                        if (PT == JD_PT_8888) pix[i] = jd_rgb8888_scalar((int)Y << 12, Cb, Cr);
-                        else {
-                            uint32_t v = jd_rgb565_scalar((int)Y << 12, Cb, Cr);
+                    for (int i = 0; i < PXI; i++) {
+                        const uint32_t Y = jd_byte(yw[i >> 2], i & 3);
+                        if (NC == 1) {
+                            uint32_t v = jd_gray565(Y);
                             if (a.big_endian) v = jd_bswap16(v);
                             pix[i] = v;
+                        } else {
+                            const int ci = i / HS;
+                            const uint32_t Cb = jd_byte(cbw[ci >> 2], ci & 3), Cr = jd_byte(crw[ci >> 2], ci & 3);
+                            if (SSE_PATH) {
+                                int tr, tg, tb;
+                                jd_chroma_terms_sse(Cb, Cr, tr, tg, tb);
+                                pix[i] = jd_pixel_sse<PT>(Y, tr, tg, tb);
+                            } else {
+                                pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
+                            }
                         }
                     }
+                    if (PT == JD_PT_8888) { ow[0] = pix[0]; ow[1] = pix[1]; ow[2] = pix[2]; ow[3] = pix[3]; }
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) ow[i] = pix[(2 * i) % PXI] | (pix[(2 * i + 1) % PXI] << 16);
+                    }
                 }
-            }
-            uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
-            const bool full = gx + 8 <= W;
-            if (PT == JD_PT_GRAY) {
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 7u) == 0)) *reinterpret_cast<uint2 *>(dst) = yy;
-                else for (uint32_t i = 0; i < 8 && gx + i < W; i++) dst[i] = (uint8_t)(((i < 4 ? yy.x : yy.y) >> ((i & 3) * 8)) & 0xFFu);
-            } else if (PT == JD_PT_565) {
+                uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
                 if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(pix[0] | (pix[1] << 16), pix[2] | (pix[3] << 16),
-                                                                  pix[4] | (pix[5] << 16), pix[6] | (pix[7] << 16));
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 } else {
-                    for (uint32_t i = 0; i < 8 && gx + i < W; i++) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)pix[i];
-                }
-            } else {
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-                    reinterpret_cast<uint4 *>(dst)[0] = make_uint4(pix[0], pix[1], pix[2], pix[3]);
-                    reinterpret_cast<uint4 *>(dst)[1] = make_uint4(pix[4], pix[5], pix[6], pix[7]);
-                } else {
-                    for (uint32_t i = 0; i < 8 && gx + i < W; i++) reinterpret_cast<uint32_t *>(dst)[i] = pix[i];
+                    for (uint32_t i = 0; i < (uint32_t)PXI && gx + i < W; i++) {
+                        if (BYPP == 4) reinterpret_cast<uint32_t *>(dst)[i] = ow[i & 3];
+                        else if (BYPP == 2) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)(ow[(i >> 1) & 3] >> ((i & 1) * 16));
+                        else dst[i] = (uint8_t)(ow[(i >> 2) & 3] >> ((i & 3) * 8));
+                    }
                 }
             }
         }
@@ -462,12 +484,9 @@ jdk_idct_color(const JDIdctArgs a)
                     Cb = (s_cb[oy * G::CSTRIDE + 2 * ox] + s_cb[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
                     Cr = (s_cr[oy * G::CSTRIDE + 2 * ox] + s_cr[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
                 }
-                if (PT == JD_PT_8888) *reinterpret_cast<uint32_t *>(dst) = jd_rgb8888_scalar(sum << 10, Cb, Cr);
-                else {
-                    uint32_t v = jd_rgb565_scalar(sum << 10, Cb, Cr);
-                    if (a.big_endian) v = jd_bswap16(v);
-                    *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
-                }
+                const uint32_t v = jd_pixel_scalar<PT>(sum << 10, Cb - 128, Cr - 128, a.big_endian != 0u);
+                if (PT == JD_PT_8888) *reinterpret_cast<uint32_t *>(dst) = v;
+                else *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
             }
         }
     }
@@ -490,27 +509,26 @@ struct JDScaledArgs {
 
 __device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h, const int16_t *q, bool eighth, uint32_t px[4])
 {
-    const int dc = (int)(short)(uint16_t)(h >> 32);
-    if (eighth) { px[0] = jd_range(dc * (int)q[0]); return; }
-    const uint32_t ri = (uint32_t)h, nrec = (uint32_t)(h >> 48) & 0xFFu;
+    const int dc = JD_HDR_DC(h);
+    const int q0 = q[0];
+    if (eighth) { px[0] = jd_range(dc * q0); return; }
+    const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h), big = JD_HDR_BIG(h);
     int m1 = 0, m8 = 0, m9 = 0;
     bool any = false;
-    uint32_t k = 1;
-    for (uint32_t i = 0; i < nrec && k < 5u; i++) {
-        const uint32_t r = a.rec[ri + i];
-        k += r >> 12;
-        const int v = (int)(r << 20) >> 20;
-        if (v != 0 && k < 5u) {
-            any = true; /* zigzag 1,2,3,4 = natural 1,8,16,9 (jpeg.inl:2117-2119) */
-            if (k == 1) m1 = v; else if (k == 2) m8 = v; else if (k == 4) m9 = v;
-        }
-        k++;
+    /* records are in zigzag order: the ones the 1/4 path keeps (zigzag 1..4 = natural 1, 8, 16, 9 =
+     * tile positions 8, 1, 2, 9; jpeg.inl:2117-2119) come first */
+    for (uint32_t i = 0; i < ncoef; i++) {
+        uint32_t t; int v;
+        if (big) { t = a.rec[ri + 2 * i] & 63u; v = (int)(short)a.rec[ri + 2 * i + 1]; }
+        else { const uint32_t r = a.rec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
+        if (t == 8u) m1 = v; else if (t == 1u) m8 = v; else if (t == 9u) m9 = v; else if (t != 2u) break;
+        any = true;
     }
-    if (!any) { px[0] = px[1] = px[2] = px[3] = jd_range(dc * (int)q[0]); return; }
-    /* 2x2 butterfly (jpeg.inl:2305-2326) */
-    int t4 = dc * q[0], t5 = m8 * q[8];
+    if (!any) { px[0] = px[1] = px[2] = px[3] = jd_range(dc * q0); return; }
+    /* 2x2 butterfly (jpeg.inl:2305-2326); q is column-major: natural 1 -> [8], natural 8 -> [1], natural 9 -> [9] */
+    int t4 = dc * q0, t5 = m8 * q[1];
     const int t0 = t4 + t5, t2 = t4 - t5;
-    t4 = m1 * q[1]; t5 = m9 * q[9];
+    t4 = m1 * q[8]; t5 = m9 * q[9];
     const int t1 = t4 + t5, t3 = t4 - t5;
     px[0] = jd_range(t0 + t1); px[1] = jd_range(t0 - t1); px[2] = jd_range(t2 + t3); px[3] = jd_range(t2 - t3);
 }

@@ -22,7 +22,7 @@ struct VecSink {
     void push(const JDEvent &e) { ev.push_back(e); }
 };
 
-static const uint8_t kDezigzag[64] = JD_DEZIGZAG_INIT;
+static const uint8_t kTpos[64] = JD_TPOS_INIT;
 
 struct Planes {
     int sshift;          /* 0 full / half (block bytes are full 8x8), 2 quarter, 3 eighth */
@@ -93,8 +93,9 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset);
         in.rec_cap = 4u * ((sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu ? seg_start[sgi + 1] : (uint32_t)size) - in.start) + 64u;
         in.seg = (uint32_t)sgi;
+        in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
-        jd_decode_segment(in, lut.data(), hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        jd_decode_segment(in, lut.data(), kTpos, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         jmap[sgi] = so.jmap;
         if (so.err_mcu >= 0) { bad = 1; break; }
     }
@@ -115,7 +116,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         uint32_t jc = (e.j1 >> (4 * phase[e.seg])) & 15u;
         if (8 * (int)jc + e.p7 + e.s > 64) {
             int v = jd_event_value(&e, jc);
-            rec[e.rec_index] = (uint16_t)((rec[e.rec_index] & 0xF000u) | ((uint32_t)v & 0xFFFu));
+            jd_patch_record(rec.data(), hdr[e.blk], e.ord, v);
             nev++;
         }
     }
@@ -137,26 +138,29 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
             int comp = (b < nluma) ? 0 : (b - nluma + 1);
             const int16_t *q = quant + comp * 64;
             jd_u64 h = hdr[(size_t)m * info.bpm + b];
-            uint32_t ri = (uint32_t)h;
-            int dc = (int16_t)(uint16_t)(h >> 32);
-            int nrec = (int)((h >> 48) & 0xFF);
-            int16_t tile[64];
+            const uint32_t ri = JD_HDR_REC(h);
+            const int dc = JD_HDR_DC(h);
+            const int ncoef = (int)JD_HDR_NCOEF(h);
+            const bool bigb = JD_HDR_BIG(h) != 0;
+            int16_t tile[64]; /* natural order here */
             memset(tile, 0, sizeof(tile));
             tile[0] = (int16_t)dc;
             uint32_t flags = 0;
-            int k = 1;
-            const int limit = (sshift >= 2) ? 5 : 64;
-            for (int i = 0; i < nrec; i++) {
-                uint32_t r = rec[ri + i];
-                k += (int)(r >> 12);
-                int v = (int)(r << 20) >> 20;
-                if (v != 0 && k < limit) {
-                    int n = kDezigzag[k];
-                    tile[n] = (int16_t)v;
-                    flags |= 1u << (n & 7);
-                    flags |= (uint32_t)n << 8;
-                }
-                k++;
+            for (int i = 0; i < ncoef; i++) {
+                uint32_t t; int v;
+                if (bigb) { t = rec[ri + 2 * i] & 63u; v = (int16_t)rec[ri + 2 * i + 1]; }
+                else { const uint32_t r = rec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
+                const int n = (int)((t & 7u) * 8u + (t >> 3));
+                /* 1/4 and 1/8 scale keep only zigzag 1..4 = natural 1, 8, 16, 9 (jpeg.inl:2117-2119) */
+                if (sshift >= 2 && !(n == 1 || n == 8 || n == 16 || n == 9)) continue;
+                tile[n] = (int16_t)v;
+                flags |= 1u << (n & 7);
+                flags |= (uint32_t)n << 8;
+            }
+            if (sshift < 2) {
+                /* the header carries the same flags for the full-size path */
+                uint32_t hf = JD_HDR_COLMASK(h) | (JD_HDR_HI(h) ? 0x2000u : 0u);
+                if ((flags & 0x20FFu) != hf) { *err = 99; }
             }
             uint8_t px[64];
             if (sshift == 3 || flags == 0) {
