@@ -171,197 +171,201 @@ typedef struct {
 #define JD_LD8(p) (*(p))
 #endif
 
+/* zigzag k -> packed word: tile position t | column bit (1 << (t >> 3)) << 8 | rows-4..7 bit << 16 */
+JD_HD uint32_t jd_tposw(uint32_t t) { return t | ((1u << (t >> 3)) << 8) | (((t >> 2) & 1u) << 16); }
+
 template <typename EventSink>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
-                             const uint8_t *tpos /* JD_TPOS_INIT table, shared/global */,
+                             const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
                              EventSink &sink, JDSegOut &out)
 {
-    const uint8_t *data = in.data;
-    uint32_t pos = in.start;
-    const uint32_t end = in.end;
-    jd_u64 bb = 0;      /* bit buffer, MSB first */
-    int nb = 0;         /* valid bits in bb */
-    bool eos = false;   /* hit a marker / end of data: feed zeros */
+    /* ---- bit reader: aligned 32-bit words, one word prefetched ahead of use ---- */
+    const uint32_t *words = (const uint32_t *)in.data;
+    const uint32_t endw = (in.end + 3u) >> 2;    /* first word index past this file */
+    uint32_t wi = in.start >> 2;                 /* index of the next word to consume */
+    uint32_t wnext = (wi < endw) ? words[wi] : 0u;
+    uint32_t skip = in.start & 3u;               /* bytes of the first word that precede the segment */
+    uint32_t ffp = 0;                            /* previous byte was 0xFF (stuffing / marker undecided) */
+    uint32_t eos = 0;                            /* marker or end of data reached: zeros from here on */
+    jd_u64 bb = 0;                               /* bit buffer, MSB first */
+    int nb = 0;                                  /* valid bits in bb */
 
     int pred0 = 0, pred1 = 0, pred2 = 0;
     uint32_t jw = JD_JW_INIT;
-    int P = 0, Pb = 0;  /* bits consumed in this segment, and P>>3 */
-    uint32_t nrec_total = 0;
+    int P = 0, Pb = 0;                           /* bits consumed in this segment, and P >> 3 */
+    uint16_t *rp = rec;                          /* next record slot */
+    uint16_t *const rend = rec + in.rec_cap;
     int err = -1;
     bool last_was_eob = true;
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
-    uint32_t nblk_total = in.nmcu * in.bpm;
+    const uint32_t nblk_total = in.nmcu * in.bpm;
     uint32_t blk_in_mcu = 0;
-    uint32_t comp = 0;
+    uint32_t b = 0;
 
-    for (uint32_t b = 0; b < nblk_total; b++) {
-        /* component of this block: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
-        comp = (blk_in_mcu < nluma) ? 0u : (blk_in_mcu - nluma + 1u);
-        const uint32_t dcsel = (in.tsel >> (2 * comp)) & 1u;
-        const uint32_t acsel = (in.tsel >> (2 * comp + 1)) & 1u;
-        const uint16_t *tdc = lut + JD_LUT_DC(dcsel);
-        const uint16_t *tac = lut + JD_LUT_AC(acsel);
-        uint32_t k = 0;            /* zigzag index: 0 = DC pending */
-        uint32_t ncoef = 0, big = 0, colmask = 0, hi = 0;
-        uint32_t rec0 = nrec_total;
-        int dcval = 0;
-        bool done = false;
-        while (!done) {
-            /* ---- refill: keep >= 32 valid bits ---- */
-            if (nb <= 32) {
-                bool fast = false;
-                if (!eos && ((pos & 3u) == 0u) && pos + 4u <= end) {
-                    uint32_t w = *(const uint32_t *)(data + pos);
-                    /* any 0xFF byte?  haszero(~w) */
-                    if ((((~w) - 0x01010101u) & w & 0x80808080u) == 0u) {
+    /* per-block state */
+    uint32_t comp = 0;
+    uint32_t k = 0;                              /* zigzag index; 0 = DC pending */
+    uint32_t ncoef = 0, big = 0, bflags = 0;     /* bflags: column mask << 8 | rows-4..7 << 16 (as in tposw) */
+    uint16_t *rec0 = rp;
+    int dcval = 0;
+    const uint16_t *tac = lut + JD_LUT_AC((in.tsel >> 1) & 1u);
+    /* current table geometry (DC at block start) */
+    const uint16_t *tb = lut + JD_LUT_DC(in.tsel & 1u);
+    uint32_t thr = 0xF800u, sh = 4u, msk = 0x7Fu;
+
+    if (nblk_total == 0) { out.status = JD_SEG_OK; out.err_mcu = -1; out.jmap = jw; out.nrec = 0; return; }
+
+    for (;;) {
+        /* ---- refill: keep >= 32 valid bits ---- */
+        while (nb <= 32) {
+            const uint32_t w = wnext;
+            wi++;
+            wnext = (wi < endw) ? words[wi] : 0u;
+            if ((((((~w) - 0x01010101u) & w & 0x80808080u)) | skip | ffp | eos) == 0u) {
 #ifdef __CUDA_ARCH__
-                        w = __byte_perm(w, 0, 0x0123);
+                const uint32_t be = __byte_perm(w, 0, 0x0123);
 #else
-                        w = __builtin_bswap32(w);
+                const uint32_t be = __builtin_bswap32(w);
 #endif
-                        bb |= (jd_u64)w << (32 - nb);
-                        nb += 32;
-                        pos += 4;
-                        fast = true;
-                    }
-                }
-                if (!fast) {
-                    /* byte path: FF00 -> FF; FFxx (xx != 0) = marker: segment data ends */
-                    for (int i = 0; i < 4 && nb <= 56; i++) {
-                        uint32_t c = 0;
-                        if (!eos && pos < end) {
-                            c = JD_LD8(data + pos);
-                            pos++;
-                            if (c == 0xFFu) {
-                                uint32_t c2 = (pos < end) ? JD_LD8(data + pos) : 0xD9u;
-                                if (c2 == 0u) pos++;
-                                else { eos = true; pos--; c = 0; }
-                            }
-                        } else {
-                            eos = true;
-                        }
-                        bb |= (jd_u64)c << (56 - nb);
-                        nb += 8;
-                        if ((pos & 3u) == 0u && !eos && nb > 32) break; /* re-aligned: go back to word loads */
-                    }
-                }
-            }
-            /* ---- window checkpoint (R1 at block entry / R3 at AC loop top; also the previous R4) ---- */
-            jw = jd_jw_ckpt(jw);
-            /* ---- code lookup ---- */
-            const uint32_t w16 = (uint32_t)(bb >> 48);
-            const bool isdc = (k == 0);
-            const uint16_t *t = isdc ? tdc : tac;
-            const uint32_t thr = isdc ? 0xF800u : 0xFC00u;
-            const uint32_t sh = isdc ? 4u : 0u;
-            const uint32_t msk = isdc ? 0x7Fu : 0x3FFu;
-            const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
-            const uint32_t e = t[idx];
-            if (e == 0u) { err = JD_SEG_BADCODE; break; }
-            const int len = (int)(e >> 8);
-            const uint32_t rs = e & 0xFFu;
-            const int s = (int)(rs & 15u);
-            bb <<= len;
-            uint32_t field = 0;
-            int v = 0;
-            if (s) {
-                field = (uint32_t)(bb >> (64 - s));
-                v = (int)field;
-                if (!(field >> (s - 1))) v -= (1 << s) - 1;
-                bb <<= s;
-            }
-            nb -= len + s;
-            if (isdc) {
-                /* DC: jpeg.inl:2128-2165.  Window reload R2 (:2149) only when the LUT has no
-                 * precomputed difference, i.e. not (SSSS != 0 && len + SSSS <= 6) (:1132). */
-                P += len;
-                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
-                if (s != 0 && len + s > 6) jw = jd_jw_ckpt(jw);
-                P += s;
-                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
-                int *pp = (comp == 0) ? &pred0 : (comp == 1 ? &pred1 : &pred2);
-                *pp += v;
-                dcval = *pp;
-                k = 1;
-                last_was_eob = false;
-            } else if (rs == 0u) {
-                /* EOB (:2241-2244): leaves without the trailing window check */
-                P += len;
-                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
-                done = true;
-                last_was_eob = true;
+                bb |= (jd_u64)be << (32 - nb);
+                nb += 32;
+            } else if (eos) {
+                nb = 64;                          /* bb's low bits are zero: the stream continues as zeros */
             } else {
-                k += rs >> 4;
-                if (s && k < 64u) {
-                    /* stored coefficient (jpeg.inl:2247-2256) */
-                    if (s > 11) { err = JD_SEG_BADSIZE; break; }
-                    if (len + s >= 18) {
-                        /* possible truncated read for some start phases */
-                        const int P1 = P + len;
-                        const uint32_t j1 = jw + (uint32_t)((P1 >> 3) - Pb) * JD_JW_ONES;
-                        const int p7 = P1 & 7;
-                        if (((j1 + 0x222222u) & 0x888888u) != 0u) {
-                            bool any = false;
-                            for (int c = 0; c < 6; c++) {
-                                int jc = (int)((j1 >> (4 * c)) & 15u);
-                                if (8 * jc + p7 + s > 64) any = true;
-                            }
-                            if (any) {
-                                JDEvent ev;
-                                ev.blk = in.blk0 + b;
-                                ev.seg = in.seg;
-                                ev.j1 = j1;
-                                ev.field = (uint16_t)field;
-                                ev.s = (uint8_t)s;
-                                ev.p7 = (uint8_t)p7;
-                                ev.ord = ncoef;
-                                sink.push(ev);
-                            }
-                        }
+                /* byte path: FF00 -> FF; FFxx (xx != 0) = marker: this segment's data ends (JPEGFilter :1519-1538) */
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t c = (w >> (8 * i)) & 0xFFu;
+                    if (skip) { skip--; continue; }
+                    if (eos) break;
+                    if (wi - 1u == (in.end >> 2) && (uint32_t)i >= (in.end & 3u)) { eos = 1; break; } /* past the file */
+                    if (ffp) {
+                        ffp = 0;
+                        if (c != 0u) { eos = 1; break; }
+                        bb |= (jd_u64)0xFFu << (56 - nb);
+                        nb += 8;
+                        continue;
                     }
-                    const uint32_t t = tpos[k];
-                    colmask |= 1u << (t >> 3);
-                    hi |= (t >> 2) & 1u;
-                    if (s >= 10 && !big) {
-                        /* first >=10-bit magnitude of this block: switch its records to (t, value) pairs */
-                        if (nrec_total + ncoef + 2u > in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
-                        for (uint32_t i = ncoef; i-- > 0u;) {
-                            const uint32_t r = rec[rec0 + i];
-                            rec[rec0 + 2u * i] = (uint16_t)(r >> 10);
-                            rec[rec0 + 2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
-                        }
-                        nrec_total += ncoef;
-                        big = 1;
-                    }
-                    if (big) {
-                        if (nrec_total + 2u > in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
-                        rec[nrec_total] = (uint16_t)t;
-                        rec[nrec_total + 1u] = (uint16_t)(int16_t)v;
-                        nrec_total += 2u;
-                    } else {
-                        if (nrec_total >= in.rec_cap) { err = JD_SEG_OVERFLOW; break; }
-                        rec[nrec_total] = (uint16_t)((t << 10) | ((uint32_t)v & 0x3FFu));
-                        nrec_total++;
-                    }
-                    ncoef++;
+                    if (c == 0xFFu) { ffp = 1; continue; }
+                    bb |= (jd_u64)c << (56 - nb);
+                    nb += 8;
                 }
-                k++;
-                P += len + s;
-                { int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
-                last_was_eob = false;
-                if (k >= 64u) done = true;
+                if (wi >= endw && !eos && nb <= 32) eos = 1;
             }
         }
-        if (err >= 0) {
-            /* undecodable from here: later stages must still find well-formed (empty) headers */
-            out.err_mcu = (int32_t)(b / in.bpm);
-            for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
-            break;
+        /* ---- window checkpoint (R1 at block entry / R3 at AC loop top; also the previous R4) ---- */
+        jw = jd_jw_ckpt(jw);
+        /* ---- code lookup ---- */
+        const uint32_t w16 = (uint32_t)(bb >> 48);
+        const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
+        const uint32_t e = tb[idx];
+        if (e == 0u) { err = JD_SEG_BADCODE; break; }
+        const int len = (int)(e >> 8);
+        const uint32_t rs = e & 0xFFu;
+        const int s = (int)(rs & 15u);
+        bb <<= len;
+        const uint32_t hi32 = (uint32_t)(bb >> 32);
+        const uint32_t field = s ? (hi32 >> (32 - s)) : 0u;
+        const uint32_t half = s ? (1u << (s - 1)) : 1u;
+        const int v = (field < half) ? (int)field - ((1 << s) - 1) : (int)field;
+        bb <<= s;
+        nb -= len + s;
+        if (k == 0u) {
+            /* DC: jpeg.inl:2128-2165.  Window reload R2 (:2149) only when the LUT has no
+             * precomputed difference, i.e. not (SSSS != 0 && len + SSSS <= 6) (:1132). */
+            P += len;
+            { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+            if (s != 0 && len + s > 6) jw = jd_jw_ckpt(jw);
+            P += s;
+            { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+            if (comp == 0u) { pred0 += v; dcval = pred0; }
+            else if (comp == 1u) { pred1 += v; dcval = pred1; }
+            else { pred2 += v; dcval = pred2; }
+            k = 1;
+            last_was_eob = false;
+            tb = tac; thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
+            continue;
         }
-        blk_hdr[b] = jd_pack_hdr(in.rec_index0 + rec0, dcval, ncoef, big, hi, colmask);
-        if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
+        if (rs == 0u) {
+            /* EOB (:2241-2244): leaves without the trailing window check */
+            k = 64;
+            last_was_eob = true;
+        } else {
+            k += rs >> 4;
+            if (s && k < 64u) {
+                /* stored coefficient (jpeg.inl:2247-2256) */
+                if (s > 11) { err = JD_SEG_BADSIZE; break; }
+                if (len + s >= 18) {
+                    /* possible truncated read for some start phases */
+                    const int P1 = P + len;
+                    const uint32_t j1 = jw + (uint32_t)((P1 >> 3) - Pb) * JD_JW_ONES;
+                    const int p7 = P1 & 7;
+                    if (((j1 + 0x222222u) & 0x888888u) != 0u) {
+                        bool any = false;
+                        for (int c = 0; c < 6; c++) {
+                            const int jc = (int)((j1 >> (4 * c)) & 15u);
+                            if (8 * jc + p7 + s > 64) any = true;
+                        }
+                        if (any) {
+                            JDEvent ev;
+                            ev.blk = in.blk0 + b;
+                            ev.seg = in.seg;
+                            ev.j1 = j1;
+                            ev.field = (uint16_t)field;
+                            ev.s = (uint8_t)s;
+                            ev.p7 = (uint8_t)p7;
+                            ev.ord = ncoef;
+                            sink.push(ev);
+                        }
+                    }
+                }
+                const uint32_t tw = tposw[k];
+                bflags |= tw;
+                if (s >= 10 && !big) {
+                    /* first >= 10-bit magnitude of this block: switch its records to (t, value) pairs */
+                    if (rp + ncoef + 2 > rend) { err = JD_SEG_OVERFLOW; break; }
+                    for (uint32_t i = ncoef; i-- > 0u;) {
+                        const uint32_t r = rec0[i];
+                        rec0[2u * i] = (uint16_t)(r >> 10);
+                        rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
+                    }
+                    rp += ncoef;
+                    big = 1;
+                }
+                if (big) {
+                    if (rp + 2 > rend) { err = JD_SEG_OVERFLOW; break; }
+                    rp[0] = (uint16_t)(tw & 63u);
+                    rp[1] = (uint16_t)(int16_t)v;
+                    rp += 2;
+                } else {
+                    if (rp >= rend) { err = JD_SEG_OVERFLOW; break; }
+                    *rp++ = (uint16_t)(((tw & 63u) << 10) | ((uint32_t)v & 0x3FFu));
+                }
+                ncoef++;
+            }
+            k++;
+            last_was_eob = false;
+        }
+        P += len + s;
+        { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+        if (k >= 64u) {
+            /* ---- block finished ---- */
+            blk_hdr[b] = jd_pack_hdr(in.rec_index0 + (uint32_t)(rec0 - rec), dcval, ncoef, big, (bflags >> 16) & 1u, (bflags >> 8) & 0xFFu);
+            if (++b == nblk_total) break;
+            if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
+            /* component of the next block: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
+            comp = (blk_in_mcu < nluma) ? 0u : (blk_in_mcu - nluma + 1u);
+            tac = lut + JD_LUT_AC((in.tsel >> (2 * comp + 1)) & 1u);
+            tb = lut + JD_LUT_DC((in.tsel >> (2 * comp)) & 1u);
+            thr = 0xF800u; sh = 4u; msk = 0x7Fu;
+            k = 0; ncoef = 0; big = 0; bflags = 0; rec0 = rp;
+        }
+    }
+    if (err >= 0) {
+        /* undecodable from here: later stages must still find well-formed (empty) headers */
+        out.err_mcu = (int32_t)(b / in.bpm);
+        for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
     }
     out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
     if (err < 0) {
@@ -372,7 +376,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         if (P & 7) jw += JD_JW_ONES;
     }
     out.jmap = jw;
-    out.nrec = nrec_total;
+    out.nrec = (uint32_t)(rp - rec);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -97,7 +97,7 @@ struct JPEGB200_BATCH {
     std::vector<const uint8_t *> datas;
     std::vector<int32_t> sizes;
     std::vector<JDImageDesc> descs;
-    std::vector<int16_t> quant;
+    std::vector<int32_t> quant;
     std::vector<uint16_t> luts;
     std::vector<uint32_t> work, cta_lut, seg_img;
     std::vector<uint64_t> comp_off; /* offset of each file in the device blob */
@@ -114,7 +114,7 @@ struct JPEGB200_BATCH {
     DevBuf<uint32_t> d_err_off;
     std::vector<JDImageDesc> descs_dl; /* descriptors read back (status, err_mcu) */
     DevBuf<JDImageDesc> d_descs;
-    DevBuf<int16_t> d_quant;
+    DevBuf<int32_t> d_quant;
     DevBuf<uint16_t> d_luts, d_rec;
     DevBuf<uint32_t> d_work, d_cta_lut, d_seg_img, d_seg_start, d_seg_jmap, d_seg_status, d_seg_nrec, d_seg_phase, d_counters;
     DevBuf<jd_u64> d_blk_hdr;
@@ -294,7 +294,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         {   /* kernels read quant column-major ([c * 8 + r]) so a lane's column is one 16-byte load */
             int16_t qn[192];
             jd_build_quant(&inf, qn);
-            int16_t *qt = &b->quant[(size_t)i * 192];
+            int32_t *qt = &b->quant[(size_t)i * 192];
             for (int cc = 0; cc < 3; cc++)
                 for (int nn = 0; nn < 64; nn++) qt[cc * 64 + (nn & 7) * 8 + (nn >> 3)] = qn[cc * 64 + nn];
         }
@@ -476,14 +476,14 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
             CK(cudaMemcpyAsync(b->d_comp.p + b->comp_off[i], b->datas[i], (size_t)b->sizes[i], cudaMemcpyHostToDevice, st));
     }
     CK(cudaMemcpyAsync(b->d_descs.p, b->descs.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->d_quant.p, b->quant.data(), sizeof(int16_t) * 192 * n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_quant.p, b->quant.data(), sizeof(int32_t) * 192 * n, cudaMemcpyHostToDevice, st));
     if (b->luts.size()) CK(cudaMemcpyAsync(b->d_luts.p, b->luts.data(), b->luts.size() * 2, cudaMemcpyHostToDevice, st));
     if (b->work.size()) CK(cudaMemcpyAsync(b->d_work.p, b->work.data(), b->work.size() * 4, cudaMemcpyHostToDevice, st));
     if (b->cta_lut.size()) CK(cudaMemcpyAsync(b->d_cta_lut.p, b->cta_lut.data(), b->cta_lut.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b->d_seg_img.p, b->seg_img.data(), b->seg_img.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(b->ev[1], st));
     b->uploaded = true;
-    b->counters[JPEGB200_C_H2D_BYTES] = (int64_t)(b->comp_total + sizeof(JDImageDesc) * n + 384 * (size_t)n + b->luts.size() * 2 +
+    b->counters[JPEGB200_C_H2D_BYTES] = (int64_t)(b->comp_total + sizeof(JDImageDesc) * n + 768 * (size_t)n + b->luts.size() * 2 +
                                                   b->work.size() * 4 + b->cta_lut.size() * 4 + b->seg_img.size() * 4);
     return 1;
 }
@@ -619,7 +619,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         int i1 = i0 + 1;
         uint32_t max_mx = f.mcus_x, max_my = f.mcus_y;
         while (i1 < n && i1 - i0 < 65535 && b->parse_status[i1] == JPEG_SUCCESS && b->infos[i1].subsample == f.subsample &&
-               b->infos[i1].ncomp == f.ncomp) {
+               b->infos[i1].ncomp == f.ncomp && (b->sshift >= 2 || (b->infos[i1].width == f.width && b->infos[i1].height == f.height))) {
             if ((uint32_t)b->infos[i1].mcus_x > max_mx) max_mx = b->infos[i1].mcus_x;
             if ((uint32_t)b->infos[i1].mcus_y > max_my) max_my = b->infos[i1].mcus_y;
             i1++;
@@ -638,6 +638,8 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             ia.out = stage_out; ia.img0 = (uint32_t)i0;
             ia.big_endian = (f.ncomp == 1) ? (b->pixel_type != RGB565_LITTLE_ENDIAN) : (b->pixel_type == RGB565_BIG_ENDIAN);
             ia.padded = (b->dither_bits || b->padded) ? 1u : 0u;
+            ia.mcus_x = (uint32_t)f.mcus_x; ia.mcus_y = (uint32_t)f.mcus_y; ia.width = (uint32_t)f.width; ia.height = (uint32_t)f.height;
+            ia.bpm = (uint32_t)f.bpm;
             int ok = 0;
             const int ar = b->ctx->arith;
             switch (f.subsample) {

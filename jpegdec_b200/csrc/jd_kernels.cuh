@@ -22,7 +22,7 @@
 #include "jd_internal.h"
 
 #define JD_NONE 0xFFFFFFFFu
-#define JD_ENTROPY_THREADS 128
+#define JD_ENTROPY_THREADS 64
 
 __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
 
@@ -120,8 +120,8 @@ struct JDEntropyArgs {
 __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
-    __shared__ uint8_t s_tpos[64];
-    if (threadIdx.x < 64) s_tpos[threadIdx.x] = c_tpos[threadIdx.x];
+    __shared__ uint32_t s_tpos[64];
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
@@ -220,8 +220,10 @@ struct JDIdctArgs {
     const JDImageDesc *imgs;
     const jd_u64 *blk_hdr;
     const uint16_t *rec;
-    const int16_t *quant;   /* [img][3][64], column-major per component: [c * 8 + r] */
+    const int32_t *quant;   /* [img][3][64] int32, column-major per component: [c * 8 + r] */
     uint8_t *out;           /* output base */
+    /* geometry shared by every image of this launch (the host groups images by size / sampling) */
+    uint32_t mcus_x, mcus_y, width, height, bpm;
     uint32_t img0;          /* first image of this launch (blockIdx.z offset) */
     uint32_t big_endian;    /* RGB565_BIG_ENDIAN requested */
     uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate / callback replay) */
@@ -298,7 +300,6 @@ jdk_idct_color(const JDIdctArgs a)
     const uint32_t img_i = a.img0 + blockIdx.z;
     const JDImageDesc &im = a.imgs[img_i];
     const uint32_t strip = blockIdx.x, my = blockIdx.y;
-    if (strip * MPB >= im.mcus_x || my >= im.mcus_y) return;
     const uint32_t tid = threadIdx.x;
 
     /* ---- phase A: expand this block's records into a column-major coefficient tile ---- */
@@ -307,22 +308,27 @@ jdk_idct_color(const JDIdctArgs a)
     const uint32_t mx = strip * MPB + ml;
     const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
     jd_u64 h = 0;
-    if (mx < im.mcus_x) h = a.blk_hdr[im.blk_base + ((size_t)my * im.mcus_x + mx) * im.bpm + blk];
     /* (block order inside an MCU in the stream = luma blocks, Cb, Cr = our blk numbering) */
+    if (mx < a.mcus_x) h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
     const uint32_t ri = JD_HDR_REC(h);
     const int dc = JD_HDR_DC(h);
     const uint32_t ncoef = JD_HDR_NCOEF(h);
     int16_t *tile = s_tile + gb * G::TSTRIDE;
     uint32_t px0, px1; /* 8 output bytes of row `c` of this block */
-    const int16_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
+    const int32_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
     if (__all_sync(0xffffffffu, ncoef == 0u)) {
         /* no stored AC coefficient in any of the warp's 4 blocks: DC-only fill (jpeg.inl:5146-5154) */
-        px0 = px1 = jd_range(dc * (int)qg[0]) * 0x01010101u;
+        px0 = px1 = jd_range(dc * __ldg(qg)) * 0x01010101u;
     } else {
         *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
         __syncwarp();
         if (!JD_HDR_BIG(h)) {
-            for (uint32_t i = c; i < ncoef; i += 8) {
+            const uint16_t *rp = a.rec + ri + c;
+            if (c < ncoef) { const uint32_t r = __ldg(rp); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            for (uint32_t i = c + 16; i < ncoef; i += 8) {
                 const uint32_t r = __ldg(a.rec + ri + i);
                 tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
             }
@@ -334,9 +340,9 @@ jdk_idct_color(const JDIdctArgs a)
         }
         __syncwarp();
         /* ---- phase B: dequant + column pass (lane = column), row pass (lane = row) ---- */
-        int m[8], qq[8], o[8];
+        int m[8], o[8];
+        const int qq[8] = {(int)q0.x, (int)q0.y, (int)q0.z, (int)q0.w, (int)q1.x, (int)q1.y, (int)q1.z, (int)q1.w};
         jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
-        jd_unpack8(__ldg(reinterpret_cast<const uint4 *>(qg + c * 8)), qq);
         if (c == 0) m[0] = dc;
         const bool r47 = JD_HDR_HI(h) == 0u;
         if (ARITH == JPEG_ARITH_SSE2) {
@@ -372,8 +378,8 @@ jdk_idct_color(const JDIdctArgs a)
 
     /* ---- phase C: colour conversion + coalesced 128-bit scanline stores ---- */
     const uint8_t *s_cb = s_c, *s_cr = s_c + 8 * G::CSTRIDE;
-    const uint32_t W = a.padded ? (uint32_t)im.mcus_x * HS * 8 : (uint32_t)im.width;
-    const uint32_t H = a.padded ? (uint32_t)im.mcus_y * VS * 8 : (uint32_t)im.height;
+    const uint32_t W = a.padded ? a.mcus_x * HS * 8 : a.width;
+    const uint32_t H = a.padded ? a.mcus_y * VS * 8 : a.height;
     uint8_t *outbase = a.out + im.out_off;
     const uint32_t pitch = im.out_pitch;
     constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
@@ -398,6 +404,23 @@ jdk_idct_color(const JDIdctArgs a)
                 else if (NCH == 4) { cbw[0] = *reinterpret_cast<const uint32_t *>(pb); crw[0] = *reinterpret_cast<const uint32_t *>(pr); }
                 else { const uint2 u = *reinterpret_cast<const uint2 *>(pb), v = *reinterpret_cast<const uint2 *>(pr); cbw[0] = u.x; cbw[1] = u.y; crw[0] = v.x; crw[1] = v.y; }
             }
+            /* SSE2-build path: packed (two-pixel) chroma terms, shared by the VS rows of this item */
+            uint32_t tpk[PXI][3];
+            if (NC == 3 && PT != JD_PT_GRAY && SSE_PATH) {
+#pragma unroll
+                for (int j = 0; j < PXI / 2; j++) {
+                    /* pixel pair j uses chroma sample j (HS == 2) or samples 2j, 2j+1 (HS == 1) */
+                    const int c0 = (HS == 2) ? j : 2 * j, c1 = (HS == 2) ? j : 2 * j + 1;
+                    int tr0, tg0, tb0, tr1, tg1, tb1;
+                    jd_chroma_terms_sse(jd_byte(cbw[c0 >> 2], c0 & 3), jd_byte(crw[c0 >> 2], c0 & 3), tr0, tg0, tb0);
+                    if (HS == 2) { tr1 = tr0; tg1 = tg0; tb1 = tb0; }
+                    else jd_chroma_terms_sse(jd_byte(cbw[c1 >> 2], c1 & 3), jd_byte(crw[c1 >> 2], c1 & 3), tr1, tg1, tb1);
+                    const int tj = (HS == 2) ? j : 2 * j;
+                    tpk[tj][0] = __byte_perm((uint32_t)tr0, (uint32_t)tr1, 0x5410);
+                    tpk[tj][1] = __byte_perm((uint32_t)tg0, (uint32_t)tg1, 0x5410);
+                    tpk[tj][2] = __byte_perm((uint32_t)tb0, (uint32_t)tb1, 0x5410);
+                }
+            }
 #pragma unroll
             for (int vr = 0; vr < VS; vr++) {
                 const uint32_t row = rg * VS + vr;
@@ -414,6 +437,28 @@ jdk_idct_color(const JDIdctArgs a)
                 if (PT == JD_PT_GRAY) {
                     ow[0] = yw[0]; ow[1] = yw[1]; ow[2] = yw[2]; ow[3] = yw[3];
                 } else {
+                    if (NC == 3 && SSE_PATH) {
+                        /* SSE2-build arithmetic, two pixels per instruction: (Y<<4 + t) clamped to [0,4095] by one
+                         * VIADDMNMX.S16x2.RELU per channel, then >>4 (== packus((Y4 + t) >> 4)); tpk[] computed above */
+#pragma unroll
+                        for (int j = 0; j < PXI / 2; j++) {
+                            const uint32_t ywj = yw[j >> 1];
+                            const uint32_t y4 = __byte_perm(ywj, 0, (j & 1) ? 0x4342 : 0x4140) << 4; /* Y(2j)<<4 | Y(2j+1)<<4 << 16 */
+                            const int tj = (HS == 2) ? j : 2 * j;  /* index into the packed chroma terms */
+                            const uint32_t r12 = __viaddmin_s16x2_relu(y4, tpk[tj][0], 0x0FFF0FFFu);
+                            const uint32_t g12 = __viaddmin_s16x2_relu(y4, tpk[tj][1], 0x0FFF0FFFu);
+                            const uint32_t b12 = __viaddmin_s16x2_relu(y4, tpk[tj][2], 0x0FFF0FFFu);
+                            if (PT == JD_PT_8888) {
+                                const uint32_t rs = r12 >> 4, gs = g12 >> 4, bs = b12 >> 4;  /* bytes 0 and 2 hold the two pixels */
+                                const uint32_t bg = __byte_perm(bs, gs, 0x6240);             /* B0 G0 B1 G1 */
+                                const uint32_t ra = __byte_perm(rs, 0xFFFFFFFFu, 0x4240);    /* R0 FF R1 FF */
+                                ow[2 * j] = __byte_perm(bg, ra, 0x5410);
+                                ow[2 * j + 1] = __byte_perm(bg, ra, 0x7632);
+                            } else {
+                                ow[j] = ((r12 << 4) & 0xF800F800u) | ((g12 >> 1) & 0x07E007E0u) | ((b12 >> 7) & 0x001F001Fu);
+                            }
+                        }
+                    } else {
                     uint32_t pix[PXI];
 #pragma unroll
                     for (int i = 0; i < PXI; i++) {
@@ -425,19 +470,14 @@ jdk_idct_color(const JDIdctArgs a)
                         } else {
                             const int ci = i / HS;
                             const uint32_t Cb = jd_byte(cbw[ci >> 2], ci & 3), Cr = jd_byte(crw[ci >> 2], ci & 3);
-                            if (SSE_PATH) {
-                                int tr, tg, tb;
-                                jd_chroma_terms_sse(Cb, Cr, tr, tg, tb);
-                                pix[i] = jd_pixel_sse<PT>(Y, tr, tg, tb);
-                            } else {
-                                pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
-                            }
+                            pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
                         }
                     }
                     if (PT == JD_PT_8888) { ow[0] = pix[0]; ow[1] = pix[1]; ow[2] = pix[2]; ow[3] = pix[3]; }
                     else {
 #pragma unroll
                         for (int i = 0; i < 4; i++) ow[i] = pix[(2 * i) % PXI] | (pix[(2 * i + 1) % PXI] << 16);
+                    }
                     }
                 }
                 uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
@@ -499,7 +539,7 @@ struct JDScaledArgs {
     const JDImageDesc *imgs;
     const jd_u64 *blk_hdr;
     const uint16_t *rec;
-    const int16_t *quant;
+    const int32_t *quant;
     uint8_t *out;
     uint32_t img0;
     uint32_t pixel_type;   /* JPEGDEC.h pixel type (after LUMA_ONLY folding) */
@@ -507,7 +547,7 @@ struct JDScaledArgs {
     uint32_t padded;
 };
 
-__device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h, const int16_t *q, bool eighth, uint32_t px[4])
+__device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h, const int32_t *q, bool eighth, uint32_t px[4])
 {
     const int dc = JD_HDR_DC(h);
     const int q0 = q[0];
@@ -544,7 +584,7 @@ __global__ void __launch_bounds__(128) jdk_scaled(const JDScaledArgs a)
     const uint32_t nluma = hs * vs;
     const bool eighth = a.eighth != 0;
     const uint32_t bs = eighth ? 1u : 2u; /* block edge in output pixels */
-    const int16_t *q = a.quant + (size_t)img_i * 192;
+    const int32_t *q = a.quant + (size_t)img_i * 192;
     const jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m * im.bpm;
     uint32_t ypx[4][4], cb[4], cr[4];
     for (uint32_t b = 0; b < nluma; b++) jd_scaled_block(a, hdr[b], q, eighth, ypx[b]);

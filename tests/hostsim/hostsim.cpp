@@ -23,6 +23,7 @@ struct VecSink {
 };
 
 static const uint8_t kTpos[64] = JD_TPOS_INIT;
+static uint32_t kTposW[64];
 
 struct Planes {
     int sshift;          /* 0 full / half (block bytes are full 8x8), 2 quarter, 3 eighth */
@@ -79,6 +80,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
     std::vector<uint32_t> jmap(nseg, 0);
     VecSink sink;
     int bad = 0;
+    for (int i = 0; i < 64; i++) kTposW[i] = jd_tposw(kTpos[i]);
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in;
         in.data = cdata;
@@ -95,7 +97,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.seg = (uint32_t)sgi;
         in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
-        jd_decode_segment(in, lut.data(), kTpos, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         jmap[sgi] = so.jmap;
         if (so.err_mcu >= 0) { bad = 1; break; }
     }
