@@ -29,8 +29,8 @@ WORKLOADS = {
     # name: (n_images, w, h, quality, pixel_type_name, algorithmic bytes per source pixel for the fused kernel)
     "hd1024": dict(n=1024, w=1920, h=1080, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3,
                    desc="1024 x 1920x1080 4:2:0 q75 -> RGB8888 (BASELINE.json configs[1])"),
-    "uhd": dict(n=256, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2, coef_bpp=3,
-                desc="256 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
+    "uhd": dict(n=512, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2, coef_bpp=3,
+                desc="512 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
     "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
 }
 

@@ -32,8 +32,6 @@ typedef struct JPEGB200_BATCH JPEGB200_BATCH; /* one decode job: n images, one p
 
 /* batch flags */
 #define JPEGB200_OUT_DEVICE 1   /* output pointers are device pointers (pixels stay in HBM) */
-#define JPEGB200_IN_DEVICE 2    /* compressed bytes already live in device memory (one blob) */
-#define JPEGB200_TIGHT_ROWS 4   /* (default) write only valid rows/columns: out is out_w x out_h */
 
 /* stage indices for JPEGB200_batchGetTimings (milliseconds, CUDA events on the batch stream) */
 enum {
@@ -72,8 +70,8 @@ void JPEGB200_hostFree(void *p);
 
 /* ---- batch job ---- */
 /* Parses the n headers on the host (no GPU work).  datas[i]/sizes[i]: JPEG files in host memory
- * (or, with JPEGB200_IN_DEVICE, offsets are taken relative to `datas[0]` inside one device blob whose
- * host mirror is given for parsing -- see batchSetDeviceInput).  pixel_type / options as in JPEGDEC.h. */
+ * (pinned memory makes the upload a straight DMA; files that sit back to back are uploaded with one copy).
+ * pixel_type / options as in JPEGDEC.h.  At most 1 GiB of compressed bytes per batch. */
 JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes,
                                      int n, int pixel_type, int options);
 void JPEGB200_batchDestroy(JPEGB200_BATCH *b);

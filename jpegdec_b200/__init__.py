@@ -25,7 +25,7 @@ JPEG_LE_PIXELS, JPEG_EXIF_THUMBNAIL, JPEG_LUMA_ONLY, JPEG_USES_DMA = 16, 32, 64,
 (JPEG_SUCCESS, JPEG_INVALID_PARAMETER, JPEG_DECODE_ERROR, JPEG_UNSUPPORTED_FEATURE,
  JPEG_INVALID_FILE, JPEG_ERROR_MEMORY) = range(6)
 JPEG_ARITH_SSE2, JPEG_ARITH_SCALAR = 0, 1
-JPEGB200_OUT_DEVICE, JPEGB200_IN_DEVICE = 1, 2
+JPEGB200_OUT_DEVICE = 1
 TIMING_NAMES = ["h2d", "prescan", "entropy", "stitch", "idct", "dither", "d2h", "total"]
 COUNTER_NAMES = ["launches", "segments", "blocks", "events", "compressed_bytes", "output_bytes",
                  "record_bytes", "h2d_bytes", "d2h_bytes"]

@@ -655,7 +655,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     }
     CK(cudaEventRecord(b->ev[6], st));
     if (b->dither_bits) {
-        jdk_dither<<<(n + 31) / 32, 32, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p, b->d_err_off.p,
+        jdk_dither<<<(n * 32 + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p, b->d_err_off.p,
                                                   out_base, (uint32_t)b->dither_bits, (uint32_t)b->sshift);
         launches++;
     }
@@ -775,46 +775,79 @@ extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *dat
 
 /* ------------------------------------------------------------------------------------ */
 /* Floyd-Steinberg dither (reference JPEGDither src/jpeg.inl:4871-4940).                    */
-/* First version: one thread per image, rows in order; the uint8 error line persists across */
-/* MCU rows and starts from the reference's DHT scratch bytes (see batchDecode).            */
+/*                                                                                          */
+/* One warp per image, 32 rows in flight as a wavefront: lane l works on row (band*32 + l)   */
+/* and trails lane l-1 by three pixels, which is exactly when the error that row l-1 sends   */
+/* down to a pixel (e2 of its left neighbour + e3 + e4 of its right neighbour, summed in     */
+/* uint8 like the reference's error line) is complete; it travels to the next lane with one  */
+/* shuffle per step.  The last lane's outgoing errors go through an error line in global     */
+/* memory to the next band -- the same line the reference keeps in usPixels: it persists     */
+/* across MCU rows, only entries 0..2 are cleared per MCU row (:4881), and before the first  */
+/* row it holds the DHT scratch bytes (the host uploads them, see batchDecode).              */
 /* ------------------------------------------------------------------------------------ */
-__global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift)
+__global__ void __launch_bounds__(128)
+jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
+           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (i >= nimg) return;
     const JDImageDesc &im = imgs[i];
     if (im.nseg == 0) return;
     const uint32_t hs = (im.subsample >> 4) ? (im.subsample >> 4) : 1, vs = (im.subsample & 15) ? (im.subsample & 15) : 1;
     const uint32_t mcu_h = (vs * 8) >> sshift;
-    const uint32_t W = (uint32_t)im.mcus_x * ((hs * 8) >> sshift); /* padded width = pitch of the gray stage */
-    const uint32_t rows = im.out_h;                                /* rows the caller sees */
+    const int W = (int)((uint32_t)im.mcus_x * ((hs * 8) >> sshift)); /* padded width = pitch of the gray stage */
+    const uint32_t rows = im.out_h;
     const uint8_t *src = gray + gray_off[i];
-    uint8_t *errors = errlines + err_off[i];
-    const uint32_t dpitch = (W * bits + 7) / 8;
-    const uint32_t mask = (bits == 4) ? 0xF0u : (bits == 2 ? 0xC0u : 0x80u);
+    uint8_t *errors = errlines + err_off[i];                          /* errors[p + 1] = error flowing into pixel p */
+    uint8_t *o = out + gray_off[nimg + i];
+    const uint32_t dpitch = ((uint32_t)W * bits + 7) / 8;
+    const int mask = (bits == 4) ? 0xF0 : (bits == 2 ? 0xC0 : 0x80);
     const uint32_t xmask = (bits == 4) ? 1u : (bits == 2 ? 3u : 7u);
-    uint8_t *o = out + gray_off[nimg + i]; /* packed-output offsets follow the gray-stage offsets */
-    for (uint32_t y = 0; y < rows; y++) {
-        if ((y % mcu_h) == 0) { errors[0] = errors[1] = errors[2] = 0; }
-        const uint8_t *p = src + (size_t)y * W;
-        uint8_t *d = o + (size_t)y * dpitch;
-        uint8_t *pe = errors + 1;
-        int lFErr = 0;
-        uint32_t cOut = 0;
-        for (uint32_t x = 0; x < W; x++) {
-            int cNew = (int)p[x] + lFErr;
-            if (cNew > 255) cNew = 255;
-            cOut = ((cOut << bits) | ((uint32_t)cNew >> (8 - bits))) & 0xFFu;
-            if ((x & xmask) == xmask) { *d++ = (uint8_t)cOut; cOut = 0; }
-            const int v = cNew - (cNew & (int)mask);
-            const int h = v >> 1;
-            const int e1 = (7 * h) >> 3, e2 = h - e1, e3 = (5 * h) >> 3, e4 = h - e3;
-            lFErr = e1 + pe[1];
-            pe[1] = (uint8_t)e2;
-            pe[0] = (uint8_t)(pe[0] + e3);
-            pe[-1] = (uint8_t)(pe[-1] + e4);
-            pe++;
+    for (uint32_t band = 0; band < rows; band += 32) {
+        const uint32_t y = band + lane;
+        const bool live = y < rows;
+        const bool mcu_first = (y % mcu_h) == 0;        /* errors[0..2] are cleared at each JPEGDither call */
+        const uint8_t *p = src + (size_t)(live ? y : 0) * W;
+        uint8_t *d = o + (size_t)(live ? y : 0) * dpitch;
+        int fwd = 0;                 /* e1 of the previous pixel + incoming error of this pixel (lFErr) */
+        int e2_prev = 0, e3_prev = 0;/* this row's e2(x-2)... bookkeeping for the outgoing error */
+        int down_m1 = 0;             /* partial outgoing error for pixel x-1: e2(x-2) + e3(x-1) */
+        uint32_t acc = 0;
+        uint32_t from_above = 0;     /* D[x+1] of the row above, delivered by the previous step's shuffle */
+        const int nsteps = W + 3 * 31 + 2;
+        for (int t = 0; t < nsteps; t++) {
+            const int x = t - 3 * (int)lane;
+            /* incoming error for pixel x+1 (used to form lFErr of the next pixel) */
+            uint32_t inc = from_above;
+            if (lane == 0 && x >= 0 && x + 1 < W) inc = errors[x + 2];
+            uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
+            if (live && x >= 0 && x < W) {
+                int c = (int)p[x] + fwd;
+                if (c > 255) c = 255;
+                acc = ((acc << bits) | ((uint32_t)c >> (8 - bits))) & 0xFFu;
+                if (((uint32_t)x & xmask) == xmask) { *d++ = (uint8_t)acc; acc = 0; }
+                const int v = c - (c & mask);
+                const int h = v >> 1;
+                const int e1 = (7 * h) >> 3, e2 = h - e1, e3 = (5 * h) >> 3, e4 = h - e3;
+                /* error arriving at pixel x+1 from the row above; the reference never feeds pixel 0 from above, and pixel 1's
+                 * slot (errors[2]) is cleared at the first row of every MCU row */
+                uint32_t up = inc & 0xFFu;
+                if (mcu_first && x + 1 == 1) up = 0;
+                fwd = e1 + (int)up;
+                dcomplete = (uint32_t)(down_m1 + e4) & 0xFFu;   /* D[x-1] = e2(x-2) + e3(x-1) + e4(x) */
+                down_m1 = e2_prev + e3;                          /* becomes D[x] once e4(x+1) arrives */
+                e2_prev = e2;
+                (void)e3_prev;
+            } else if (live && x == W) {
+                dcomplete = (uint32_t)down_m1 & 0xFFu;           /* D[W-1] = e2(W-2) + e3(W-1) (no right neighbour) */
+                down_m1 = e2_prev;                               /* D[W] = e2(W-1): lands in errors[W+1], read by nobody */
+            }
+            /* lane 31 (or the last live row) parks its outgoing errors in the line for the next band */
+            if (live && (lane == 31 || y + 1 == rows) && x >= 1 && x <= W) errors[x] = (uint8_t)dcomplete;
+            /* next step lane l+1 handles pixel x-2 and needs D[x-1] of this row */
+            from_above = __shfl_up_sync(0xffffffffu, dcomplete, 1);
         }
+        __syncwarp();
     }
 }

@@ -52,27 +52,27 @@ def main():
         o = op[1] if op[0].startswith("@") else op[0]
         c[o.split(".")[0]] += int(r[iex])
     print("opcode shares:", ", ".join("%s %.1f%%" % (o, 100.0 * n / tot) for o, n in c.most_common(18)), file=out)
-    crows = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda"]))))
-    # find the per-file tables: rows with line numbers and instruction counts
-    print("\nsource lines by executed warp instructions (top 40):", file=out)
+    crows = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
+    print("\nsource lines by executed warp instructions (top 45; second column = share of stall samples):", file=out)
     best = []
     cur_file = None
     hdr2 = None
     for r in crows:
-        if len(r) >= 2 and r[0] == "File Name":
-            cur_file = r[1]; hdr2 = None; continue
+        if len(r) >= 2 and r[0] == "File Path":
+            cur_file = r[1]; continue
         if len(r) > 3 and r[0] == "Line No":
             hdr2 = r; continue
-        if hdr2 and len(r) == len(hdr2) and "Instructions Executed" in hdr2:
+        if hdr2 and len(r) == len(hdr2) and r[2] == "-":
             try:
-                n = int(r[hdr2.index("Instructions Executed")])
+                n = int(r[hdr2.index("Instructions Executed")]); ss = int(r[hdr2.index("# Samples")])
             except ValueError:
                 continue
             if n:
-                best.append((n, cur_file.split("/")[-1], r[0], r[hdr2.index("Source")].strip()[:110]))
+                best.append((n, ss, cur_file.split("/")[-1], r[0], r[1].strip()[:105]))
+    tots = sum(x[1] for x in best) or 1
     best.sort(reverse=True)
-    for n, f, ln, src in best[:40]:
-        print("%5.1f%%  %s:%s  %s" % (100.0 * n / tot, f, ln, src), file=out)
+    for n, ss, f, ln, src in best[:45]:
+        print("%5.1f%% %5.1f%%  %s:%s  %s" % (100.0 * n / tot, 100.0 * ss / tots, f, ln, src), file=out)
 
 
 if __name__ == "__main__":
