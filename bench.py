@@ -31,6 +31,8 @@ WORKLOADS = {
                    desc="1024 x 1920x1080 4:2:0 q75 -> RGB8888 (BASELINE.json configs[1])"),
     "uhd": dict(n=512, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2, coef_bpp=3,
                 desc="512 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
+    "dither": dict(n=256, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=2, gray=True,
+                   desc="256 x 2048x1536 1-component q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4] shape)"),
     "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
 }
 
@@ -111,7 +113,7 @@ class ClockSampler:
 
 def make_images(wl, rank, unique):
     from tests import synth
-    jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique)
+    jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False))
     return jp
 
 
@@ -121,7 +123,7 @@ def cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=3):
     ref = refdrv.Ref("sse")
     datas = [jpegs[i % len(jpegs)] for i in range(n_sample)]
     rows = ((wl["h"] + 15) // 16) * 16 + 16
-    bypp = wl["bpp_out"]
+    bypp = max(1, int(wl["bpp_out"]))
     # one framebuffer per worker slot is enough for timing (image i -> worker i % threads writes fbs[i])
     pool = [np.empty(rows * wl["w"] * bypp + 4096, dtype=np.uint8) for _ in range(min(threads, n_sample))]
     fbs = [pool[i % len(pool)] for i in range(n_sample)]
@@ -275,7 +277,7 @@ def main():
     parity = None
     try:
         from oracle import refdrv
-        if refdrv.available("sse") and rank == 0:
+        if refdrv.available("sse") and rank == 0 and pixel_type <= J.EIGHT_BIT_GRAYSCALE:
             ref = refdrv.Ref("sse")
             nchk = min(4, unique)
             outs_h, st_h, _, _ = J.decode_batch_to_host(ctx, jpegs[:nchk], pixel_type, 0)
@@ -292,7 +294,7 @@ def main():
     # ---- end to end through the public C ABI with host buffers (`e2e`) ----
     e2e = None
     if not args.no_e2e:
-        out_bytes = wl["w"] * wl["h"] * wl["bpp_out"]
+        out_bytes = int(wl["w"] * wl["h"] * wl["bpp_out"])
         stride = (out_bytes + 255) & ~255
         out_ptr = L.JPEGB200_hostAlloc(stride * n_img + 256)
         if out_ptr:
@@ -327,7 +329,7 @@ def main():
 
     # ---- roofline of the dominant kernel (fused IDCT + colour) ----
     peak, peak_src = load_peaks()
-    alg_bytes = n_img * wl["w"] * wl["h"] * (wl["bpp_out"] + wl["coef_bpp"])
+    alg_bytes = int(n_img * wl["w"] * wl["h"] * (wl["bpp_out"] + wl["coef_bpp"]))
     achieved = alg_bytes / (idct_ms / 1e3) / 1e9
     out_gbs = n_img * wl["w"] * wl["h"] * wl["bpp_out"] / (idct_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "jdk_idct_color", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -337,7 +339,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and pixel_type <= J.EIGHT_BIT_GRAYSCALE:
         try:
             from oracle import refdrv
             if refdrv.available("sse"):

@@ -576,8 +576,9 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             /* initial error line = the reference's DHT scratch bytes (they share usPixels, jpeg.inl:843 / :4881) */
             const size_t el = ((size_t)pw + 16 + 15) & ~(size_t)15;
             b->errinit.resize(eo + el, 0);
-            const size_t cp = el < JD_HUFFVALS_BYTES ? el : JD_HUFFVALS_BYTES;
-            memcpy(&b->errinit[eo], inf.p.huffvals, cp);
+            /* device line S[x] = errors[x + 2] */
+            const size_t cp = (el + 2 < JD_HUFFVALS_BYTES) ? el : JD_HUFFVALS_BYTES - 2;
+            memcpy(&b->errinit[eo], inf.p.huffvals + 2, cp);
             eo += el;
         }
         CK(b->d_errline.alloc(eo + 16));
@@ -796,58 +797,85 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     if (im.nseg == 0) return;
     const uint32_t hs = (im.subsample >> 4) ? (im.subsample >> 4) : 1, vs = (im.subsample & 15) ? (im.subsample & 15) : 1;
     const uint32_t mcu_h = (vs * 8) >> sshift;
-    const int W = (int)((uint32_t)im.mcus_x * ((hs * 8) >> sshift)); /* padded width = pitch of the gray stage */
+    const int W = (int)((uint32_t)im.mcus_x * ((hs * 8) >> sshift)); /* padded width = pitch of the gray stage (multiple of 8) */
     const uint32_t rows = im.out_h;
     const uint8_t *src = gray + gray_off[i];
-    uint8_t *errors = errlines + err_off[i];                          /* errors[p + 1] = error flowing into pixel p */
+    /* S[x] = error flowing from the row above into pixel x+1 (the reference's errors[x + 2]); 16-byte aligned */
+    uint8_t *S = errlines + err_off[i];
     uint8_t *o = out + gray_off[nimg + i];
     const uint32_t dpitch = ((uint32_t)W * bits + 7) / 8;
     const int mask = (bits == 4) ? 0xF0 : (bits == 2 ? 0xC0 : 0x80);
     const uint32_t xmask = (bits == 4) ? 1u : (bits == 2 ? 3u : 7u);
+    const bool vec = ((W & 15) == 0);   /* 16-byte chunked row reads (always true for 16-px MCUs; else byte loads) */
     for (uint32_t band = 0; band < rows; band += 32) {
         const uint32_t y = band + lane;
         const bool live = y < rows;
         const bool mcu_first = (y % mcu_h) == 0;        /* errors[0..2] are cleared at each JPEGDither call */
         const uint8_t *p = src + (size_t)(live ? y : 0) * W;
         uint8_t *d = o + (size_t)(live ? y : 0) * dpitch;
-        int fwd = 0;                 /* e1 of the previous pixel + incoming error of this pixel (lFErr) */
-        int e2_prev = 0, e3_prev = 0;/* this row's e2(x-2)... bookkeeping for the outgoing error */
+        int fwd = 0;                 /* lFErr: e1 of the previous pixel + error arriving from above */
+        int e2_prev = 0;             /* e2(x-1) */
         int down_m1 = 0;             /* partial outgoing error for pixel x-1: e2(x-2) + e3(x-1) */
         uint32_t acc = 0;
         uint32_t from_above = 0;     /* D[x+1] of the row above, delivered by the previous step's shuffle */
+        uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;     /* 16 source pixels in flight + the next 16 */
+        uint4 ecur = cur, enxt = cur;                      /* lane 0: same for the incoming error line */
         const int nsteps = W + 3 * 31 + 2;
         for (int t = 0; t < nsteps; t++) {
             const int x = t - 3 * (int)lane;
-            /* incoming error for pixel x+1 (used to form lFErr of the next pixel) */
-            uint32_t inc = from_above;
-            if (lane == 0 && x >= 0 && x + 1 < W) inc = errors[x + 2];
+            const bool inrow = live && x >= 0 && x < W;
+            uint32_t pix = 0, inc = from_above;
+            if (inrow) {
+                if (vec) {
+                    if (x == 0) {
+                        cur = *reinterpret_cast<const uint4 *>(p);
+                        if (16 < W) nxt = *reinterpret_cast<const uint4 *>(p + 16);
+                        if (lane == 0) { ecur = *reinterpret_cast<const uint4 *>(S); if (16 < W) enxt = *reinterpret_cast<const uint4 *>(S + 16); }
+                    }
+                    pix = cur.x & 0xFFu;
+                    cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8);
+                    cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
+                    if (lane == 0) {
+                        inc = ecur.x & 0xFFu;
+                        ecur.x = __funnelshift_r(ecur.x, ecur.y, 8); ecur.y = __funnelshift_r(ecur.y, ecur.z, 8);
+                        ecur.z = __funnelshift_r(ecur.z, ecur.w, 8); ecur.w >>= 8;
+                    }
+                    if ((x & 15) == 15) {
+                        cur = nxt;
+                        if (x + 17 < W) nxt = *reinterpret_cast<const uint4 *>(p + x + 17);
+                        if (lane == 0) { ecur = enxt; if (x + 17 < W) enxt = *reinterpret_cast<const uint4 *>(S + x + 17); }
+                    }
+                } else {
+                    pix = p[x];
+                    if (lane == 0) inc = S[x];
+                }
+            }
             uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
-            if (live && x >= 0 && x < W) {
-                int c = (int)p[x] + fwd;
+            if (inrow) {
+                int c = (int)pix + fwd;
                 if (c > 255) c = 255;
                 acc = ((acc << bits) | ((uint32_t)c >> (8 - bits))) & 0xFFu;
                 if (((uint32_t)x & xmask) == xmask) { *d++ = (uint8_t)acc; acc = 0; }
                 const int v = c - (c & mask);
                 const int h = v >> 1;
                 const int e1 = (7 * h) >> 3, e2 = h - e1, e3 = (5 * h) >> 3, e4 = h - e3;
-                /* error arriving at pixel x+1 from the row above; the reference never feeds pixel 0 from above, and pixel 1's
-                 * slot (errors[2]) is cleared at the first row of every MCU row */
+                /* error arriving at pixel x+1 from the row above; pixel 1's slot (errors[2]) is cleared at the first row of
+                 * every MCU row, and nothing ever reaches pixel 0 from above (lFErr starts at 0) */
                 uint32_t up = inc & 0xFFu;
-                if (mcu_first && x + 1 == 1) up = 0;
+                if (mcu_first && x == 0) up = 0;
                 fwd = e1 + (int)up;
                 dcomplete = (uint32_t)(down_m1 + e4) & 0xFFu;   /* D[x-1] = e2(x-2) + e3(x-1) + e4(x) */
                 down_m1 = e2_prev + e3;                          /* becomes D[x] once e4(x+1) arrives */
                 e2_prev = e2;
-                (void)e3_prev;
             } else if (live && x == W) {
                 dcomplete = (uint32_t)down_m1 & 0xFFu;           /* D[W-1] = e2(W-2) + e3(W-1) (no right neighbour) */
-                down_m1 = e2_prev;                               /* D[W] = e2(W-1): lands in errors[W+1], read by nobody */
             }
-            /* lane 31 (or the last live row) parks its outgoing errors in the line for the next band */
-            if (live && (lane == 31 || y + 1 == rows) && x >= 1 && x <= W) errors[x] = (uint8_t)dcomplete;
+            /* the last row of the band parks what it sends down: D[x-1] feeds pixel x-1 of the next band's first row = S[x-2] */
+            if (live && (lane == 31 || y + 1 == rows) && x >= 2 && x <= W) S[x - 2] = (uint8_t)dcomplete;
             /* next step lane l+1 handles pixel x-2 and needs D[x-1] of this row */
             from_above = __shfl_up_sync(0xffffffffu, dcomplete, 1);
         }
         __syncwarp();
+        __threadfence_block();
     }
 }
