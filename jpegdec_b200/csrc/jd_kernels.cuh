@@ -316,7 +316,7 @@ jdk_idct_color(const JDIdctArgs a)
     int16_t *tile = s_tile + gb * G::TSTRIDE;
     uint32_t px0, px1; /* 8 output bytes of row `c` of this block */
     const int32_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
-    if (__all_sync(0xffffffffu, ncoef == 0u)) {
+    if (__builtin_expect(__all_sync(0xffffffffu, ncoef == 0u), 0)) {
         /* no stored AC coefficient in any of the warp's 4 blocks: DC-only fill (jpeg.inl:5146-5154) */
         px0 = px1 = jd_range(dc * __ldg(qg)) * 0x01010101u;
     } else {

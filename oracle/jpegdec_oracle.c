@@ -488,3 +488,9 @@ int oracle_decode(const uint8_t *jpeg, int len, int pixel_type, int options, int
     free(PY); free(PB); free(PR); free(F); free(H);
     return rc;
 }
+
+/* test hook: one block through the restated IDCT (flags as JPEGDecodeMCU leaves them; mode 0 full, 2 quarter) */
+void oracle_idct(const int16_t *coef, const int16_t *quant, unsigned flags, int arith, int mode, uint8_t *out)
+{
+    or_idct(coef, quant, flags, arith, mode, out);
+}

@@ -11,4 +11,5 @@ enum { OR_RGB565_LE = 0, OR_RGB565_BE, OR_RGB8888, OR_GRAY8, OR_DITHER4, OR_DITH
  * out: tight ceil(w/s) x ceil(h/s) image, out_pitch bytes per row.  Returns 1 ok, 0 failure. */
 int oracle_decode(const uint8_t *jpeg, int len, int pixel_type, int options, int arith,
                   uint8_t *out, int out_pitch, int *out_w, int *out_h);
+void oracle_idct(const int16_t *coef, const int16_t *quant, unsigned flags, int arith, int mode, uint8_t *out);
 #endif

@@ -192,6 +192,22 @@ int ref_decode_dither(const uint8_t *data, int len, int pixel_type, int options,
     return rc;
 }
 
+/* ---- one 8x8 block through the reference's JPEGIDCT (static, but in this TU) ----
+ * coef: 64 int16 natural order; quant: 64 prescaled int16 natural order; flags: u16MCUFlags as JPEGDecodeMCU
+ * would have left them; options: 0 or JPEG_SCALE_QUARTER.  out: the 64 bytes JPEGIDCT writes over the slot. */
+void ref_idct(const int16_t *coef, const int16_t *quant, int flags, int options, uint8_t *out)
+{
+    JPEGIMAGE *img = (JPEGIMAGE *)calloc(1, sizeof(JPEGIMAGE));
+    img->sMCUs = img->sUnalignedMCUs;
+    memcpy(img->sMCUs, coef, 64 * sizeof(int16_t));
+    memcpy(img->sQuantTable, quant, 64 * sizeof(int16_t));
+    img->u16MCUFlags = (uint16_t)flags;
+    img->iOptions = options;
+    JPEGIDCT(img, 0, 0);
+    memcpy(out, img->sMCUs, 64);
+    free(img);
+}
+
 /* ---- multi-threaded batch (CPU baseline) --------------------------------- */
 typedef struct {
     const uint8_t **datas; const int *lens; uint8_t **fbs;

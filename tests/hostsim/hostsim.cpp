@@ -287,3 +287,30 @@ extern "C" int hostsim_open(const uint8_t *data, int size, int *w, int *h, int *
     *bpp = info.bpp;
     return rc;
 }
+
+/* one block through the kernels' per-thread IDCT code (column pass per lane, (short) store, row pass per lane) */
+extern "C" void hostsim_idct(const int16_t *coef, const int16_t *quant, unsigned flags, int arith, uint8_t *out)
+{
+    int16_t col[64];
+    const bool r47 = (flags & 0x2000u) == 0;
+    for (int c = 0; c < 8; c++) {
+        int o[8];
+        if (arith == JPEG_ARITH_SSE2) {
+            int d[8];
+            for (int r = 0; r < 8; r++) d[r] = coef[r * 8 + c] * quant[r * 8 + c];
+            jd_col_sse16(d, r47, o);
+        } else {
+            int mm[8], qq[8];
+            for (int r = 0; r < 8; r++) { mm[r] = coef[r * 8 + c]; qq[r] = quant[r * 8 + c]; }
+            jd_col_scalar(mm, qq, r47, o);
+        }
+        for (int r = 0; r < 8; r++) col[r * 8 + c] = (int16_t)o[r];
+    }
+    for (int r = 0; r < 8; r++) {
+        int p[8];
+        uint32_t o[8];
+        for (int c = 0; c < 8; c++) p[c] = col[r * 8 + c];
+        jd_row(p, flags & 0xFFu, o);
+        for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)o[c];
+    }
+}
