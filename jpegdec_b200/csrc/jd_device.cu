@@ -786,6 +786,23 @@ extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *dat
 /* across MCU rows, only entries 0..2 are cleared per MCU row (:4881), and before the first  */
 /* row it holds the DHT scratch bytes (the host uploads them, see batchDecode).              */
 /* ------------------------------------------------------------------------------------ */
+/* 16 bytes starting at byte offset `mo` (0..15) of the 32-byte pair (a, b) */
+__device__ __forceinline__ uint4 jd_window16(const uint4 a, const uint4 b, uint32_t mo)
+{
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const uint32_t ws = mo >> 2, bs = (mo & 3u) * 8u;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        /* v[i] = w[ws + i] without dynamic register indexing */
+        uint32_t x = w[i];
+        if (ws == 1) x = w[i + 1]; else if (ws == 2) x = w[i + 2]; else if (ws == 3) x = (i + 3 < 8) ? w[i + 3] : 0u;
+        v[i] = x;
+    }
+    return make_uint4(__funnelshift_r(v[0], v[1], bs), __funnelshift_r(v[1], v[2], bs), __funnelshift_r(v[2], v[3], bs),
+                      __funnelshift_r(v[3], v[4], bs));
+}
+
 __global__ void __launch_bounds__(128)
 jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
            uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift)
@@ -806,7 +823,15 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     const uint32_t dpitch = ((uint32_t)W * bits + 7) / 8;
     const int mask = (bits == 4) ? 0xF0 : (bits == 2 ? 0xC0 : 0x80);
     const uint32_t xmask = (bits == 4) ? 1u : (bits == 2 ? 3u : 7u);
-    const bool vec = ((W & 15) == 0);   /* 16-byte chunked row reads (always true for 16-px MCUs; else byte loads) */
+    const bool vec = ((W & 15) == 0);
+    /* Lane l works on pixel x = t - 3l at step t.  To keep every global load at a warp-uniform step (a load into a
+     * register that other lanes are still consuming would serialise the whole warp on the scoreboard), each lane reads
+     * its row through a pointer skewed by 3l bytes: at step t every lane needs byte t of its skewed row, so all lanes
+     * cross 16-byte boundaries together.  The skewed 16 bytes are cut out of two aligned chunks (jd_window16). */
+    const int skew = 3 * (int)lane;
+    const uint32_t mo = (uint32_t)((16 - (skew & 15)) & 15);   /* byte offset of the window inside the aligned pair */
+    const int jsh = (skew + 15) >> 4;                           /* aligned chunk index of window m = m - jsh */
+    const int nchunks = W >> 4;
     for (uint32_t band = 0; band < rows; band += 32) {
         const uint32_t y = band + lane;
         const bool live = y < rows;
@@ -818,37 +843,40 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         int down_m1 = 0;             /* partial outgoing error for pixel x-1: e2(x-2) + e3(x-1) */
         uint32_t acc = 0;
         uint32_t from_above = 0;     /* D[x+1] of the row above, delivered by the previous step's shuffle */
-        uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;     /* 16 source pixels in flight + the next 16 */
-        uint4 ecur = cur, enxt = cur;                      /* lane 0: same for the incoming error line */
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        /* aligned chunks A0 = chunk(m - jsh), A1 = chunk(m - jsh + 1), A2 = prefetch of chunk(m - jsh + 2) */
+        uint4 A0 = zero4, A1 = zero4, A2 = zero4, win = zero4, ewin = zero4, enext = zero4;
+        auto chunk = [&](int j) -> uint4 {
+            return (live && j >= 0 && j < nchunks) ? *reinterpret_cast<const uint4 *>(p + 16 * j) : zero4;
+        };
+        if (vec) {
+            A0 = chunk(-jsh); A1 = chunk(1 - jsh); A2 = chunk(2 - jsh);
+            if (lane == 0) { ewin = *reinterpret_cast<const uint4 *>(S); enext = (1 < nchunks) ? *reinterpret_cast<const uint4 *>(S + 16) : zero4; }
+            win = jd_window16(A0, A1, mo);
+        }
         const int nsteps = W + 3 * 31 + 2;
         for (int t = 0; t < nsteps; t++) {
-            const int x = t - 3 * (int)lane;
+            const int x = t - skew;
             const bool inrow = live && x >= 0 && x < W;
-            uint32_t pix = 0, inc = from_above;
-            if (inrow) {
-                if (vec) {
-                    if (x == 0) {
-                        cur = *reinterpret_cast<const uint4 *>(p);
-                        if (16 < W) nxt = *reinterpret_cast<const uint4 *>(p + 16);
-                        if (lane == 0) { ecur = *reinterpret_cast<const uint4 *>(S); if (16 < W) enxt = *reinterpret_cast<const uint4 *>(S + 16); }
-                    }
-                    pix = cur.x & 0xFFu;
-                    cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8);
-                    cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
-                    if (lane == 0) {
-                        inc = ecur.x & 0xFFu;
-                        ecur.x = __funnelshift_r(ecur.x, ecur.y, 8); ecur.y = __funnelshift_r(ecur.y, ecur.z, 8);
-                        ecur.z = __funnelshift_r(ecur.z, ecur.w, 8); ecur.w >>= 8;
-                    }
-                    if ((x & 15) == 15) {
-                        cur = nxt;
-                        if (x + 17 < W) nxt = *reinterpret_cast<const uint4 *>(p + x + 17);
-                        if (lane == 0) { ecur = enxt; if (x + 17 < W) enxt = *reinterpret_cast<const uint4 *>(S + x + 17); }
-                    }
-                } else {
-                    pix = p[x];
-                    if (lane == 0) inc = S[x];
+            uint32_t pix, inc = from_above;
+            if (vec) {
+                /* warp-uniform: byte t of every lane's skewed row, and (lane 0) byte t of the error line */
+                pix = win.x & 0xFFu;
+                win.x = __funnelshift_r(win.x, win.y, 8); win.y = __funnelshift_r(win.y, win.z, 8);
+                win.z = __funnelshift_r(win.z, win.w, 8); win.w >>= 8;
+                if (lane == 0) inc = ewin.x & 0xFFu;
+                ewin.x = __funnelshift_r(ewin.x, ewin.y, 8); ewin.y = __funnelshift_r(ewin.y, ewin.z, 8);
+                ewin.z = __funnelshift_r(ewin.z, ewin.w, 8); ewin.w >>= 8;
+                if ((t & 15) == 15) {
+                    const int m = (t + 1) >> 4;            /* next window index */
+                    A0 = A1; A1 = A2; A2 = chunk(m - jsh + 2);
+                    win = jd_window16(A0, A1, mo);
+                    ewin = enext;
+                    enext = (lane == 0 && m + 1 < nchunks) ? *reinterpret_cast<const uint4 *>(S + 16 * (m + 1)) : zero4;
                 }
+            } else {
+                pix = inrow ? p[x] : 0u;
+                if (lane == 0 && inrow) inc = S[x];
             }
             uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
             if (inrow) {
