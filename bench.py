@@ -33,6 +33,8 @@ WORKLOADS = {
                 desc="512 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
     "dither": dict(n=256, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=2, gray=True,
                    desc="256 x 2048x1536 1-component q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4] shape)"),
+    "hd_norst": dict(n=1024, w=1920, h=1080, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, restart_rows=0,
+                     desc="1024 x 1920x1080 4:2:0 q75 WITHOUT restart markers -> RGB8888 (SURVEY 8(f)2: chunk-parallel entropy decode)"),
     "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
 }
 
@@ -113,7 +115,8 @@ class ClockSampler:
 
 def make_images(wl, rank, unique):
     from tests import synth
-    jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False))
+    jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False),
+                         restart_rows=wl.get("restart_rows", 1))
     return jp
 
 

@@ -1,0 +1,242 @@
+/*
+ * jd_chunk.h -- per-thread code of the parallel entropy decode for scans WITHOUT restart markers
+ * (SURVEY.md section 8(f) item 2).  One restart-free scan is one long dependent bit stream; the reference
+ * (JPEGDecodeMCU, src/jpeg.inl:2090-2274, driven by DecodeJPEG :5128-5275) walks it on one core.  Here the
+ * un-stuffed stream (jdk_unstuff = JPEGFilter :1431-1540) is cut into fixed-size chunks:
+ *
+ *   1. jd_chunk_parse  every chunk is parsed from a guessed entry state (bit offset, zigzag index, block-in-MCU
+ *                      index); Huffman streams self-synchronise, so after a few passes in which each chunk hands
+ *                      its exit state to its right neighbour the entry states are exact (fix point).
+ *   2. prefix sums     blocks started before each chunk.
+ *   3. jd_chunk_emit   every chunk decodes the blocks that START inside it (running past its end to finish the
+ *                      last one) and writes the same headers/records jd_decode_segment writes, tracking the
+ *                      reference's six bit-window phase candidates exactly as jd_decode_segment does; DC values are
+ *                      local to the chunk and fixed up after a scan over the chunks (jd kernels jdk_chunk_*).
+ *
+ * `__host__ __device__` like jd_core.h: tests/hostsim steps it on the CPU against the compiled reference.
+ */
+#ifndef JD_CHUNK_H
+#define JD_CHUNK_H
+#include "jd_core.h"
+
+#define JD_CHUNK_BYTES 512u
+
+/* entry/exit state of a chunk: bit offset past the chunk start (symbols straddle by < 32 bits), zigzag index k
+ * (0 = next symbol is a DC), block-in-MCU index.  JD_CS_NONE = nothing decodable here (past the end). */
+#define JD_CS_PACK(bit, k, bim) (((uint32_t)(bit) & 0xFFu) | (((uint32_t)(k) & 0x7Fu) << 8) | (((uint32_t)(bim) & 0xFu) << 16))
+#define JD_CS_BIT(s) ((s) & 0xFFu)
+#define JD_CS_K(s) (((s) >> 8) & 0x7Fu)
+#define JD_CS_BIM(s) (((s) >> 16) & 0xFu)
+#define JD_CS_NONE 0xFFFFFFFFu
+
+typedef struct {
+    const uint8_t *filt;   /* un-stuffed stream buffer (same offsets as the raw buffer) */
+    uint32_t f0;           /* byte offset of the scan's first un-stuffed byte */
+    uint32_t flen;         /* un-stuffed length in bytes (zeros follow up to the raw length + 8) */
+    uint32_t bpm, ncomp, tsel;
+    uint32_t total_blocks; /* blocks in the scan */
+} JDScanIn;
+
+/* 32 bits of the stream starting at bit `rel` (relative to f0), MSB first */
+JD_HD uint32_t jd_peek32(const JDScanIn &sc, uint32_t rel)
+{
+    const uint32_t ap = sc.f0 * 8u + rel;
+    const uint32_t *words = (const uint32_t *)sc.filt;
+    uint32_t hi = words[ap >> 5], lo = words[(ap >> 5) + 1];
+#ifdef __CUDA_ARCH__
+    hi = __byte_perm(hi, 0, 0x0123); lo = __byte_perm(lo, 0, 0x0123);
+    return __funnelshift_l(lo, hi, ap & 31u);
+#else
+    hi = __builtin_bswap32(hi); lo = __builtin_bswap32(lo);
+    const uint32_t sft = ap & 31u;
+    return sft ? (hi << sft) | (lo >> (32 - sft)) : hi;
+#endif
+}
+
+struct JDTabSel { const uint16_t *dc, *ac; };
+JD_HD JDTabSel jd_tables_for(const uint16_t *lut, uint32_t tsel, uint32_t bim, uint32_t bpm, uint32_t ncomp, uint32_t *comp)
+{
+    const uint32_t nluma = (ncomp == 3) ? bpm - 2 : bpm;
+    const uint32_t c = (bim < nluma) ? 0u : (bim - nluma + 1u);
+    *comp = c;
+    JDTabSel t;
+    t.dc = lut + JD_LUT_DC((tsel >> (2 * c)) & 1u);
+    t.ac = lut + JD_LUT_AC((tsel >> (2 * c + 1)) & 1u);
+    return t;
+}
+
+/* Pass 1: parse chunk `ci` from `entry`; returns the state at which the first symbol of chunk ci+1 starts
+ * (JD_CS_NONE if the stream ends before) and counts the DC symbols (= block starts) inside this chunk. */
+JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t ci, uint32_t entry, uint32_t *nstart, uint32_t *bad)
+{
+    *nstart = 0; *bad = 0;
+    if (entry == JD_CS_NONE) return JD_CS_NONE;
+    const uint32_t c0 = ci * JD_CHUNK_BYTES * 8u, c1 = c0 + JD_CHUNK_BYTES * 8u, endbits = sc.flen * 8u;
+    uint32_t rel = c0 + JD_CS_BIT(entry), k = JD_CS_K(entry), bim = JD_CS_BIM(entry);
+    if (c0 >= endbits) return JD_CS_NONE;
+    uint32_t comp;
+    JDTabSel t = jd_tables_for(lut, sc.tsel, bim, sc.bpm, sc.ncomp, &comp);
+    uint32_t n = 0;
+    while (rel < c1) {
+        if (rel >= endbits) { *nstart = n; return JD_CS_NONE; }
+        const uint32_t w16 = jd_peek32(sc, rel) >> 16;
+        uint32_t e;
+        if (k == 0) { e = t.dc[(w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)]; }
+        else { e = t.ac[(w16 >= 0xFC00u) ? (1024u + (w16 & 0x3FFu)) : (w16 >> 6)]; }
+        if (e == 0u) {
+            /* an invalid code under a guessed entry state only says the guess was wrong: let the right neighbour keep
+             * speculating from its own first bit (a truly corrupt stream is reported by jd_chunk_emit) */
+            *bad = 1; *nstart = n;
+            return JD_CS_PACK(0, 0, 0);
+        }
+        const uint32_t rs = e & 0xFFu;
+        rel += (e >> 8) + (rs & 15u);
+        if (k == 0) { n++; k = 1; }
+        else if (rs == 0u) k = 64;
+        else k += (rs >> 4) + 1u;
+        if (k >= 64u) {
+            k = 0;
+            if (++bim == sc.bpm) bim = 0;
+            t = jd_tables_for(lut, sc.tsel, bim, sc.bpm, sc.ncomp, &comp);
+        }
+    }
+    *nstart = n;
+    return JD_CS_PACK(rel - c1, k, bim);
+}
+
+typedef struct {
+    uint32_t jmap;       /* window-phase candidates at the point where the next chunk's first symbol starts */
+    int32_t dcsum[3];    /* per component: sum of the DC differences of the blocks owned by this chunk */
+    uint32_t status;     /* JD_SEG_* */
+    uint32_t nown;       /* blocks owned (started here and inside the scan) */
+} JDChunkOut;
+
+/* Pass 3: decode and emit the blocks that start in chunk `ci`.
+ *   blk_first : index (within the scan) of the first block that starts in this chunk
+ *   next_entry: entry state of chunk ci+1 (where to snapshot the phase map), JD_CS_NONE for the last chunk
+ *   blk_hdr   : headers of the scan (indexed by block index within the scan)
+ *   rec/rec_index0/rec_cap: this chunk's record area
+ *   slot      : phase slot id written into events (the stitch resolves the true phase per slot)
+ *   blk0      : global index of the scan's first block (events) */
+template <typename EventSink>
+JD_HD void jd_chunk_emit(const JDScanIn &sc, const uint16_t *lut, const uint32_t *tposw, uint32_t ci, uint32_t entry,
+                         uint32_t next_entry, uint32_t blk_first, jd_u64 *blk_hdr, uint16_t *rec, uint32_t rec_index0,
+                         uint32_t rec_cap, uint32_t slot, uint32_t blk0, EventSink &sink, JDChunkOut &out)
+{
+    out.jmap = JD_JW_INIT; out.dcsum[0] = out.dcsum[1] = out.dcsum[2] = 0; out.status = JD_SEG_OK; out.nown = 0;
+    if (entry == JD_CS_NONE) return;
+    const uint32_t c0 = ci * JD_CHUNK_BYTES * 8u, c1 = c0 + JD_CHUNK_BYTES * 8u, endbits = sc.flen * 8u;
+    if (c0 >= endbits) return;
+    const uint32_t snap_at = (next_entry == JD_CS_NONE) ? 0xFFFFFFFFu : c1 + JD_CS_BIT(next_entry);
+    uint32_t rel = c0 + JD_CS_BIT(entry), k = JD_CS_K(entry), bim = JD_CS_BIM(entry);
+    uint32_t comp;
+    JDTabSel t = jd_tables_for(lut, sc.tsel, bim, sc.bpm, sc.ncomp, &comp);
+    uint32_t jw = JD_JW_INIT;
+    int Pb = (int)(rel >> 3);            /* P = rel: bit position in the un-stuffed scan (no restart: segment == scan) */
+    bool snapped = false, last_was_eob = true;
+    bool own = false;                    /* the block being parsed is owned by this chunk */
+    uint32_t bi = blk_first;             /* index of the next block to start */
+    uint16_t *rp = rec, *const rend = rec + rec_cap, *rec0 = rec;
+    uint32_t ncoef = 0, big = 0, bflags = 0;
+    int pred[3] = {0, 0, 0}, dcval = 0;
+    for (;;) {
+        if (!snapped && rel >= snap_at) { out.jmap = jw; snapped = true; }   /* before the checkpoint, like a segment end */
+        if (k == 0) {
+            /* a block starts here: ours only if it starts inside the chunk and inside the scan */
+            if (rel >= c1 || bi >= sc.total_blocks || rel >= endbits) break;
+            own = true;
+            ncoef = 0; big = 0; bflags = 0; rec0 = rp;
+        } else if (rel >= endbits) break;
+        jw = jd_jw_ckpt(jw);
+        const uint32_t p32 = jd_peek32(sc, rel);
+        const uint32_t w16 = p32 >> 16;
+        uint32_t e;
+        if (k == 0) e = t.dc[(w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)];
+        else e = t.ac[(w16 >= 0xFC00u) ? (1024u + (w16 & 0x3FFu)) : (w16 >> 6)];
+        if (e == 0u) { out.status = JD_SEG_BADCODE; break; }
+        const int len = (int)(e >> 8);
+        const uint32_t rs = e & 0xFFu;
+        const int s = (int)(rs & 15u);
+        const uint32_t field = s ? ((p32 << len) >> (32 - s)) : 0u;
+        const uint32_t half = s ? (1u << (s - 1)) : 1u;
+        const int v = (field < half) ? (int)field - ((1 << s) - 1) : (int)field;
+        if (k == 0) {
+            rel += (uint32_t)len;
+            { const int nPb = (int)(rel >> 3); jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+            if (s != 0 && len + s > 6) jw = jd_jw_ckpt(jw);
+            rel += (uint32_t)s;
+            { const int nPb = (int)(rel >> 3); jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+            pred[comp] += v;
+            dcval = pred[comp];
+            k = 1;
+            last_was_eob = false;
+            continue;
+        }
+        if (rs == 0u) {
+            k = 64;
+            last_was_eob = true;
+        } else {
+            k += rs >> 4;
+            if (s && k < 64u && own) {
+                if (s > 11) { out.status = JD_SEG_BADSIZE; break; }
+                if (len + s >= 18) {
+                    const uint32_t P1 = rel + (uint32_t)len;
+                    const uint32_t j1 = jw + (uint32_t)((int)(P1 >> 3) - Pb) * JD_JW_ONES;
+                    const int p7 = (int)(P1 & 7u);
+                    if (((j1 + 0x222222u) & 0x888888u) != 0u) {
+                        bool any = false;
+                        for (int c = 0; c < 6; c++) if (8 * (int)((j1 >> (4 * c)) & 15u) + p7 + s > 64) any = true;
+                        if (any) {
+                            JDEvent ev;
+                            ev.blk = blk0 + bi; ev.seg = slot; ev.j1 = j1; ev.field = (uint16_t)field;
+                            ev.s = (uint8_t)s; ev.p7 = (uint8_t)p7; ev.ord = ncoef;
+                            sink.push(ev);
+                        }
+                    }
+                }
+                const uint32_t tw = tposw[k];
+                bflags |= tw;
+                if (s >= 10 && !big) {
+                    if (rp + ncoef + 2 > rend) { out.status = JD_SEG_OVERFLOW; break; }
+                    for (uint32_t i = ncoef; i-- > 0u;) {
+                        const uint32_t r = rec0[i];
+                        rec0[2u * i] = (uint16_t)(r >> 10);
+                        rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
+                    }
+                    rp += ncoef;
+                    big = 1;
+                }
+                if (big) {
+                    if (rp + 2 > rend) { out.status = JD_SEG_OVERFLOW; break; }
+                    rp[0] = (uint16_t)(tw & 63u); rp[1] = (uint16_t)(int16_t)v; rp += 2;
+                } else {
+                    if (rp >= rend) { out.status = JD_SEG_OVERFLOW; break; }
+                    *rp++ = (uint16_t)(((tw & 63u) << 10) | ((uint32_t)v & 0x3FFu));
+                }
+                ncoef++;
+            }
+            k++;
+            last_was_eob = false;
+        }
+        rel += (uint32_t)(len + s);
+        { const int nPb = (int)(rel >> 3); jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+        if (k >= 64u) {
+            if (own) {
+                blk_hdr[bi] = jd_pack_hdr(rec_index0 + (uint32_t)(rec0 - rec), dcval, ncoef, big, (bflags >> 16) & 1u, (bflags >> 8) & 0xFFu);
+                out.nown++;
+                bi++;
+                own = false;
+            }
+            k = 0;
+            if (++bim == sc.bpm) bim = 0;
+            t = jd_tables_for(lut, sc.tsel, bim, sc.bpm, sc.ncomp, &comp);
+        }
+    }
+    if (!snapped) {
+        /* last chunk: the scan ends here; state as jd_decode_segment leaves it (only the image-end matters to nobody) */
+        if (!last_was_eob) jw = jd_jw_ckpt(jw);
+        out.jmap = jw;
+    }
+    out.dcsum[0] = pred[0]; out.dcsum[1] = pred[1]; out.dcsum[2] = pred[2];
+}
+#endif

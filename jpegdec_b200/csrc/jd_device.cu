@@ -120,6 +120,13 @@ struct JPEGB200_BATCH {
     DevBuf<jd_u64> d_blk_hdr;
     DevBuf<JDEvent> d_events;
     std::vector<uint64_t> arena_off; /* per-image offset inside d_out */
+    /* restart-free scans decoded chunk-parallel (jd_chunk.h) */
+    std::vector<uint32_t> cimg_list, chunk_img;
+    uint32_t nchunks;
+    DevBuf<uint8_t> d_filt;
+    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
+    DevBuf<int32_t> d_cdcs, d_cpe;
+    uint32_t h_changed;
     cudaEvent_t ev[JPEGB200_NUM_TIMINGS + 2];
     bool have_ev;
     float ms[JPEGB200_NUM_TIMINGS];
@@ -235,6 +242,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
     b->ptclass = (pixel_type == RGB8888) ? JD_PT_8888 : (b->gray_out ? JD_PT_GRAY : JD_PT_565);
     b->dither_bits = (pixel_type == FOUR_BIT_DITHERED) ? 4 : (pixel_type == TWO_BIT_DITHERED) ? 2 : (pixel_type == ONE_BIT_DITHERED) ? 1 : 0;
     b->stream = nullptr;
+    b->nchunks = 0;
     b->uploaded = false; b->out_device = false; b->arena_owned = false; b->have_ev = false;
     memset(b->ms, 0, sizeof(b->ms));
     memset(b->counters, 0, sizeof(b->counters));
@@ -317,6 +325,15 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         d.subsample = (uint8_t)inf.subsample; d.ncomp = (uint8_t)inf.ncomp; d.bpm = (uint8_t)inf.bpm; d.tsel = (uint8_t)inf.tsel;
         d.mcus_per_seg = mps;
         d.nseg = (total_mcus + mps - 1) / mps;
+        d.chunk_base = 0; d.nch = 0;
+        if (inf.restart_interval == 0 && d.nseg == 1 && sizes[i] - inf.scan_offset >= 4096) {
+            /* no restart markers: one long dependent stream -> chunk-parallel decode */
+            d.chunk_base = b->nchunks;
+            d.nch = ((uint32_t)(sizes[i] - inf.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;
+            b->nchunks += d.nch;
+            b->cimg_list.push_back((uint32_t)i);
+            for (uint32_t cc = 0; cc < d.nch; cc++) b->chunk_img.push_back((uint32_t)i);
+        }
         d.seg_base = seg;
         d.blk_base = (uint32_t)blk;
         d.lutset = li;
@@ -349,7 +366,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         for (int i = 0; i < n; i++) {
             const JDImageDesc &d = b->descs[i];
             if (d.nseg == 0 || b->parse_status[i] != JPEG_SUCCESS || d.lutset != li) continue;
-            for (uint32_t s2 = 0; s2 < d.nseg; s2++) { b->seg_img[d.seg_base + s2] = (uint32_t)i; b->work.push_back(d.seg_base + s2); }
+            for (uint32_t s2 = 0; s2 < d.nseg; s2++) { b->seg_img[d.seg_base + s2] = (uint32_t)i; if (d.nch == 0) b->work.push_back(d.seg_base + s2); }
         }
         while (b->work.size() % JD_ENTROPY_THREADS) b->work.push_back(JD_NONE);
         while (b->cta_lut.size() < b->work.size() / JD_ENTROPY_THREADS) b->cta_lut.push_back(li);
@@ -364,6 +381,8 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release();
+    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release();
+    b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
     b->d_seg_jmap.release(); b->d_seg_status.release(); b->d_seg_nrec.release(); b->d_seg_phase.release();
@@ -460,7 +479,14 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
     CK(b->d_seg_img.alloc(b->seg_img.size()));
     const size_t ns = b->nseg ? b->nseg : 1;
     CK(b->d_seg_start.alloc(ns + 1)); CK(b->d_seg_jmap.alloc(ns)); CK(b->d_seg_status.alloc(ns));
-    CK(b->d_seg_nrec.alloc(ns)); CK(b->d_seg_phase.alloc(ns));
+    CK(b->d_seg_nrec.alloc(ns)); CK(b->d_seg_phase.alloc(ns + b->nchunks));
+    if (b->nchunks) {
+        const size_t nc = b->nchunks;
+        CK(b->d_filt.alloc(b->comp_total + 512));
+        CK(b->d_cimg_list.alloc(b->cimg_list.size())); CK(b->d_chunk_img.alloc(nc)); CK(b->d_flen.alloc(n));
+        CK(b->d_E0.alloc(nc + 1)); CK(b->d_E1.alloc(nc + 1)); CK(b->d_cn.alloc(nc)); CK(b->d_cpre.alloc(nc)); CK(b->d_cjmap.alloc(nc));
+        CK(b->d_cstatus.alloc(nc)); CK(b->d_cnown.alloc(nc)); CK(b->d_cdcs.alloc(3 * nc)); CK(b->d_cpe.alloc(3 * nc));
+    }
     CK(b->d_counters.alloc(4));
     CK(b->d_blk_hdr.alloc(b->nblk ? b->nblk : 1));
     CK(b->d_rec.alloc(4 * b->comp_total + 1024));
@@ -481,6 +507,10 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
     if (b->work.size()) CK(cudaMemcpyAsync(b->d_work.p, b->work.data(), b->work.size() * 4, cudaMemcpyHostToDevice, st));
     if (b->cta_lut.size()) CK(cudaMemcpyAsync(b->d_cta_lut.p, b->cta_lut.data(), b->cta_lut.size() * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(b->d_seg_img.p, b->seg_img.data(), b->seg_img.size() * 4, cudaMemcpyHostToDevice, st));
+    if (b->nchunks) {
+        CK(cudaMemcpyAsync(b->d_cimg_list.p, b->cimg_list.data(), b->cimg_list.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_chunk_img.p, b->chunk_img.data(), b->chunk_img.size() * 4, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaEventRecord(b->ev[1], st));
     b->uploaded = true;
     b->counters[JPEGB200_C_H2D_BYTES] = (int64_t)(b->comp_total + sizeof(JDImageDesc) * n + 768 * (size_t)n + b->luts.size() * 2 +
@@ -590,6 +620,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     }
     CK(cudaMemcpyAsync(b->d_descs.p, descs_stage.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(b->d_counters.p, 0, 16, st));
+    if (b->nchunks) CK(cudaMemsetAsync(b->d_blk_hdr.p, 0, (size_t)b->nblk * 8, st)); /* blocks a truncated restart-free scan never reaches stay empty */
 
     CK(cudaEventRecord(b->ev[2], st));
     jdk_prescan<<<n, 256, 0, st>>>(b->d_comp.p, b->d_descs.p, b->d_seg_start.p);
@@ -605,6 +636,42 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0;
         jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
         launches++;
+    }
+    if (b->nchunks) {
+        /* restart-free scans: un-stuff, iterate the chunk entry states to their fix point, then emit */
+        JDChunkArgs ca;
+        ca.comp = b->d_comp.p; ca.filt = b->d_filt.p; ca.imgs = b->d_descs.p; ca.luts = b->d_luts.p;
+        ca.cimg_list = b->d_cimg_list.p; ca.ncimg = (uint32_t)b->cimg_list.size(); ca.flen = b->d_flen.p;
+        ca.chunk_img = b->d_chunk_img.p; ca.nchunks = b->nchunks;
+        ca.cn = b->d_cn.p; ca.cpre = b->d_cpre.p; ca.cjmap = b->d_cjmap.p; ca.cstatus = b->d_cstatus.p; ca.cnown = b->d_cnown.p;
+        ca.cdcs = b->d_cdcs.p; ca.cpe = b->d_cpe.p; ca.changed = b->d_counters.p + 2;
+        ca.blk_hdr = b->d_blk_hdr.p; ca.rec = b->d_rec.p; ca.rec_total = (uint32_t)(4 * b->comp_total + 1024);
+        ca.events = b->d_events.p; ca.event_count = b->d_counters.p; ca.event_cap = JD_EVENT_CAP;
+        ca.seg_phase = b->d_seg_phase.p; ca.seg_jmap = b->d_seg_jmap.p; ca.seg_status = b->d_seg_status.p; ca.nseg_total = b->nseg;
+        const unsigned gc = (b->nchunks + 127) / 128, gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
+        CK(cudaMemsetAsync(b->d_E0.p, 0, (size_t)(b->nchunks + 1) * 4, st));    /* guess: every chunk starts a block at its first bit */
+        jdk_unstuff<<<gi, 128, 0, st>>>(ca);
+        launches++;
+        uint32_t *Ein = b->d_E0.p, *Eout = b->d_E1.p;
+        int passes = 0;
+        for (;;) {
+            for (int k = 0; k < 3; k++) {
+                if (k == 2) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
+                ca.E_in = Ein; ca.E_out = Eout;
+                jdk_chunk_parse<<<gc, 128, 0, st>>>(ca);
+                launches++; passes++;
+                uint32_t *tmp = Ein; Ein = Eout; Eout = tmp;
+            }
+            CK(cudaMemcpyAsync(&b->h_changed, b->d_counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (!b->h_changed || passes > (int)b->nchunks + 8) break;
+        }
+        ca.E_in = Ein; ca.E_out = Eout;
+        jdk_chunk_prefix<<<((unsigned)b->cimg_list.size() + 63) / 64, 64, 0, st>>>(ca);
+        jdk_chunk_emit<<<(b->nchunks + 63) / 64, 64, 0, st>>>(ca);
+        jdk_chunk_stitch<<<((unsigned)b->cimg_list.size() + 63) / 64, 64, 0, st>>>(ca);
+        jdk_chunk_dcfix<<<gc, 128, 0, st>>>(ca);
+        launches += 4;
     }
     CK(cudaEventRecord(b->ev[4], st));
     jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p);

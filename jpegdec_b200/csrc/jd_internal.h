@@ -42,7 +42,7 @@ void jd_build_quant(const JDInfo *info, int16_t *q /* [3][64] natural order, per
 uint64_t jd_tables_hash(const JDInfo *info);
 const int *jd_aan_table(void);
 
-/* Device-visible per-image descriptor (64 B). */
+/* Device-visible per-image descriptor (72 B). */
 typedef struct {
     uint32_t scan_off;      /* absolute offset of first entropy byte in the batch buffer */
     uint32_t scan_end;      /* absolute end of this file's bytes */
@@ -59,6 +59,8 @@ typedef struct {
     uint32_t out_w, out_h;  /* output size in pixels after scaling */
     uint32_t status;        /* written by kernels: 0 ok */
     uint32_t err_mcu;
+    uint32_t chunk_base;    /* restart-free scans decoded in parallel chunks: first global chunk index ... */
+    uint32_t nch;           /* ... and number of chunks (0 = the scan is decoded per restart segment) */
 } JDImageDesc;
 
 #ifdef __cplusplus

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "jd_core.h"
+#include "jd_chunk.h"
 #include "jd_internal.h"
 
 #define JD_NONE 0xFFFFFFFFu
@@ -206,6 +207,181 @@ __global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__
             jd_patch_record(rec, blk_hdr[e.blk], e.ord, jd_event_value(&e, jc));
             atomicAdd(applied, 1u);
         }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* restart-free scans: un-stuff, then chunk-parallel entropy decode (jd_chunk.h)            */
+/* ------------------------------------------------------------------------------------ */
+struct JDChunkArgs {
+    const uint8_t *comp;           /* raw batch buffer */
+    uint8_t *filt;                 /* un-stuffed copy (same offsets) */
+    JDImageDesc *imgs;
+    const uint16_t *luts;
+    const uint32_t *cimg_list;     /* indices of the chunked images */
+    uint32_t ncimg;
+    uint32_t *flen;                /* per image: un-stuffed scan length */
+    const uint32_t *chunk_img;     /* per chunk: image index */
+    uint32_t nchunks;
+    uint32_t *E_in, *E_out;        /* entry states (double buffered across passes) */
+    uint32_t *cn, *cpre, *cjmap, *cstatus, *cnown;
+    int32_t *cdcs, *cpe;           /* per chunk x 3: DC sums / DC predictor at entry */
+    uint32_t *changed;
+    jd_u64 *blk_hdr;
+    uint16_t *rec;
+    uint32_t rec_total;
+    JDEvent *events;
+    uint32_t *event_count;
+    uint32_t event_cap;
+    uint32_t *seg_phase, *seg_jmap, *seg_status;
+    uint32_t nseg_total;           /* phase slot of chunk g = nseg_total + g */
+};
+
+/* one warp per restart-free scan: FF00 -> FF, stop at the first marker (JPEGFilter, jpeg.inl:1431-1540) */
+__global__ void __launch_bounds__(128) jdk_unstuff(const JDChunkArgs a)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (w >= a.ncimg) return;
+    const uint32_t ii = a.cimg_list[w];
+    const JDImageDesc &im = a.imgs[ii];
+    const uint8_t *src = a.comp + im.scan_off;
+    uint8_t *dst = a.filt + im.scan_off;
+    const uint32_t len = im.scan_end - im.scan_off;
+    uint32_t base = 0;
+    bool done = false;
+    for (uint32_t p0 = 0; p0 < len && !done; p0 += 128) {
+        const uint32_t p = p0 + lane * 4;
+        uint32_t b[6]; /* b[0] = byte before, b[1..4] = mine, b[5] = byte after */
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const int q = (int)p + i - 1;
+            b[i] = (q >= 0 && (uint32_t)q < len) ? (uint32_t)__ldg(src + q) : ((uint32_t)q >= len && q >= 0 ? 0xD9u : 0u);
+        }
+        uint32_t keep = 0, endpos = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 1; i <= 4; i++) {
+            const uint32_t q = p + (uint32_t)i - 1u;
+            if (q >= len) { if (endpos == 0xFFFFFFFFu) endpos = q; continue; }
+            if (b[i] == 0xFFu) { if (b[i + 1] == 0u) keep |= 1u << (i - 1); else if (endpos == 0xFFFFFFFFu) endpos = q; }
+            else if (!(b[i] == 0u && b[i - 1] == 0xFFu)) keep |= 1u << (i - 1);
+        }
+        const uint32_t stop = __reduce_min_sync(0xffffffffu, endpos);
+        if (stop != 0xFFFFFFFFu) {
+            done = true;
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (p + (uint32_t)i >= stop) keep &= ~(1u << i);
+        }
+        const uint32_t cnt = __popc(keep);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+        uint32_t o = base + x - cnt;
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)b[i + 1];
+        base += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane < 24) dst[base + lane] = 0; /* reads run a few bytes past the end */
+    if (lane == 0) a.flen[ii] = base;
+}
+
+__device__ __forceinline__ JDScanIn jd_scan_of(const JDChunkArgs &a, const JDImageDesc &im, uint32_t ii)
+{
+    JDScanIn sc;
+    sc.filt = a.filt; sc.f0 = im.scan_off; sc.flen = a.flen[ii];
+    sc.bpm = im.bpm; sc.ncomp = im.ncomp; sc.tsel = im.tsel;
+    sc.total_blocks = (uint32_t)im.mcus_x * im.mcus_y * im.bpm;
+    return sc;
+}
+
+__global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nchunks) return;
+    const uint32_t ii = a.chunk_img[g];
+    const JDImageDesc &im = a.imgs[ii];
+    const uint32_t c = g - im.chunk_base;
+    const JDScanIn sc = jd_scan_of(a, im, ii);
+    const uint32_t entry = (c == 0) ? JD_CS_PACK(0, 0, 0) : a.E_in[g];
+    uint32_t nstart, bad;
+    const uint32_t ex = jd_chunk_parse(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, c, entry, &nstart, &bad);
+    a.cn[g] = nstart;
+    if (c == 0) a.E_out[g] = JD_CS_PACK(0, 0, 0);
+    if (c + 1 < im.nch) {
+        a.E_out[g + 1] = ex;
+        if (ex != a.E_in[g + 1]) atomicOr(a.changed, 1u);
+    }
+}
+
+__global__ void jdk_chunk_prefix(const JDChunkArgs a)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.ncimg) return;
+    const JDImageDesc &im = a.imgs[a.cimg_list[w]];
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < im.nch; c++) { a.cpre[im.chunk_base + c] = run; run += a.cn[im.chunk_base + c]; }
+}
+
+__global__ void __launch_bounds__(64) jdk_chunk_emit(const JDChunkArgs a)
+{
+    __shared__ uint32_t s_tpos[64];
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
+    __syncthreads();
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nchunks) return;
+    const uint32_t ii = a.chunk_img[g];
+    const JDImageDesc &im = a.imgs[ii];
+    const uint32_t c = g - im.chunk_base;
+    const JDScanIn sc = jd_scan_of(a, im, ii);
+    const uint32_t entry = a.E_in[g];
+    const uint32_t next = (c + 1 < im.nch) ? a.E_in[g + 1] : JD_CS_NONE;
+    uint32_t ri0 = 4u * (im.scan_off + c * JD_CHUNK_BYTES);
+    uint32_t cap = 4u * JD_CHUNK_BYTES;
+    if ((uint64_t)ri0 + cap > a.rec_total) cap = (ri0 < a.rec_total) ? a.rec_total - ri0 : 0u;
+    JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
+    JDChunkOut co;
+    jd_chunk_emit(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,
+                  a.rec + ri0, ri0, cap, a.nseg_total + g, im.blk_base, sink, co);
+    a.cjmap[g] = co.jmap;
+    a.cstatus[g] = co.status;
+    a.cnown[g] = co.nown;
+    a.cdcs[3 * g] = co.dcsum[0]; a.cdcs[3 * g + 1] = co.dcsum[1]; a.cdcs[3 * g + 2] = co.dcsum[2];
+}
+
+/* per restart-free scan: true window phase and DC predictors at each chunk entry; folds the chunk statuses */
+__global__ void jdk_chunk_stitch(const JDChunkArgs a)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= a.ncimg) return;
+    const JDImageDesc &im = a.imgs[a.cimg_list[w]];
+    uint32_t cur = 0, status = 0, err_mcu = 0;
+    int run0 = 0, run1 = 0, run2 = 0;
+    for (uint32_t c = 0; c < im.nch; c++) {
+        const uint32_t g = im.chunk_base + c;
+        a.seg_phase[a.nseg_total + g] = cur;
+        const uint32_t j = (a.cjmap[g] >> (4 * cur)) & 15u;
+        cur = (j >= 6u) ? 0u : j;
+        a.cpe[3 * g] = run0; a.cpe[3 * g + 1] = run1; a.cpe[3 * g + 2] = run2;
+        run0 += a.cdcs[3 * g]; run1 += a.cdcs[3 * g + 1]; run2 += a.cdcs[3 * g + 2];
+        if (a.cstatus[g] != 0u && status == 0u) { status = a.cstatus[g]; err_mcu = (a.cpre[g] + a.cnown[g]) / im.bpm; }
+    }
+    /* the scan is one "segment" for the per-image stitch (jdk_stitch) */
+    a.seg_jmap[im.seg_base] = JD_JW_INIT;
+    a.seg_status[im.seg_base] = status ? ((status << 28) | (err_mcu & 0x0FFFFFFFu)) : 0u;
+}
+
+__global__ void __launch_bounds__(128) jdk_chunk_dcfix(const JDChunkArgs a)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.nchunks) return;
+    const JDImageDesc &im = a.imgs[a.chunk_img[g]];
+    const uint32_t nl = (im.ncomp == 3) ? (uint32_t)im.bpm - 2u : (uint32_t)im.bpm;
+    jd_u64 *hdr = a.blk_hdr + im.blk_base;
+    const uint32_t b0 = a.cpre[g], b1 = b0 + a.cnown[g];
+    for (uint32_t bi = b0; bi < b1; bi++) {
+        const uint32_t bim = bi % im.bpm, comp = (bim < nl) ? 0u : bim - nl + 1u;
+        const jd_u64 h = hdr[bi];
+        const int dc = JD_HDR_DC(h) + a.cpe[3 * g + comp];
+        hdr[bi] = (h & ~((jd_u64)0xFFFFu << 32)) | ((jd_u64)(uint16_t)(int16_t)dc << 32);
     }
 }
 

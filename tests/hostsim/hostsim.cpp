@@ -13,8 +13,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <stdio.h>
 
 #include "../../jpegdec_b200/csrc/jd_core.h"
+#include "../../jpegdec_b200/csrc/jd_chunk.h"
 #include "../../jpegdec_b200/csrc/jd_internal.h"
 
 struct VecSink {
@@ -24,6 +26,8 @@ struct VecSink {
 
 static const uint8_t kTpos[64] = JD_TPOS_INIT;
 static uint32_t kTposW[64];
+static int g_chunk_iters = 0;
+extern "C" int hostsim_last_chunk_iters(void) { return g_chunk_iters; }
 
 struct Planes {
     int sshift;          /* 0 full / half (block bytes are full 8x8), 2 quarter, 3 eighth */
@@ -81,6 +85,65 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
     VecSink sink;
     int bad = 0;
     for (int i = 0; i < 64; i++) kTposW[i] = jd_tposw(kTpos[i]);
+    const bool chunked = (options & 0x20000) && nseg == 1;   /* test hook: restart-free parallel path (jd_chunk.h) */
+    std::vector<uint32_t> phase_slot;                          /* chunked: true phase per chunk */
+    int chunk_iters = 0;
+    if (chunked) {
+        /* jdk_unstuff: FF00 -> FF, stop at the first marker; zero tail */
+        std::vector<uint32_t> fbuf((size + 64) / 4 + 64, 0);
+        uint8_t *filt = (uint8_t *)fbuf.data();
+        uint32_t flen = 0;
+        for (int i = info.scan_offset; i < size; i++) {
+            if (data[i] == 0xFF) { if (i + 1 < size && data[i + 1] == 0) { filt[info.scan_offset + flen++] = 0xFF; i++; } else break; }
+            else filt[info.scan_offset + flen++] = data[i];
+        }
+        JDScanIn sc;
+        sc.filt = filt; sc.f0 = (uint32_t)info.scan_offset; sc.flen = flen;
+        sc.bpm = (uint32_t)info.bpm; sc.ncomp = (uint32_t)info.ncomp; sc.tsel = (uint32_t)info.tsel; sc.total_blocks = (uint32_t)nblk;
+        const uint32_t nch = ((uint32_t)(size - info.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;
+        std::vector<uint32_t> E(nch, JD_CS_PACK(0, 0, 0)), E2(nch), nst(nch, 0), pre(nch, 0);
+        for (;;) {   /* fix point of the entry states */
+            bool changed = false;
+            E2[0] = E[0];
+            for (uint32_t c = 0; c < nch; c++) {
+                uint32_t badc;
+                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], &nst[c], &badc);
+                if (c + 1 < nch) { E2[c + 1] = ex; if (ex != E[c + 1]) changed = true; }
+            }
+            E.swap(E2);
+            chunk_iters++;
+            if (getenv("HOSTSIM_TRACE")) { int nchg = 0, firstchg = -1; for (uint32_t c = 0; c < nch; c++) if (E[c] != E2[c]) { nchg++; if (firstchg < 0) firstchg = (int)c; } fprintf(stderr, "iter %d changed %d first %d\n", chunk_iters, nchg, firstchg); }
+            if (!changed || chunk_iters > (int)nch + 2) break;
+        }
+        g_chunk_iters = chunk_iters;
+        { uint32_t run = 0; for (uint32_t c = 0; c < nch; c++) { pre[c] = run; run += nst[c]; } }
+        std::vector<JDChunkOut> co(nch);
+        for (uint32_t c = 0; c < nch; c++) {
+            const uint32_t ri0 = 4u * (c * JD_CHUNK_BYTES);
+            jd_chunk_emit(sc, lut.data(), kTposW, c, E[c], (c + 1 < nch) ? E[c + 1] : JD_CS_NONE, pre[c], hdr.data(), rec.data() + ri0, ri0,
+                          4u * JD_CHUNK_BYTES, c, 0u, sink, co[c]);
+            if (co[c].status != JD_SEG_OK) bad = 1;
+        }
+        /* stitch over chunks: true phase per chunk, DC predictor at each chunk entry */
+        phase_slot.assign(nch, 0);
+        std::vector<int> pe(nch * 3, 0);
+        { uint32_t cur = 0; int run[3] = {0, 0, 0};
+          for (uint32_t c = 0; c < nch; c++) {
+              phase_slot[c] = cur;
+              uint32_t j = (co[c].jmap >> (4 * cur)) & 15u; cur = (j >= 6) ? 0 : j;
+              for (int q = 0; q < 3; q++) { pe[c * 3 + q] = run[q]; run[q] += co[c].dcsum[q]; }
+          } }
+        /* dc fix */
+        const uint32_t nl = (info.ncomp == 3) ? (uint32_t)info.bpm - 2 : (uint32_t)info.bpm;
+        for (uint32_t c = 0; c < nch; c++)
+            for (uint32_t bi = pre[c]; bi < pre[c] + co[c].nown; bi++) {
+                const uint32_t bim = bi % (uint32_t)info.bpm, comp = (bim < nl) ? 0u : bim - nl + 1u;
+                jd_u64 h = hdr[bi];
+                const int dc = JD_HDR_DC(h) + pe[c * 3 + comp];
+                hdr[bi] = (h & ~((jd_u64)0xFFFFu << 32)) | ((jd_u64)(uint16_t)(int16_t)dc << 32);
+            }
+        jmap[0] = JD_JW_INIT;
+    } else
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in;
         in.data = cdata;
@@ -115,7 +178,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
     int nev = 0;
     for (size_t i = 0; i < sink.ev.size(); i++) {
         const JDEvent &e = sink.ev[i];
-        uint32_t jc = (e.j1 >> (4 * phase[e.seg])) & 15u;
+        uint32_t jc = (e.j1 >> (4 * (chunked ? phase_slot[e.seg] : phase[e.seg]))) & 15u;
         if (8 * (int)jc + e.p7 + e.s > 64) {
             int v = jd_event_value(&e, jc);
             jd_patch_record(rec.data(), hdr[e.blk], e.ord, v);
