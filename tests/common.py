@@ -69,12 +69,16 @@ def hostsim():
         L = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "_build", "libhostsim.so"))
         L.hostsim_decode.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
         L.hostsim_open.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 9
+        L.hostsim_last_chunk_iters.restype = C.c_int
         _sim = L
     return _sim
 
 
-def hostsim_decode(data, pt, opt, arith, w, h):
+def hostsim_decode(data, pt, opt, arith, w, h, chunked=False):
+    """chunked=True forces the restart-free chunk-parallel path (jd_chunk.h) for scans without restart markers."""
     oh, pitch = tight_shape(w, h, pt, opt)
+    if chunked:
+        opt |= 0x20000
     out = np.zeros((oh, pitch), dtype=np.uint8)
     v = [C.c_int() for _ in range(4)]
     rc = hostsim().hostsim_decode(data, len(data), pt, opt, arith, out.ctypes.data, pitch, *[C.byref(x) for x in v])

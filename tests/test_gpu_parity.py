@@ -218,6 +218,13 @@ def test_corrupt_inputs_do_not_poison_the_batch(ctxs):
         for _ in range(4):
             b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
         blobs.append(bytes(b))
+    base2 = T.image("sciopero")                 # no restart markers: chunk-parallel path
+    for k in range(8):
+        b = bytearray(base2)
+        for _ in range(3):
+            b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
+        blobs.append(bytes(b))
+    blobs.append(bytes(base2[:len(base2) // 2]) + b"\x00" * 64)   # truncated scan
     blobs.append(good)
     outs, st, tim, cnt = J.decode_batch_to_host(ctxs[0], blobs, 0, 0)
     assert all(s in range(6) for s in st)
@@ -260,3 +267,21 @@ def test_batch_properties_at_baseline_size(ctxs):
     rc, want = T.oracle_decode(uniq[3], J.RGB8888, 0, 0, 1920, 1080)
     assert rc == 1 and np.array_equal(alone[3], want)
     assert cnt["segments"] == n * 68 and cnt["blocks"] == n * 8160 * 6
+
+
+def test_restart_free_scans_chunk_parallel(ctxs):
+    """files without restart markers (one long dependent bit stream) are decoded chunk-parallel."""
+    cases = {"hd": (synth.synth_jpeg(1920, 1080, 9, 75, restart_rows=0), 1920, 1080),
+             "uhd": (synth.synth_jpeg(3840, 2160, 3, 85, restart_rows=0), 3840, 2160),
+             "gray": (synth.synth_jpeg(2048, 1536, 1, 75, gray=True, restart_rows=0), 2048, 1536),
+             "s444": (synth.synth_jpeg(1024, 768, 2, 96, subsampling="4:4:4", restart_rows=0), 1024, 768),
+             "q98": (synth.synth_jpeg(512, 512, 5, 98, restart_rows=0), 512, 512)}
+    names = list(cases)
+    for arith in (0, 1):
+        for pt in (0, 3):
+            outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], [cases[n][0] for n in names], pt, 0)
+            assert st == [0] * len(names)
+            for n, o in zip(names, outs):
+                data, w, h = cases[n]
+                rc, want = T.oracle_decode(data, pt, 0, arith, w, h)
+                assert rc == 1 and np.array_equal(o, want), (n, arith, pt)

@@ -97,3 +97,34 @@ def test_synthetic_formats_vs_live_reference():
                     assert rc == rc1 == rc2 == 1
                     assert np.array_equal(o1, img), (n, mode, ptn, sn)
                     assert np.array_equal(o2, img), (n, mode, ptn, sn)
+
+
+@pytest.mark.parametrize("name", ["sciopero", "st_peters", "zebra", "octocat_small", "batman", "ncc1701", "lange"])
+def test_chunk_parallel_decode_of_restart_free_scans(name):
+    """scans without restart markers go through jd_chunk.h (speculative chunk parse to a fix point,
+    prefix sums, emit, phase/DC stitch).  Same digests as the reference, and the entry states settle in a few passes."""
+    d = T.digests()[name]
+    data = T.image(name)
+    w, h = d["info"]["width"], d["info"]["height"]
+    assert d["info"]["res_interval"] == 0
+    for mode, arith in MODES:
+        for pt, ptn in T.PTS:
+            for opt, sn in ((0, "full"), (4, "quarter")):
+                want = d["%s/%s/%s" % (mode, ptn, sn)]
+                rc, out, nev = T.hostsim_decode(data, pt, opt, arith, w, h, chunked=True)
+                assert rc == want["rc"] and T.sha(out) == want["sha"], (name, mode, ptn, sn)
+    assert 2 <= T.hostsim().hostsim_last_chunk_iters() <= 8
+
+
+def test_chunk_parallel_decode_synthetic_vs_restatement():
+    from tests import synth
+    cases = {"hd": (synth.synth_jpeg(1920, 1080, 9, 75, restart_rows=0), 1920, 1080),
+             "gray": (synth.synth_jpeg(640, 360, 1, 75, gray=True, restart_rows=0), 640, 360),
+             "s444": (synth.synth_jpeg(333, 251, 2, 96, subsampling="4:4:4", restart_rows=0), 333, 251),
+             "s422": (synth.synth_jpeg(333, 251, 3, 80, subsampling="4:2:2", restart_rows=0), 333, 251)}
+    for n, (data, w, h) in cases.items():
+        for arith in (0, 1):
+            rc1, want = T.oracle_decode(data, 0, 0, arith, w, h)
+            rc2, got, _ = T.hostsim_decode(data, 0, 0, arith, w, h, chunked=True)
+            assert rc1 == rc2 == 1 and np.array_equal(got, want), n
+            assert T.hostsim().hostsim_last_chunk_iters() <= 8
