@@ -68,6 +68,9 @@ def test_synthetic_formats(ctxs, mode, arith):
     ok, enc = cv2.imencode(".jpg", synth.synth_pixels(200, 150, 7),
                            [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440])
     cases["s440"] = enc.tobytes()
+    from tests.test_oracle import _odd_restart_cases
+    odd = _odd_restart_cases()                     # DRI = 1 / 7 MCUs / 2 rows, q100, q5 (all 333x251)
+    cases.update(odd)
     ref = _ref(mode)
     for pt, ptn in T.PTS:
         for opt, sn in T.SCALES:
@@ -78,8 +81,8 @@ def test_synthetic_formats(ctxs, mode, arith):
                 if n == "s440" and pt == 2 and opt == 4:
                     continue  # reference bug: JPEGPutMCU12 1/4 RGB8888 writes through &pOutput (jpeg.inl:4629)
                 info = J.Batch  # noqa
-                w = {"gray": 640, "s444": 333, "s422": 333, "odd420": 301, "q98": 256, "hd": 1920, "s440": 200}[n]
-                h = {"gray": 360, "s444": 251, "s422": 251, "odd420": 203, "q98": 256, "hd": 1080, "s440": 150}[n]
+                w = {"gray": 640, "s444": 333, "s422": 333, "odd420": 301, "q98": 256, "hd": 1920, "s440": 200}.get(n, 333)
+                h = {"gray": 360, "s444": 251, "s422": 251, "odd420": 203, "q98": 256, "hd": 1080, "s440": 150}.get(n, 251)
                 rc, want = T.oracle_decode(cases[n], pt, opt, arith, w, h)
                 assert rc == 1 and np.array_equal(o, want), (n, mode, ptn, sn)
                 if ref is not None and n in ("hd", "s422"):

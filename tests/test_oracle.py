@@ -128,3 +128,32 @@ def test_chunk_parallel_decode_synthetic_vs_restatement():
             rc2, got, _ = T.hostsim_decode(data, 0, 0, arith, w, h, chunked=True)
             assert rc1 == rc2 == 1 and np.array_equal(got, want), n
             assert T.hostsim().hostsim_last_chunk_iters() <= 8
+
+
+def _odd_restart_cases():
+    import io
+    from PIL import Image
+    from tests import synth
+    img = Image.fromarray(synth.synth_pixels(333, 251, 7))
+    out = {}
+    for name, kw in [("dri1", dict(restart_marker_blocks=1)), ("dri7", dict(restart_marker_blocks=7)),
+                     ("rows2", dict(restart_marker_rows=2)), ("q100", dict(restart_marker_rows=1, quality=100)),
+                     ("q5", dict(restart_marker_rows=1, quality=5))]:
+        b = io.BytesIO()
+        k = dict(quality=80, subsampling="4:2:0")
+        k.update(kw)
+        img.save(b, "JPEG", **k)
+        out[name] = b.getvalue()
+    return out
+
+
+def test_unusual_restart_intervals_and_qualities():
+    """DRI = 1 MCU (a marker after every MCU), 7 MCUs (not a divisor of the row), 2 rows; q100 (>= 10-bit magnitudes -> pair
+    records) and q5 (almost all blocks DC-only): restatement and kernel stepper agree on every pixel."""
+    for n, data in _odd_restart_cases().items():
+        for arith in (0, 1):
+            for pt in (0, 2):
+                for opt in (0, 2, 8):
+                    rc1, want = T.oracle_decode(data, pt, opt, arith, 333, 251)
+                    rc2, got, _ = T.hostsim_decode(data, pt, opt, arith, 333, 251)
+                    assert rc1 == rc2 == 1 and np.array_equal(got, want), (n, arith, pt, opt)
