@@ -532,10 +532,28 @@ static void launch_idct_pt(const JDIdctArgs &a, dim3 grid, int arith, bool half,
     }
 }
 
+static int g_use_tb = -1; /* thread-per-block IDCT kernel (default) unless JPEGDEC_B200_IDCT=lanes */
+
+template <int HS, int VS, int NC, int MPB, int PT>
+static void launch_idct_tb(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, int arith, cudaStream_t st)
+{
+    using G = JDGeoTB<HS, VS, NC, MPB>;
+    dim3 grid((mcus_x + MPB - 1) / MPB, mcus_y, nimg);
+    if (arith == JPEG_ARITH_SSE2) jdk_idct_tb<HS, VS, NC, MPB, PT, JPEG_ARITH_SSE2><<<grid, G::THREADS, 0, st>>>(a);
+    else jdk_idct_tb<HS, VS, NC, MPB, PT, JPEG_ARITH_SCALAR><<<grid, G::THREADS, 0, st>>>(a);
+}
+
 template <int HS, int VS, int MPB3, int MPB1>
 static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, int ncomp, int ptclass,
                            int arith, bool half, cudaStream_t st)
 {
+    if (g_use_tb < 0) { const char *e = getenv("JPEGDEC_B200_IDCT"); g_use_tb = (e && strcmp(e, "lanes") == 0) ? 0 : 1; }
+    if (g_use_tb && !half && HS == 2 && VS == 2 && ncomp == 3 && ptclass != JD_PT_GRAY) {
+        /* 4:2:0 colour, full size: the throughput configuration */
+        if (ptclass == JD_PT_565) launch_idct_tb<2, 2, 3, 16, JD_PT_565>(a, mcus_x, mcus_y, nimg, arith, st);
+        else launch_idct_tb<2, 2, 3, 16, JD_PT_8888>(a, mcus_x, mcus_y, nimg, arith, st);
+        return 1;
+    }
     if (ptclass == JD_PT_GRAY) {
         dim3 grid((mcus_x + MPB1 - 1) / MPB1, mcus_y, nimg);
         launch_idct_pt<HS, VS, 1, MPB1, JD_PT_GRAY>(a, grid, arith, half, st);

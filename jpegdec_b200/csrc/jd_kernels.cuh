@@ -464,6 +464,123 @@ __device__ __forceinline__ uint32_t jd_pixel_scalar(int Y12, int cb, int cr, boo
     return v;
 }
 
+/* Phase C of the fused kernels (full size): colour conversion of the staged planes + coalesced 16-byte scanline stores.
+ * s_y: (VS*8) rows x YSTRIDE luma bytes, s_cb/s_cr: 8 rows x CSTRIDE chroma bytes, covering WCTA pixels of MCU row `my`. */
+template <int HS, int VS, int NC, int PT, int ARITH, int WCTA, int YSTRIDE, int CSTRIDE, int NTHREADS>
+__device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8_t *s_y, const uint8_t *s_cb, const uint8_t *s_cr,
+                                                uint32_t strip, uint32_t my, uint32_t tid, uint32_t W, uint32_t H,
+                                                uint8_t *outbase, uint32_t pitch)
+{
+    constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
+    /* one item = PXI pixels (one 16-byte store) in each of the VS rows that share chroma */
+    constexpr int PXI = 16 / BYPP;              /* 4 (8888), 8 (565), 16 (gray) */
+    constexpr int IPR = WCTA / PXI;          /* items per row */
+    constexpr int NITEM = IPR * 8;              /* x (HCTA / VS) row groups */
+    constexpr bool SSE_PATH = (ARITH == JPEG_ARITH_SSE2) && (HS == VS); /* jpeg.inl:3409-3517, :4006-4308 */
+    for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) {
+        const uint32_t rg = it / IPR, xg = it - rg * IPR;
+        const uint32_t gx = strip * WCTA + xg * PXI;
+        if (gx >= W) continue;
+        const bool full = (gx + PXI <= W);
+        /* chroma samples covering these PXI pixels: PXI / HS of each */
+        uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
+        if (NC == 3 && PT != JD_PT_GRAY) {
+            constexpr int NCH = PXI / HS; /* 2, 4 or 8 bytes */
+            const uint8_t *pb = s_cb + rg * CSTRIDE + xg * NCH, *pr = s_cr + rg * CSTRIDE + xg * NCH;
+            if (NCH == 2) { cbw[0] = *reinterpret_cast<const uint16_t *>(pb); crw[0] = *reinterpret_cast<const uint16_t *>(pr); }
+            else if (NCH == 4) { cbw[0] = *reinterpret_cast<const uint32_t *>(pb); crw[0] = *reinterpret_cast<const uint32_t *>(pr); }
+            else { const uint2 u = *reinterpret_cast<const uint2 *>(pb), v = *reinterpret_cast<const uint2 *>(pr); cbw[0] = u.x; cbw[1] = u.y; crw[0] = v.x; crw[1] = v.y; }
+        }
+        /* SSE2-build path: packed (two-pixel) chroma terms, shared by the VS rows of this item */
+        uint32_t tpk[PXI][3];
+        if (NC == 3 && PT != JD_PT_GRAY && SSE_PATH) {
+#pragma unroll
+            for (int j = 0; j < PXI / 2; j++) {
+                /* pixel pair j uses chroma sample j (HS == 2) or samples 2j, 2j+1 (HS == 1) */
+                const int c0 = (HS == 2) ? j : 2 * j, c1 = (HS == 2) ? j : 2 * j + 1;
+                int tr0, tg0, tb0, tr1, tg1, tb1;
+                jd_chroma_terms_sse(jd_byte(cbw[c0 >> 2], c0 & 3), jd_byte(crw[c0 >> 2], c0 & 3), tr0, tg0, tb0);
+                if (HS == 2) { tr1 = tr0; tg1 = tg0; tb1 = tb0; }
+                else jd_chroma_terms_sse(jd_byte(cbw[c1 >> 2], c1 & 3), jd_byte(crw[c1 >> 2], c1 & 3), tr1, tg1, tb1);
+                const int tj = (HS == 2) ? j : 2 * j;
+                tpk[tj][0] = __byte_perm((uint32_t)tr0, (uint32_t)tr1, 0x5410);
+                tpk[tj][1] = __byte_perm((uint32_t)tg0, (uint32_t)tg1, 0x5410);
+                tpk[tj][2] = __byte_perm((uint32_t)tb0, (uint32_t)tb1, 0x5410);
+            }
+        }
+#pragma unroll
+        for (int vr = 0; vr < VS; vr++) {
+            const uint32_t row = rg * VS + vr;
+            const uint32_t gy = my * (VS * 8) + row;
+            if (gy >= H) continue;
+            uint32_t yw[4];
+            {
+                const uint8_t *py = s_y + row * YSTRIDE + xg * PXI;
+                if (PXI == 4) yw[0] = *reinterpret_cast<const uint32_t *>(py);
+                else if (PXI == 8) { const uint2 u = *reinterpret_cast<const uint2 *>(py); yw[0] = u.x; yw[1] = u.y; }
+                else { const uint4 u = *reinterpret_cast<const uint4 *>(py); yw[0] = u.x; yw[1] = u.y; yw[2] = u.z; yw[3] = u.w; }
+            }
+            uint32_t ow[4]; /* the 16 output bytes */
+            if (PT == JD_PT_GRAY) {
+                ow[0] = yw[0]; ow[1] = yw[1]; ow[2] = yw[2]; ow[3] = yw[3];
+            } else {
+                if (NC == 3 && SSE_PATH) {
+                    /* SSE2-build arithmetic, two pixels per instruction: (Y<<4 + t) clamped to [0,4095] by one
+                     * VIADDMNMX.S16x2.RELU per channel, then >>4 (== packus((Y4 + t) >> 4)); tpk[] computed above */
+#pragma unroll
+                    for (int j = 0; j < PXI / 2; j++) {
+                        const uint32_t ywj = yw[j >> 1];
+                        const uint32_t y4 = __byte_perm(ywj, 0, (j & 1) ? 0x4342 : 0x4140) << 4; /* Y(2j)<<4 | Y(2j+1)<<4 << 16 */
+                        const int tj = (HS == 2) ? j : 2 * j;  /* index into the packed chroma terms */
+                        const uint32_t r12 = __viaddmin_s16x2_relu(y4, tpk[tj][0], 0x0FFF0FFFu);
+                        const uint32_t g12 = __viaddmin_s16x2_relu(y4, tpk[tj][1], 0x0FFF0FFFu);
+                        const uint32_t b12 = __viaddmin_s16x2_relu(y4, tpk[tj][2], 0x0FFF0FFFu);
+                        if (PT == JD_PT_8888) {
+                            const uint32_t rs = r12 >> 4, gs = g12 >> 4, bs = b12 >> 4;  /* bytes 0 and 2 hold the two pixels */
+                            const uint32_t bg = __byte_perm(bs, gs, 0x6240);             /* B0 G0 B1 G1 */
+                            const uint32_t ra = __byte_perm(rs, 0xFFFFFFFFu, 0x4240);    /* R0 FF R1 FF */
+                            ow[2 * j] = __byte_perm(bg, ra, 0x5410);
+                            ow[2 * j + 1] = __byte_perm(bg, ra, 0x7632);
+                        } else {
+                            ow[j] = ((r12 << 4) & 0xF800F800u) | ((g12 >> 1) & 0x07E007E0u) | ((b12 >> 7) & 0x001F001Fu);
+                        }
+                    }
+                } else {
+                uint32_t pix[PXI];
+#pragma unroll
+                for (int i = 0; i < PXI; i++) {
+                    const uint32_t Y = jd_byte(yw[i >> 2], i & 3);
+                    if (NC == 1) {
+                        uint32_t v = jd_gray565(Y);
+                        if (a.big_endian) v = jd_bswap16(v);
+                        pix[i] = v;
+                    } else {
+                        const int ci = i / HS;
+                        const uint32_t Cb = jd_byte(cbw[ci >> 2], ci & 3), Cr = jd_byte(crw[ci >> 2], ci & 3);
+                        pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
+                    }
+                }
+                if (PT == JD_PT_8888) { ow[0] = pix[0]; ow[1] = pix[1]; ow[2] = pix[2]; ow[3] = pix[3]; }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ow[i] = pix[(2 * i) % PXI] | (pix[(2 * i + 1) % PXI] << 16);
+                }
+                }
+            }
+            uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+                *reinterpret_cast<uint4 *>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            } else {
+                for (uint32_t i = 0; i < (uint32_t)PXI && gx + i < W; i++) {
+                    if (BYPP == 4) reinterpret_cast<uint32_t *>(dst)[i] = ow[i & 3];
+                    else if (BYPP == 2) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)(ow[(i >> 1) & 3] >> ((i & 1) * 16));
+                    else dst[i] = (uint8_t)(ow[(i >> 2) & 3] >> ((i & 3) * 8));
+                }
+            }
+        }
+    }
+}
+
 template <int HS, int VS, int NC, int MPB, int PT, int ARITH, bool HALF>
 __global__ void __launch_bounds__(JDGeo<HS, VS, NC, MPB>::THREADS)
 jdk_idct_color(const JDIdctArgs a)
@@ -561,113 +678,7 @@ jdk_idct_color(const JDIdctArgs a)
     constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
 
     if (!HALF) {
-        /* one item = PXI pixels (one 16-byte store) in each of the VS rows that share chroma */
-        constexpr int PXI = 16 / BYPP;              /* 4 (8888), 8 (565), 16 (gray) */
-        constexpr int IPR = G::WCTA / PXI;          /* items per row */
-        constexpr int NITEM = IPR * 8;              /* x (HCTA / VS) row groups */
-        constexpr bool SSE_PATH = (ARITH == JPEG_ARITH_SSE2) && (HS == VS); /* jpeg.inl:3409-3517, :4006-4308 */
-        for (uint32_t it = tid; it < (uint32_t)NITEM; it += G::THREADS) {
-            const uint32_t rg = it / IPR, xg = it - rg * IPR;
-            const uint32_t gx = strip * G::WCTA + xg * PXI;
-            if (gx >= W) continue;
-            const bool full = (gx + PXI <= W);
-            /* chroma samples covering these PXI pixels: PXI / HS of each */
-            uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
-            if (NC == 3 && PT != JD_PT_GRAY) {
-                constexpr int NCH = PXI / HS; /* 2, 4 or 8 bytes */
-                const uint8_t *pb = s_cb + rg * G::CSTRIDE + xg * NCH, *pr = s_cr + rg * G::CSTRIDE + xg * NCH;
-                if (NCH == 2) { cbw[0] = *reinterpret_cast<const uint16_t *>(pb); crw[0] = *reinterpret_cast<const uint16_t *>(pr); }
-                else if (NCH == 4) { cbw[0] = *reinterpret_cast<const uint32_t *>(pb); crw[0] = *reinterpret_cast<const uint32_t *>(pr); }
-                else { const uint2 u = *reinterpret_cast<const uint2 *>(pb), v = *reinterpret_cast<const uint2 *>(pr); cbw[0] = u.x; cbw[1] = u.y; crw[0] = v.x; crw[1] = v.y; }
-            }
-            /* SSE2-build path: packed (two-pixel) chroma terms, shared by the VS rows of this item */
-            uint32_t tpk[PXI][3];
-            if (NC == 3 && PT != JD_PT_GRAY && SSE_PATH) {
-#pragma unroll
-                for (int j = 0; j < PXI / 2; j++) {
-                    /* pixel pair j uses chroma sample j (HS == 2) or samples 2j, 2j+1 (HS == 1) */
-                    const int c0 = (HS == 2) ? j : 2 * j, c1 = (HS == 2) ? j : 2 * j + 1;
-                    int tr0, tg0, tb0, tr1, tg1, tb1;
-                    jd_chroma_terms_sse(jd_byte(cbw[c0 >> 2], c0 & 3), jd_byte(crw[c0 >> 2], c0 & 3), tr0, tg0, tb0);
-                    if (HS == 2) { tr1 = tr0; tg1 = tg0; tb1 = tb0; }
-                    else jd_chroma_terms_sse(jd_byte(cbw[c1 >> 2], c1 & 3), jd_byte(crw[c1 >> 2], c1 & 3), tr1, tg1, tb1);
-                    const int tj = (HS == 2) ? j : 2 * j;
-                    tpk[tj][0] = __byte_perm((uint32_t)tr0, (uint32_t)tr1, 0x5410);
-                    tpk[tj][1] = __byte_perm((uint32_t)tg0, (uint32_t)tg1, 0x5410);
-                    tpk[tj][2] = __byte_perm((uint32_t)tb0, (uint32_t)tb1, 0x5410);
-                }
-            }
-#pragma unroll
-            for (int vr = 0; vr < VS; vr++) {
-                const uint32_t row = rg * VS + vr;
-                const uint32_t gy = my * G::HCTA + row;
-                if (gy >= H) continue;
-                uint32_t yw[4];
-                {
-                    const uint8_t *py = s_y + row * G::YSTRIDE + xg * PXI;
-                    if (PXI == 4) yw[0] = *reinterpret_cast<const uint32_t *>(py);
-                    else if (PXI == 8) { const uint2 u = *reinterpret_cast<const uint2 *>(py); yw[0] = u.x; yw[1] = u.y; }
-                    else { const uint4 u = *reinterpret_cast<const uint4 *>(py); yw[0] = u.x; yw[1] = u.y; yw[2] = u.z; yw[3] = u.w; }
-                }
-                uint32_t ow[4]; /* the 16 output bytes */
-                if (PT == JD_PT_GRAY) {
-                    ow[0] = yw[0]; ow[1] = yw[1]; ow[2] = yw[2]; ow[3] = yw[3];
-                } else {
-                    if (NC == 3 && SSE_PATH) {
-                        /* SSE2-build arithmetic, two pixels per instruction: (Y<<4 + t) clamped to [0,4095] by one
-                         * VIADDMNMX.S16x2.RELU per channel, then >>4 (== packus((Y4 + t) >> 4)); tpk[] computed above */
-#pragma unroll
-                        for (int j = 0; j < PXI / 2; j++) {
-                            const uint32_t ywj = yw[j >> 1];
-                            const uint32_t y4 = __byte_perm(ywj, 0, (j & 1) ? 0x4342 : 0x4140) << 4; /* Y(2j)<<4 | Y(2j+1)<<4 << 16 */
-                            const int tj = (HS == 2) ? j : 2 * j;  /* index into the packed chroma terms */
-                            const uint32_t r12 = __viaddmin_s16x2_relu(y4, tpk[tj][0], 0x0FFF0FFFu);
-                            const uint32_t g12 = __viaddmin_s16x2_relu(y4, tpk[tj][1], 0x0FFF0FFFu);
-                            const uint32_t b12 = __viaddmin_s16x2_relu(y4, tpk[tj][2], 0x0FFF0FFFu);
-                            if (PT == JD_PT_8888) {
-                                const uint32_t rs = r12 >> 4, gs = g12 >> 4, bs = b12 >> 4;  /* bytes 0 and 2 hold the two pixels */
-                                const uint32_t bg = __byte_perm(bs, gs, 0x6240);             /* B0 G0 B1 G1 */
-                                const uint32_t ra = __byte_perm(rs, 0xFFFFFFFFu, 0x4240);    /* R0 FF R1 FF */
-                                ow[2 * j] = __byte_perm(bg, ra, 0x5410);
-                                ow[2 * j + 1] = __byte_perm(bg, ra, 0x7632);
-                            } else {
-                                ow[j] = ((r12 << 4) & 0xF800F800u) | ((g12 >> 1) & 0x07E007E0u) | ((b12 >> 7) & 0x001F001Fu);
-                            }
-                        }
-                    } else {
-                    uint32_t pix[PXI];
-#pragma unroll
-                    for (int i = 0; i < PXI; i++) {
-                        const uint32_t Y = jd_byte(yw[i >> 2], i & 3);
-                        if (NC == 1) {
-                            uint32_t v = jd_gray565(Y);
-                            if (a.big_endian) v = jd_bswap16(v);
-                            pix[i] = v;
-                        } else {
-                            const int ci = i / HS;
-                            const uint32_t Cb = jd_byte(cbw[ci >> 2], ci & 3), Cr = jd_byte(crw[ci >> 2], ci & 3);
-                            pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
-                        }
-                    }
-                    if (PT == JD_PT_8888) { ow[0] = pix[0]; ow[1] = pix[1]; ow[2] = pix[2]; ow[3] = pix[3]; }
-                    else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) ow[i] = pix[(2 * i) % PXI] | (pix[(2 * i + 1) % PXI] << 16);
-                    }
-                    }
-                }
-                uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
-                if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                } else {
-                    for (uint32_t i = 0; i < (uint32_t)PXI && gx + i < W; i++) {
-                        if (BYPP == 4) reinterpret_cast<uint32_t *>(dst)[i] = ow[i & 3];
-                        else if (BYPP == 2) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)(ow[(i >> 1) & 3] >> ((i & 1) * 16));
-                        else dst[i] = (uint8_t)(ow[(i >> 2) & 3] >> ((i & 3) * 8));
-                    }
-                }
-            }
-        }
+        jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
     } else {
         /* 1/2 scale: 2x2 luma sums; scalar colour code in both builds (jpeg.inl:3297-3322, :3577-3626) */
         const uint32_t OW = (W + 1) >> 1, OH = (H + 1) >> 1;
@@ -706,6 +717,199 @@ jdk_idct_color(const JDIdctArgs a)
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* fused expand + dequant + IDCT + colour, one THREAD per 8x8 block                          */
+/*                                                                                          */
+/* At the qualities the benchmark uses ~90 % of the blocks hold coefficients only in their  */
+/* top-left 4x4 (rows 4-7 empty, columns 4-7 empty).  With 8 lanes per block half the lanes  */
+/* then transform empty columns.  Here a thread owns a block: it expands the records into   */
+/* its private tile, runs the column pass only over populated columns (4 of them for the    */
+/* common class, results kept in registers -- no transpose through shared memory, no warp    */
+/* syncs) and the 8 row passes.  Blocks are first binned by class inside the CTA so that     */
+/* the lanes of a warp take the same path.  Colour phase shared with jdk_idct_color.         */
+/* ------------------------------------------------------------------------------------ */
+template <int HS, int VS, int NC, int MPB>
+struct JDGeoTB {
+    static constexpr int BPMEFF = HS * VS + (NC == 3 ? 2 : 0);
+    static constexpr int NB = MPB * BPMEFF;                       /* blocks per CTA */
+    static constexpr int NW = (NB + 31) / 32 > 4 ? (NB + 31) / 32 : 4;
+    static constexpr int THREADS = NW * 32;
+    static constexpr int WCTA = MPB * HS * 8;
+    static constexpr int HCTA = VS * 8;
+    static constexpr int YSTRIDE = WCTA + 16;
+    static constexpr int CSTRIDE = MPB * 8 + 8;
+    static constexpr int TSTRIDE = 72;                            /* int16 per private tile (144 B: conflict-free LDS.128 per quarter warp) */
+};
+
+__device__ __forceinline__ void jd_unpack4(const uint2 v, int m[4])
+{
+    m[0] = (int)(short)(v.x & 0xFFFF); m[1] = (int)v.x >> 16;
+    m[2] = (int)(short)(v.y & 0xFFFF); m[3] = (int)v.y >> 16;
+}
+
+__device__ __forceinline__ uint2 jd_clamp_pack8(const int ob[8])
+{
+    int t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = ((ob[i] << 17) >> 22) + 128; /* ucRangeTable as arithmetic; the packs saturate */
+    return make_uint2(jd_pack_sat(t[1], t[0], jd_pack_sat(t[3], t[2], 0u)), jd_pack_sat(t[5], t[4], jd_pack_sat(t[7], t[6], 0u)));
+}
+
+template <int HS, int VS, int NC, int MPB, int PT, int ARITH>
+__global__ void __launch_bounds__(JDGeoTB<HS, VS, NC, MPB>::THREADS)
+jdk_idct_tb(const JDIdctArgs a)
+{
+    using G = JDGeoTB<HS, VS, NC, MPB>;
+    __shared__ __align__(16) int16_t s_tile[G::NB * G::TSTRIDE];
+    __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
+    __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
+    __shared__ __align__(16) int16_t s_q[NC * 64];      /* column-major prescaled quant */
+    __shared__ jd_u64 s_hdr[G::NB];
+    __shared__ uint16_t s_perm[G::NB];
+    __shared__ uint32_t s_wc[3][G::NW];
+
+    const uint32_t img_i = a.img0 + blockIdx.z;
+    const JDImageDesc &im = a.imgs[img_i];
+    const uint32_t strip = blockIdx.x, my = blockIdx.y;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+
+    for (uint32_t i = tid; i < (uint32_t)(NC * 64); i += G::THREADS) s_q[i] = (int16_t)__ldg(a.quant + (size_t)img_i * 192 + i);
+
+    /* ---- headers + binning: class 0 = top-left 4x4 only (3-4 columns), 1 = anything else with AC, 2 = DC only ---- */
+    uint32_t cls = 3;
+    if (tid < (uint32_t)G::NB) {
+        const uint32_t ml = tid / G::BPMEFF, blk = tid - ml * G::BPMEFF;
+        const uint32_t mx = strip * MPB + ml;
+        if (mx < a.mcus_x) {
+            const jd_u64 h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
+            s_hdr[tid] = h;
+            const uint32_t n = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h);
+            cls = (n == 0u) ? 2u : ((JD_HDR_HI(h) == 0u && (cm & 0xF0u) == 0u && (cm & 0xFCu) != 0u) ? 0u : 1u);
+        }
+    }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, cls == 0u), b1 = __ballot_sync(0xffffffffu, cls == 1u), b2 = __ballot_sync(0xffffffffu, cls == 2u);
+    if (lane == 0) { s_wc[0][wid] = __popc(b0); s_wc[1][wid] = __popc(b1); s_wc[2][wid] = __popc(b2); }
+    __syncthreads();
+    uint32_t n0 = 0, n1 = 0, n2 = 0, pre = 0;
+    {
+        uint32_t before[3] = {0, 0, 0};
+#pragma unroll
+        for (int w2 = 0; w2 < G::NW; w2++) {
+            const uint32_t c0 = s_wc[0][w2], c1 = s_wc[1][w2], c2 = s_wc[2][w2];
+            if ((uint32_t)w2 < wid) { before[0] += c0; before[1] += c1; before[2] += c2; }
+            n0 += c0; n1 += c1; n2 += c2;
+        }
+        const uint32_t lt = (1u << lane) - 1u;
+        if (cls == 0u) pre = before[0] + __popc(b0 & lt);
+        else if (cls == 1u) pre = n0 + before[1] + __popc(b1 & lt);
+        else if (cls == 2u) pre = n0 + n1 + before[2] + __popc(b2 & lt);
+    }
+    if (cls < 3u) s_perm[pre] = (uint16_t)tid;
+    __syncthreads();
+    const uint32_t nact = n0 + n1 + n2;
+
+    /* ---- phases A + B: this thread's block ---- */
+    if (tid < nact) {
+        const uint32_t pb = s_perm[tid];
+        const jd_u64 h = s_hdr[pb];
+        const uint32_t ml = pb / G::BPMEFF, blk = pb - ml * G::BPMEFF;
+        const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
+        const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h);
+        const int dc = JD_HDR_DC(h);
+        const int16_t *q = s_q + comp * 64;
+        int16_t *tile = s_tile + pb * G::TSTRIDE;
+        uint8_t *prow;  /* first output row of this block in the staged plane */
+        uint32_t pstride;
+        if (comp == 0) {
+            const uint32_t lx = (HS == 2) ? (blk & 1u) : 0u;
+            const uint32_t ly = (HS == 2 && VS == 2) ? (blk >> 1) : ((VS == 2) ? blk : 0u);
+            prow = s_y + (ly * 8) * G::YSTRIDE + (ml * HS + lx) * 8; pstride = G::YSTRIDE;
+        } else {
+            prow = s_c + ((comp - 1) * 8) * G::CSTRIDE + ml * 8; pstride = G::CSTRIDE;
+        }
+        if (tid < n0) {
+            /* ---- class 0: coefficients only in rows 0-3 x columns 0-3 ---- */
+#pragma unroll
+            for (int c = 0; c < 4; c++) *reinterpret_cast<uint2 *>(tile + c * 8) = make_uint2(0, 0);
+            if (!JD_HDR_BIG(h)) {
+                for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            } else {
+                for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+            }
+            int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+                jd_unpack4(*reinterpret_cast<const uint2 *>(tile + c * 8), m);
+                jd_unpack4(*reinterpret_cast<const uint2 *>(q + c * 8), qq);
+                if (c == 0) m[0] = dc;
+                if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++) m[r] *= qq[r];
+                    jd_col_sse16(m, true, o);
+                } else {
+                    jd_col_scalar(m, qq, true, o);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const int p8[8] = {cr[r][0], cr[r][1], cr[r][2], cr[r][3], 0, 0, 0, 0};
+                int ob[8];
+                jd_row_raw(p8, 0x0Fu, ob);       /* 4-column variant (jpeg.inl:2698-2718) */
+                *reinterpret_cast<uint2 *>(prow + r * pstride) = jd_clamp_pack8(ob);
+            }
+        } else if (tid < n0 + n1) {
+            /* ---- class 1: general block; column results go back into the private tile ---- */
+#pragma unroll
+            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
+            if (!JD_HDR_BIG(h)) {
+                for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            } else {
+                for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+            }
+            const bool r47 = JD_HDR_HI(h) == 0u;
+            for (int c = 0; c < 8; c++) {
+                int m[8], qq[8], o[8];
+                jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
+                jd_unpack8(*reinterpret_cast<const uint4 *>(q + c * 8), qq);
+                if (c == 0) m[0] = dc;
+                if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) m[r] *= qq[r];
+                    jd_col_sse16(m, r47, o);
+                } else {
+                    jd_col_scalar(m, qq, r47, o);
+                }
+                uint4 w;
+                w.x = ((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16); w.y = ((uint32_t)o[2] & 0xFFFFu) | ((uint32_t)o[3] << 16);
+                w.z = ((uint32_t)o[4] & 0xFFFFu) | ((uint32_t)o[5] << 16); w.w = ((uint32_t)o[6] & 0xFFFFu) | ((uint32_t)o[7] << 16);
+                *reinterpret_cast<uint4 *>(tile + c * 8) = w;
+            }
+            for (int r = 0; r < 8; r++) {
+                int p8[8], ob[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) p8[c] = (int)tile[c * 8 + r];
+                jd_row_raw(p8, cm, ob);
+                *reinterpret_cast<uint2 *>(prow + r * pstride) = jd_clamp_pack8(ob);
+            }
+        } else {
+            /* ---- class 2: DC only (jpeg.inl:5146-5154) ---- */
+            const uint32_t v = jd_range(dc * (int)q[0]) * 0x01010101u;
+#pragma unroll
+            for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(prow + r * pstride) = make_uint2(v, v);
+        }
+    }
+    __syncthreads();
+
+    /* ---- phase C ---- */
+    const uint32_t W = a.padded ? a.mcus_x * HS * 8 : a.width;
+    const uint32_t H = a.padded ? a.mcus_y * VS * 8 : a.height;
+    jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H,
+                                                                                         a.out + im.out_off, im.out_pitch);
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -377,3 +377,47 @@ extern "C" void hostsim_idct(const int16_t *coef, const int16_t *quant, unsigned
         for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)o[c];
     }
 }
+
+/* statistics of the block classes the IDCT kernel branches on (development aid) */
+extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /* 8 */)
+{
+    JDInfo info;
+    if (!jd_parse_header(data, size, 0, &info)) return 0;
+    std::vector<uint16_t> lut(JD_LUT_ENTRIES);
+    jd_build_lut(&info, lut.data());
+    for (int i = 0; i < 64; i++) kTposW[i] = jd_tposw(kTpos[i]);
+    const int total_mcus = info.mcus_x * info.mcus_y;
+    const int mps = info.restart_interval ? info.restart_interval : total_mcus;
+    const int nseg = (total_mcus + mps - 1) / mps;
+    std::vector<uint32_t> seg_start(nseg, 0xFFFFFFFFu);
+    seg_start[0] = (uint32_t)info.scan_offset;
+    { int k = 1; for (int i = info.scan_offset; i + 1 < size && k < nseg; i++) if (data[i] == 0xFF && data[i + 1] >= 0xD0 && data[i + 1] <= 0xD7) { seg_start[k++] = (uint32_t)(i + 2); i++; } }
+    std::vector<uint32_t> padded((size + 64) / 4 + 16, 0);
+    memcpy(padded.data(), data, (size_t)size);
+    const int nblk = total_mcus * info.bpm;
+    std::vector<jd_u64> hdr(nblk, 0);
+    std::vector<uint16_t> rec((size_t)size * 4 + 1024, 0);
+    VecSink sink;
+    for (int sgi = 0; sgi < nseg; sgi++) {
+        JDSegIn in; in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
+        int m0 = sgi * mps; in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
+        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
+        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset); in.rec_cap = 1u << 30; in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
+        JDSegOut so;
+        jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+    }
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    for (int b = 0; b < nblk; b++) {
+        jd_u64 h = hdr[b];
+        uint32_t n = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h), hi = JD_HDR_HI(h);
+        out[0] += (n == 0);
+        out[1] += (n != 0 && (cm & 0xfc) == 0);
+        out[2] += (n != 0 && (cm & 0xfc) != 0 && (cm & 0xf0) == 0);
+        out[3] += ((cm & 0xf0) != 0);
+        out[4] += (n != 0 && hi == 0);
+        out[5] += (hi != 0);
+        out[6] += n;
+        out[7] += JD_HDR_BIG(h);
+    }
+    return nblk;
+}
