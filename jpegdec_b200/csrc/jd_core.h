@@ -507,8 +507,10 @@ JD_HD void jd_col_scalar(const int m[8], const int q[8], bool rows47_empty, int 
 
 /* Row pass (both builds, jpeg.inl:2681-2797).  p[c] = int16 column results of one row
  * (sign-extended); colmask = low byte of the block's u16MCUFlags.  Writes 8 pixel bytes. */
-JD_HD void jd_row_raw(const int p[8], uint32_t colmask, int o[8])
+JD_HD void jd_row_terms(const int p[8], uint32_t colmask, int t[8])
 {
+    /* t[0..3] = even part (tmp0..tmp3), t[4..7] = odd part (tmp4..tmp7); the 8 outputs are
+     * t0+t7, t1+t6, t2+t5, t3-t4, t3+t4, t2-t5, t1-t6, t0-t7 */
     int tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, tmp6, tmp7;
     if ((colmask & 0xf0u) == 0u) {
         if ((colmask & 0xfcu) == 0u) { /* 1-2 columns: approximation (:2688-2697) */
@@ -547,8 +549,15 @@ JD_HD void jd_row_raw(const int p[8], uint32_t colmask, int o[8])
         tmp5 = tmp11 - tmp6;
         tmp4 = tmp10 + tmp5;
     }
-    o[0] = tmp0 + tmp7; o[1] = tmp1 + tmp6; o[2] = tmp2 + tmp5; o[3] = tmp3 - tmp4;
-    o[4] = tmp3 + tmp4; o[5] = tmp2 - tmp5; o[6] = tmp1 - tmp6; o[7] = tmp0 - tmp7;
+    t[0] = tmp0; t[1] = tmp1; t[2] = tmp2; t[3] = tmp3; t[4] = tmp4; t[5] = tmp5; t[6] = tmp6; t[7] = tmp7;
+}
+
+JD_HD void jd_row_raw(const int p[8], uint32_t colmask, int o[8])
+{
+    int t[8];
+    jd_row_terms(p, colmask, t);
+    o[0] = t[0] + t[7]; o[1] = t[1] + t[6]; o[2] = t[2] + t[5]; o[3] = t[3] - t[4];
+    o[4] = t[3] + t[4]; o[5] = t[2] - t[5]; o[6] = t[1] - t[6]; o[7] = t[0] - t[7];
 }
 
 JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])

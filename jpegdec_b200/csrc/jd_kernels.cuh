@@ -466,7 +466,7 @@ __device__ __forceinline__ uint32_t jd_pixel_scalar(int Y12, int cb, int cr, boo
 
 /* Phase C of the fused kernels (full size): colour conversion of the staged planes + coalesced 16-byte scanline stores.
  * s_y: (VS*8) rows x YSTRIDE luma bytes, s_cb/s_cr: 8 rows x CSTRIDE chroma bytes, covering WCTA pixels of MCU row `my`. */
-template <int HS, int VS, int NC, int PT, int ARITH, int WCTA, int YSTRIDE, int CSTRIDE, int NTHREADS>
+template <int HS, int VS, int NC, int PT, int ARITH, int WCTA, int YSTRIDE, int CSTRIDE, int NTHREADS, bool INTERIOR = false>
 __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8_t *s_y, const uint8_t *s_cb, const uint8_t *s_cr,
                                                 uint32_t strip, uint32_t my, uint32_t tid, uint32_t W, uint32_t H,
                                                 uint8_t *outbase, uint32_t pitch)
@@ -480,8 +480,8 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
     for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) {
         const uint32_t rg = it / IPR, xg = it - rg * IPR;
         const uint32_t gx = strip * WCTA + xg * PXI;
-        if (gx >= W) continue;
-        const bool full = (gx + PXI <= W);
+        if (!INTERIOR && gx >= W) continue;
+        const bool full = INTERIOR || (gx + PXI <= W);
         /* chroma samples covering these PXI pixels: PXI / HS of each */
         uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
         if (NC == 3 && PT != JD_PT_GRAY) {
@@ -512,7 +512,7 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
         for (int vr = 0; vr < VS; vr++) {
             const uint32_t row = rg * VS + vr;
             const uint32_t gy = my * (VS * 8) + row;
-            if (gy >= H) continue;
+            if (!INTERIOR && gy >= H) continue;
             uint32_t yw[4];
             {
                 const uint8_t *py = s_y + row * YSTRIDE + xg * PXI;
@@ -568,7 +568,7 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
                 }
             }
             uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
-            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+            if (INTERIOR || (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0))) {
                 *reinterpret_cast<uint4 *>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             } else {
                 for (uint32_t i = 0; i < (uint32_t)PXI && gx + i < W; i++) {
@@ -749,12 +749,22 @@ __device__ __forceinline__ void jd_unpack4(const uint2 v, int m[4])
     m[2] = (int)(short)(v.y & 0xFFFF); m[3] = (int)v.y >> 16;
 }
 
-__device__ __forceinline__ uint2 jd_clamp_pack8(const int ob[8])
+/* The 8 butterflies that end a row pass + the ucRangeTable clamp, two pixels per instruction.  Only bits 5..14 of a row
+ * output reach the range table (10-bit index, jpeg.inl:2721-2797), so 16-bit lanes are exact.  The caller has added
+ * JD_ROW_BIAS = (128 + 384) << 5 to the row's DC term (it enters every output with weight 1), which makes the 10-bit
+ * field non-negative: pixel = clamp(field - 384, 0, 255) -- one VIADDMNMX.S16x2.RELU per pixel pair. */
+#define JD_ROW_BIAS 16384
+__device__ __forceinline__ uint32_t jd_clamp2(uint32_t v)
 {
-    int t[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) t[i] = ((ob[i] << 17) >> 22) + 128; /* ucRangeTable as arithmetic; the packs saturate */
-    return make_uint2(jd_pack_sat(t[1], t[0], jd_pack_sat(t[3], t[2], 0u)), jd_pack_sat(t[5], t[4], jd_pack_sat(t[7], t[6], 0u)));
+    return __viaddmin_s16x2_relu((v >> 5) & 0x03FF03FFu, 0xFE80FE80u, 0x00FF00FFu);
+}
+__device__ __forceinline__ uint2 jd_row_finish_packed(const int t[8])
+{
+    const uint32_t a01 = __byte_perm((uint32_t)t[0], (uint32_t)t[1], 0x5410), a23 = __byte_perm((uint32_t)t[2], (uint32_t)t[3], 0x5410);
+    const uint32_t b76 = __byte_perm((uint32_t)t[7], (uint32_t)t[6], 0x5410), b54 = __byte_perm((uint32_t)t[5], (uint32_t)(-t[4]), 0x5410);
+    const uint32_t s01 = jd_clamp2(__vadd2(a01, b76)), s23 = jd_clamp2(__vadd2(a23, b54)); /* o0,o1 | o2,o3 */
+    const uint32_t d76 = jd_clamp2(__vsub2(a01, b76)), d54 = jd_clamp2(__vsub2(a23, b54)); /* o7,o6 | o5,o4 */
+    return make_uint2(__byte_perm(s01, s23, 0x6420), __byte_perm(d54, d76, 0x4602));
 }
 
 template <int HS, int VS, int NC, int MPB, int PT, int ARITH>
@@ -765,20 +775,17 @@ jdk_idct_tb(const JDIdctArgs a)
     __shared__ __align__(16) int16_t s_tile[G::NB * G::TSTRIDE];
     __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
     __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
-    __shared__ __align__(16) int16_t s_q[NC * 64];      /* column-major prescaled quant */
     __shared__ jd_u64 s_hdr[G::NB];
     __shared__ uint16_t s_perm[G::NB];
-    __shared__ uint32_t s_wc[3][G::NW];
+    __shared__ uint32_t s_wc[2][G::NW];
 
     const uint32_t img_i = a.img0 + blockIdx.z;
     const JDImageDesc &im = a.imgs[img_i];
     const uint32_t strip = blockIdx.x, my = blockIdx.y;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
-    for (uint32_t i = tid; i < (uint32_t)(NC * 64); i += G::THREADS) s_q[i] = (int16_t)__ldg(a.quant + (size_t)img_i * 192 + i);
-
-    /* ---- headers + binning: class 0 = top-left 4x4 only (3-4 columns), 1 = anything else with AC, 2 = DC only ---- */
-    uint32_t cls = 3;
+    /* ---- headers + binning: the blocks whose coefficients sit in the top-left 4x4 (3-4 columns) first, the rest after ---- */
+    uint32_t cls = 2;
     if (tid < (uint32_t)G::NB) {
         const uint32_t ml = tid / G::BPMEFF, blk = tid - ml * G::BPMEFF;
         const uint32_t mx = strip * MPB + ml;
@@ -786,39 +793,37 @@ jdk_idct_tb(const JDIdctArgs a)
             const jd_u64 h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
             s_hdr[tid] = h;
             const uint32_t n = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h);
-            cls = (n == 0u) ? 2u : ((JD_HDR_HI(h) == 0u && (cm & 0xF0u) == 0u && (cm & 0xFCu) != 0u) ? 0u : 1u);
+            cls = (n != 0u && JD_HDR_HI(h) == 0u && (cm & 0xF0u) == 0u && (cm & 0xFCu) != 0u) ? 0u : 1u;
         }
     }
-    const uint32_t b0 = __ballot_sync(0xffffffffu, cls == 0u), b1 = __ballot_sync(0xffffffffu, cls == 1u), b2 = __ballot_sync(0xffffffffu, cls == 2u);
-    if (lane == 0) { s_wc[0][wid] = __popc(b0); s_wc[1][wid] = __popc(b1); s_wc[2][wid] = __popc(b2); }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, cls == 0u), b1 = __ballot_sync(0xffffffffu, cls == 1u);
+    if (lane == 0) { s_wc[0][wid] = __popc(b0); s_wc[1][wid] = __popc(b1); }
     __syncthreads();
-    uint32_t n0 = 0, n1 = 0, n2 = 0, pre = 0;
+    uint32_t n0 = 0, n1 = 0, pre = 0;
     {
-        uint32_t before[3] = {0, 0, 0};
+        uint32_t before0 = 0, before1 = 0;
 #pragma unroll
         for (int w2 = 0; w2 < G::NW; w2++) {
-            const uint32_t c0 = s_wc[0][w2], c1 = s_wc[1][w2], c2 = s_wc[2][w2];
-            if ((uint32_t)w2 < wid) { before[0] += c0; before[1] += c1; before[2] += c2; }
-            n0 += c0; n1 += c1; n2 += c2;
+            const uint32_t c0 = s_wc[0][w2], c1 = s_wc[1][w2];
+            if ((uint32_t)w2 < wid) { before0 += c0; before1 += c1; }
+            n0 += c0; n1 += c1;
         }
         const uint32_t lt = (1u << lane) - 1u;
-        if (cls == 0u) pre = before[0] + __popc(b0 & lt);
-        else if (cls == 1u) pre = n0 + before[1] + __popc(b1 & lt);
-        else if (cls == 2u) pre = n0 + n1 + before[2] + __popc(b2 & lt);
+        pre = (cls == 0u) ? before0 + __popc(b0 & lt) : n0 + before1 + __popc(b1 & lt);
     }
-    if (cls < 3u) s_perm[pre] = (uint16_t)tid;
+    if (cls < 2u) s_perm[pre] = (uint16_t)tid;
     __syncthreads();
-    const uint32_t nact = n0 + n1 + n2;
+    const uint32_t nact = n0 + n1;
 
-    /* ---- phases A + B: this thread's block ---- */
-    if (tid < nact) {
+    /* ---- phases A + B, common class: this thread's block ---- */
+    if (tid < n0) {
         const uint32_t pb = s_perm[tid];
         const jd_u64 h = s_hdr[pb];
         const uint32_t ml = pb / G::BPMEFF, blk = pb - ml * G::BPMEFF;
         const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
-        const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h);
+        const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
         const int dc = JD_HDR_DC(h);
-        const int16_t *q = s_q + comp * 64;
+        const int32_t *q = a.quant + (size_t)img_i * 192 + comp * 64;   /* L1-resident */
         int16_t *tile = s_tile + pb * G::TSTRIDE;
         uint8_t *prow;  /* first output row of this block in the staged plane */
         uint32_t pstride;
@@ -829,78 +834,111 @@ jdk_idct_tb(const JDIdctArgs a)
         } else {
             prow = s_c + ((comp - 1) * 8) * G::CSTRIDE + ml * 8; pstride = G::CSTRIDE;
         }
-        if (tid < n0) {
-            /* ---- class 0: coefficients only in rows 0-3 x columns 0-3 ---- */
 #pragma unroll
-            for (int c = 0; c < 4; c++) *reinterpret_cast<uint2 *>(tile + c * 8) = make_uint2(0, 0);
-            if (!JD_HDR_BIG(h)) {
-                for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
-            } else {
-                for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
-            }
-            int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                int m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
-                jd_unpack4(*reinterpret_cast<const uint2 *>(tile + c * 8), m);
-                jd_unpack4(*reinterpret_cast<const uint2 *>(q + c * 8), qq);
-                if (c == 0) m[0] = dc;
-                if (ARITH == JPEG_ARITH_SSE2) {
-#pragma unroll
-                    for (int r = 0; r < 4; r++) m[r] *= qq[r];
-                    jd_col_sse16(m, true, o);
-                } else {
-                    jd_col_scalar(m, qq, true, o);
-                }
-#pragma unroll
-                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
-            }
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int p8[8] = {cr[r][0], cr[r][1], cr[r][2], cr[r][3], 0, 0, 0, 0};
-                int ob[8];
-                jd_row_raw(p8, 0x0Fu, ob);       /* 4-column variant (jpeg.inl:2698-2718) */
-                *reinterpret_cast<uint2 *>(prow + r * pstride) = jd_clamp_pack8(ob);
-            }
-        } else if (tid < n0 + n1) {
-            /* ---- class 1: general block; column results go back into the private tile ---- */
-#pragma unroll
-            for (int c = 0; c < 8; c++) *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
-            if (!JD_HDR_BIG(h)) {
-                for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
-            } else {
-                for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
-            }
-            const bool r47 = JD_HDR_HI(h) == 0u;
-            for (int c = 0; c < 8; c++) {
-                int m[8], qq[8], o[8];
-                jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
-                jd_unpack8(*reinterpret_cast<const uint4 *>(q + c * 8), qq);
-                if (c == 0) m[0] = dc;
-                if (ARITH == JPEG_ARITH_SSE2) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) m[r] *= qq[r];
-                    jd_col_sse16(m, r47, o);
-                } else {
-                    jd_col_scalar(m, qq, r47, o);
-                }
-                uint4 w;
-                w.x = ((uint32_t)o[0] & 0xFFFFu) | ((uint32_t)o[1] << 16); w.y = ((uint32_t)o[2] & 0xFFFFu) | ((uint32_t)o[3] << 16);
-                w.z = ((uint32_t)o[4] & 0xFFFFu) | ((uint32_t)o[5] << 16); w.w = ((uint32_t)o[6] & 0xFFFFu) | ((uint32_t)o[7] << 16);
-                *reinterpret_cast<uint4 *>(tile + c * 8) = w;
-            }
-            for (int r = 0; r < 8; r++) {
-                int p8[8], ob[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) p8[c] = (int)tile[c * 8 + r];
-                jd_row_raw(p8, cm, ob);
-                *reinterpret_cast<uint2 *>(prow + r * pstride) = jd_clamp_pack8(ob);
-            }
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint2 *>(tile + c * 8) = make_uint2(0, 0);
+        if (!JD_HDR_BIG(h)) {
+            for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
         } else {
-            /* ---- class 2: DC only (jpeg.inl:5146-5154) ---- */
-            const uint32_t v = jd_range(dc * (int)q[0]) * 0x01010101u;
+            for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+        }
+        int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
 #pragma unroll
-            for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(prow + r * pstride) = make_uint2(v, v);
+        for (int c = 0; c < 4; c++) {
+            int m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+            jd_unpack4(*reinterpret_cast<const uint2 *>(tile + c * 8), m);
+            { const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(q + c * 8)); qq[0] = (int)qv.x; qq[1] = (int)qv.y; qq[2] = (int)qv.z; qq[3] = (int)qv.w; }
+            if (c == 0) m[0] = dc;
+            if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) m[r] *= qq[r];
+                if (c == 0) m[0] += JD_ROW_BIAS;   /* mod 2^16, additive through both passes */
+                jd_col_sse16(m, true, o);
+            } else {
+                jd_col_scalar(m, qq, true, o);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int p8[8] = {cr[r][0] + (ARITH == JPEG_ARITH_SSE2 ? 0 : JD_ROW_BIAS), cr[r][1], cr[r][2], cr[r][3], 0, 0, 0, 0};
+            int t8[8];
+            jd_row_terms(p8, 0x0Fu, t8);     /* 4-column variant (jpeg.inl:2698-2718) */
+            *reinterpret_cast<uint2 *>(prow + r * pstride) = jd_row_finish_packed(t8);
+        }
+    }
+    /* ---- phases A + B, every other block: 8 lanes per block (lane = column, then row), 4 blocks per warp pass.
+     * The passes go to the warps that hold no common-class block when there are such warps (they would otherwise idle
+     * at the barrier), else round-robin over all warps. ---- */
+    {
+        const uint32_t npass = (n1 + 3u) >> 2;
+        const uint32_t busy = (n0 + 31u) >> 5;
+        const uint32_t nfree = (busy < (uint32_t)G::NW) ? (uint32_t)G::NW - busy : 0u;
+        const uint32_t first = nfree ? wid - busy : wid, step = nfree ? nfree : (uint32_t)G::NW;
+        if (!nfree || wid >= busy) {
+            const uint32_t c = lane & 7u;
+            for (uint32_t j = first; j < npass; j += step) {
+                const uint32_t oi = j * 4u + (lane >> 3);
+                const bool valid = oi < n1;
+                const uint32_t pb = valid ? s_perm[n0 + oi] : 0u;
+                const jd_u64 h = valid ? s_hdr[pb] : 0;
+                const uint32_t ml = pb / G::BPMEFF, blk = pb - ml * G::BPMEFF;
+                const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
+                const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
+                const int dc = JD_HDR_DC(h);
+                const int32_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
+                int16_t *tile = s_tile + pb * G::TSTRIDE;
+                uint2 px;
+                if (__all_sync(0xffffffffu, ncoef == 0u)) {
+                    /* DC only (jpeg.inl:5146-5154) */
+                    px.x = px.y = jd_range(dc * __ldg(qg)) * 0x01010101u;
+                } else {
+                    if (valid) *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
+                    const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8));
+                    const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
+                    __syncwarp();
+                    if (!JD_HDR_BIG(h)) {
+                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+                    } else {
+                        for (uint32_t i = c; i < ncoef; i += 8) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+                    }
+                    __syncwarp();
+                    int m[8], o[8];
+                    const int qq[8] = {(int)q0.x, (int)q0.y, (int)q0.z, (int)q0.w, (int)q1.x, (int)q1.y, (int)q1.z, (int)q1.w};
+                    if (valid) jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
+                    else { for (int r = 0; r < 8; r++) m[r] = 0; }
+                    if (c == 0) m[0] = dc;
+                    const bool r47 = JD_HDR_HI(h) == 0u;
+                    if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) m[r] *= qq[r];
+                        jd_col_sse16(m, r47, o);
+                    } else {
+                        jd_col_scalar(m, qq, r47, o);
+                    }
+                    __syncwarp();
+                    if (valid) {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) tile[r * 8 + c] = (int16_t)o[r];
+                    }
+                    __syncwarp();
+                    int p8[8], t8[8];
+                    if (valid) jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), p8);
+                    else { for (int r = 0; r < 8; r++) p8[r] = 0; }
+                    p8[0] += JD_ROW_BIAS;
+                    jd_row_terms(p8, JD_HDR_COLMASK(h), t8);
+                    px = jd_row_finish_packed(t8);
+                }
+                if (valid) {
+                    if (comp == 0) {
+                        const uint32_t lx = (HS == 2) ? (blk & 1u) : 0u;
+                        const uint32_t ly = (HS == 2 && VS == 2) ? (blk >> 1) : ((VS == 2) ? blk : 0u);
+                        *reinterpret_cast<uint2 *>(s_y + (ly * 8 + c) * G::YSTRIDE + (ml * HS + lx) * 8) = px;
+                    } else {
+                        *reinterpret_cast<uint2 *>(s_c + ((comp - 1) * 8 + c) * G::CSTRIDE + ml * 8) = px;
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -908,8 +946,12 @@ jdk_idct_tb(const JDIdctArgs a)
     /* ---- phase C ---- */
     const uint32_t W = a.padded ? a.mcus_x * HS * 8 : a.width;
     const uint32_t H = a.padded ? a.mcus_y * VS * 8 : a.height;
-    jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H,
-                                                                                         a.out + im.out_off, im.out_pitch);
+    uint8_t *outbase = a.out + im.out_off;
+    const uint32_t pitch = im.out_pitch;
+    if ((strip + 1) * G::WCTA <= W && (my + 1) * G::HCTA <= H && ((reinterpret_cast<uintptr_t>(outbase) | pitch) & 15u) == 0u)
+        jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, true>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H, outbase, pitch);
+    else
+        jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, false>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H, outbase, pitch);
 }
 
 /* ------------------------------------------------------------------------------------ */
