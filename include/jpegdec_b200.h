@@ -99,11 +99,16 @@ int JPEGB200_batchGetTimings(JPEGB200_BATCH *b, float *ms /* JPEGB200_NUM_TIMING
 int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters /* JPEGB200_NUM_COUNTERS */);
 void *JPEGB200_batchStream(JPEGB200_BATCH *b);          /* cudaStream_t the job runs on */
 
-/* One-call convenience: create + upload + decode + (download) + wait + destroy.
- * outs[i]: destination (host, or device with JPEGB200_OUT_DEVICE); pitches may be NULL (tight). */
+/* One call for a whole batch: create + upload + decode + (download) + wait + destroy.
+ * outs[i]: destination (host, or device with JPEGB200_OUT_DEVICE); pitches may be NULL (tight).
+ * With host outputs the batch is run as a pipeline of smaller jobs on separate streams, so the pixels of one job
+ * cross PCIe while the next job's kernels run (the reference equivalent is a loop of JPEG_openRAM + JPEG_decode,
+ * src/JPEGDEC.cpp:157-224).  Returns 1 = all images decoded, 2 = some images failed (see status[]), 0 = call failed. */
 int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
                          int pixel_type, int options, void *const *outs, const int64_t *pitches,
                          int flags, int32_t *status);
+/* JPEGB200_NUM_COUNTERS counters summed over the jobs of the last JPEGB200_decodeBatch on this context */
+int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters);
 
 /* ---- shared-table blob (multi-GPU: rank 0 exports, NCCL broadcast, other ranks import) ---- */
 #define JPEGB200_TABLE_BLOB_BYTES (6400 * 2 + 3 * 64 * 2 + 16)

@@ -111,6 +111,7 @@ def lib():
     L.JPEGB200_batchStream.restype = vp
     L.JPEGB200_decodeBatch.argtypes = [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(vp), C.POINTER(C.c_int64), C.c_int, i32p]
+    L.JPEGB200_lastCallCounters.argtypes = [vp, C.POINTER(C.c_int64)]
     L.JPEGB200_exportTables.argtypes = [C.c_char_p, C.c_int, vp]
     L.JPEGB200_setSharedTables.argtypes = [vp, vp]
     L.JPEGB200_sharedTableHits.argtypes = [vp]
@@ -285,6 +286,21 @@ class Batch:
         if self.h:
             lib().JPEGB200_batchDestroy(self.h)
             self.h = None
+
+
+def decode_batch(ctx, ptrs, sizes, pixel_type, options, outs, pitches=None, flags=0):
+    """JPEGB200_decodeBatch: one call for n files (host pointers) -> n outputs (host pointers, or device pointers with
+    JPEGB200_OUT_DEVICE).  Returns (rc, per-image status list, counters summed over the internal jobs)."""
+    n = len(ptrs)
+    pa = (C.c_void_p * n)(*ptrs)
+    sa = (C.c_int32 * n)(*sizes)
+    oa = (C.c_void_p * n)(*outs)
+    pi = (C.c_int64 * n)(*pitches) if pitches is not None else None
+    st = (C.c_int32 * n)()
+    rc = lib().JPEGB200_decodeBatch(ctx.h, pa, sa, n, pixel_type, options, oa, pi, flags, st)
+    cnt = (C.c_int64 * len(COUNTER_NAMES))()
+    lib().JPEGB200_lastCallCounters(ctx.h, cnt)
+    return rc, list(st), dict(zip(COUNTER_NAMES, list(cnt)))
 
 
 def decode_batch_to_host(ctx, jpegs, pixel_type, options=0):

@@ -48,6 +48,25 @@ struct JDPool {
     void drain() { for (auto &s : free_) cudaFree(s.p); free_.clear(); }
 };
 
+/* Pinned host staging blocks (status read-back) recycled the same way: a D2H copy into pageable memory would make
+ * batchDownload wait for the whole job, which is what keeps several jobs from being in flight from one host thread. */
+struct JDPinPool {
+    struct Slot { void *p; size_t bytes; };
+    std::vector<Slot> free_;
+    void *get(size_t bytes, size_t *got)
+    {
+        for (size_t i = 0; i < free_.size(); i++)
+            if (free_[i].bytes >= bytes) { void *q = free_[i].p; *got = free_[i].bytes; free_.erase(free_.begin() + i); return q; }
+        void *q = nullptr;
+        size_t need = (bytes + 4095) & ~(size_t)4095;
+        if (cudaHostAlloc(&q, need, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *got = need;
+        return q;
+    }
+    void put(void *p, size_t bytes) { free_.push_back(Slot{p, bytes}); }
+    void drain() { for (auto &s : free_) cudaFreeHost(s.p); free_.clear(); }
+};
+
 struct JPEGB200_CTX {
     int device;
     int arith;
@@ -57,6 +76,8 @@ struct JPEGB200_CTX {
     uint16_t shared_lut[JD_LUT_ENTRIES];
     int shared_hits;
     JDPool pool;
+    JDPinPool pinpool;
+    int64_t last_counters[JPEGB200_NUM_COUNTERS]; /* summed over the jobs of the last JPEGB200_decodeBatch */
 };
 
 static JDPool *g_cur_pool = nullptr; /* pool of the context whose batch is being set up (calls are serialised per context) */
@@ -112,7 +133,9 @@ struct JPEGB200_BATCH {
     DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
     DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
     DevBuf<uint32_t> d_err_off;
-    std::vector<JDImageDesc> descs_dl; /* descriptors read back (status, err_mcu) */
+    JDImageDesc *descs_dl;             /* descriptors read back (status, err_mcu); pinned, from ctx->pinpool */
+    size_t descs_dl_bytes;
+    bool downloaded;
     DevBuf<JDImageDesc> d_descs;
     DevBuf<int32_t> d_quant;
     DevBuf<uint16_t> d_luts, d_rec;
@@ -131,7 +154,7 @@ struct JPEGB200_BATCH {
     bool have_ev;
     float ms[JPEGB200_NUM_TIMINGS];
     int64_t counters[JPEGB200_NUM_COUNTERS];
-    uint32_t h_counters[4];
+    uint32_t *h_counters;              /* 4 words at the end of the descs_dl block */
 };
 
 static char *ctx_err() { return g_err; }
@@ -171,6 +194,7 @@ extern "C" JPEGB200_CTX *JPEGB200_create(int device, int arith_mode)
     c->err[0] = 0;
     c->has_shared = false;
     c->shared_hits = 0;
+    memset(c->last_counters, 0, sizeof(c->last_counters));
     return c;
 }
 
@@ -180,6 +204,7 @@ extern "C" void JPEGB200_destroy(JPEGB200_CTX *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->pool.drain();
+    ctx->pinpool.drain();
     delete ctx;
 }
 
@@ -242,6 +267,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
     b->ptclass = (pixel_type == RGB8888) ? JD_PT_8888 : (b->gray_out ? JD_PT_GRAY : JD_PT_565);
     b->dither_bits = (pixel_type == FOUR_BIT_DITHERED) ? 4 : (pixel_type == TWO_BIT_DITHERED) ? 2 : (pixel_type == ONE_BIT_DITHERED) ? 1 : 0;
     b->stream = nullptr;
+    b->descs_dl = nullptr; b->descs_dl_bytes = 0; b->downloaded = false; b->h_counters = nullptr;
     b->nchunks = 0;
     b->uploaded = false; b->out_device = false; b->arena_owned = false; b->have_ev = false;
     memset(b->ms, 0, sizeof(b->ms));
@@ -389,6 +415,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     b->d_counters.release(); b->d_blk_hdr.release(); b->d_events.release();
     if (b->have_ev) for (auto &e : b->ev) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->descs_dl) b->ctx->pinpool.put(b->descs_dl, b->descs_dl_bytes);
     delete b;
 }
 
@@ -788,9 +815,14 @@ extern "C" int JPEGB200_batchDownload(JPEGB200_BATCH *b)
             }
         }
     }
-    b->descs_dl.resize(b->n);
-    CK(cudaMemcpyAsync(b->descs_dl.data(), b->d_descs.p, sizeof(JDImageDesc) * b->n, cudaMemcpyDeviceToHost, st));
+    if (!b->descs_dl) {
+        b->descs_dl = (JDImageDesc *)b->ctx->pinpool.get(sizeof(JDImageDesc) * b->n + 16, &b->descs_dl_bytes);
+        if (!b->descs_dl) { snprintf(g_err, sizeof(g_err), "pinned status buffer allocation failed"); return 0; }
+        b->h_counters = (uint32_t *)(b->descs_dl + b->n);
+    }
+    CK(cudaMemcpyAsync(b->descs_dl, b->d_descs.p, sizeof(JDImageDesc) * b->n, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    b->downloaded = true;
     bytes += (int64_t)sizeof(JDImageDesc) * b->n + 16;
     CK(cudaEventRecord(b->ev[9], st));
     b->counters[JPEGB200_C_D2H_BYTES] = bytes;
@@ -806,11 +838,11 @@ extern "C" int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status)
     int all_ok = 1;
     for (int i = 0; i < b->n; i++) {
         int st = b->parse_status[i];
-        if (st == JPEG_SUCCESS && (int)b->descs_dl.size() == b->n && b->descs_dl[i].status != 0) st = JPEG_DECODE_ERROR; /* jpeg.inl:5354 */
+        if (st == JPEG_SUCCESS && b->downloaded && b->descs_dl[i].status != 0) st = JPEG_DECODE_ERROR; /* jpeg.inl:5354 */
         if (status) status[i] = st;
         if (st != JPEG_SUCCESS) all_ok = 0;
     }
-    b->counters[JPEGB200_C_EVENTS] = b->h_counters[1];
+    if (b->downloaded) b->counters[JPEGB200_C_EVENTS] = b->h_counters[1];
     float t;
     auto el = [&](int a, int c) { t = 0; cudaEventElapsedTime(&t, b->ev[a], b->ev[c]); return t; };
     b->ms[JPEGB200_T_H2D] = el(0, 1);
@@ -828,7 +860,7 @@ extern "C" int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status)
 extern "C" int JPEGB200_batchErrMcu(JPEGB200_BATCH *b, int i)
 {
     if (!b || i < 0 || i >= b->n) return -1;
-    if ((int)b->descs_dl.size() != b->n) return -1;
+    if (!b->downloaded) return -1;
     return b->descs_dl[i].status ? (int)b->descs_dl[i].err_mcu : -1;
 }
 
@@ -846,17 +878,65 @@ extern "C" int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters)
     return 1;
 }
 
+/* One call for a whole batch.  With host outputs the batch is cut into jobs of JD_PIPE_IMAGES images, each on its own
+ * stream, all enqueued before the first wait: job k's pixels cross PCIe while job k+1's kernels run and job k+2's
+ * compressed bytes go up, so the call costs about one D2H of the pixels instead of H2D + kernels + D2H. */
+#define JD_PIPE_IMAGES 64
+#define JD_PIPE_MIN_BYTES ((int64_t)64 << 20)
 extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
                                     int pixel_type, int options, void *const *outs, const int64_t *pitches,
                                     int flags, int32_t *status)
 {
-    JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas, sizes, n, pixel_type, options);
-    if (!b) return 0;
-    for (int i = 0; i < n; i++) JPEGB200_batchSetOutput(b, i, outs ? outs[i] : nullptr, pitches ? pitches[i] : 0);
-    int rc = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, flags) && JPEGB200_batchDownload(b);
-    if (rc) rc = JPEGB200_batchWait(b, status);
-    JPEGB200_batchDestroy(b);
-    return rc;
+    if (!ctx || n <= 0) return 0;
+    memset(ctx->last_counters, 0, sizeof(ctx->last_counters));
+    std::vector<JPEGB200_BATCH *> jobs;
+    std::vector<int> first;
+    int rc = 1;
+    for (int i0 = 0; i0 < n && rc;) {
+        int cnt = n - i0;
+        if (!(flags & JPEGB200_OUT_DEVICE) && cnt > JD_PIPE_IMAGES) {
+            /* grow the job until it holds JD_PIPE_IMAGES images and JD_PIPE_MIN_BYTES of pixels (estimated from the first image) */
+            cnt = JD_PIPE_IMAGES;
+        }
+        JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas + i0, sizes + i0, cnt, pixel_type, options);
+        if (!b) { rc = 0; break; }
+        if (!(flags & JPEGB200_OUT_DEVICE) && i0 + cnt < n) {
+            int64_t ob = 0;
+            for (int i = 0; i < cnt; i++) { int64_t pb = 0; ob += JPEGB200_batchOutputBytes(b, i, &pb); }
+            if (ob < JD_PIPE_MIN_BYTES) { /* small images: redo with a job big enough to keep the kernels efficient */
+                int64_t per = ob > 0 ? (ob + cnt - 1) / cnt : 1;
+                int64_t want = (JD_PIPE_MIN_BYTES + per - 1) / per;
+                int cnt2 = (int)(want < (int64_t)(n - i0) ? want : (int64_t)(n - i0));
+                if (cnt2 > cnt) {
+                    JPEGB200_batchDestroy(b);
+                    cnt = cnt2;
+                    b = JPEGB200_batchCreate(ctx, datas + i0, sizes + i0, cnt, pixel_type, options);
+                    if (!b) { rc = 0; break; }
+                }
+            }
+        }
+        jobs.push_back(b); first.push_back(i0);
+        for (int i = 0; i < cnt; i++) JPEGB200_batchSetOutput(b, i, outs ? outs[i0 + i] : nullptr, pitches ? pitches[i0 + i] : 0);
+        rc = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, flags) && JPEGB200_batchDownload(b);
+        i0 += cnt;
+    }
+    int all = rc ? 1 : 0;
+    for (size_t k = 0; k < jobs.size(); k++) {
+        if (rc) {
+            const int r = JPEGB200_batchWait(jobs[k], status ? status + first[k] : nullptr);
+            if (r == 0) all = 0; else if (r == 2 && all == 1) all = 2;
+            for (int c = 0; c < JPEGB200_NUM_COUNTERS; c++) ctx->last_counters[c] += jobs[k]->counters[c];
+        }
+        JPEGB200_batchDestroy(jobs[k]);
+    }
+    return all;
+}
+
+extern "C" int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters)
+{
+    if (!ctx || !counters) return 0;
+    memcpy(counters, ctx->last_counters, sizeof(ctx->last_counters));
+    return 1;
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -740,7 +740,8 @@ struct JDGeoTB {
     static constexpr int HCTA = VS * 8;
     static constexpr int YSTRIDE = WCTA + 16;
     static constexpr int CSTRIDE = MPB * 8 + 8;
-    static constexpr int TSTRIDE = 72;                            /* int16 per private tile (144 B: conflict-free LDS.128 per quarter warp) */
+    static constexpr int TSTRIDE = 72;                            /* int16 per full tile (144 B: conflict-free LDS.128 per quarter warp) */
+    static constexpr int T0STRIDE = 36;                           /* int16 per 4-column tile (72 B: conflict-free LDS.64 per half warp) */
 };
 
 __device__ __forceinline__ void jd_unpack4(const uint2 v, int m[4])
@@ -772,7 +773,8 @@ __global__ void __launch_bounds__(JDGeoTB<HS, VS, NC, MPB>::THREADS)
 jdk_idct_tb(const JDIdctArgs a)
 {
     using G = JDGeoTB<HS, VS, NC, MPB>;
-    __shared__ __align__(16) int16_t s_tile[G::NB * G::TSTRIDE];
+    __shared__ __align__(16) int16_t s_tile0[G::NB * G::T0STRIDE];          /* common class: 4 columns x 4 rows, one per thread */
+    __shared__ __align__(16) int16_t s_tileL[G::NW * 4 * G::TSTRIDE];       /* 8-lane mode: 4 full tiles per warp */
     __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
     __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
     __shared__ jd_u64 s_hdr[G::NB];
@@ -824,7 +826,7 @@ jdk_idct_tb(const JDIdctArgs a)
         const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
         const int dc = JD_HDR_DC(h);
         const int32_t *q = a.quant + (size_t)img_i * 192 + comp * 64;   /* L1-resident */
-        int16_t *tile = s_tile + pb * G::TSTRIDE;
+        int16_t *tile = s_tile0 + tid * G::T0STRIDE;   /* positions c * 8 + r, c < 4, r < 4 */
         uint8_t *prow;  /* first output row of this block in the staged plane */
         uint32_t pstride;
         if (comp == 0) {
@@ -887,7 +889,7 @@ jdk_idct_tb(const JDIdctArgs a)
                 const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
                 const int dc = JD_HDR_DC(h);
                 const int32_t *qg = a.quant + (size_t)img_i * 192 + comp * 64;
-                int16_t *tile = s_tile + pb * G::TSTRIDE;
+                int16_t *tile = s_tileL + (wid * 4u + (lane >> 3)) * G::TSTRIDE;
                 uint2 px;
                 if (__all_sync(0xffffffffu, ncoef == 0u)) {
                     /* DC only (jpeg.inl:5146-5154) */

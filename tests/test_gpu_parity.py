@@ -288,3 +288,31 @@ def test_restart_free_scans_chunk_parallel(ctxs):
                 data, w, h = cases[n]
                 rc, want = T.oracle_decode(data, pt, 0, arith, w, h)
                 assert rc == 1 and np.array_equal(o, want), (n, arith, pt)
+
+
+def test_one_call_decode_batch_pipelines_jobs_and_matches_the_single_job_path(ctxs):
+    """JPEGB200_decodeBatch with host outputs cuts the batch into jobs on separate streams (more than 64 images, and
+    small images so that a job is grown to hold enough pixels); every image must equal the one-job result, a corrupt
+    file must get its own status at its own index, and the summed counters must cover every image."""
+    ref = _ref("sse")
+    base = [synth.synth_jpeg(160 + 16 * (s % 5), 96 + 8 * (s % 3), s, 70 + s % 20) for s in range(12)]
+    big = [synth.synth_jpeg(1920, 1080, 100 + s, 75) for s in range(3)]
+    jp = [base[i % 12] for i in range(200)] + [big[i % 3] for i in range(70)]
+    bad = 137
+    jp[bad] = jp[bad][:200]
+    want, st_want, _, _ = J.decode_batch_to_host(ctxs[0], jp, J.RGB8888, 0)
+    bufs = [np.frombuffer(j, dtype=np.uint8) for j in jp]
+    outs = [np.zeros_like(w) if w is not None else np.zeros(16, dtype=np.uint8) for w in want]
+    pitches = [int(o.shape[1]) if o.ndim == 2 else 0 for o in outs]
+    rc, st, cnt = J.decode_batch(ctxs[0], [b.ctypes.data for b in bufs], [len(b) for b in bufs], J.RGB8888, 0,
+                                 [o.ctypes.data for o in outs], pitches)
+    assert rc == 2 and st == st_want and st[bad] != 0 and sum(1 for x in st if x) == 1
+    for i, (o, w) in enumerate(zip(outs, want)):
+        if w is not None and st[i] == 0:
+            assert np.array_equal(o, w), i
+    assert cnt["output_bytes"] == sum(int(w.size) for w in want if w is not None)
+    assert cnt["launches"] >= 10           # several jobs ran
+    if ref is not None:
+        for i in (0, 7, 199, 200, 269):
+            rc1, err, img, _ = ref.decode_cb(jp[i], J.RGB8888, 0, want_log=False)
+            assert rc1 == 1 and np.array_equal(img, outs[i][:, :img.shape[1]]), i
