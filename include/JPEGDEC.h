@@ -29,8 +29,16 @@
 #ifndef __JPEGDEC__
 #define __JPEGDEC__
 
+/* the reference header pulls these in for hosted builds and its example programs rely on that (src/JPEGDEC.h:16-30) */
+#include <stdlib.h>
+#include <string.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdio.h>
+#ifndef PROGMEM
+#define memcpy_P memcpy
+#define PROGMEM
+#endif
 
 #ifdef __cplusplus
 extern "C" {

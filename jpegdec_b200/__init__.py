@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjpegdec_b200.so")
+LIB_PATH = os.environ.get("JPEGDEC_B200_LIB") or os.path.join(HERE, "libjpegdec_b200.so")  # env override: A/B of kernel variants
 
 # --- constants (reference src/JPEGDEC.h:68-75, :102-111, :119-126) ---
 JPEG_AUTO_ROTATE, JPEG_SCALE_HALF, JPEG_SCALE_QUARTER, JPEG_SCALE_EIGHTH = 1, 2, 4, 8

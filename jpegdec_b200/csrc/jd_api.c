@@ -324,6 +324,8 @@ static int decode_common(JPEGIMAGE *p)
     jd.iBpp = bpp;
     jd.iHeight = mh;
     int keep_going = 1;
+    const int sse_mcu_writes = p->pFramebuffer && p->ucArithMode == JPEG_ARITH_SSE2 && shift == 0 && p->ucNumComponents == 3 &&
+                               pt <= RGB8888 && (p->ucSubSample == 0x11 || p->ucSubSample == 0x22);
     const int dpitch = dither ? (cx * mw * bpp + 7) / 8 : 0;
     for (int y = 0; y < cy && keep_going; y++) {
         const int skip_row = (y * mh < p->iCropY);
@@ -346,12 +348,28 @@ static int decode_common(JPEGIMAGE *p)
                     /* packed rows come from the dither kernel; nothing to gather per MCU */
                 } else if (p->pFramebuffer) {
                     int rows = mh;
-                    if (y * mh + rows > cur_h) rows = cur_h - y * mh; /* never write below the image */
-                    if (rows > 0) {
-                        const uint8_t *src = frame + (size_t)y * mh * frame_pitch + (size_t)x * mw * bypp;
-                        int cols = pitch_px - xoff; if (cols > mw) cols = mw;
-                        for (int r = 0; r < rows && cols > 0; r++)
-                            memcpy(rowbase + ((size_t)r * pitch_px + xoff) * bypp, src + (size_t)r * frame_pitch, (size_t)cols * bypp);
+                    const uint8_t *src = frame + (size_t)y * mh * frame_pitch + (size_t)x * mw * bypp;
+                    if (sse_mcu_writes) {
+                        /* the reference's SSE2 colour paths store whole MCUs with no edge clipping (jpeg.inl:3409, :4006):
+                         * the right-edge MCU runs on into the start of the next line (and is partly overwritten later, in
+                         * MCU order), the bottom MCU row continues below the image -- which is why the caller's buffer
+                         * must cover whole MCU rows (c_cmdline/main.c:180).  Same writes, same order; clipped only at the
+                         * end of that MCU-row-aligned buffer. */
+                        const size_t fb_px = (size_t)pitch_px * (size_t)(cy * mh - p->iCropY);
+                        for (int r = 0; r < rows; r++) {
+                            const size_t at = (size_t)(y * mh - p->iCropY + r) * pitch_px + xoff;
+                            size_t n = (size_t)mw;
+                            if (at >= fb_px) break;
+                            if (at + n > fb_px) n = fb_px - at;
+                            memcpy((uint8_t *)p->pFramebuffer + at * bypp, src + (size_t)r * frame_pitch, n * bypp);
+                        }
+                    } else {
+                        if (y * mh + rows > cur_h) rows = cur_h - y * mh; /* scalar paths clip at the image edges (:3520-3524, :4311-4332) */
+                        if (rows > 0) {
+                            int cols = pitch_px - xoff; if (cols > mw) cols = mw;
+                            for (int r = 0; r < rows && cols > 0; r++)
+                                memcpy(rowbase + ((size_t)r * pitch_px + xoff) * bypp, src + (size_t)r * frame_pitch, (size_t)cols * bypp);
+                        }
                     }
                 } else {
                     uint8_t *dst = (uint8_t *)(pixbuf + dma_off) + (size_t)xoff * bypp;

@@ -222,7 +222,7 @@ JD_HD void jd_chunk_emit(const JDScanIn &sc, const uint16_t *lut, const uint32_t
         { const int nPb = (int)(rel >> 3); jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
         if (k >= 64u) {
             if (own) {
-                blk_hdr[bi] = jd_pack_hdr(rec_index0 + (uint32_t)(rec0 - rec), dcval, ncoef, big, (bflags >> 16) & 1u, (bflags >> 8) & 0xFFu);
+                blk_hdr[bi] = jd_pack_hdr(rec_index0 + (uint32_t)(rec0 - rec), dcval, ncoef, big, JD_BF_HI(bflags), JD_BF_COLMASK(bflags));
                 out.nown++;
                 bi++;
                 own = false;

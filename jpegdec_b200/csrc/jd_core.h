@@ -171,8 +171,12 @@ typedef struct {
 #define JD_LD8(p) (*(p))
 #endif
 
-/* zigzag k -> packed word: tile position t | column bit (1 << (t >> 3)) << 8 | rows-4..7 bit << 16 */
-JD_HD uint32_t jd_tposw(uint32_t t) { return t | ((1u << (t >> 3)) << 8) | (((t >> 2) & 1u) << 16); }
+/* zigzag k -> packed word: tile position t | rows-4..7 bit << 23 | column bit (1 << (t >> 3)) << 24 -- the flag bits sit
+ * where the block header's high word keeps them, so OR-ing the words of a block's coefficients builds that word */
+JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u << (t >> 3)) << 24); }
+#define JD_BF_HI(bf) (((bf) >> 23) & 1u)
+#define JD_BF_COLMASK(bf) ((bf) >> 24)
+#define JD_BF_MASK 0xFF800000u
 
 template <typename EventSink>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
@@ -201,18 +205,36 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
     const uint32_t nblk_total = in.nmcu * in.bpm;
-    uint32_t blk_in_mcu = 0;
-    uint32_t b = 0;
+    /* per-MCU block schedule, one nibble per block: component (2 bits) | DC table << 2 | AC table << 3 */
+    uint32_t sched = 0;
+    for (uint32_t i = 0; i < in.bpm && i < 8u; i++) {
+        const uint32_t c = (i < nluma) ? 0u : (i - nluma + 1u);
+        sched |= (c | (((in.tsel >> (2 * c)) & 1u) << 2) | (((in.tsel >> (2 * c + 1)) & 1u) << 3)) << (4 * i);
+    }
+    const uint32_t bsh_end = 4u * in.bpm;
+    uint32_t bsh = 0;                            /* 4 * (block index inside the MCU) */
+    uint32_t cur = sched & 15u;                  /* schedule nibble of the current block */
+    uint32_t nleft = nblk_total;                 /* blocks still to finish */
+    jd_u64 *hp = blk_hdr;
 
     /* per-block state */
-    uint32_t comp = 0;
     uint32_t k = 0;                              /* zigzag index; 0 = DC pending */
-    uint32_t ncoef = 0, big = 0, bflags = 0;     /* bflags: column mask << 8 | rows-4..7 << 16 (as in tposw) */
-    uint16_t *rec0 = rp;
+    uint32_t cnt = 0, bflags = 0;                /* cnt: stored coefficients << 16 | BIG << 22 (header layout); bflags: OR of tposw words */
+    uint32_t ridx0 = in.rec_index0;              /* global index of this block's first record */
+    const uint32_t rec_lo = (uint32_t)(uintptr_t)rec;
     int dcval = 0;
-    const uint16_t *tac = lut + JD_LUT_AC((in.tsel >> 1) & 1u);
     /* current table geometry (DC at block start) */
-    const uint16_t *tb = lut + JD_LUT_DC(in.tsel & 1u);
+#ifndef JD_V_PTR
+#define JD_V_PTR 1
+#endif
+#ifndef JD_V_PRED
+#define JD_V_PRED 1
+#endif
+#if JD_V_PTR
+    const uint16_t *tb = lut + JD_LUT_DC((cur >> 2) & 1u);
+#else
+    uint32_t toff = JD_LUT_DC((cur >> 2) & 1u);
+#endif
     uint32_t thr = 0xF800u, sh = 4u, msk = 0x7Fu;
 
     if (nblk_total == 0) { out.status = JD_SEG_OK; out.err_mcu = -1; out.jmap = jw; out.nrec = 0; return; }
@@ -259,7 +281,11 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         /* ---- code lookup ---- */
         const uint32_t w16 = (uint32_t)(bb >> 48);
         const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
+#if JD_V_PTR
         const uint32_t e = tb[idx];
+#else
+        const uint32_t e = lut[toff + idx];
+#endif
         if (e == 0u) { err = JD_SEG_BADCODE; break; }
         const int len = (int)(e >> 8);
         const uint32_t rs = e & 0xFFu;
@@ -279,18 +305,31 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             if (s != 0 && len + s > 6) jw = jd_jw_ckpt(jw);
             P += s;
             { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+            const uint32_t comp = cur & 3u;
+#if JD_V_PRED
+            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + v;
+            pred0 = (comp == 0u) ? pv : pred0;
+            pred1 = (comp == 1u) ? pv : pred1;
+            pred2 = (comp >= 2u) ? pv : pred2;
+            dcval = pv;
+#else
             if (comp == 0u) { pred0 += v; dcval = pred0; }
             else if (comp == 1u) { pred1 += v; dcval = pred1; }
             else { pred2 += v; dcval = pred2; }
+#endif
             k = 1;
-            last_was_eob = false;
-            tb = tac; thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
+#if JD_V_PTR
+            tb = lut + JD_LUT_AC(cur >> 3);
+#else
+            toff = JD_LUT_AC(cur >> 3);
+#endif
+            thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
             continue;
         }
+        last_was_eob = (rs == 0u);
         if (rs == 0u) {
             /* EOB (:2241-2244): leaves without the trailing window check */
             k = 64;
-            last_was_eob = true;
         } else {
             k += rs >> 4;
             if (s && k < 64u) {
@@ -309,21 +348,23 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                         }
                         if (any) {
                             JDEvent ev;
-                            ev.blk = in.blk0 + b;
+                            ev.blk = in.blk0 + (nblk_total - nleft);
                             ev.seg = in.seg;
                             ev.j1 = j1;
                             ev.field = (uint16_t)field;
                             ev.s = (uint8_t)s;
                             ev.p7 = (uint8_t)p7;
-                            ev.ord = ncoef;
+                            ev.ord = (cnt >> 16) & 63u;
                             sink.push(ev);
                         }
                     }
                 }
                 const uint32_t tw = tposw[k];
                 bflags |= tw;
-                if (s >= 10 && !big) {
+                if (s >= 10 && !(cnt & (1u << 22))) {
                     /* first >= 10-bit magnitude of this block: switch its records to (t, value) pairs */
+                    const uint32_t ncoef = (cnt >> 16) & 63u;
+                    uint16_t *rec0 = rec + (ridx0 - in.rec_index0);
                     if (rp + ncoef + 2 > rend) { err = JD_SEG_OVERFLOW; break; }
                     for (uint32_t i = ncoef; i-- > 0u;) {
                         const uint32_t r = rec0[i];
@@ -331,37 +372,42 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                         rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
                     }
                     rp += ncoef;
-                    big = 1;
+                    cnt |= 1u << 22;
                 }
-                if (big) {
+                if (cnt & (1u << 22)) {
                     if (rp + 2 > rend) { err = JD_SEG_OVERFLOW; break; }
                     rp[0] = (uint16_t)(tw & 63u);
                     rp[1] = (uint16_t)(int16_t)v;
                     rp += 2;
                 } else {
                     if (rp >= rend) { err = JD_SEG_OVERFLOW; break; }
-                    *rp++ = (uint16_t)(((tw & 63u) << 10) | ((uint32_t)v & 0x3FFu));
+                    *rp++ = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
                 }
-                ncoef++;
+                cnt += 1u << 16;
             }
             k++;
-            last_was_eob = false;
         }
         P += len + s;
         { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
         if (k >= 64u) {
-            /* ---- block finished ---- */
-            blk_hdr[b] = jd_pack_hdr(in.rec_index0 + (uint32_t)(rec0 - rec), dcval, ncoef, big, (bflags >> 16) & 1u, (bflags >> 8) & 0xFFu);
-            if (++b == nblk_total) break;
-            if (++blk_in_mcu == in.bpm) blk_in_mcu = 0;
-            /* component of the next block: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
-            comp = (blk_in_mcu < nluma) ? 0u : (blk_in_mcu - nluma + 1u);
-            tac = lut + JD_LUT_AC((in.tsel >> (2 * comp + 1)) & 1u);
-            tb = lut + JD_LUT_DC((in.tsel >> (2 * comp)) & 1u);
+            /* ---- block finished: header = first record | dc << 32 | count << 48 | BIG << 54 | rows-4..7 << 55 | columns << 56 ---- */
+            *hp++ = (jd_u64)ridx0 | ((jd_u64)((bflags & JD_BF_MASK) | cnt | ((uint32_t)dcval & 0xFFFFu)) << 32);
+            if (--nleft == 0u) break;
+            /* next block of the MCU: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
+            bsh += 4u;
+            if (bsh == bsh_end) bsh = 0u;
+            cur = (sched >> bsh) & 15u;
+#if JD_V_PTR
+            tb = lut + JD_LUT_DC((cur >> 2) & 1u);
+#else
+            toff = JD_LUT_DC((cur >> 2) & 1u);
+#endif
             thr = 0xF800u; sh = 4u; msk = 0x7Fu;
-            k = 0; ncoef = 0; big = 0; bflags = 0; rec0 = rp;
+            k = 0; cnt = 0; bflags = 0;
+            ridx0 = in.rec_index0 + (((uint32_t)(uintptr_t)rp - rec_lo) >> 1);
         }
     }
+    const uint32_t b = nblk_total - nleft;       /* blocks finished */
     if (err >= 0) {
         /* undecodable from here: later stages must still find well-formed (empty) headers */
         out.err_mcu = (int32_t)(b / in.bpm);

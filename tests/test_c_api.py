@@ -56,3 +56,60 @@ def test_c_and_cpp_callers_match_reference(tmp_path):
     assert r.returncode == 0 and "callbacks=150 pixels=307200" in r.stdout, r.stdout
     r = subprocess.run([os.path.join(OUT, "accept_cpp"), img], stdout=subprocess.PIPE, text=True)
     assert r.returncode == 0 and r.stdout.count("rc=1") == 4, r.stdout
+
+
+# ---- the reference's own programs, unmodified ----
+def _ref_examples():
+    """Binaries built by tests/c_api/build_reference_examples.py.  Built here when the reference sources are present
+    (this container); on the GPU box the prebuilt files travel with the snapshot."""
+    from tests.c_api import build_reference_examples as B
+    if B.available():
+        B.build()
+    names = ["ref_c_cmdline", "ref_perf_test", "ref_jpegdec_test"]
+    paths = {n: os.path.join(B.OUT, n) for n in names}
+    return paths if all(os.path.exists(p) for p in paths.values()) else None
+
+
+def test_reference_programs_compile_unmodified_against_this_library():
+    from tests.c_api import build_reference_examples as B
+    if not B.available():
+        pytest.skip("reference sources not on this machine")
+    ex = _ref_examples()
+    assert ex is not None
+    # the shadow tree holds links, not copies
+    assert os.path.islink(os.path.join(B.SHADOW, "linux/examples/c_cmdline/main.c"))
+    if J.lib().JPEGB200_deviceCount() == 0:
+        r = subprocess.run([ex["ref_c_cmdline"], os.path.join(T.GOLD, "images", "tulips.jpg"), "/dev/null"],
+                           stdout=subprocess.PIPE, text=True)
+        assert r.returncode != 0 and "Decode failed" in r.stdout     # no CPU fallback behind the reference's API either
+
+
+@pytest.mark.gpu
+def test_reference_programs_run_on_the_gpu_and_match_the_reference_build(tmp_path):
+    import hashlib
+    import json
+    ex = _ref_examples()
+    if ex is None:
+        pytest.skip("prebuilt reference programs not present (build them where /root/reference exists)")
+    gold = json.load(open(os.path.join(T.GOLD, "ref_examples.json")))["fixtures"]
+    for name, g in gold.items():
+        bmp = str(tmp_path / (name + ".bmp"))
+        r = subprocess.run([ex["ref_c_cmdline"], os.path.join(T.GOLD, "images", name + ".jpg"), bmp], stdout=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (name, r.stdout)
+        data = open(bmp, "rb").read()
+        assert len(data) == g["bmp_bytes"] and hashlib.sha256(data).hexdigest() == g["bmp_sha256"], name
+    r = subprocess.run([ex["ref_c_cmdline"]], stdout=subprocess.PIPE, text=True)             # in-memory tulips, 4 scales
+    assert r.returncode == 0 and all(s in r.stdout for s in ("full sized", "half sized", "quarter sized", "eighth sized")), r.stdout
+    r = subprocess.run([ex["ref_perf_test"]], stdout=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.count("sized decode in") == 4, r.stdout
+    r = subprocess.run([ex["ref_jpegdec_test"]], stdout=subprocess.PIPE, text=True, timeout=600)
+    out = r.stdout
+    assert r.returncode == 0 and "Total tests: 12" in out, out[-2000:]
+    # every functional test of the reference's harness passes; its test 3 is a CPU timing heuristic (luma-only decode
+    # must be >= 37.5 % faster than colour), which a launch-latency-bound single-image GPU decode does not satisfy
+    for t in ("JPEG full image decode - PASSED", "JPEG DMA ping-pong buffer - PASSED", "JPEG EXIF Thumbnail - PASSED",
+              "Single Byte Sequential Corruption Test - PASSED", "Multi-Byte Random Corruption Test - PASSED"):
+        assert t in out, out[-3000:]
+    assert out.count("JPEG full image decode - PASSED") == 2
+    failed = int(out.split("passed,")[1].split("failed")[0])
+    assert failed <= 1 and (failed == 0 or "JPEG color->gray image decode - FAILED" in out), out[-3000:]

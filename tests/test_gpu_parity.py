@@ -169,6 +169,17 @@ def test_single_image_api_framebuffer_crop_thumb_dither(mode, arith):
         assert j.decode(0, 0, 0) == rc_r == 1
         n = 640 * 480 * T.bpp_of(pt) // 8
         assert np.array_equal(fb[:n], fb_r[:n])
+    # framebuffer mode, width / height not multiples of the MCU: the reference's SSE2 build stores whole MCUs (the right
+    # edge runs on into the next line), its scalar build clips -- the visible w x h region must match either way
+    for name, w, h in (("sciopero", 300, 300), ("ncc1701", 240, 77), ("zebra", 320, 240)):
+        d2 = T.image(name)
+        for pt in (0, 2):
+            rc_r, err_r, fb_r = ref.decode_fb(d2, pt, 0)
+            j = J.JPEGDEC(); assert j.openRAM(d2); j.setArithMode(arith); j.setPixelType(pt)
+            fb = np.zeros_like(fb_r); j.setFramebuffer(fb)
+            assert j.decode(0, 0, 0) == rc_r == 1
+            n = w * h * T.bpp_of(pt) // 8
+            assert np.array_equal(fb[:n], fb_r[:n]), (name, pt, mode)
     # crop through callbacks (reference test 2): exactly the snapped rectangle, same pixels
     rc_r, err_r, img_r, log_r = ref.decode_cb(data, 0, 0, crop=(50, 50, 125, 170))
     j = J.JPEGDEC(); draw, log, blocks = _collect(j, 0, 0)
