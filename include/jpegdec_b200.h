@@ -71,7 +71,10 @@ void JPEGB200_hostFree(void *p);
 /* ---- batch job ---- */
 /* Parses the n headers on the host (no GPU work).  datas[i]/sizes[i]: JPEG files in host memory
  * (pinned memory makes the upload a straight DMA; files that sit back to back are uploaded with one copy).
- * pixel_type / options as in JPEGDEC.h.  At most 1 GiB of compressed bytes per batch. */
+ * pixel_type / options as in JPEGDEC.h.  At most 1 GiB of compressed bytes per batch.
+ * Progressive files are accepted when options has JPEG_SCALE_EIGHTH: like the reference (src/jpeg.inl:4964-4966,
+ * JPEGDecodeMCU_P :1819-1884) only the DC coefficients of the first scan are decoded; otherwise that image's status
+ * is JPEG_UNSUPPORTED_FEATURE. */
 JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes,
                                      int n, int pixel_type, int options);
 void JPEGB200_batchDestroy(JPEGB200_BATCH *b);

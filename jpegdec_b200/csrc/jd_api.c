@@ -251,7 +251,7 @@ static int decode_common(JPEGIMAGE *p)
 {
     int options = p->iOptions;
     if (!p->pFileData) { p->iError = JPEG_INVALID_PARAMETER; return 0; }
-    if (p->ucMode == 0xc2) { p->iError = JPEG_UNSUPPORTED_FEATURE; return 0; } /* progressive DC thumbnails: out of scope */
+    if (p->ucMode == 0xc2) options = (p->iOptions |= JPEG_SCALE_EIGHTH); /* progressive: DC-only 1/8 image (jpeg.inl:4964-4966) */
     if (options & JPEG_EXIF_THUMBNAIL) {
         if (p->iThumbData == 0 || p->iThumbWidth == 0) { p->iError = JPEG_INVALID_PARAMETER; return 0; } /* jpeg.inl:4969 */
     }

@@ -149,6 +149,7 @@ typedef struct {
     uint32_t rec_cap;     /* record capacity of this segment */
     uint32_t seg;         /* global segment index (for events) */
     uint32_t blk0;        /* global index of this segment's first block (for events) */
+    uint32_t al;          /* progressive DC scan: point transform (DC_ONLY instantiation) */
 } JDSegIn;
 
 typedef struct {
@@ -178,7 +179,9 @@ JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u 
 #define JD_BF_COLMASK(bf) ((bf) >> 24)
 #define JD_BF_MASK 0xFF800000u
 
-template <typename EventSink>
+/* DC_ONLY: first scan of a progressive file (Ss = Se = 0): each block is one DC symbol, difference << Al
+ * (reference JPEGDecodeMCU_P, src/jpeg.inl:1849-1884; no window quirk there: it reloads at bit offset > 47). */
+template <typename EventSink, bool DC_ONLY = false>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
                              const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
@@ -307,7 +310,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
             const uint32_t comp = cur & 3u;
 #if JD_V_PRED
-            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + v;
+            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + (DC_ONLY ? (int)((uint32_t)v << in.al) : v);
             pred0 = (comp == 0u) ? pv : pred0;
             pred1 = (comp == 1u) ? pv : pred1;
             pred2 = (comp >= 2u) ? pv : pred2;
@@ -317,15 +320,18 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             else if (comp == 1u) { pred1 += v; dcval = pred1; }
             else { pred2 += v; dcval = pred2; }
 #endif
-            k = 1;
+            if (!DC_ONLY) {
+                k = 1;
 #if JD_V_PTR
-            tb = lut + JD_LUT_AC(cur >> 3);
+                tb = lut + JD_LUT_AC(cur >> 3);
 #else
-            toff = JD_LUT_AC(cur >> 3);
+                toff = JD_LUT_AC(cur >> 3);
 #endif
-            thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
-            continue;
-        }
+                thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
+                continue;
+            }
+            k = 64;
+        } else {
         last_was_eob = (rs == 0u);
         if (rs == 0u) {
             /* EOB (:2241-2244): leaves without the trailing window check */
@@ -389,6 +395,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         }
         P += len + s;
         { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
+        }
         if (k >= 64u) {
             /* ---- block finished: header = first record | dc << 32 | count << 48 | BIG << 54 | rows-4..7 << 55 | columns << 56 ---- */
             *hp++ = (jd_u64)ridx0 | ((jd_u64)((bflags & JD_BF_MASK) | cnt | ((uint32_t)dcval & 0xFFFFu)) << 32);

@@ -317,7 +317,15 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
             if (inf.thumb_data == 0 || inf.thumb_w == 0) { ok = 0; st = JPEG_INVALID_PARAMETER; }
             else { ok = jd_parse_header(datas[i], sizes[i], inf.thumb_data, &inf); if (!ok) st = inf.error; }
         }
-        if (ok && inf.mode != 0xC0) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; } /* progressive thumbnails: out of scope */
+        bool prog = false;
+        if (ok && inf.mode == 0xC2) {
+            /* progressive: like the reference, only the DC coefficients of the first scan are decoded and a 1/8-size image
+             * is produced (jpeg.inl:4964-4966, JPEGDecodeMCU_P :1819-1884).  That needs a first scan that is the interleaved
+             * DC scan of every component (Ss = Se = 0, Ah = 0) -- what every common encoder writes -- and 1/8 scale. */
+            prog = true;
+            if (b->sshift != 3 || inf.p.ncomp_in_scan != inf.ncomp || inf.p.scan_start != 0 || inf.p.scan_end != 0 || (inf.approx >> 4) != 0 ||
+                (inf.approx & 15) > 13) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; }
+        } else if (ok && inf.mode != 0xC0) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; }
         if (ok && !inf.tables_ok) { ok = 0; st = JPEG_DECODE_ERROR; }           /* jpeg.inl:2166 */
         if (ok && inf.ncomp == 1 && pixel_type == RGB8888) { ok = 0; st = JPEG_INVALID_PARAMETER; }
         b->parse_status[i] = st;
@@ -352,7 +360,8 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         d.mcus_per_seg = mps;
         d.nseg = (total_mcus + mps - 1) / mps;
         d.chunk_base = 0; d.nch = 0;
-        if (inf.restart_interval == 0 && d.nseg == 1 && sizes[i] - inf.scan_offset >= 4096) {
+        d.prog = prog ? (1u | ((uint32_t)(inf.approx & 15) << 8)) : 0u;
+        if (!prog && inf.restart_interval == 0 && d.nseg == 1 && sizes[i] - inf.scan_offset >= 4096) {
             /* no restart markers: one long dependent stream -> chunk-parallel decode */
             d.chunk_base = b->nchunks;
             d.nch = ((uint32_t)(sizes[i] - inf.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;

@@ -206,7 +206,7 @@ int jd_parse_header(const uint8_t *data, int size, int start, JDInfo *info)
         if (!bad) {
             info->p.scan_start = s[off++];
             info->p.scan_end = s[off++];
-            off++; /* successive approximation */
+            info->approx = s[off++]; /* successive approximation: Ah << 4 | Al (:1417) */
         }
     }
     info->scan_offset = off;

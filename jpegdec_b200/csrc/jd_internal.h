@@ -31,6 +31,7 @@ typedef struct {
     int tsel;               /* per comp c: bit 2c = DC table, bit 2c+1 = AC table */
     int tables_ok;          /* scan uses only tables 0/1 (DC and AC) */
     int error;              /* JPEG_* error code when parse fails */
+    int approx;             /* first scan's successive-approximation byte (Ah << 4 | Al); progressive files */
     JDPARSED p;
 } JDInfo;
 
@@ -42,7 +43,7 @@ void jd_build_quant(const JDInfo *info, int16_t *q /* [3][64] natural order, per
 uint64_t jd_tables_hash(const JDInfo *info);
 const int *jd_aan_table(void);
 
-/* Device-visible per-image descriptor (72 B). */
+/* Device-visible per-image descriptor (80 B). */
 typedef struct {
     uint32_t scan_off;      /* absolute offset of first entropy byte in the batch buffer */
     uint32_t scan_end;      /* absolute end of this file's bytes */
@@ -55,6 +56,8 @@ typedef struct {
     uint32_t blk_base;      /* first global block index */
     uint32_t lutset;        /* index of the Huffman LUT set */
     uint32_t out_pitch;     /* bytes */
+    uint32_t prog;          /* bit 0: progressive file, only the DC coefficients of its first scan are decoded (reference
+                             * JPEGDecodeMCU_P, src/jpeg.inl:1819-2084, 1/8-scale output); bits 8..11: point transform Al */
     uint64_t out_off;       /* byte offset from the output base pointer */
     uint32_t out_w, out_h;  /* output size in pixels after scaling */
     uint32_t status;        /* written by kernels: 0 ok */

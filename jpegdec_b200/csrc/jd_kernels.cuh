@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     if ((uint64_t)in.rec_index0 + cap > a.rec_total) cap = (in.rec_index0 < a.rec_total) ? a.rec_total - in.rec_index0 : 0u;
     in.rec_cap = cap;
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
-    jd_decode_segment(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
+    if (im.prog & 1u) { in.al = (im.prog >> 8) & 15u; jd_decode_segment<JDEventSinkDev, true>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so); }
+    else { in.al = 0; jd_decode_segment<JDEventSinkDev, false>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so); }
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
     a.seg_nrec[seg] = so.nrec;

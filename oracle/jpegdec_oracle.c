@@ -34,6 +34,7 @@ static const uint8_t ZZ_NAT[64] = { /* zigzag position -> natural index */
 
 typedef struct {
     int w, h, ncomp, sub, dri, scan;
+    int prog, scan_nc, ss, se, ahal;   /* SOF2: first-scan parameters (jpeg.inl:1406-1418) */
     int cq[4], cdc[4], cac[4];
     uint16_t q[4][64];
     uint8_t bits[8][16], vals[8][256];
@@ -53,7 +54,8 @@ static int or_parse(const uint8_t *d, int n, OrHdr *H)
         int m = be16(d + off), len = be16(d + off + 2);
         off += 2;
         if (m < 0xFFC0 || m == 0xFFFF) { off++; continue; }
-        if (m == 0xFFC0) {
+        if (m == 0xFFC0 || m == 0xFFC2) {
+            H->prog = (m == 0xFFC2);
             H->h = be16(d + off + 3); H->w = be16(d + off + 5); H->ncomp = d[off + 7];
             if (H->ncomp > 4) return 0;
             for (int i = 0; i < H->ncomp; i++) {
@@ -62,7 +64,7 @@ static int or_parse(const uint8_t *d, int n, OrHdr *H)
                 H->cdc[i] = d[off + 8 + 3 * i]; /* component id, matched at SOS */
             }
             if (H->ncomp == 1) H->sub = 0;
-        } else if (m == 0xFFC1 || m == 0xFFC2 || m == 0xFFC3) {
+        } else if (m == 0xFFC1 || m == 0xFFC3) {
             return 0;
         } else if (m == 0xFFDD) {
             H->dri = be16(d + off + 2);
@@ -95,6 +97,7 @@ static int or_parse(const uint8_t *d, int n, OrHdr *H)
                 int id = d[off + 3 + 2 * i], tb = d[off + 4 + 2 * i];
                 for (int j = 0; j < H->ncomp; j++) if (ids[j] == id) { H->cdc[j] = tb >> 4; H->cac[j] = tb & 15; }
             }
+            H->scan_nc = nc; H->ss = d[off + 3 + 2 * nc]; H->se = d[off + 4 + 2 * nc]; H->ahal = d[off + 5 + 2 * nc];
             H->scan = off + len;
             return 1;
         }
@@ -191,6 +194,28 @@ static int or_decode_block(OrWin *W, const OrHuff *dc, const OrHuff *ac, int *pr
         W->off += s;
         k++;
         or_rebase(W);                                /* :2259 */
+    }
+    return 0;
+}
+
+/* JPEGDecodeMCU_P for the only case the reference can finish: first scan = DC scan (iScanStart = iScanEnd = 0,
+ * cApproxBitsHigh = 0), jpeg.inl:1837-1884: window reload at bit offset > 47 before the code and before the extra bits
+ * (so no truncated reads), difference << cApproxBitsLow added to the predictor. */
+static int or_decode_dc_prog(OrWin *W, const OrHuff *dc, int *pred, int al)
+{
+    int len;
+    or_rebase(W);
+    int s = or_code(W, dc, 12, &len);
+    if (s < 0) return -1;
+    s &= 15;
+    W->off += len;
+    if (s) {
+        or_rebase(W);
+        uint64_t c = W->bits << W->off;
+        int v = (int)(c >> (64 - s));
+        if (!(c >> 63)) v -= (1 << s) - 1;
+        W->off += s;
+        *pred += (int)((unsigned)v << al);
     }
     return 0;
 }
@@ -389,7 +414,9 @@ int oracle_decode(const uint8_t *jpeg, int len, int pixel_type, int options, int
     int hs = 1, vs = 1;
     switch (H->sub) { case 0x00: case 0x11: break; case 0x21: hs = 2; break; case 0x12: vs = 2; break; case 0x22: hs = vs = 2; break; default: free(H); return 0; }
     if (H->ncomp != 1 && H->ncomp != 3) { free(H); return 0; }
+    if (H->prog) options |= OR_SCALE_EIGHTH;         /* progressive: DC of the first scan only -> 1/8 image (:4964-4966) */
     const int sh = (options & OR_SCALE_HALF) ? 1 : (options & OR_SCALE_QUARTER) ? 2 : (options & OR_SCALE_EIGHTH) ? 3 : 0;
+    if (H->prog && (sh != 3 || H->scan_nc != H->ncomp || H->ss != 0 || H->se != 0 || (H->ahal >> 4) != 0)) { free(H); return 0; }
     if ((options & OR_LUMA_ONLY) && pixel_type < OR_GRAY8) pixel_type = OR_GRAY8;
     const int dbits = pixel_type == OR_DITHER4 ? 4 : pixel_type == OR_DITHER2 ? 2 : pixel_type == OR_DITHER1 ? 1 : 0;
     const int gray_out = pixel_type >= OR_GRAY8;
@@ -416,6 +443,10 @@ int oracle_decode(const uint8_t *jpeg, int len, int pixel_type, int options, int
                 unsigned flags;
                 const int skip = comp > 0 && gray_out;  /* chroma parsed with MCU_SKIP (:5225-5233) */
                 const int limit = skip ? 1 : (sh >= 2 ? 5 : 64);
+                if (H->prog) {
+                    flags = 0;
+                    if (H->cdc[comp] > 1 || or_decode_dc_prog(&W, &dct[H->cdc[comp]], &pred[comp], H->ahal & 15)) { rc = 0; break; }
+                } else
                 if (H->cdc[comp] > 1 || H->cac[comp] > 1 || or_decode_block(&W, &dct[H->cdc[comp]], &act[H->cac[comp]], &pred[comp], blk, limit, &flags)) { rc = 0; break; }
                 if (skip) continue;
                 const int16_t *q = Q[H->cq[comp] & 3];

@@ -48,7 +48,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         start = info.thumb_data;
         if (!jd_parse_header(data, size, start, &info)) { *err = info.error; return 0; }
     }
-    if (info.mode != 0xC0 || !info.tables_ok) { *err = JPEG_UNSUPPORTED_FEATURE; return 0; }
+    if ((info.mode != 0xC0 && info.mode != 0xC2) || !info.tables_ok) { *err = JPEG_UNSUPPORTED_FEATURE; return 0; }
     *err = 0;
     std::vector<uint16_t> lut(JD_LUT_ENTRIES);
     jd_build_lut(&info, lut.data());
@@ -59,6 +59,11 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
     if (options & JPEG_SCALE_HALF) sshift = 1;
     else if (options & JPEG_SCALE_QUARTER) sshift = 2;
     else if (options & JPEG_SCALE_EIGHTH) sshift = 3;
+    const bool prog = info.mode == 0xC2;   /* progressive: DC of the first scan -> 1/8 image (as batchCreate / JPEG_decode) */
+    if (prog) {
+        if (!(options & (JPEG_SCALE_HALF | JPEG_SCALE_QUARTER))) sshift = 3;
+        if (sshift != 3 || info.p.ncomp_in_scan != info.ncomp || info.p.scan_start != 0 || info.p.scan_end != 0 || (info.approx >> 4) != 0) { *err = JPEG_UNSUPPORTED_FEATURE; return 0; }
+    }
     if ((options & JPEG_LUMA_ONLY) && pixel_type < EIGHT_BIT_GRAYSCALE) pixel_type = EIGHT_BIT_GRAYSCALE;
 
     /* ---- prescan: restart segments ---- */
@@ -160,7 +165,9 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.seg = (uint32_t)sgi;
         in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
-        jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        in.al = prog ? (uint32_t)(info.approx & 15) : 0u;
+        if (prog) jd_decode_segment<VecSink, true>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        else jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         jmap[sgi] = so.jmap;
         if (so.err_mcu >= 0) { bad = 1; break; }
     }

@@ -20,7 +20,7 @@ def synth_pixels(w, h, seed):
     return np.clip(acc, 0, 255).astype(np.uint8)
 
 
-def synth_jpeg(w, h, seed, quality=75, subsampling="4:2:0", gray=False, restart_rows=1, optimize=False):
+def synth_jpeg(w, h, seed, quality=75, subsampling="4:2:0", gray=False, restart_rows=1, optimize=False, progressive=False):
     img = Image.fromarray(synth_pixels(w, h, seed))
     if gray:
         img = img.convert("L")
@@ -30,6 +30,8 @@ def synth_jpeg(w, h, seed, quality=75, subsampling="4:2:0", gray=False, restart_
         kw["subsampling"] = subsampling
     if restart_rows:
         kw["restart_marker_rows"] = restart_rows
+    if progressive:
+        kw["progressive"] = True   # libjpeg's default script: first scan = interleaved DC of all components, Al = 1
     img.save(b, "JPEG", **kw)
     return b.getvalue()
 

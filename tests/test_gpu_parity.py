@@ -327,3 +327,40 @@ def test_one_call_decode_batch_pipelines_jobs_and_matches_the_single_job_path(ct
         for i in (0, 7, 199, 200, 269):
             rc1, err, img, _ = ref.decode_cb(jp[i], J.RGB8888, 0, want_log=False)
             assert rc1 == 1 and np.array_equal(img, outs[i][:, :img.shape[1]]), i
+
+
+def test_progressive_files_give_the_dc_thumbnail(ctxs):
+    """SURVEY.md 8(f)4.  Batch API: progressive files decode at JPEG_SCALE_EIGHTH (DC of the first scan), next to baseline
+    files in the same batch; without the 1/8 option a progressive file gets JPEG_UNSUPPORTED_FEATURE at its own index.
+    Single-image API: JPEG_decode forces 1/8 like the reference (src/jpeg.inl:4964-4966)."""
+    g = json.load(open(T.GOLD + "/progressive.json"))
+    names = ["prog_420", "prog_420_dri", "prog_444", "prog_422", "prog_gray"]
+    base = T.image("tulips")
+    for mode, arith in MODES:
+        for pt, ptn in ((0, "565le"), (1, "565be"), (2, "8888")):
+            use = [n for n in names if "%s/%s/opt8" % (mode, ptn) in g[n]]
+            blobs = [base] + [T.image(n) for n in use] + [base]
+            outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], blobs, pt, J.JPEG_SCALE_EIGHTH)
+            assert st == [0] * len(blobs)
+            assert np.array_equal(outs[0], outs[-1])
+            for n, o in zip(use, outs[1:-1]):
+                want = g[n]["%s/%s/opt8" % (mode, ptn)]
+                assert list(o.shape) == want["shape"] and T.sha(o) == want["sha"], (n, mode, ptn)
+            ref = _ref(mode)
+            if ref is not None:
+                rc, err, img, _ = ref.decode_cb(base, pt, J.JPEG_SCALE_EIGHTH, want_log=False)
+                assert np.array_equal(outs[0], img)
+    outs, st, tim, cnt = J.decode_batch_to_host(ctxs[0], [base, T.image("prog_420"), base], 0, 0)
+    assert st[0] == 0 and st[2] == 0 and st[1] == 3 and np.array_equal(outs[0], outs[2])     # JPEG_UNSUPPORTED_FEATURE
+    # single-image API, options = 0, through the callback
+    for name in ("prog_420", "prog_gray"):
+        data = T.image(name)
+        j = J.JPEGDEC(); draw, log, blocks = _collect(j, 0, 0)
+        assert j.openRAM(data, draw) and j.getJPEGType() == 1
+        assert j.decode(0, 0, 0) == 1
+        oh, ow2 = g[name]["sse/565le/opt0"]["shape"]
+        out = np.zeros((oh, ow2), np.uint8)
+        for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+            a = np.frombuffer(buf, dtype=np.uint8).reshape(h, w * 2)
+            out[y:y + h, x * 2:(x + wu) * 2] = a[:, :wu * 2]
+        assert T.sha(out) == g[name]["sse/565le/opt0"]["sha"], name

@@ -157,3 +157,29 @@ def test_unusual_restart_intervals_and_qualities():
                     rc1, want = T.oracle_decode(data, pt, opt, arith, 333, 251)
                     rc2, got, _ = T.hostsim_decode(data, pt, opt, arith, 333, 251)
                     assert rc1 == rc2 == 1 and np.array_equal(got, want), (n, arith, pt, opt)
+
+
+PROG = ["prog_420", "prog_420_dri", "prog_444", "prog_422", "prog_gray"]
+
+
+@pytest.mark.parametrize("name", PROG)
+def test_progressive_dc_thumbnail_restatement_and_kernel_stepper(name):
+    """progressive files -> DC coefficients of the first scan -> 1/8 image (reference
+    JPEGDecodeMCU_P src/jpeg.inl:1819-1884, forced JPEG_SCALE_EIGHTH :4964-4966).  The C restatement and the per-thread
+    device code stepped on the CPU must both reproduce the digests recorded from the compiled reference."""
+    import json
+    import os
+    g = json.load(open(os.path.join(T.GOLD, "progressive.json")))[name]
+    data = T.image(name)
+    for mode, arith in (("sse", 0), ("scalar", 1)):
+        for pt, ptn in ((0, "565le"), (1, "565be"), (2, "8888")):
+            key = "%s/%s/opt8" % (mode, ptn)
+            if key not in g:
+                continue
+            assert g[key] == g["%s/%s/opt0" % (mode, ptn)]            # option 0 is forced to 1/8 by the reference
+            rc, img = T.oracle_decode(data, pt, 8, arith, g["w"], g["h"])
+            assert rc == 1 and list(img.shape) == g[key]["shape"] and T.sha(img) == g[key]["sha"], (name, key, "restatement")
+            for opt in (0, 8):
+                oh, pitch = T.tight_shape(g["w"], g["h"], pt, 8)
+                rc, sim, nev = T.hostsim_decode(data, pt, opt | 8 if opt else 8, arith, g["w"], g["h"])
+                assert rc == 1 and T.sha(sim) == g[key]["sha"], (name, key, "stepper")
