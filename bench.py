@@ -35,6 +35,12 @@ WORKLOADS = {
                    desc="256 x 2048x1536 1-component q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4] shape)"),
     "hd_norst": dict(n=1024, w=1920, h=1080, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, restart_rows=0,
                      desc="1024 x 1920x1080 4:2:0 q75 WITHOUT restart markers -> RGB8888 (SURVEY 8(f)2: chunk-parallel entropy decode)"),
+    "uhd_quarter": dict(n=512, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2.0 / 16, coef_bpp=0.1875, opt=4, kernel="jdk_scaled",
+                        desc="512 x 3840x2160 4:2:0 q85 -> RGB565 at JPEG_SCALE_QUARTER (BASELINE.json configs[3]); MP = source pixels"),
+    "uhd_eighth": dict(n=512, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2.0 / 64, coef_bpp=0.046875, opt=8, kernel="jdk_scaled",
+                       desc="512 x 3840x2160 4:2:0 q85 -> RGB565 at JPEG_SCALE_EIGHTH (BASELINE.json configs[3]); MP = source pixels"),
+    "dither444": dict(n=256, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=6, subsampling="4:4:4",
+                      desc="256 x 2048x1536 4:4:4 colour q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4], colour variant)"),
     "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
 }
 
@@ -116,7 +122,7 @@ class ClockSampler:
 def make_images(wl, rank, unique):
     from tests import synth
     jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False),
-                         restart_rows=wl.get("restart_rows", 1))
+                         restart_rows=wl.get("restart_rows", 1), subsampling=wl.get("subsampling", "4:2:0"))
     return jp
 
 
@@ -132,7 +138,7 @@ def cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=3):
     fbs = [pool[i % len(pool)] for i in range(n_sample)]
     best = None
     for _ in range(passes):
-        fails, secs = ref.decode_batch(datas, pixel_type, 0, threads, fbs)
+        fails, secs = ref.decode_batch(datas, pixel_type, wl.get("opt", 0), threads, fbs)
         if fails:
             raise RuntimeError("reference failed on %d images" % fails)
         best = secs if best is None else min(best, secs)
@@ -245,7 +251,8 @@ def main():
     ptrs = [in_ptr + off for off in offs]
 
     # ---- device-resident throughput (`value`) ----
-    b = J.Batch(ctx, ptrs, sizes, pixel_type, 0)
+    opt = int(wl.get("opt", 0))
+    b = J.Batch(ctx, ptrs, sizes, pixel_type, opt)
     b.alloc_device_output()
     b.upload()
     b.decode(J.JPEGB200_OUT_DEVICE); b.download(); st = b.wait()
@@ -283,10 +290,10 @@ def main():
         if refdrv.available("sse") and rank == 0 and pixel_type <= J.EIGHT_BIT_GRAYSCALE:
             ref = refdrv.Ref("sse")
             nchk = min(4, unique)
-            outs_h, st_h, _, _ = J.decode_batch_to_host(ctx, jpegs[:nchk], pixel_type, 0)
+            outs_h, st_h, _, _ = J.decode_batch_to_host(ctx, jpegs[:nchk], pixel_type, opt)
             okc = 0
             for i in range(nchk):
-                rc, err, img, _ = ref.decode_cb(jpegs[i], pixel_type, 0, want_log=False)
+                rc, err, img, _ = ref.decode_cb(jpegs[i], pixel_type, opt, want_log=False)
                 okc += int(rc == 1 and st_h[i] == 0 and img.shape == outs_h[i].shape and np.array_equal(img, outs_h[i]))
             parity = "%d/%d sampled images bit-exact vs reference (SSE2 build)" % (okc, nchk)
     except Exception as e:  # parity is asserted in tests/; here it is informational
@@ -304,7 +311,7 @@ def main():
             outs = [out_ptr + i * stride for i in range(n_img)]
 
             def one_call():
-                rc, s2, c2 = J.decode_batch(ctx, ptrs, sizes, pixel_type, 0, outs)
+                rc, s2, c2 = J.decode_batch(ctx, ptrs, sizes, pixel_type, opt, outs)
                 if rc != 1:
                     raise SystemExit("e2e decodeBatch failed: rc=%d %s" % (rc, s2[:8]))
                 return s2, c2
@@ -331,7 +338,7 @@ def main():
     alg_bytes = int(n_img * wl["w"] * wl["h"] * (wl["bpp_out"] + wl["coef_bpp"]))
     achieved = alg_bytes / (idct_ms / 1e3) / 1e9
     out_gbs = n_img * wl["w"] * wl["h"] * wl["bpp_out"] / (idct_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "jdk_idct_color", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": wl.get("kernel", "jdk_idct_tb / jdk_idct_color (fused expand + dequant + IDCT + colour)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": idct_ms,
                 "write_only_gbs": out_gbs, "write_frac": out_gbs / peak}

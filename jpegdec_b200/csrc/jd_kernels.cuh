@@ -742,7 +742,7 @@ struct JDGeoTB {
     static constexpr int YSTRIDE = WCTA + 16;
     static constexpr int CSTRIDE = MPB * 8 + 8;
     static constexpr int TSTRIDE = 72;                            /* int16 per full tile (144 B: conflict-free LDS.128 per quarter warp) */
-    static constexpr int T0STRIDE = 36;                           /* int16 per 4-column tile (72 B: conflict-free LDS.64 per half warp) */
+    static constexpr int T0STRIDE = 40;                           /* int16 per 4-column tile (80 B: 16-byte aligned, conflict-free LDS.128 per quarter warp) */
 };
 
 __device__ __forceinline__ void jd_unpack4(const uint2 v, int m[4])
@@ -769,8 +769,11 @@ __device__ __forceinline__ uint2 jd_row_finish_packed(const int t[8])
     return make_uint2(__byte_perm(s01, s23, 0x6420), __byte_perm(d54, d76, 0x4602));
 }
 
+#ifndef JD_TB_MINB
+#define JD_TB_MINB 10   /* 48 registers: 10 CTAs per SM measured faster than 56 registers / 9 CTAs and than 40 / 12 */
+#endif
 template <int HS, int VS, int NC, int MPB, int PT, int ARITH>
-__global__ void __launch_bounds__(JDGeoTB<HS, VS, NC, MPB>::THREADS)
+__global__ void __launch_bounds__(JDGeoTB<HS, VS, NC, MPB>::THREADS, JD_TB_MINB)
 jdk_idct_tb(const JDIdctArgs a)
 {
     using G = JDGeoTB<HS, VS, NC, MPB>;
@@ -780,15 +783,17 @@ jdk_idct_tb(const JDIdctArgs a)
     __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
     __shared__ jd_u64 s_hdr[G::NB];
     __shared__ uint16_t s_perm[G::NB];
-    __shared__ uint32_t s_wc[2][G::NW];
+    __shared__ uint32_t s_wc[3][G::NW];
 
     const uint32_t img_i = a.img0 + blockIdx.z;
     const JDImageDesc &im = a.imgs[img_i];
     const uint32_t strip = blockIdx.x, my = blockIdx.y;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
 
-    /* ---- headers + binning: the blocks whose coefficients sit in the top-left 4x4 (3-4 columns) first, the rest after ---- */
-    uint32_t cls = 2;
+    /* ---- headers + binning.  Thread-per-block classes: coefficients in columns 0-3 only (3-4 columns occupied), split by
+     * whether rows 4-7 are empty (the reference picks its reduced column pass on that flag, jpeg.inl:2330): class 0 = rows
+     * 4-7 empty, class 1 = not.  Everything else (class 2: > 4 columns, <= 2 columns, DC only) goes to the 8-lane passes. ---- */
+    uint32_t cls = 3;
     if (tid < (uint32_t)G::NB) {
         const uint32_t ml = tid / G::BPMEFF, blk = tid - ml * G::BPMEFF;
         const uint32_t mx = strip * MPB + ml;
@@ -796,27 +801,27 @@ jdk_idct_tb(const JDIdctArgs a)
             const jd_u64 h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
             s_hdr[tid] = h;
             const uint32_t n = JD_HDR_NCOEF(h), cm = JD_HDR_COLMASK(h);
-            cls = (n != 0u && JD_HDR_HI(h) == 0u && (cm & 0xF0u) == 0u && (cm & 0xFCu) != 0u) ? 0u : 1u;
+            cls = (n != 0u && (cm & 0xF0u) == 0u && (cm & 0xFCu) != 0u) ? JD_HDR_HI(h) : 2u;
         }
     }
-    const uint32_t b0 = __ballot_sync(0xffffffffu, cls == 0u), b1 = __ballot_sync(0xffffffffu, cls == 1u);
-    if (lane == 0) { s_wc[0][wid] = __popc(b0); s_wc[1][wid] = __popc(b1); }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, cls == 0u), b1 = __ballot_sync(0xffffffffu, cls == 1u), b2 = __ballot_sync(0xffffffffu, cls == 2u);
+    if (lane == 0) { s_wc[0][wid] = __popc(b0); s_wc[1][wid] = __popc(b1); s_wc[2][wid] = __popc(b2); }
     __syncthreads();
-    uint32_t n0 = 0, n1 = 0, pre = 0;
+    uint32_t n0a = 0, n0b = 0, n1 = 0, pre = 0;
     {
-        uint32_t before0 = 0, before1 = 0;
+        uint32_t before0 = 0, before1 = 0, before2 = 0;
 #pragma unroll
         for (int w2 = 0; w2 < G::NW; w2++) {
-            const uint32_t c0 = s_wc[0][w2], c1 = s_wc[1][w2];
-            if ((uint32_t)w2 < wid) { before0 += c0; before1 += c1; }
-            n0 += c0; n1 += c1;
+            const uint32_t c0 = s_wc[0][w2], c1 = s_wc[1][w2], c2 = s_wc[2][w2];
+            if ((uint32_t)w2 < wid) { before0 += c0; before1 += c1; before2 += c2; }
+            n0a += c0; n0b += c1; n1 += c2;
         }
         const uint32_t lt = (1u << lane) - 1u;
-        pre = (cls == 0u) ? before0 + __popc(b0 & lt) : n0 + before1 + __popc(b1 & lt);
+        pre = (cls == 0u) ? before0 + __popc(b0 & lt) : (cls == 1u) ? n0a + before1 + __popc(b1 & lt) : n0a + n0b + before2 + __popc(b2 & lt);
     }
-    if (cls < 2u) s_perm[pre] = (uint16_t)tid;
+    if (cls < 3u) s_perm[pre] = (uint16_t)tid;
     __syncthreads();
-    const uint32_t nact = n0 + n1;
+    const uint32_t n0 = n0a + n0b;
 
     /* ---- phases A + B, common class: this thread's block ---- */
     if (tid < n0) {
@@ -827,7 +832,8 @@ jdk_idct_tb(const JDIdctArgs a)
         const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
         const int dc = JD_HDR_DC(h);
         const int32_t *q = a.quant + (size_t)img_i * 192 + comp * 64;   /* L1-resident */
-        int16_t *tile = s_tile0 + tid * G::T0STRIDE;   /* positions c * 8 + r, c < 4, r < 4 */
+        int16_t *tile = s_tile0 + tid * G::T0STRIDE;   /* positions c * 8 + r, c < 4 */
+        const bool r47 = tid < n0a;                    /* rows 4-7 empty: the reduced column pass */
         uint8_t *prow;  /* first output row of this block in the staged plane */
         uint32_t pstride;
         if (comp == 0) {
@@ -838,29 +844,53 @@ jdk_idct_tb(const JDIdctArgs a)
             prow = s_c + ((comp - 1) * 8) * G::CSTRIDE + ml * 8; pstride = G::CSTRIDE;
         }
 #pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<uint2 *>(tile + c * 8) = make_uint2(0, 0);
+        for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
         if (!JD_HDR_BIG(h)) {
             for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
         } else {
             for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
         }
         int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
+        if (r47) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
-            jd_unpack4(*reinterpret_cast<const uint2 *>(tile + c * 8), m);
-            { const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(q + c * 8)); qq[0] = (int)qv.x; qq[1] = (int)qv.y; qq[2] = (int)qv.z; qq[3] = (int)qv.w; }
-            if (c == 0) m[0] = dc;
-            if (ARITH == JPEG_ARITH_SSE2) {
+            for (int c = 0; c < 4; c++) {
+                int m[8] = {0, 0, 0, 0, 0, 0, 0, 0}, qq[8] = {0, 0, 0, 0, 0, 0, 0, 0}, o[8];
+                jd_unpack4(*reinterpret_cast<const uint2 *>(tile + c * 8), m);
+                { const uint4 qv = __ldg(reinterpret_cast<const uint4 *>(q + c * 8)); qq[0] = (int)qv.x; qq[1] = (int)qv.y; qq[2] = (int)qv.z; qq[3] = (int)qv.w; }
+                if (c == 0) m[0] = dc;
+                if (ARITH == JPEG_ARITH_SSE2) {
 #pragma unroll
-                for (int r = 0; r < 4; r++) m[r] *= qq[r];
-                if (c == 0) m[0] += JD_ROW_BIAS;   /* mod 2^16, additive through both passes */
-                jd_col_sse16(m, true, o);
-            } else {
-                jd_col_scalar(m, qq, true, o);
+                    for (int r = 0; r < 4; r++) m[r] *= qq[r];
+                    if (c == 0) m[0] += JD_ROW_BIAS;   /* mod 2^16, additive through both passes */
+                    jd_col_sse16(m, true, o);
+                } else {
+                    jd_col_scalar(m, qq, true, o);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
             }
+        } else {
 #pragma unroll
-            for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+            for (int c = 0; c < 4; c++) {
+                int m[8], qq[8], o[8];
+                jd_unpack8(*reinterpret_cast<const uint4 *>(tile + c * 8), m);
+                {
+                    const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(q + c * 8)), q1 = __ldg(reinterpret_cast<const uint4 *>(q + c * 8 + 4));
+                    qq[0] = (int)q0.x; qq[1] = (int)q0.y; qq[2] = (int)q0.z; qq[3] = (int)q0.w;
+                    qq[4] = (int)q1.x; qq[5] = (int)q1.y; qq[6] = (int)q1.z; qq[7] = (int)q1.w;
+                }
+                if (c == 0) m[0] = dc;
+                if (ARITH == JPEG_ARITH_SSE2) {
+#pragma unroll
+                    for (int r = 0; r < 8; r++) m[r] *= qq[r];
+                    if (c == 0) m[0] += JD_ROW_BIAS;
+                    jd_col_sse16(m, false, o);
+                } else {
+                    jd_col_scalar(m, qq, false, o);
+                }
+#pragma unroll
+                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+            }
         }
 #pragma unroll
         for (int r = 0; r < 8; r++) {
