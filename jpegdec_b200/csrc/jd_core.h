@@ -450,10 +450,16 @@ JD_HD uint32_t jd_range(int v)
 /* mulhi of the SSE2 build: _mm_mulhi_epi16(_mm_slli_epi16(x,2), K) with x taken mod 2^16.
  * (int16)(x<<2) << 16 == x << 18 in 32-bit wrap arithmetic, so the whole thing is a 32x32
  * high multiply of (x << 18) by K. */
+#ifndef JD_MH2_MULHI
+#define JD_MH2_MULHI 0
+#endif
 JD_HD int jd_mh2(int x, int K)
 {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && JD_MH2_MULHI
     return __mulhi((int)((uint32_t)x << 18), K);
+#elif defined(__CUDA_ARCH__)
+    /* (int16)(x << 2) * K fits 32 bits (|K| < 2^15): a full-rate multiply and two shifts instead of IMAD.HI */
+    return (((int)((uint32_t)x << 18) >> 16) * K) >> 16;
 #else
     return (int)(((int64_t)(int32_t)((uint32_t)x << 18) * (int64_t)K) >> 32);
 #endif
@@ -560,6 +566,17 @@ JD_HD void jd_col_scalar(const int m[8], const int q[8], bool rows47_empty, int 
 
 /* Row pass (both builds, jpeg.inl:2681-2797).  p[c] = int16 column results of one row
  * (sign-extended); colmask = low byte of the block's u16MCUFlags.  Writes 8 pixel bytes. */
+/* (x * K) >> 8 of the row pass.  On the device as a high multiply of (x << 8) by (K << 16): exact for |x| < 2^23
+ * (x is a sum of at most four int16 values) and |K| < 2^15, and both instructions issue on the FMA pipe -- the shift of
+ * the plain form would go to the ALU pipe, which bounds the IDCT kernel. */
+#ifndef JD_ROW_MULHI
+#define JD_ROW_MULHI 0   /* measured slower on B200 (IMAD.HI is not a full-rate instruction): 3.53 -> 3.75 ms */
+#endif
+#if defined(__CUDA_ARCH__) && JD_ROW_MULHI
+#define JD_MS8(x, K) __mulhi((int)((uint32_t)(x) << 8), (K) * 65536)
+#else
+#define JD_MS8(x, K) (((x) * (K)) >> 8)
+#endif
 JD_HD void jd_row_terms(const int p[8], uint32_t colmask, int t[8])
 {
     /* t[0..3] = even part (tmp0..tmp3), t[4..7] = odd part (tmp4..tmp7); the 8 outputs are
@@ -569,19 +586,19 @@ JD_HD void jd_row_terms(const int p[8], uint32_t colmask, int t[8])
         if ((colmask & 0xfcu) == 0u) { /* 1-2 columns: approximation (:2688-2697) */
             tmp0 = tmp1 = tmp2 = tmp3 = p[0];
             tmp7 = p[1];
-            tmp6 = (tmp7 * 217) >> 8;
-            tmp5 = (tmp7 * 145) >> 8;
-            tmp4 = -((tmp7 * 51) >> 8);
+            tmp6 = JD_MS8(tmp7, 217);
+            tmp5 = JD_MS8(tmp7, 145);
+            tmp4 = -JD_MS8(tmp7, 51);
         } else {
             int tmp10 = p[0], tmp13 = p[2];
-            int tmp12 = (tmp13 * 106) >> 8;
+            int tmp12 = JD_MS8(tmp13, 106);
             tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp10 + tmp12; tmp2 = tmp10 - tmp12;
             int z13 = p[3], z11 = p[1];
             tmp7 = z11 + z13;
-            int tmp11 = ((z11 - z13) * 362) >> 8;
-            int z5 = ((z11 - z13) * 473) >> 8;
-            tmp10 = ((z11 * 277) >> 8) - z5;
-            tmp12 = ((z13 * 669) >> 8) + z5;
+            int tmp11 = JD_MS8(z11 - z13, 362);
+            int z5 = JD_MS8(z11 - z13, 473);
+            tmp10 = JD_MS8(z11, 277) - z5;
+            tmp12 = JD_MS8(z13, 669) + z5;
             tmp6 = tmp12 - tmp7;
             tmp5 = tmp11 - tmp6;
             tmp4 = tmp10 + tmp5;
@@ -589,15 +606,15 @@ JD_HD void jd_row_terms(const int p[8], uint32_t colmask, int t[8])
     } else {
         int tmp10 = p[0] + p[4], tmp11 = p[0] - p[4];
         int tmp13 = p[2] + p[6];
-        int tmp12 = (((p[2] - p[6]) * 362) >> 8) - tmp13;
+        int tmp12 = JD_MS8((p[2] - p[6]), 362) - tmp13;
         tmp0 = tmp10 + tmp13; tmp3 = tmp10 - tmp13; tmp1 = tmp11 + tmp12; tmp2 = tmp11 - tmp12;
         int z13 = p[5] + p[3], z10 = p[5] - p[3];
         int z11 = p[1] + p[7], z12 = p[1] - p[7];
         tmp7 = z11 + z13;
-        tmp11 = ((z11 - z13) * 362) >> 8;
-        int z5 = ((z10 + z12) * 473) >> 8;
-        tmp10 = ((z12 * 277) >> 8) - z5;
-        tmp12 = ((z10 * -669) >> 8) + z5;
+        tmp11 = JD_MS8(z11 - z13, 362);
+        int z5 = JD_MS8(z10 + z12, 473);
+        tmp10 = JD_MS8(z12, 277) - z5;
+        tmp12 = JD_MS8(z10, -669) + z5;
         tmp6 = tmp12 - tmp7;
         tmp5 = tmp11 - tmp6;
         tmp4 = tmp10 + tmp5;

@@ -537,9 +537,11 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
                         const uint32_t g12 = __viaddmin_s16x2_relu(y4, tpk[tj][1], 0x0FFF0FFFu);
                         const uint32_t b12 = __viaddmin_s16x2_relu(y4, tpk[tj][2], 0x0FFF0FFFu);
                         if (PT == JD_PT_8888) {
-                            const uint32_t rs = r12 >> 4, gs = g12 >> 4, bs = b12 >> 4;  /* bytes 0 and 2 hold the two pixels */
-                            const uint32_t bg = __byte_perm(bs, gs, 0x6240);             /* B0 G0 B1 G1 */
-                            const uint32_t ra = __byte_perm(rs, 0xFFFFFFFFu, 0x4240);    /* R0 FF R1 FF */
+                            /* 12-bit values << 4: bytes 1 and 3 hold the two pixels (a left shift issues on the FMA pipe,
+                             * the ALU pipe is this kernel's bound) */
+                            const uint32_t rs = r12 << 4, gs = g12 << 4, bs = b12 << 4;
+                            const uint32_t bg = __byte_perm(bs, gs, 0x7351);             /* B0 G0 B1 G1 */
+                            const uint32_t ra = __byte_perm(rs, 0xFFFFFFFFu, 0x4341);    /* R0 FF R1 FF */
                             ow[2 * j] = __byte_perm(bg, ra, 0x5410);
                             ow[2 * j + 1] = __byte_perm(bg, ra, 0x7632);
                         } else {
@@ -888,7 +890,7 @@ jdk_idct_tb(const JDIdctArgs a)
                     jd_col_scalar(m, qq, true, o);
                 }
 #pragma unroll
-                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+                for (int r = 0; r < 8; r++) cr[r][c] = (c == 0) ? o[r] : (int)(short)o[r];   /* column 0 only ever gets added: mod 2^16 is enough */
             }
         } else {
 #pragma unroll
@@ -910,7 +912,7 @@ jdk_idct_tb(const JDIdctArgs a)
                     jd_col_scalar(m, qq, false, o);
                 }
 #pragma unroll
-                for (int r = 0; r < 8; r++) cr[r][c] = (int)(short)o[r];
+                for (int r = 0; r < 8; r++) cr[r][c] = (c == 0) ? o[r] : (int)(short)o[r];   /* column 0 only ever gets added: mod 2^16 is enough */
             }
         }
 #pragma unroll
