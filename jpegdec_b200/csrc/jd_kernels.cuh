@@ -406,6 +406,10 @@ struct JDIdctArgs {
     uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate / callback replay) */
 };
 
+/* x / B for x < 4096 without a high multiply (IMAD.HI is a slow instruction on this part) */
+template <int B>
+__device__ __forceinline__ uint32_t jd_div_small(uint32_t x) { return (x * (uint32_t)(65536 / B + 1)) >> 16; }
+
 template <int HS, int VS, int NC, int MPB>
 struct JDGeo {
     static constexpr int BPMEFF = HS * VS + (NC == 3 ? 2 : 0);
@@ -499,11 +503,11 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
             for (int j = 0; j < PXI / 2; j++) {
                 /* pixel pair j uses chroma sample j (HS == 2) or samples 2j, 2j+1 (HS == 1) */
                 const int c0 = (HS == 2) ? j : 2 * j, c1 = (HS == 2) ? j : 2 * j + 1;
+                const int tj = (HS == 2) ? j : 2 * j;
                 int tr0, tg0, tb0, tr1, tg1, tb1;
                 jd_chroma_terms_sse(jd_byte(cbw[c0 >> 2], c0 & 3), jd_byte(crw[c0 >> 2], c0 & 3), tr0, tg0, tb0);
                 if (HS == 2) { tr1 = tr0; tg1 = tg0; tb1 = tb0; }
                 else jd_chroma_terms_sse(jd_byte(cbw[c1 >> 2], c1 & 3), jd_byte(crw[c1 >> 2], c1 & 3), tr1, tg1, tb1);
-                const int tj = (HS == 2) ? j : 2 * j;
                 tpk[tj][0] = __byte_perm((uint32_t)tr0, (uint32_t)tr1, 0x5410);
                 tpk[tj][1] = __byte_perm((uint32_t)tg0, (uint32_t)tg1, 0x5410);
                 tpk[tj][2] = __byte_perm((uint32_t)tb0, (uint32_t)tb1, 0x5410);
@@ -600,7 +604,7 @@ jdk_idct_color(const JDIdctArgs a)
 
     /* ---- phase A: expand this block's records into a column-major coefficient tile ---- */
     const uint32_t gb = tid >> 3, c = tid & 7;           /* block within CTA, lane within block */
-    const uint32_t ml = gb / G::BPMEFF, blk = gb - ml * G::BPMEFF;
+    const uint32_t ml = jd_div_small<G::BPMEFF>(gb), blk = gb - ml * G::BPMEFF;
     const uint32_t mx = strip * MPB + ml;
     const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
     jd_u64 h = 0;
@@ -800,7 +804,7 @@ jdk_idct_tb(const JDIdctArgs a)
      * 4-7 empty, class 1 = not.  Everything else (class 2: > 4 columns, <= 2 columns, DC only) goes to the 8-lane passes. ---- */
     uint32_t cls = 3;
     if (tid < (uint32_t)G::NB) {
-        const uint32_t ml = tid / G::BPMEFF, blk = tid - ml * G::BPMEFF;
+        const uint32_t ml = jd_div_small<G::BPMEFF>(tid), blk = tid - ml * G::BPMEFF;
         const uint32_t mx = strip * MPB + ml;
         if (mx < a.mcus_x) {
             const jd_u64 h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
@@ -832,7 +836,7 @@ jdk_idct_tb(const JDIdctArgs a)
     if (tid < n0) {
         const uint32_t pb = s_perm[tid];
         const jd_u64 h = s_hdr[pb];
-        const uint32_t ml = pb / G::BPMEFF, blk = pb - ml * G::BPMEFF;
+        const uint32_t ml = jd_div_small<G::BPMEFF>(pb), blk = pb - ml * G::BPMEFF;
         const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
         const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
         const int dc = JD_HDR_DC(h);
@@ -938,7 +942,7 @@ jdk_idct_tb(const JDIdctArgs a)
                 const bool valid = oi < n1;
                 const uint32_t pb = valid ? s_perm[n0 + oi] : 0u;
                 const jd_u64 h = valid ? s_hdr[pb] : 0;
-                const uint32_t ml = pb / G::BPMEFF, blk = pb - ml * G::BPMEFF;
+                const uint32_t ml = jd_div_small<G::BPMEFF>(pb), blk = pb - ml * G::BPMEFF;
                 const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
                 const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
                 const int dc = JD_HDR_DC(h);
