@@ -132,7 +132,9 @@ struct JPEGB200_BATCH {
     bool uploaded, out_device, arena_owned;
     DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
     DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
-    DevBuf<uint32_t> d_err_off;
+    DevBuf<uint32_t> d_err_off, d_dprog;
+    DevBuf<uint4> d_dbands;        /* dither: (image, band, warp of the band above, -) per warp */
+    std::vector<uint4> dbands;
     JDImageDesc *descs_dl;             /* descriptors read back (status, err_mcu); pinned, from ctx->pinpool */
     size_t descs_dl_bytes;
     bool downloaded;
@@ -415,7 +417,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     cudaSetDevice(b->ctx->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
-    b->d_gray_off.release(); b->d_err_off.release();
+    b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
     b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
@@ -606,7 +608,8 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
 }
 
 __global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift);
+                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift,
+                           const uint4 *bands, uint32_t nbands, uint32_t *progress);
 
 extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
 {
@@ -671,6 +674,25 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         /* pageable sources: the runtime stages them before returning, so the vectors may go out of scope */
         CK(cudaMemcpyAsync(b->d_gray_off.p, gray_off.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->d_err_off.p, err_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        /* one warp per band of 32 rows, band-major (band k of every image, then band k + 1): a band's producer is always
+         * launched before it, and the warps resident at any time are bands that can actually run (a band may start ~113
+         * steps after the one above it, so only ~W/113 bands of an image are ever active together) */
+        b->dbands.clear();
+        {
+            uint32_t maxb = 0;
+            std::vector<uint32_t> nb(n, 0), prevpos(n, 0);
+            for (int i = 0; i < n; i++) if (b->parse_status[i] == JPEG_SUCCESS) { nb[i] = (b->descs[i].out_h + 31) / 32; if (nb[i] > maxb) maxb = nb[i]; }
+            for (uint32_t k = 0; k < maxb; k++)
+                for (int i = 0; i < n; i++) {
+                    if (k >= nb[i]) continue;
+                    const uint32_t pos = (uint32_t)b->dbands.size();
+                    b->dbands.push_back(make_uint4((uint32_t)i, k, prevpos[i], 0u));
+                    prevpos[i] = pos;
+                }
+        }
+        CK(b->d_dbands.alloc(b->dbands.size() ? b->dbands.size() : 1)); CK(b->d_dprog.alloc(b->dbands.size() + 1));
+        if (!b->dbands.empty()) CK(cudaMemcpyAsync(b->d_dbands.p, b->dbands.data(), b->dbands.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(b->d_dprog.p, 0, (b->dbands.size() + 1) * 4, st));
     }
     CK(cudaMemcpyAsync(b->d_descs.p, descs_stage.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(b->d_counters.p, 0, 16, st));
@@ -777,9 +799,12 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     }
     CK(cudaEventRecord(b->ev[6], st));
     if (b->dither_bits) {
-        jdk_dither<<<(n * 32 + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p, b->d_err_off.p,
-                                                  out_base, (uint32_t)b->dither_bits, (uint32_t)b->sshift);
-        launches++;
+        if (!b->dbands.empty()) {
+            jdk_dither<<<((unsigned)b->dbands.size() * 32 + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p,
+                                                                                  b->d_err_off.p, out_base, (uint32_t)b->dither_bits, (uint32_t)b->sshift,
+                                                                                  b->d_dbands.p, (uint32_t)b->dbands.size(), b->d_dprog.p);
+            launches++;
+        }
     }
     CK(cudaEventRecord(b->ev[7], st));
     CK(cudaGetLastError());
@@ -951,14 +976,19 @@ extern "C" int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters)
 /* ------------------------------------------------------------------------------------ */
 /* Floyd-Steinberg dither (reference JPEGDither src/jpeg.inl:4871-4940).                    */
 /*                                                                                          */
-/* One warp per image, 32 rows in flight as a wavefront: lane l works on row (band*32 + l)   */
-/* and trails lane l-1 by three pixels, which is exactly when the error that row l-1 sends   */
-/* down to a pixel (e2 of its left neighbour + e3 + e4 of its right neighbour, summed in     */
-/* uint8 like the reference's error line) is complete; it travels to the next lane with one  */
-/* shuffle per step.  The last lane's outgoing errors go through an error line in global     */
-/* memory to the next band -- the same line the reference keeps in usPixels: it persists     */
-/* across MCU rows, only entries 0..2 are cleared per MCU row (:4881), and before the first  */
-/* row it holds the DHT scratch bytes (the host uploads them, see batchDecode).              */
+/* One warp per band of 32 rows, a wavefront inside the warp and a second one across the warps  */
+/* of an image.  Inside: lane l works on row (band*32 + l) and trails lane l-1 by three pixels,*/
+/* which is exactly when the error that row l-1 sends down to a pixel (e2 of its left          */
+/* neighbour + e3 + e4 of its right neighbour, summed in uint8 like the reference's error      */
+/* line) is complete; it travels to the next lane with one shuffle per step.  Across: the last */
+/* lane's outgoing errors go through an error line in global memory to the next band -- the    */
+/* same line the reference keeps in usPixels: it persists across MCU rows, only entries 0..2   */
+/* are cleared per MCU row (:4881), and before the first row it holds the DHT scratch bytes    */
+/* (the host uploads them, see batchDecode).  Band b+1 runs concurrently, JD_DITHER_LAG steps  */
+/* behind band b: every 16 steps a band publishes how many steps it has completed and checks   */
+/* its predecessor's count before it reads the next 16 bytes of the line.  Each entry of the   */
+/* line is read by band b+1 before band b+1 overwrites it (95 steps later) and after band b    */
+/* wrote it, so one line per image serves all bands, as in the reference.                      */
 /* ------------------------------------------------------------------------------------ */
 /* 16 bytes starting at byte offset `mo` (0..15) of the 32-byte pair (a, b) */
 __device__ __forceinline__ uint4 jd_window16(const uint4 a, const uint4 b, uint32_t mo)
@@ -977,15 +1007,28 @@ __device__ __forceinline__ uint4 jd_window16(const uint4 a, const uint4 b, uint3
                       __funnelshift_r(v[3], v[4], bs));
 }
 
+__device__ __forceinline__ uint32_t jd_ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void jd_st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(128)
 jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift)
+           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift,
+           const uint4 *bands, uint32_t nbands, uint32_t *progress)
 {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   /* global warp = band */
     const uint32_t lane = threadIdx.x & 31u;
-    if (i >= nimg) return;
+    if (wg >= nbands) return;
+    const uint4 bd = bands[wg];
+    const uint32_t i = bd.x, bi = bd.y;
     const JDImageDesc &im = imgs[i];
-    if (im.nseg == 0) return;
     const uint32_t hs = (im.subsample >> 4) ? (im.subsample >> 4) : 1, vs = (im.subsample & 15) ? (im.subsample & 15) : 1;
     const uint32_t mcu_h = (vs * 8) >> sshift;
     const int W = (int)((uint32_t)im.mcus_x * ((hs * 8) >> sshift)); /* padded width = pitch of the gray stage (multiple of 8) */
@@ -1006,7 +1049,17 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     const uint32_t mo = (uint32_t)((16 - (skew & 15)) & 15);   /* byte offset of the window inside the aligned pair */
     const int jsh = (skew + 15) >> 4;                           /* aligned chunk index of window m = m - jsh */
     const int nchunks = W >> 4;
-    for (uint32_t band = 0; band < rows; band += 32) {
+    const uint32_t *prev = (bi > 0) ? progress + bd.z : nullptr;     /* steps the band above has completed */
+    uint32_t *mine = progress + wg;
+    /* the line entry S[j] is written by the band above at its step j + 95; lane 0 is about to read entries < `upto` */
+    auto wait_for = [&](int upto) {
+        if (prev) {
+            if (lane == 0) { const uint32_t need = (uint32_t)(upto + 96); while (jd_ld_acquire(prev) < need) __nanosleep(64); }
+            __syncwarp();
+        }
+    };
+    {
+        const uint32_t band = bi * 32u;
         const uint32_t y = band + lane;
         const bool live = y < rows;
         const bool mcu_first = (y % mcu_h) == 0;        /* errors[0..2] are cleared at each JPEGDither call */
@@ -1025,32 +1078,29 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         };
         if (vec) {
             A0 = chunk(-jsh); A1 = chunk(1 - jsh); A2 = chunk(2 - jsh);
-            if (lane == 0) { ewin = *reinterpret_cast<const uint4 *>(S); enext = (1 < nchunks) ? *reinterpret_cast<const uint4 *>(S + 16) : zero4; }
+            wait_for(32);
+            if (lane == 0) { ewin = __ldcg(reinterpret_cast<const uint4 *>(S)); enext = (1 < nchunks) ? __ldcg(reinterpret_cast<const uint4 *>(S + 16)) : zero4; }
             win = jd_window16(A0, A1, mo);
+        } else {
+            wait_for(W + 2);         /* unusual widths: the band above finishes first */
         }
         const int nsteps = W + 3 * 31 + 2;
-        for (int t = 0; t < nsteps; t++) {
+        for (int tb = 0; tb < nsteps; tb += 16) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {                    /* unrolled: byte k of the 16-byte windows is a constant extract */
+            const int t = tb + k;
             const int x = t - skew;
             const bool inrow = live && x >= 0 && x < W;
             uint32_t pix, inc = from_above;
             if (vec) {
                 /* warp-uniform: byte t of every lane's skewed row, and (lane 0) byte t of the error line */
-                pix = win.x & 0xFFu;
-                win.x = __funnelshift_r(win.x, win.y, 8); win.y = __funnelshift_r(win.y, win.z, 8);
-                win.z = __funnelshift_r(win.z, win.w, 8); win.w >>= 8;
-                if (lane == 0) inc = ewin.x & 0xFFu;
-                ewin.x = __funnelshift_r(ewin.x, ewin.y, 8); ewin.y = __funnelshift_r(ewin.y, ewin.z, 8);
-                ewin.z = __funnelshift_r(ewin.z, ewin.w, 8); ewin.w >>= 8;
-                if ((t & 15) == 15) {
-                    const int m = (t + 1) >> 4;            /* next window index */
-                    A0 = A1; A1 = A2; A2 = chunk(m - jsh + 2);
-                    win = jd_window16(A0, A1, mo);
-                    ewin = enext;
-                    enext = (lane == 0 && m + 1 < nchunks) ? *reinterpret_cast<const uint4 *>(S + 16 * (m + 1)) : zero4;
-                }
+                const uint32_t ww = (k < 4) ? win.x : (k < 8) ? win.y : (k < 12) ? win.z : win.w;
+                const uint32_t ee = (k < 4) ? ewin.x : (k < 8) ? ewin.y : (k < 12) ? ewin.z : ewin.w;
+                pix = (ww >> (8 * (k & 3))) & 0xFFu;
+                if (lane == 0) inc = (ee >> (8 * (k & 3))) & 0xFFu;
             } else {
                 pix = inrow ? p[x] : 0u;
-                if (lane == 0 && inrow) inc = S[x];
+                if (lane == 0 && inrow) inc = __ldcg(S + x);
             }
             uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
             if (inrow) {
@@ -1077,7 +1127,19 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
             /* next step lane l+1 handles pixel x-2 and needs D[x-1] of this row */
             from_above = __shfl_up_sync(0xffffffffu, dcomplete, 1);
         }
+            /* ---- every 16 steps: next windows, and publish progress ---- */
+            if (vec) {
+                const int m = (tb >> 4) + 1;               /* next window index */
+                A0 = A1; A1 = A2; A2 = chunk(m - jsh + 2);
+                win = jd_window16(A0, A1, mo);
+                ewin = enext;
+                if (m + 1 < nchunks) wait_for(16 * (m + 2));
+                enext = (lane == 0 && m + 1 < nchunks) ? __ldcg(reinterpret_cast<const uint4 *>(S + 16 * (m + 1))) : zero4;
+            }
+            /* tb + 16 steps done (the shuffles ordered the warp's stores before lane 31's release) */
+            if (lane == 31) { __threadfence(); jd_st_release(mine, (uint32_t)(tb + 16)); }
+        }
         __syncwarp();
-        __threadfence_block();
+        if (lane == 31) { __threadfence(); jd_st_release(mine, 0x7FFFFFFFu); }
     }
 }
