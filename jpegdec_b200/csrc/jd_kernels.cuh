@@ -477,15 +477,19 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
                                                 uint8_t *outbase, uint32_t pitch)
 {
     constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
-    /* one item = PXI pixels (one 16-byte store) in each of the VS rows that share chroma */
-    constexpr int PXI = 16 / BYPP;              /* 4 (8888), 8 (565), 16 (gray) */
+    /* one item = PXI pixels (OWN 16-byte stores) in each of the VS rows that share chroma */
+#ifndef JD_PXI_8888
+#define JD_PXI_8888 4   /* 8-pixel items (two stores per row) measured slower: 3.37 -> 3.64 ms */
+#endif
+    constexpr int PXI = (PT == JD_PT_8888) ? JD_PXI_8888 : 16 / BYPP;   /* 8 (8888: two stores), 8 (565), 16 (gray) */
+    constexpr int OWN = PXI * BYPP / 16;
     constexpr int IPR = WCTA / PXI;          /* items per row */
     constexpr int NITEM = IPR * 8;              /* x (HCTA / VS) row groups */
     constexpr bool SSE_PATH = (ARITH == JPEG_ARITH_SSE2) && (HS == VS); /* jpeg.inl:3409-3517, :4006-4308 */
-    for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) {
-        const uint32_t rg = it / IPR, xg = it - rg * IPR;
+    /* item (rg, xg): PXI pixels at x = xg * PXI in the VS rows of row group rg */
+    auto item = [&](const uint32_t rg, const uint32_t xg) {
         const uint32_t gx = strip * WCTA + xg * PXI;
-        if (!INTERIOR && gx >= W) continue;
+        if (!INTERIOR && gx >= W) return;
         const bool full = INTERIOR || (gx + PXI <= W);
         /* chroma samples covering these PXI pixels: PXI / HS of each */
         uint32_t cbw[2] = {0, 0}, crw[2] = {0, 0};
@@ -525,7 +529,7 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
                 else if (PXI == 8) { const uint2 u = *reinterpret_cast<const uint2 *>(py); yw[0] = u.x; yw[1] = u.y; }
                 else { const uint4 u = *reinterpret_cast<const uint4 *>(py); yw[0] = u.x; yw[1] = u.y; yw[2] = u.z; yw[3] = u.w; }
             }
-            uint32_t ow[4]; /* the 16 output bytes */
+            uint32_t ow[4 * OWN]; /* the output bytes of this row */
             if (PT == JD_PT_GRAY) {
                 ow[0] = yw[0]; ow[1] = yw[1]; ow[2] = yw[2]; ow[3] = yw[3];
             } else {
@@ -567,7 +571,10 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
                         pix[i] = jd_pixel_scalar<PT>((int)Y << 12, (int)Cb - 128, (int)Cr - 128, a.big_endian != 0u);
                     }
                 }
-                if (PT == JD_PT_8888) { ow[0] = pix[0]; ow[1] = pix[1]; ow[2] = pix[2]; ow[3] = pix[3]; }
+                if (PT == JD_PT_8888) {
+#pragma unroll
+                    for (int i = 0; i < PXI; i++) ow[i] = pix[i];
+                }
                 else {
 #pragma unroll
                     for (int i = 0; i < 4; i++) ow[i] = pix[(2 * i) % PXI] | (pix[(2 * i + 1) % PXI] << 16);
@@ -576,15 +583,23 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
             }
             uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
             if (INTERIOR || (full && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0))) {
-                *reinterpret_cast<uint4 *>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+#pragma unroll
+                for (int q = 0; q < OWN; q++) reinterpret_cast<uint4 *>(dst)[q] = make_uint4(ow[4 * q], ow[4 * q + 1], ow[4 * q + 2], ow[4 * q + 3]);
             } else {
                 for (uint32_t i = 0; i < (uint32_t)PXI && gx + i < W; i++) {
-                    if (BYPP == 4) reinterpret_cast<uint32_t *>(dst)[i] = ow[i & 3];
+                    if (BYPP == 4) reinterpret_cast<uint32_t *>(dst)[i] = ow[i % (4 * OWN)];
                     else if (BYPP == 2) reinterpret_cast<uint16_t *>(dst)[i] = (uint16_t)(ow[(i >> 1) & 3] >> ((i & 1) * 16));
                     else dst[i] = (uint8_t)(ow[(i >> 2) & 3] >> ((i & 3) * 8));
                 }
             }
         }
+        };
+    if (NTHREADS % IPR == 0) {
+        /* the thread keeps its x position; only the row group advances (no division, x addressing hoisted) */
+        const uint32_t xg = tid % IPR;
+        for (uint32_t rg = tid / IPR; rg < 8u; rg += NTHREADS / IPR) item(rg, xg);
+    } else {
+        for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) { const uint32_t rg = it / IPR; item(rg, it - rg * IPR); }
     }
 }
 
