@@ -179,9 +179,14 @@ JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u 
 #define JD_BF_COLMASK(bf) ((bf) >> 24)
 #define JD_BF_MASK 0xFF800000u
 
-/* DC_ONLY: first scan of a progressive file (Ss = Se = 0): each block is one DC symbol, difference << Al
- * (reference JPEGDecodeMCU_P, src/jpeg.inl:1849-1884; no window quirk there: it reloads at bit offset > 47). */
-template <typename EventSink, bool DC_ONLY = false>
+/* MODE 0: baseline.  MODE 1 (JD_MODE_DC_SCAN): first scan of a progressive file (Ss = Se = 0): each block is one DC
+ * symbol, difference << Al (reference JPEGDecodeMCU_P, src/jpeg.inl:1849-1884; no window quirk there: it reloads at bit
+ * offset > 47).  MODE 2 (JD_MODE_PARSE_AC): baseline parse for 1/8-scale output, which uses DC only (jpeg.inl:5146-5154
+ * with bThumbnail): AC symbols are walked over but nothing is stored -- like the reference's store limit (:2247). */
+#define JD_MODE_BASELINE 0
+#define JD_MODE_DC_SCAN 1
+#define JD_MODE_PARSE_AC 2
+template <typename EventSink, int MODE = JD_MODE_BASELINE>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
                              const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
@@ -310,7 +315,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
             const uint32_t comp = cur & 3u;
 #if JD_V_PRED
-            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + (DC_ONLY ? (int)((uint32_t)v << in.al) : v);
+            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + ((MODE == JD_MODE_DC_SCAN) ? (int)((uint32_t)v << in.al) : v);
             pred0 = (comp == 0u) ? pv : pred0;
             pred1 = (comp == 1u) ? pv : pred1;
             pred2 = (comp >= 2u) ? pv : pred2;
@@ -320,7 +325,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             else if (comp == 1u) { pred1 += v; dcval = pred1; }
             else { pred2 += v; dcval = pred2; }
 #endif
-            if (!DC_ONLY) {
+            if (MODE != JD_MODE_DC_SCAN) {
                 k = 1;
 #if JD_V_PTR
                 tb = lut + JD_LUT_AC(cur >> 3);
@@ -338,7 +343,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             k = 64;
         } else {
             k += rs >> 4;
-            if (s && k < 64u) {
+            if (MODE != JD_MODE_PARSE_AC && s && k < 64u) {
                 /* stored coefficient (jpeg.inl:2247-2256) */
                 if (s > 11) { err = JD_SEG_BADSIZE; break; }
                 if (len + s >= 18) {
