@@ -67,56 +67,94 @@ def load_traffic(workload):
 
 
 class ClockSampler:
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): an NVML polling
+    thread (5 ms period; the timed region of a short run is only tens of milliseconds), nvidia-smi -lms as the fallback."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (time, sm_mhz, max_mhz, reasons bitmask)
         self.gpu = gpu_index
+        self.stop_flag = False
+        self.t = None
+        self.mode = None
+
+    def _nvml_loop(self, pynvml, h, mx):
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.time(), float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                bits = 0
+                for (bit, _), v in zip(self.REASONS, f[3:7]):
+                    if v.lower().startswith("active"):
+                        bits |= bit
+                self.rows.append((time.time(), float(f[0]), float(f[1]), bits))
+            except Exception:
+                continue
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(pynvml, h, mx), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.mode = "nvidia-smi"
+            self.t = threading.Thread(target=self._smi_loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            self.mode = None
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.15:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:  # region shorter than one sample: take the nearest sample
-            for ts, line in self.rows[-3:]:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[0])); mx = float(f[1])
-                except Exception:
-                    pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"], "samples": 0}
+        if self.mode == "nvidia-smi":
+            time.sleep(0.1)
+            self.proc.terminate()
+        self.stop_flag = True
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        note = None
+        if not inside and self.rows:   # region shorter than one sample: nearest samples
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+            note = "no sample inside the timed region; nearest samples used"
+        sm = [r[1] for r in inside]
+        bits = 0
+        for r in inside:
+            bits |= r[3]
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": inside[0][2] if inside else None,
+               "reasons": [name for bit, name in self.REASONS if bits & bit], "samples": len(sm), "source": self.mode}
+        if note:
+            out["note"] = note
+        return out
 
 
 def make_images(wl, rank, unique):
@@ -262,7 +300,7 @@ def main():
         b.decode(J.JPEGB200_OUT_DEVICE); b.download(); b.wait()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.02)
     barrier()
     t0 = time.time()
     dev_ms, stage = 0.0, {k: 0.0 for k in J.TIMING_NAMES}
