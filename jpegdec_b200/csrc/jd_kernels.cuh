@@ -409,10 +409,6 @@ struct JDIdctArgs {
     uint32_t padded;        /* 1: write the whole MCU-aligned area (dither intermediate / callback replay) */
 };
 
-/* x / B for x < 4096 without a high multiply (IMAD.HI is a slow instruction on this part) */
-template <int B>
-__device__ __forceinline__ uint32_t jd_div_small(uint32_t x) { return (x * (uint32_t)(65536 / B + 1)) >> 16; }
-
 template <int HS, int VS, int NC, int MPB>
 struct JDGeo {
     static constexpr int BPMEFF = HS * VS + (NC == 3 ? 2 : 0);
@@ -440,6 +436,10 @@ __device__ __forceinline__ uint32_t jd_pack_sat(int a, int b, uint32_t c)
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+
+/* x / B for x < 4096 without a high multiply (IMAD.HI is a slow instruction on this part) */
+template <int B>
+__device__ __forceinline__ uint32_t jd_div_small(uint32_t x) { return (x * (uint32_t)(65536 / B + 1)) >> 16; }
 
 __device__ __forceinline__ uint32_t jd_byte(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
 
@@ -602,7 +602,7 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
         const uint32_t xg = tid % IPR;
         for (uint32_t rg = tid / IPR; rg < 8u; rg += NTHREADS / IPR) item(rg, xg);
     } else {
-        for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) { const uint32_t rg = it / IPR; item(rg, it - rg * IPR); }
+        for (uint32_t it = tid; it < (uint32_t)NITEM; it += NTHREADS) { const uint32_t rg = jd_div_small<IPR>(it); item(rg, it - rg * IPR); }
     }
 }
 
@@ -952,10 +952,17 @@ jdk_idct_tb(const JDIdctArgs a)
         const uint32_t npass = (n1 + 3u) >> 2;
         const uint32_t busy = (n0 + 31u) >> 5;
         const uint32_t nfree = (busy < (uint32_t)G::NW) ? (uint32_t)G::NW - busy : 0u;
-        const uint32_t first = nfree ? wid - busy : wid, step = nfree ? nfree : (uint32_t)G::NW;
-        if (!nfree || wid >= busy) {
+        /* a thread-per-block warp runs ~720 instructions, a pass ~200: the free warps take up to 4 passes each first,
+         * what remains goes round-robin over all warps */
+        const uint32_t base = (npass < 4u * nfree) ? npass : 4u * nfree;
+        {
             const uint32_t c = lane & 7u;
-            for (uint32_t j = first; j < npass; j += step) {
+            /* this warp's passes: (free warps only) wid - busy, + nfree, ... below `base`, then base + wid, + NW, ...
+             * (one loop on purpose: two loops around a shared body measured 12 % slower on UHD q85) */
+            bool first = wid >= busy;
+            for (uint32_t j = first ? wid - busy : base + wid;; j += first ? nfree : (uint32_t)G::NW) {
+                if (first && j >= base) { first = false; j = base + wid; }
+                if (!first && j >= npass) break;
                 const uint32_t oi = j * 4u + (lane >> 3);
                 const bool valid = oi < n1;
                 const uint32_t pb = valid ? s_perm[n0 + oi] : 0u;
