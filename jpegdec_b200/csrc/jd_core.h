@@ -232,17 +232,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     const uint32_t rec_lo = (uint32_t)(uintptr_t)rec;
     int dcval = 0;
     /* current table geometry (DC at block start) */
-#ifndef JD_V_PTR
-#define JD_V_PTR 1
-#endif
-#ifndef JD_V_PRED
-#define JD_V_PRED 1
-#endif
-#if JD_V_PTR
     const uint16_t *tb = lut + JD_LUT_DC((cur >> 2) & 1u);
-#else
-    uint32_t toff = JD_LUT_DC((cur >> 2) & 1u);
-#endif
     uint32_t thr = 0xF800u, sh = 4u, msk = 0x7Fu;
 
     if (nblk_total == 0) { out.status = JD_SEG_OK; out.err_mcu = -1; out.jmap = jw; out.nrec = 0; return; }
@@ -289,11 +279,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         /* ---- code lookup ---- */
         const uint32_t w16 = (uint32_t)(bb >> 48);
         const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
-#if JD_V_PTR
         const uint32_t e = tb[idx];
-#else
-        const uint32_t e = lut[toff + idx];
-#endif
         if (e == 0u) { err = JD_SEG_BADCODE; break; }
         const int len = (int)(e >> 8);
         const uint32_t rs = e & 0xFFu;
@@ -314,24 +300,14 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             P += s;
             { const int nPb = P >> 3; jw += (uint32_t)(nPb - Pb) * JD_JW_ONES; Pb = nPb; }
             const uint32_t comp = cur & 3u;
-#if JD_V_PRED
             const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + ((MODE == JD_MODE_DC_SCAN) ? (int)((uint32_t)v << in.al) : v);
             pred0 = (comp == 0u) ? pv : pred0;
             pred1 = (comp == 1u) ? pv : pred1;
             pred2 = (comp >= 2u) ? pv : pred2;
             dcval = pv;
-#else
-            if (comp == 0u) { pred0 += v; dcval = pred0; }
-            else if (comp == 1u) { pred1 += v; dcval = pred1; }
-            else { pred2 += v; dcval = pred2; }
-#endif
             if (MODE != JD_MODE_DC_SCAN) {
                 k = 1;
-#if JD_V_PTR
                 tb = lut + JD_LUT_AC(cur >> 3);
-#else
-                toff = JD_LUT_AC(cur >> 3);
-#endif
                 thr = 0xFC00u; sh = 0u; msk = 0x3FFu;
                 continue;
             }
@@ -409,11 +385,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             bsh += 4u;
             if (bsh == bsh_end) bsh = 0u;
             cur = (sched >> bsh) & 15u;
-#if JD_V_PTR
             tb = lut + JD_LUT_DC((cur >> 2) & 1u);
-#else
-            toff = JD_LUT_DC((cur >> 2) & 1u);
-#endif
             thr = 0xF800u; sh = 4u; msk = 0x7Fu;
             k = 0; cnt = 0; bflags = 0;
             ridx0 = in.rec_index0 + (((uint32_t)(uintptr_t)rp - rec_lo) >> 1);
@@ -455,15 +427,11 @@ JD_HD uint32_t jd_range(int v)
 /* mulhi of the SSE2 build: _mm_mulhi_epi16(_mm_slli_epi16(x,2), K) with x taken mod 2^16.
  * (int16)(x<<2) << 16 == x << 18 in 32-bit wrap arithmetic, so the whole thing is a 32x32
  * high multiply of (x << 18) by K. */
-#ifndef JD_MH2_MULHI
-#define JD_MH2_MULHI 0
-#endif
 JD_HD int jd_mh2(int x, int K)
 {
-#if defined(__CUDA_ARCH__) && JD_MH2_MULHI
-    return __mulhi((int)((uint32_t)x << 18), K);
-#elif defined(__CUDA_ARCH__)
-    /* (int16)(x << 2) * K fits 32 bits (|K| < 2^15): a full-rate multiply and two shifts instead of IMAD.HI */
+#ifdef __CUDA_ARCH__
+    /* (int16)(x << 2) * K fits 32 bits (|K| < 2^15): a full-rate multiply and two shifts; the equivalent __mulhi
+     * (IMAD.HI) measured 4 % slower for the whole IDCT kernel */
     return (((int)((uint32_t)x << 18) >> 16) * K) >> 16;
 #else
     return (int)(((int64_t)(int32_t)((uint32_t)x << 18) * (int64_t)K) >> 32);
@@ -571,17 +539,8 @@ JD_HD void jd_col_scalar(const int m[8], const int q[8], bool rows47_empty, int 
 
 /* Row pass (both builds, jpeg.inl:2681-2797).  p[c] = int16 column results of one row
  * (sign-extended); colmask = low byte of the block's u16MCUFlags.  Writes 8 pixel bytes. */
-/* (x * K) >> 8 of the row pass.  On the device as a high multiply of (x << 8) by (K << 16): exact for |x| < 2^23
- * (x is a sum of at most four int16 values) and |K| < 2^15, and both instructions issue on the FMA pipe -- the shift of
- * the plain form would go to the ALU pipe, which bounds the IDCT kernel. */
-#ifndef JD_ROW_MULHI
-#define JD_ROW_MULHI 0   /* measured slower on B200 (IMAD.HI is not a full-rate instruction): 3.53 -> 3.75 ms */
-#endif
-#if defined(__CUDA_ARCH__) && JD_ROW_MULHI
-#define JD_MS8(x, K) __mulhi((int)((uint32_t)(x) << 8), (K) * 65536)
-#else
+/* (x * K) >> 8 of the row pass (a mulhi formulation that moves the shift to the FMA pipe measured slower: IMAD.HI) */
 #define JD_MS8(x, K) (((x) * (K)) >> 8)
-#endif
 JD_HD void jd_row_terms(const int p[8], uint32_t colmask, int t[8])
 {
     /* t[0..3] = even part (tmp0..tmp3), t[4..7] = odd part (tmp4..tmp7); the 8 outputs are

@@ -793,9 +793,6 @@ __device__ __forceinline__ uint2 jd_row_finish_packed(const int t[8])
     return make_uint2(__byte_perm(s01, s23, 0x6420), __byte_perm(d54, d76, 0x4602));
 }
 
-#ifndef JD_TB_WIDE_SCATTER
-#define JD_TB_WIDE_SCATTER 1
-#endif
 #ifndef JD_TB_MINB
 #define JD_TB_MINB 10   /* 48 registers: 10 CTAs per SM measured faster than 56 registers / 9 CTAs and than 40 / 12 */
 #endif
@@ -873,7 +870,6 @@ jdk_idct_tb(const JDIdctArgs a)
 #pragma unroll
         for (int c = 0; c < 4; c++) *reinterpret_cast<uint4 *>(tile + c * 8) = make_uint4(0, 0, 0, 0);
         if (!JD_HDR_BIG(h)) {
-#if JD_TB_WIDE_SCATTER
             /* the first 10 halfwords that cover the records come in as five independent aligned 32-bit loads (one round
              * trip instead of a chain of 2-byte loads); longer blocks finish in the loop below */
             const uint32_t off = ri & 1u, total = off + ncoef;
@@ -889,9 +885,6 @@ jdk_idct_tb(const JDIdctArgs a)
                 }
             }
             for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
-#else
-            for (uint32_t i = 0; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
-#endif
         } else {
             for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
         }
