@@ -182,10 +182,13 @@ JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u 
 /* MODE 0: baseline.  MODE 1 (JD_MODE_DC_SCAN): first scan of a progressive file (Ss = Se = 0): each block is one DC
  * symbol, difference << Al (reference JPEGDecodeMCU_P, src/jpeg.inl:1849-1884; no window quirk there: it reloads at bit
  * offset > 47).  MODE 2 (JD_MODE_PARSE_AC): baseline parse for 1/8-scale output, which uses DC only (jpeg.inl:5146-5154
- * with bThumbnail): AC symbols are walked over but nothing is stored -- like the reference's store limit (:2247). */
+ * with bThumbnail): AC symbols are walked over but nothing is stored -- like the reference's store limit (:2247).
+ * MODE 3 (JD_MODE_STORE_LOW): 1/4-scale output uses zigzag positions 1..4 only (natural 1, 8, 16, 9; the reference stores
+ * nothing beyond them either, :2247 with its quarter-scale limit). */
 #define JD_MODE_BASELINE 0
 #define JD_MODE_DC_SCAN 1
 #define JD_MODE_PARSE_AC 2
+#define JD_MODE_STORE_LOW 3
 template <typename EventSink, int MODE = JD_MODE_BASELINE>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
                              const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
@@ -319,7 +322,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             k = 64;
         } else {
             k += rs >> 4;
-            if (MODE != JD_MODE_PARSE_AC && s && k < 64u) {
+            if (MODE != JD_MODE_PARSE_AC && s && k < ((MODE == JD_MODE_STORE_LOW) ? 5u : 64u)) {
                 /* stored coefficient (jpeg.inl:2247-2256) */
                 if (s > 11) { err = JD_SEG_BADSIZE; break; }
                 if (len + s >= 18) {

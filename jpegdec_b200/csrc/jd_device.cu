@@ -728,7 +728,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ea.rec_total = (uint32_t)(4 * b->comp_total + 1024);
         ea.seg_jmap = b->d_seg_jmap.p; ea.seg_status = b->d_seg_status.p; ea.seg_nrec = b->d_seg_nrec.p;
         ea.events = b->d_events.p; ea.event_count = b->d_counters.p; ea.event_cap = JD_EVENT_CAP;
-        ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0; ea.dc_output = (b->sshift == 3) ? 1u : 0u;
+        ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0; ea.dc_output = (b->sshift == 3) ? 1u : (b->sshift == 2) ? 2u : 0u;
         jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
         launches++;
     }

@@ -116,7 +116,7 @@ struct JDEntropyArgs {
     uint32_t event_cap;
     uint32_t nwork;
     uint32_t data_base;           /* byte offset subtracted when sizing the record area */
-    uint32_t dc_output;           /* 1: 1/8-scale job, only DC values are consumed downstream */
+    uint32_t dc_output;           /* 1: 1/8-scale job, only DC values are consumed downstream; 2: 1/4-scale job, zigzag 1..4 */
 };
 
 __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     in.al = (im.prog >> 8) & 15u;
     if (im.prog & 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_DC_SCAN>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
-    else if (a.dc_output) jd_decode_segment<JDEventSinkDev, JD_MODE_PARSE_AC>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
+    else if (a.dc_output == 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_PARSE_AC>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
+    else if (a.dc_output == 2u) jd_decode_segment<JDEventSinkDev, JD_MODE_STORE_LOW>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
     else jd_decode_segment<JDEventSinkDev, JD_MODE_BASELINE>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));

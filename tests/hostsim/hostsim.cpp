@@ -168,6 +168,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.al = prog ? (uint32_t)(info.approx & 15) : 0u;
         if (prog) jd_decode_segment<VecSink, JD_MODE_DC_SCAN>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         else if (sshift == 3) jd_decode_segment<VecSink, JD_MODE_PARSE_AC>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        else if (sshift == 2) jd_decode_segment<VecSink, JD_MODE_STORE_LOW>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         else jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
         jmap[sgi] = so.jmap;
         if (so.err_mcu >= 0) { bad = 1; break; }
