@@ -35,9 +35,9 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdio.h>
-#ifndef PROGMEM
-#define memcpy_P memcpy
+#if !defined(PROGMEM)   /* hosted build: flash-resident arrays are ordinary arrays */
 #define PROGMEM
+#define memcpy_P(dst, src, n) memcpy((dst), (src), (n))
 #endif
 
 #ifdef __cplusplus
@@ -57,38 +57,15 @@ extern "C" {
 #define MAX_BUFFERED_PIXELS 2048 /* reference src/JPEGDEC.h:65: draw-callback batching unit */
 
 /* Supported decode modes (reference src/JPEGDEC.h:95-99) */
-enum {
-    JPEG_MODE_BASELINE = 0,
-    JPEG_MODE_PROGRESSIVE,
-    JPEG_MODE_INVALID
-};
+enum { JPEG_MODE_BASELINE = 0, JPEG_MODE_PROGRESSIVE, JPEG_MODE_INVALID };
 
 /* Pixel types (reference src/JPEGDEC.h:102-111) */
-enum {
-    RGB565_LITTLE_ENDIAN = 0,
-    RGB565_BIG_ENDIAN,
-    RGB8888,
-    EIGHT_BIT_GRAYSCALE,
-    FOUR_BIT_DITHERED,
-    TWO_BIT_DITHERED,
-    ONE_BIT_DITHERED,
-    INVALID_PIXEL_TYPE
-};
+enum { RGB565_LITTLE_ENDIAN = 0, RGB565_BIG_ENDIAN, RGB8888, EIGHT_BIT_GRAYSCALE, FOUR_BIT_DITHERED, TWO_BIT_DITHERED, ONE_BIT_DITHERED, INVALID_PIXEL_TYPE };
 
-enum {
-    JPEG_MEM_RAM = 0,
-    JPEG_MEM_FLASH
-};
+enum { JPEG_MEM_RAM = 0, JPEG_MEM_FLASH };
 
 /* Error codes returned by getLastError() (reference src/JPEGDEC.h:119-126) */
-enum {
-    JPEG_SUCCESS = 0,
-    JPEG_INVALID_PARAMETER,
-    JPEG_DECODE_ERROR,
-    JPEG_UNSUPPORTED_FEATURE,
-    JPEG_INVALID_FILE,
-    JPEG_ERROR_MEMORY
-};
+enum { JPEG_SUCCESS = 0, JPEG_INVALID_PARAMETER, JPEG_DECODE_ERROR, JPEG_UNSUPPORTED_FEATURE, JPEG_INVALID_FILE, JPEG_ERROR_MEMORY };
 
 /* Which reference build the pixels are bit-exact with (the reference has two
  * different x86-64 arithmetic paths, src/jpeg.inl:49-55). */
@@ -165,36 +142,36 @@ typedef struct jpeg_image_tag {
 } JPEGIMAGE;
 
 /* ---- C API (reference src/JPEGDEC.h:290-309) ---- */
-int JPEG_openRAM(JPEGIMAGE *pJPEG, uint8_t *pData, int iDataSize, JPEG_DRAW_CALLBACK *pfnDraw);
-int JPEG_openFile(JPEGIMAGE *pJPEG, const char *szFilename, JPEG_DRAW_CALLBACK *pfnDraw);
+int JPEG_openRAM(JPEGIMAGE *img, uint8_t *jpeg_bytes, int jpeg_size, JPEG_DRAW_CALLBACK *draw);
+int JPEG_openFile(JPEGIMAGE *img, const char *path, JPEG_DRAW_CALLBACK *draw);
 /* generic callback I/O open (what the reference's C++ open(name, cbs...) does, src/JPEGDEC.cpp:155-229) */
-int JPEG_openCallbacks(JPEGIMAGE *pJPEG, const char *szFilename, void *fHandle, int iDataSize,
+int JPEG_openCallbacks(JPEGIMAGE *img, const char *szFilename, void *fHandle, int iDataSize,
                        JPEG_OPEN_CALLBACK *pfnOpen, JPEG_CLOSE_CALLBACK *pfnClose,
                        JPEG_READ_CALLBACK *pfnRead, JPEG_SEEK_CALLBACK *pfnSeek,
                        JPEG_DRAW_CALLBACK *pfnDraw);
-void JPEG_setFramebuffer(JPEGIMAGE *pJPEG, void *pFramebuffer);
-void JPEG_setCropArea(JPEGIMAGE *pJPEG, int x, int y, int w, int h);
-void JPEG_getCropArea(JPEGIMAGE *pJPEG, int *x, int *y, int *w, int *h);
-int JPEG_getWidth(JPEGIMAGE *pJPEG);
-int JPEG_getHeight(JPEGIMAGE *pJPEG);
-int JPEG_decode(JPEGIMAGE *pJPEG, int x, int y, int iOptions);
-int JPEG_decodeDither(JPEGIMAGE *pJPEG, uint8_t *pDither, int iOptions);
-void JPEG_close(JPEGIMAGE *pJPEG);
-int JPEG_getLastError(JPEGIMAGE *pJPEG);
-int JPEG_getOrientation(JPEGIMAGE *pJPEG);
-int JPEG_getBpp(JPEGIMAGE *pJPEG);
-int JPEG_getSubSample(JPEGIMAGE *pJPEG);
-int JPEG_getJPEGType(JPEGIMAGE *pJPEG);
-int JPEG_hasThumb(JPEGIMAGE *pJPEG);
-int JPEG_getThumbWidth(JPEGIMAGE *pJPEG);
-int JPEG_getThumbHeight(JPEGIMAGE *pJPEG);
-void JPEG_setPixelType(JPEGIMAGE *pJPEG, int iType);
-int JPEG_getPixelType(JPEGIMAGE *pJPEG);
-void JPEG_setMaxOutputSize(JPEGIMAGE *pJPEG, int iMaxMCUs);
-void JPEG_setUserPointer(JPEGIMAGE *pJPEG, void *p);
+void JPEG_setFramebuffer(JPEGIMAGE *img, void *framebuffer);
+void JPEG_setCropArea(JPEGIMAGE *img, int crop_x, int crop_y, int crop_w, int crop_h);
+void JPEG_getCropArea(JPEGIMAGE *img, int *crop_x, int *crop_y, int *crop_w, int *crop_h);
+int JPEG_getWidth(JPEGIMAGE *img);
+int JPEG_getHeight(JPEGIMAGE *img);
+int JPEG_decode(JPEGIMAGE *img, int x_offset, int y_offset, int options);
+int JPEG_decodeDither(JPEGIMAGE *img, uint8_t *dither_rows, int options);
+void JPEG_close(JPEGIMAGE *img);
+int JPEG_getLastError(JPEGIMAGE *img);
+int JPEG_getOrientation(JPEGIMAGE *img);
+int JPEG_getBpp(JPEGIMAGE *img);
+int JPEG_getSubSample(JPEGIMAGE *img);
+int JPEG_getJPEGType(JPEGIMAGE *img);
+int JPEG_hasThumb(JPEGIMAGE *img);
+int JPEG_getThumbWidth(JPEGIMAGE *img);
+int JPEG_getThumbHeight(JPEGIMAGE *img);
+void JPEG_setPixelType(JPEGIMAGE *img, int pixel_type);
+int JPEG_getPixelType(JPEGIMAGE *img);
+void JPEG_setMaxOutputSize(JPEGIMAGE *img, int max_mcus);
+void JPEG_setUserPointer(JPEGIMAGE *img, void *p);
 /* extensions */
-void JPEG_setArithMode(JPEGIMAGE *pJPEG, int iMode);   /* JPEG_ARITH_SSE2 | JPEG_ARITH_SCALAR */
-void JPEG_setDevice(JPEGIMAGE *pJPEG, int iDevice);    /* CUDA ordinal for this handle */
+void JPEG_setArithMode(JPEGIMAGE *img, int iMode);   /* JPEG_ARITH_SSE2 | JPEG_ARITH_SCALAR */
+void JPEG_setDevice(JPEGIMAGE *img, int iDevice);    /* CUDA ordinal for this handle */
 int JPEG_sizeofImage(void);                            /* sizeof(JPEGIMAGE) for FFI callers */
 
 #ifdef __cplusplus
