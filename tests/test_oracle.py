@@ -183,3 +183,38 @@ def test_progressive_dc_thumbnail_restatement_and_kernel_stepper(name):
                 oh, pitch = T.tight_shape(g["w"], g["h"], pt, 8)
                 rc, sim, nev = T.hostsim_decode(data, pt, opt | 8 if opt else 8, arith, g["w"], g["h"])
                 assert rc == 1 and T.sha(sim) == g[key]["sha"], (name, key, "stepper")
+
+
+def test_seeded_random_sweep_vs_live_reference():
+    """120 seeded random files (size 8..260, quality 15..100, every sampling, gray, restart interval 0 / rows, baseline and
+    progressive): the C restatement and the kernel stepper against the compiled reference, random pixel type and scale."""
+    from oracle import refdrv
+    from tests import synth
+    if not refdrv.available("sse"):
+        pytest.skip("oracle/_ref not built here")
+    rng = np.random.default_rng(20240923)
+    refs = {m: refdrv.Ref(m) for m, _ in MODES}
+    checked = 0
+    for case in range(120):
+        w, h = int(rng.integers(8, 261)), int(rng.integers(8, 261))
+        q = int(rng.integers(15, 101))
+        gray = bool(rng.integers(0, 5) == 0)
+        sub = ["4:2:0", "4:2:2", "4:4:4"][int(rng.integers(0, 3))]
+        rr = int(rng.integers(0, 3))
+        prog = bool(rng.integers(0, 4) == 0)
+        data = synth.synth_jpeg(w, h, 1000 + case, q, subsampling=sub, gray=gray, restart_rows=rr, progressive=prog)
+        mode, arith = MODES[int(rng.integers(0, 2))]
+        pts = [0, 1, 3] if gray else [0, 1, 2, 3]
+        if prog:
+            pts = [p for p in pts if p != 3]          # the reference crashes on progressive -> 8-bit gray
+        pt = pts[int(rng.integers(0, len(pts)))]
+        opt = 8 if prog else [0, 2, 4, 8][int(rng.integers(0, 4))]
+        rc, err, img, _ = refs[mode].decode_cb(data, pt, opt, want_log=False)
+        assert rc == 1, (case, w, h, q, sub, gray, rr, prog, err)
+        rc1, o1 = T.oracle_decode(data, pt, opt, arith, w, h)
+        rc2, o2, _ = T.hostsim_decode(data, pt, opt, arith, w, h)
+        assert rc1 == 1 and rc2 == 1, (case, rc1, rc2)
+        assert np.array_equal(o1, img), ("restatement", case, w, h, q, sub, gray, rr, prog, mode, pt, opt)
+        assert np.array_equal(o2, img), ("stepper", case, w, h, q, sub, gray, rr, prog, mode, pt, opt)
+        checked += 1
+    assert checked == 120
