@@ -364,3 +364,29 @@ def test_progressive_files_give_the_dc_thumbnail(ctxs):
             a = np.frombuffer(buf, dtype=np.uint8).reshape(h, w * 2)
             out[y:y + h, x * 2:(x + wu) * 2] = a[:, :wu * 2]
         assert T.sha(out) == g[name]["sse/565le/opt0"]["sha"], name
+
+
+def test_seeded_random_sweep_on_the_gpu(ctxs):
+    """Seeded random 4:2:0 / 4:4:4 / 4:2:2 / gray files of random size and quality (15..100: every mix of the IDCT kernel's
+    block classes), random restart interval, decoded in mixed batches per pixel type at full size and 1/2, both arithmetic
+    modes, against the compiled reference."""
+    rng = np.random.default_rng(77)
+    files = []
+    for case in range(48):
+        w, h = int(rng.integers(16, 420)), int(rng.integers(16, 300))
+        q = int(rng.integers(15, 101))
+        gray = bool(rng.integers(0, 6) == 0)
+        sub = ["4:2:0", "4:2:0", "4:2:2", "4:4:4"][int(rng.integers(0, 4))]
+        files.append((synth.synth_jpeg(w, h, 5000 + case, q, subsampling=sub, gray=gray, restart_rows=int(rng.integers(0, 3))), gray))
+    for mode, arith in MODES:
+        ref = _ref(mode)
+        if ref is None:
+            pytest.skip("oracle/_ref not present")
+        for pt in (0, 2, 3):
+            for opt in (0, 2):
+                use = [d for d, g in files if not (g and pt == 2)]
+                outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], use, pt, opt)
+                assert st == [0] * len(use)
+                for k, (d, o) in enumerate(zip(use, outs)):
+                    rc, err, img, _ = ref.decode_cb(d, pt, opt, want_log=False)
+                    assert rc == 1 and np.array_equal(o, img), (k, mode, pt, opt)
