@@ -410,6 +410,15 @@ def main():
             "stages_ms": {k: v / K for k, v in stage.items()}, "wall_ms_per_step": wall_ms_step,
             "entropy_symbol_stage_ms": entropy_ms, "quirk_events_per_step": int(cnt["events"]),
             "shared_table_hits": table_hits, "parity_spot_check": parity}
+        try:   # the entropy stage is reported as compressed MB/s; scaled workloads also as output pixels
+            comp_mb = float(cnt["compressed_bytes"]) / 1e6
+            line["entropy_compressed_mb_per_s"] = world * comp_mb / (entropy_ms / 1e3) if entropy_ms > 0 else None
+            sh = {2: 1, 4: 2, 8: 3}.get(int(wl.get("opt", 0)) & 14, 0)
+            if sh:
+                ow, oh = (wl["w"] + (1 << sh) - 1) >> sh, (wl["h"] + (1 << sh) - 1) >> sh
+                line["output_mpixels_per_s"] = value * (ow * oh) / float(wl["w"] * wl["h"])
+        except Exception:
+            pass
         print(json.dumps(line))
     return 0
 
