@@ -11,10 +11,12 @@
  *
  * Per stage, which reference function it replaces:
  *   jdk_prescan        <- JPEGFilter marker handling (:1431-1540) + restart bookkeeping (:5337-5348)
- *   jdk_entropy        <- JPEGDecodeMCU (:2090-2274) incl. the 64-bit window behaviour
+ *   jdk_entropy        <- JPEGDecodeMCU (:2090-2274) incl. the 64-bit window behaviour; for progressive files the DC part
+ *                         of JPEGDecodeMCU_P (:1819-1884); parse-only / low-frequency-only variants for 1/8 and 1/4 scale
  *   jdk_stitch/_patch  <- cross-segment window phase of the same function
- *   jdk_idct_color_*   <- JPEGIDCT + DC-only shortcut (:5146-5154) + JPEGPutMCU22/11/Gray/8BitGray
- *   jdk_scaled_*       <- the 1/4 and 1/8 paths of the above (:2305-2326, :3323-3396, :3627-3748)
+ *   jdk_unstuff, jdk_chunk_* <- the same for scans without restart markers (chunk-parallel, self-synchronising)
+ *   jdk_idct_tb, jdk_idct_color <- JPEGIDCT + DC-only shortcut (:5146-5154) + JPEGPutMCU22/11/12/21/Gray/8BitGray
+ *   jdk_scaled         <- the 1/4 and 1/8 paths of the above (:2305-2326, :3323-3396, :3627-3748)
  *   jdk_dither         <- JPEGDither (:4871-4940)
  */
 #ifndef JPEGDEC_B200_H
