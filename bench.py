@@ -159,8 +159,11 @@ class ClockSampler:
 
 def make_images(wl, rank, unique):
     from tests import synth
+    # every rank generates its own images at the same time: share the host cores between the ranks
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    workers = max(2, min(64, (os.cpu_count() or 8) // world))
     jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False),
-                         restart_rows=wl.get("restart_rows", 1), subsampling=wl.get("subsampling", "4:2:0"))
+                         restart_rows=wl.get("restart_rows", 1), subsampling=wl.get("subsampling", "4:2:0"), workers=workers)
     return jp
 
 
