@@ -936,6 +936,7 @@ extern "C" int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters)
  * compressed bytes go up, so the call costs about one D2H of the pixels instead of H2D + kernels + D2H. */
 #define JD_PIPE_IMAGES 64
 #define JD_PIPE_MIN_BYTES ((int64_t)64 << 20)
+#define JD_PIPE_INFLIGHT 6
 extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
                                     int pixel_type, int options, void *const *outs, const int64_t *pitches,
                                     int flags, int32_t *status)
@@ -944,13 +945,21 @@ extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *dat
     memset(ctx->last_counters, 0, sizeof(ctx->last_counters));
     std::vector<JPEGB200_BATCH *> jobs;
     std::vector<int> first;
-    int rc = 1;
+    int rc = 1, all = 1;
+    size_t retired = 0;
+    /* jobs complete in order; retiring one = wait + per-image status + counters + buffers back to the context's pools */
+    auto retire = [&](size_t k) {
+        if (rc) {
+            const int r = JPEGB200_batchWait(jobs[k], status ? status + first[k] : nullptr);
+            if (r == 0) all = 0; else if (r == 2 && all == 1) all = 2;
+            for (int c = 0; c < JPEGB200_NUM_COUNTERS; c++) ctx->last_counters[c] += jobs[k]->counters[c];
+        }
+        JPEGB200_batchDestroy(jobs[k]);
+        jobs[k] = nullptr;
+    };
     for (int i0 = 0; i0 < n && rc;) {
         int cnt = n - i0;
-        if (!(flags & JPEGB200_OUT_DEVICE) && cnt > JD_PIPE_IMAGES) {
-            /* grow the job until it holds JD_PIPE_IMAGES images and JD_PIPE_MIN_BYTES of pixels (estimated from the first image) */
-            cnt = JD_PIPE_IMAGES;
-        }
+        if (!(flags & JPEGB200_OUT_DEVICE) && cnt > JD_PIPE_IMAGES) cnt = JD_PIPE_IMAGES;
         JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas + i0, sizes + i0, cnt, pixel_type, options);
         if (!b) { rc = 0; break; }
         if (!(flags & JPEGB200_OUT_DEVICE) && i0 + cnt < n) {
@@ -972,17 +981,11 @@ extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *dat
         for (int i = 0; i < cnt; i++) JPEGB200_batchSetOutput(b, i, outs ? outs[i0 + i] : nullptr, pitches ? pitches[i0 + i] : 0);
         rc = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, flags) && JPEGB200_batchDownload(b);
         i0 += cnt;
+        /* bound the device memory of a very large batch: at most JD_PIPE_INFLIGHT jobs hold buffers at a time */
+        while (rc && jobs.size() - retired > JD_PIPE_INFLIGHT) retire(retired++);
     }
-    int all = rc ? 1 : 0;
-    for (size_t k = 0; k < jobs.size(); k++) {
-        if (rc) {
-            const int r = JPEGB200_batchWait(jobs[k], status ? status + first[k] : nullptr);
-            if (r == 0) all = 0; else if (r == 2 && all == 1) all = 2;
-            for (int c = 0; c < JPEGB200_NUM_COUNTERS; c++) ctx->last_counters[c] += jobs[k]->counters[c];
-        }
-        JPEGB200_batchDestroy(jobs[k]);
-    }
-    return all;
+    while (retired < jobs.size()) retire(retired++);
+    return rc ? all : 0;
 }
 
 extern "C" int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters)
