@@ -430,3 +430,65 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     }
     return nblk;
 }
+
+/* ---- two-phase entropy prototype (jd_tokens.h) against the single walk (jd_core.h): returns the number of mismatches ---- */
+#include "../../jpegdec_b200/csrc/jd_tokens.h"
+extern "C" int hostsim_tokens_check(const uint8_t *data, int size, int *n_segments, int *n_tokens, int *n_events, int *n_bad_segments)
+{
+    JDInfo info;
+    if (!jd_parse_header(data, size, 0, &info) || info.mode != 0xC0 || !info.tables_ok) return -1;
+    std::vector<uint16_t> lut(JD_LUT_ENTRIES);
+    jd_build_lut(&info, lut.data());
+    for (int i = 0; i < 64; i++) kTposW[i] = jd_tposw(kTpos[i]);
+    const int total_mcus = info.mcus_x * info.mcus_y;
+    const int mps = info.restart_interval ? info.restart_interval : total_mcus;
+    const int nseg = (total_mcus + mps - 1) / mps;
+    std::vector<uint32_t> seg_start(nseg, 0xFFFFFFFFu);
+    seg_start[0] = (uint32_t)info.scan_offset;
+    { int k = 1; for (int i = info.scan_offset; i + 1 < size && k < nseg; i++) if (data[i] == 0xFF && data[i + 1] >= 0xD0 && data[i + 1] <= 0xD7) { seg_start[k++] = (uint32_t)(i + 2); i++; } }
+    std::vector<uint32_t> padded((size + 64) / 4 + 16, 0);
+    memcpy(padded.data(), data, (size_t)size);
+    const int nblk = total_mcus * info.bpm;
+    std::vector<jd_u64> hdrA(nblk, 0), hdrB(nblk, 0);
+    std::vector<uint16_t> recA((size_t)size * 4 + 4096, 0), recB((size_t)size * 4 + 4096, 0);
+    std::vector<uint32_t> tok((size_t)size * 8 + 4096), blk_tok(nblk, 0);
+    int bad = 0, ntok = 0, nev = 0, nbadseg = 0;
+    for (int sgi = 0; sgi < nseg; sgi++) {
+        if (seg_start[sgi] == 0xFFFFFFFFu) break;
+        JDSegIn in;
+        in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
+        const int m0 = sgi * mps;
+        in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
+        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
+        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset); in.seg = (uint32_t)sgi;
+        in.rec_cap = (uint32_t)(recA.size() - in.rec_index0 - 64);
+        in.blk0 = (uint32_t)(m0 * info.bpm); in.al = 0;
+        const uint32_t nb = in.nmcu * in.bpm;
+        VecSink sA, sB;
+        JDSegOut so;
+        jd_decode_segment(in, lut.data(), kTposW, hdrA.data() + in.blk0, recA.data() + in.rec_index0, sA, so);
+        JDParseOut po;
+        jd_parse_segment(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
+        uint32_t nrecB = 0;
+        if (jd_materialize_segment(in, kTposW, tok.data(), blk_tok.data() + in.blk0, po.err_blk, hdrB.data() + in.blk0, recB.data() + in.rec_index0, &nrecB) != JD_SEG_OK) po.status = JD_SEG_OVERFLOW;
+        ntok += (int)po.ntok; nev += (int)sA.ev.size();
+        if (so.status == JD_SEG_OVERFLOW || po.status == JD_SEG_OVERFLOW) { nbadseg++; continue; }   /* capacities differ between the two forms */
+        if (so.status != po.status) bad++;
+        if (so.status != JD_SEG_OK) nbadseg++;
+        if (so.status == JD_SEG_OK && (so.jmap != po.jmap || so.nrec != nrecB || po.err_blk != nb)) bad++;
+        if (so.status != JD_SEG_OK && (int32_t)(po.err_blk / in.bpm) != so.err_mcu) bad++;
+        if (sA.ev.size() != sB.ev.size()) bad++;
+        else for (size_t e = 0; e < sA.ev.size(); e++) if (memcmp(&sA.ev[e], &sB.ev[e], sizeof(JDEvent)) != 0) { bad++; break; }
+        for (uint32_t b = 0; b < nb; b++) {
+            const jd_u64 ha = hdrA[in.blk0 + b], hb = hdrB[in.blk0 + b];
+            if (ha != hb) { bad++; continue; }
+            const uint32_t n = JD_HDR_NCOEF(ha) * (JD_HDR_BIG(ha) ? 2u : 1u);
+            if (n && memcmp(recA.data() + JD_HDR_REC(ha), recB.data() + JD_HDR_REC(hb), n * 2u) != 0) bad++;
+        }
+    }
+    if (n_segments) *n_segments = nseg;
+    if (n_tokens) *n_tokens = ntok;
+    if (n_events) *n_events = nev;
+    if (n_bad_segments) *n_bad_segments = nbadseg;
+    return bad;
+}

@@ -218,3 +218,36 @@ def test_seeded_random_sweep_vs_live_reference():
         assert np.array_equal(o2, img), ("stepper", case, w, h, q, sub, gray, rr, prog, mode, pt, opt)
         checked += 1
     assert checked == 120
+
+
+def test_two_phase_entropy_equals_the_single_walk():
+    """jd_tokens.h (prototype of a two-phase entropy stage: a minimal sequential parse that emits tokens, then a per-block
+    materialisation): headers, records, window-phase maps and truncation events must equal jd_decode_segment's on every
+    baseline fixture, on synthetic files of every sampling, and on corrupted scans (same status, same failing MCU)."""
+    import ctypes as C
+    import glob
+    import os
+    from tests import synth
+    L = T.hostsim()
+    L.hostsim_tokens_check.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+    files = {os.path.basename(f): open(f, "rb").read() for f in sorted(glob.glob(os.path.join(T.GOLD, "images", "*.jpg")))}
+    files["hd"] = synth.synth_jpeg(1920, 1080, 3, 75)
+    files["q98"] = synth.synth_jpeg(320, 240, 4, 98, restart_rows=0)
+    files["s422"] = synth.synth_jpeg(333, 251, 5, 85, subsampling="4:2:2", restart_rows=2)
+    files["s444"] = synth.synth_jpeg(333, 251, 6, 60, subsampling="4:4:4")
+    files["gray"] = synth.synth_jpeg(640, 360, 7, 75, gray=True)
+    rng = np.random.default_rng(11)
+    for k in range(40):                      # corrupted entropy data
+        b = bytearray(files["tulips.jpg" if k % 2 else "sciopero.jpg"])
+        for _ in range(3):
+            b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
+        files["corrupt_scan_%d" % k] = bytes(b)
+    checked = tokens = events = badsegs = 0
+    for name, data in files.items():
+        v = [C.c_int() for _ in range(4)]
+        r = L.hostsim_tokens_check(data, len(data), *[C.byref(x) for x in v])
+        if r == -1:
+            continue                          # header rejected / progressive: not this path
+        assert r == 0, (name, r)
+        checked += 1; tokens += v[1].value; events += v[2].value; badsegs += v[3].value
+    assert checked >= 55 and tokens > 1000000 and events > 50 and badsegs > 0
