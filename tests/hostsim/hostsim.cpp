@@ -468,7 +468,8 @@ extern "C" int hostsim_tokens_check(const uint8_t *data, int size, int *n_segmen
         JDSegOut so;
         jd_decode_segment(in, lut.data(), kTposW, hdrA.data() + in.blk0, recA.data() + in.rec_index0, sA, so);
         JDParseOut po;
-        jd_parse_segment(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
+        if (getenv("HOSTSIM_TOKENS_UNIFORM")) jd_parse_segment_uniform(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
+        else jd_parse_segment(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
         uint32_t nrecB = 0;
         if (jd_materialize_segment(in, kTposW, tok.data(), blk_tok.data() + in.blk0, po.err_blk, hdrB.data() + in.blk0, recB.data() + in.rec_index0, &nrecB) != JD_SEG_OK) po.status = JD_SEG_OVERFLOW;
         ntok += (int)po.ntok; nev += (int)sA.ev.size();

@@ -242,12 +242,18 @@ def test_two_phase_entropy_equals_the_single_walk():
         for _ in range(3):
             b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
         files["corrupt_scan_%d" % k] = bytes(b)
-    checked = tokens = events = badsegs = 0
-    for name, data in files.items():
-        v = [C.c_int() for _ in range(4)]
-        r = L.hostsim_tokens_check(data, len(data), *[C.byref(x) for x in v])
-        if r == -1:
-            continue                          # header rejected / progressive: not this path
-        assert r == 0, (name, r)
-        checked += 1; tokens += v[1].value; events += v[2].value; badsegs += v[3].value
-    assert checked >= 55 and tokens > 1000000 and events > 50 and badsegs > 0
+    for uniform in (False, True):            # the branchy parse and its one-instruction-stream form
+        if uniform:
+            os.environ["HOSTSIM_TOKENS_UNIFORM"] = "1"
+        else:
+            os.environ.pop("HOSTSIM_TOKENS_UNIFORM", None)
+        checked = tokens = events = badsegs = 0
+        for name, data in files.items():
+            v = [C.c_int() for _ in range(4)]
+            r = L.hostsim_tokens_check(data, len(data), *[C.byref(x) for x in v])
+            if r == -1:
+                continue                          # header rejected / progressive: not this path
+            assert r == 0, (name, r, uniform)
+            checked += 1; tokens += v[1].value; events += v[2].value; badsegs += v[3].value
+        assert checked >= 55 and tokens > 1000000 and events > 50 and badsegs > 0
+    os.environ.pop("HOSTSIM_TOKENS_UNIFORM", None)
