@@ -216,16 +216,20 @@ JD_HD void jd_parse_segment_uniform(const JDSegIn &in, const uint16_t *lut, uint
     const uint32_t bsh_end = 4u * in.bpm;
     uint32_t bsh = 0, cur = sched & 15u;
     uint32_t b = 0, k = 0, cursor = 0, blk_start = 0;
+    uint32_t off_dc = JD_LUT_DC((cur >> 2) & 1u), off_ac = JD_LUT_AC(cur >> 3);   /* tables of the current block */
+    uint32_t *tp = tok;                                                           /* next token slot */
+    uint32_t *bp = blk_tok;                                                       /* next block's cursor slot */
 
     if (nblk_total == 0) { out.status = JD_SEG_OK; out.err_blk = 0; out.jmap = jw; out.ntok = 0; return; }
-    if (tok_cap < 2u) { out.status = JD_SEG_OVERFLOW; out.err_blk = 0; out.jmap = jw; out.ntok = 0; for (uint32_t i = 0; i < nblk_total; i++) blk_tok[i] = 0; return; }
+    if (tok_cap < 64u) { out.status = JD_SEG_OVERFLOW; out.err_blk = 0; out.jmap = jw; out.ntok = 0; for (uint32_t i = 0; i < nblk_total; i++) blk_tok[i] = 0; return; }
 
     for (;;) {
         /* ---- refill: the common case (no 0xFF in the next word) as selects ---- */
         {
             const uint32_t w = wnext;
             const bool need = nb <= 32;
-            const bool clean = ((((~w) - 0x01010101u) & w & 0x80808080u) | skip | ffp | eos) == 0u;
+            /* fast path: no 0xFF in the word, nothing pending, and the word after it still inside the file */
+            const bool clean = (((((~w) - 0x01010101u) & w & 0x80808080u) | skip | ffp | eos) == 0u) && (wi + 2u < endw);
             if (need && !clean) {
                 /* rare: byte path / end of data, as in jd_decode_segment */
                 while (nb <= 32) {
@@ -272,13 +276,13 @@ JD_HD void jd_parse_segment_uniform(const JDSegIn &in, const uint16_t *lut, uint
                 bb |= need ? ((jd_u64)be << shl) : 0ull;
                 nb += need ? 32 : 0;
                 wi += need ? 1u : 0u;
-                if (need) wnext = (wi < endw) ? words[wi] : 0u;
+                if (need) wnext = words[wi];
             }
         }
         jw = jd_jw_ckpt(jw);
         /* ---- code lookup: the table and its geometry follow from (k == 0) and the block's schedule nibble ---- */
         const bool is_dc = (k == 0u);
-        const uint32_t toff = is_dc ? JD_LUT_DC((cur >> 2) & 1u) : JD_LUT_AC(cur >> 3);
+        const uint32_t toff = is_dc ? off_dc : off_ac;
         const uint32_t thr = is_dc ? 0xF800u : 0xFC00u, sh = is_dc ? 4u : 0u, msk = is_dc ? 0x7Fu : 0x3FFu;
         const uint32_t w16 = (uint32_t)(bb >> 48);
         const uint32_t idx = (w16 >= thr) ? (1024u + ((w16 >> sh) & msk)) : (w16 >> 6);
@@ -321,16 +325,16 @@ JD_HD void jd_parse_segment_uniform(const JDSegIn &in, const uint16_t *lut, uint
         P = P1 + s;
         { const int nPb = P >> 3; jw = j1c + (uint32_t)(nPb - (P1 >> 3)) * JD_JW_ONES; Pb = nPb; }
         /* ---- token ---- */
-        if (store) {
-            if (cursor >= tok_cap) { err = JD_SEG_OVERFLOW; break; }
-            tok[cursor] = is_dc ? (JD_TOK_DC | ((uint32_t)v & 0xFFFFu)) : ((kpos << 16) | ((uint32_t)v & 0xFFFFu));
-        }
+        if (is_dc && cursor + 64u > tok_cap) { err = JD_SEG_OVERFLOW; break; }   /* a block emits at most 64 tokens */
+        if (store) *tp = ((is_dc ? 0x8000u : kpos) << 16) | ((uint32_t)v & 0xFFFFu);
+        tp += store ? 1 : 0;
         cursor += store ? 1u : 0u;
         last_eob = is_dc ? last_eob : (is_eob ? 1u : 0u);
         /* ---- zigzag index, block end ---- */
         k = is_dc ? 1u : (is_eob ? 64u : kpos + 1u);
         const bool done = k >= 64u;
-        if (done) blk_tok[b] = cursor;
+        if (done) *bp = cursor;
+        bp += done ? 1 : 0;
         blk_start = done ? cursor : blk_start;
         b += done ? 1u : 0u;
         if (b == nblk_total) break;
@@ -339,6 +343,7 @@ JD_HD void jd_parse_segment_uniform(const JDSegIn &in, const uint16_t *lut, uint
             nb2 = (nb2 == bsh_end) ? 0u : nb2;
             bsh = done ? nb2 : bsh;
             cur = (sched >> bsh) & 15u;
+            off_dc = JD_LUT_DC((cur >> 2) & 1u); off_ac = JD_LUT_AC(cur >> 3);
             k = done ? 0u : k;
         }
     }
