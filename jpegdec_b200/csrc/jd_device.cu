@@ -133,6 +133,7 @@ struct JPEGB200_BATCH {
     DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
     DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
     DevBuf<uint32_t> d_err_off, d_dprog;
+    DevBuf<uint32_t> d_tok, d_blk_tok, d_seg_errblk;   /* opt-in two-phase entropy stage (jd_tokens.h) */
     DevBuf<uint4> d_dbands;        /* dither: (image, band, warp of the band above, -) per warp */
     std::vector<uint4> dbands;
     JDImageDesc *descs_dl;             /* descriptors read back (status, err_mcu); pinned, from ctx->pinpool */
@@ -418,6 +419,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
+    b->d_tok.release(); b->d_blk_tok.release(); b->d_seg_errblk.release();
     b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
@@ -729,8 +731,22 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ea.seg_jmap = b->d_seg_jmap.p; ea.seg_status = b->d_seg_status.p; ea.seg_nrec = b->d_seg_nrec.p;
         ea.events = b->d_events.p; ea.event_count = b->d_counters.p; ea.event_cap = JD_EVENT_CAP;
         ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0; ea.dc_output = (b->sshift == 3) ? 1u : (b->sshift == 2) ? 2u : 0u;
-        jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
-        launches++;
+        static int use_tokens = -1;   /* JPEGDEC_B200_ENTROPY=tokens: two-phase stage (prototype, baseline full / half size only) */
+        if (use_tokens < 0) { const char *e = getenv("JPEGDEC_B200_ENTROPY"); use_tokens = (e && strcmp(e, "tokens") == 0) ? 1 : 0; }
+        bool any_prog = false;
+        for (int i = 0; i < n; i++) if (b->descs[i].prog & 1u) any_prog = true;
+        if (use_tokens && !any_prog && b->sshift < 2) {
+            JDTokenArgs ta;
+            ta.e = ea;
+            CK(b->d_tok.alloc(4 * b->comp_total + 64 * (size_t)b->nseg + 1024)); CK(b->d_blk_tok.alloc(b->nblk ? b->nblk : 1)); CK(b->d_seg_errblk.alloc(b->nseg ? b->nseg : 1));
+            ta.tok = b->d_tok.p; ta.tok_total = (uint32_t)(4 * b->comp_total + 64 * (size_t)b->nseg + 1024); ta.blk_tok = b->d_blk_tok.p; ta.seg_errblk = b->d_seg_errblk.p;
+            jdk_tokens_parse<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ta);
+            jdk_tokens_materialize<<<(unsigned)((b->work.size() * 32 + 127) / 128), 128, 0, st>>>(ta);
+            launches += 2;
+        } else {
+            jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
+            launches++;
+        }
     }
     if (b->nchunks) {
         /* restart-free scans: un-stuff, iterate the chunk entry states to their fix point, then emit */

@@ -20,6 +20,7 @@
 #include <stdint.h>
 #include "jd_core.h"
 #include "jd_chunk.h"
+#include "jd_tokens.h"
 #include "jd_internal.h"
 
 #define JD_NONE 0xFFFFFFFFu
@@ -175,6 +176,153 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
     a.seg_nrec[seg] = so.nrec;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* two-phase entropy stage (jd_tokens.h) -- OPT-IN (JPEGDEC_B200_ENTROPY=tokens), not yet measured on a B200:      */
+/*   jdk_tokens_parse        1 thread per restart segment, one instruction stream per symbol, emits tokens          */
+/*   jdk_tokens_materialize  1 warp per restart segment, lane = block: DC predictors and record indices as warp      */
+/*                           scans carried over 32-block chunks, then records + headers exactly as jdk_entropy       */
+/* ------------------------------------------------------------------------------------ */
+struct JDTokenArgs {
+    JDEntropyArgs e;
+    uint32_t *tok;            /* tokens: a segment's tokens live at 4 x its byte offset + 64 x its index (u32 units): room for
+                               * 4 tokens per compressed byte plus one whole block, without a prefix sum over segments */
+    uint32_t tok_total;
+    uint32_t *blk_tok;        /* per block: tokens of its segment up to and including it */
+    uint32_t *seg_errblk;     /* per segment: first block without complete tokens; JD_NONE = segment missing */
+};
+
+__device__ __forceinline__ bool jd_token_seg_setup(const JDTokenArgs &a, uint32_t seg, JDSegIn &in, uint32_t &tok_index0, uint32_t &tok_cap)
+{
+    const JDImageDesc &im = a.e.imgs[a.e.seg_img[seg]];
+    const uint32_t sl = seg - im.seg_base;
+    const uint32_t total_mcus = (uint32_t)im.mcus_x * im.mcus_y;
+    const uint32_t m0 = sl * im.mcus_per_seg;
+    in.data = a.e.data;
+    in.start = a.e.seg_start[seg];
+    in.end = im.scan_end;
+    in.nmcu = (m0 + im.mcus_per_seg <= total_mcus) ? im.mcus_per_seg : total_mcus - m0;
+    in.bpm = im.bpm; in.ncomp = im.ncomp; in.tsel = im.tsel; in.seg = seg; in.al = 0;
+    in.blk0 = im.blk_base + m0 * im.bpm;
+    if (in.start == JD_NONE || in.start < im.scan_off || in.start > im.scan_end) return false;
+    const uint32_t next = (sl + 1 < im.nseg) ? a.e.seg_start[seg + 1] : JD_NONE;
+    const uint32_t seg_end = (next != JD_NONE) ? next : im.scan_end;
+    const uint32_t len = seg_end > in.start ? seg_end - in.start : 0u;
+    in.rec_index0 = 4u * (in.start - a.e.data_base);
+    uint32_t cap = 4u * len;
+    if ((uint64_t)in.rec_index0 + cap > a.e.rec_total) cap = (in.rec_index0 < a.e.rec_total) ? a.e.rec_total - in.rec_index0 : 0u;
+    in.rec_cap = cap;
+    tok_index0 = in.rec_index0 + 64u * seg;
+    tok_cap = 4u * len + 64u;
+    if ((uint64_t)tok_index0 + tok_cap > a.tok_total) tok_cap = (tok_index0 < a.tok_total) ? a.tok_total - tok_index0 : 0u;
+    return true;
+}
+
+__global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_tokens_parse(const JDTokenArgs a)
+{
+    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.e.luts + (size_t)a.e.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+        for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
+    if (wi >= a.e.nwork) return;
+    const uint32_t seg = a.e.work[wi];
+    if (seg == JD_NONE) return;
+    JDSegIn in;
+    uint32_t tok_cap = 0, tok_index0 = 0;
+    if (!jd_token_seg_setup(a, seg, in, tok_index0, tok_cap)) {
+        a.e.seg_jmap[seg] = JD_JW_INIT;
+        a.e.seg_status[seg] = ((uint32_t)JD_SEG_MISSING << 28);
+        a.seg_errblk[seg] = JD_NONE;
+        return;
+    }
+    JDEventSinkDev sink{a.e.events, a.e.event_count, a.e.event_cap};
+    JDParseOut po;
+    jd_parse_segment_uniform(in, s_lut, a.tok + tok_index0, tok_cap, a.blk_tok + in.blk0, sink, po);
+    a.e.seg_jmap[seg] = po.jmap;
+    a.e.seg_status[seg] = (po.status == JD_SEG_OK) ? 0u : ((po.status << 28) | ((po.err_blk / in.bpm) & 0x0FFFFFFFu));
+    a.seg_errblk[seg] = po.err_blk;
+}
+
+__device__ __forceinline__ uint32_t jd_warp_incl_scan(uint32_t v, uint32_t lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (uint32_t)d) v += t; }
+    return v;
+}
+
+__global__ void __launch_bounds__(128) jdk_tokens_materialize(const JDTokenArgs a)
+{
+    __shared__ uint32_t s_tpos[64];
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
+    __syncthreads();
+    const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (wi >= a.e.nwork) return;
+    const uint32_t seg = a.e.work[wi];
+    if (seg == JD_NONE) return;
+    JDSegIn in;
+    uint32_t tok_cap = 0, tok_index0 = 0;
+    const bool present = jd_token_seg_setup(a, seg, in, tok_index0, tok_cap);
+    const uint32_t nblk = in.nmcu * in.bpm;
+    jd_u64 *hdr = a.e.blk_hdr + in.blk0;
+    if (!present) {                       /* restart marker missing: empty headers, as jdk_entropy */
+        for (uint32_t b = lane; b < nblk; b += 32) hdr[b] = 0ull;
+        if (lane == 0) a.e.seg_nrec[seg] = 0;
+        return;
+    }
+    const uint32_t errblk = a.seg_errblk[seg];
+    const uint32_t *tok = a.tok + tok_index0;
+    const uint32_t *btok = a.blk_tok + in.blk0;
+    uint16_t *rec = a.e.rec + in.rec_index0;
+    const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
+    int pred0 = 0, pred1 = 0, pred2 = 0;  /* carried over the chunks, identical in every lane */
+    uint32_t ri = 0, overflow_blk = JD_NONE;
+    for (uint32_t base = 0; base < nblk; base += 32) {
+        const uint32_t b = base + lane;
+        const bool inseg = b < nblk;
+        bool valid = inseg && b < errblk;
+        const uint32_t t0 = (valid && b) ? btok[b - 1] : 0u, t1 = valid ? btok[b] : 0u;
+        const uint32_t ncoef = valid ? t1 - t0 - 1u : 0u;
+        const int diff = valid ? JD_TOK_VAL(tok[t0]) : 0;
+        uint32_t big = 0;
+        for (uint32_t i = 0; i < ncoef; i++) { const int v = JD_TOK_VAL(tok[t0 + 1 + i]); if (v > 511 || v < -511) big = 1; }
+        const uint32_t nrec = big ? 2 * ncoef : ncoef;
+        const uint32_t bim = inseg ? b % in.bpm : 0u, comp = (bim < nluma) ? 0u : (bim - nluma + 1u);
+        /* prefix sums over the 32 blocks of this chunk */
+        const uint32_t s0 = jd_warp_incl_scan((uint32_t)((comp == 0u) ? diff : 0), lane);
+        const uint32_t s1 = jd_warp_incl_scan((uint32_t)((comp == 1u) ? diff : 0), lane);
+        const uint32_t s2 = jd_warp_incl_scan((uint32_t)((comp == 2u) ? diff : 0), lane);
+        const uint32_t sr = jd_warp_incl_scan(nrec, lane);
+        const int dc = (comp == 0u) ? pred0 + (int)s0 : (comp == 1u) ? pred1 + (int)s1 : pred2 + (int)s2;
+        const uint32_t rstart = ri + sr - nrec;
+        if (valid && rstart + nrec > in.rec_cap) valid = false;      /* record area exhausted: this block and all later ones */
+        const uint32_t firstbad = __ballot_sync(0xffffffffu, inseg && b < errblk && !valid);
+        if (firstbad && overflow_blk == JD_NONE) overflow_blk = base + (uint32_t)__ffs((int)firstbad) - 1u;
+        if (valid) {
+            uint32_t bflags = 0;
+            for (uint32_t i = 0; i < ncoef; i++) {
+                const uint32_t t = tok[t0 + 1 + i], tw = s_tpos[JD_TOK_K(t)];
+                const int v = JD_TOK_VAL(t);
+                bflags |= tw;
+                if (big) { rec[rstart + 2 * i] = (uint16_t)(tw & 63u); rec[rstart + 2 * i + 1] = (uint16_t)(int16_t)v; }
+                else rec[rstart + i] = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+            }
+            hdr[b] = jd_pack_hdr(in.rec_index0 + rstart, dc, ncoef, big, JD_BF_HI(bflags), JD_BF_COLMASK(bflags));
+        } else if (inseg) {
+            hdr[b] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
+        }
+        pred0 += (int)__shfl_sync(0xffffffffu, s0, 31); pred1 += (int)__shfl_sync(0xffffffffu, s1, 31);
+        pred2 += (int)__shfl_sync(0xffffffffu, s2, 31); ri += __shfl_sync(0xffffffffu, sr, 31);
+    }
+    if (lane == 0) {
+        a.e.seg_nrec[seg] = ri;
+        if (overflow_blk != JD_NONE && a.e.seg_status[seg] == 0u)
+            a.e.seg_status[seg] = ((uint32_t)JD_SEG_OVERFLOW << 28) | ((overflow_blk / in.bpm) & 0x0FFFFFFFu);
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */

@@ -390,3 +390,37 @@ def test_seeded_random_sweep_on_the_gpu(ctxs):
                 for k, (d, o) in enumerate(zip(use, outs)):
                     rc, err, img, _ = ref.decode_cb(d, pt, opt, want_log=False)
                     assert rc == 1 and np.array_equal(o, img), (k, mode, pt, opt)
+
+
+def test_two_phase_entropy_stage_opt_in():
+    """The opt-in two-phase entropy stage (JPEGDEC_B200_ENTROPY=tokens; jd_tokens.h) against the default stage, in a
+    subprocess because the switch is read once.  Not part of the default GPU tier until it has been run on a B200:
+    set JPEGDEC_B200_TEST_TOKENS=1 to include it."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("JPEGDEC_B200_TEST_TOKENS") != "1":
+        pytest.skip("opt-in prototype: set JPEGDEC_B200_TEST_TOKENS=1")
+    code = r'''
+import sys, zlib, numpy as np
+sys.path.insert(0, %r)
+import jpegdec_b200 as J
+from tests import common as T, synth
+blobs = [T.image(n) for n in ("tulips", "sciopero", "st_peters", "zebra", "croptest", "lange", "ncc1701", "corrupt2")]
+blobs += [synth.synth_jpeg(1920, 1080, s, 75) for s in range(4)] + [synth.synth_jpeg(333, 251, 9, 97, subsampling="4:4:4", restart_rows=0)]
+ctx = J.Context(0, 0)
+for pt in (0, 2, 3):
+    for opt in (0, 2):
+        outs, st, tim, cnt = J.decode_batch_to_host(ctx, blobs, pt, opt)
+        print(pt, opt, st, [zlib.crc32(o.tobytes()) if o is not None else None for o in outs], cnt["events"])
+''' % T.ROOT
+    res = []
+    for mode in ("", "tokens"):
+        env = dict(os.environ)
+        env.pop("JPEGDEC_B200_ENTROPY", None)
+        if mode:
+            env["JPEGDEC_B200_ENTROPY"] = mode
+        r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:]
+        res.append(r.stdout)
+    assert res[0] == res[1]
