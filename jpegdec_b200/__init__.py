@@ -28,8 +28,8 @@ JPEG_ARITH_SSE2, JPEG_ARITH_SCALAR = 0, 1
 JPEGB200_OUT_DEVICE = 1
 TIMING_NAMES = ["h2d", "prescan", "entropy", "stitch", "idct", "dither", "d2h", "total"]
 COUNTER_NAMES = ["launches", "segments", "blocks", "events", "compressed_bytes", "output_bytes",
-                 "record_bytes", "h2d_bytes", "d2h_bytes"]
-TABLE_BLOB_BYTES = 6400 * 2 + 3 * 64 * 2 + 16
+                 "record_bytes", "h2d_bytes", "d2h_bytes", "event_candidates"]
+TABLE_BLOB_BYTES = 8448 * 2 + 3 * 64 * 2 + 16
 
 
 class JPEGDRAW(C.Structure):
@@ -112,6 +112,16 @@ def lib():
     L.JPEGB200_decodeBatch.argtypes = [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(vp), C.POINTER(C.c_int64), C.c_int, i32p]
     L.JPEGB200_lastCallCounters.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.JPEGB200_lastCallTimings.argtypes = [vp, C.POINTER(C.c_float), ip]
+    L.JPEGB200_setPipelineDepth.argtypes = [vp, C.c_int]
+    L.JPEGB200_numaNode.argtypes = [vp]
+    L.JPEGB200_bindHostToDevice.argtypes = [vp]
+    L.JPEGB200_deviceAlloc.argtypes = [vp, C.c_size_t]
+    L.JPEGB200_deviceAlloc.restype = vp
+    L.JPEGB200_deviceFree.argtypes = [vp, vp]
+    L.JPEGB200_deviceFree.restype = None
+    L.JPEGB200_deviceRead.argtypes = [vp, vp, vp, C.c_size_t]
+    L.JPEGB200_digestDevice.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_uint64)]
     L.JPEGB200_exportTables.argtypes = [C.c_char_p, C.c_int, vp]
     L.JPEGB200_setSharedTables.argtypes = [vp, vp]
     L.JPEGB200_sharedTableHits.argtypes = [vp]
@@ -216,6 +226,61 @@ class Context:
 
     def shared_table_hits(self):
         return lib().JPEGB200_sharedTableHits(self.h)
+
+    def numa_node(self):
+        return lib().JPEGB200_numaNode(self.h)
+
+    def bind_host_to_device(self):
+        """Pin the calling thread to the CPUs next to this context's GPU (see include/jpegdec_b200.h)."""
+        return lib().JPEGB200_bindHostToDevice(self.h)
+
+    def set_pipeline_depth(self, jobs):
+        return lib().JPEGB200_setPipelineDepth(self.h, jobs)
+
+    def last_call_timings(self):
+        ms = (C.c_float * len(TIMING_NAMES))()
+        jobs = C.c_int()
+        lib().JPEGB200_lastCallTimings(self.h, ms, C.byref(jobs))
+        return dict(zip(TIMING_NAMES, list(ms))), jobs.value
+
+    def device_alloc(self, nbytes):
+        p = lib().JPEGB200_deviceAlloc(self.h, nbytes)
+        if not p:
+            raise RuntimeError("deviceAlloc(%d) failed" % nbytes)
+        return p
+
+    def device_free(self, p):
+        lib().JPEGB200_deviceFree(self.h, p)
+
+    def device_read(self, dev_ptr, nbytes):
+        o = np.empty(nbytes, dtype=np.uint8)
+        if not lib().JPEGB200_deviceRead(self.h, o.ctypes.data, dev_ptr, nbytes):
+            raise RuntimeError("deviceRead failed: " + lib().JPEGB200_lastErrorString(self.h).decode())
+        return o
+
+    def digest_device(self, ptrs, lengths):
+        """64-bit digests of device byte ranges, computed on the GPU (same function as digest_host)."""
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*ptrs)
+        la = (C.c_int64 * n)(*lengths)
+        out = (C.c_uint64 * n)()
+        if not lib().JPEGB200_digestDevice(self.h, pa, la, n, out):
+            raise RuntimeError("digestDevice failed: " + lib().JPEGB200_lastErrorString(self.h).decode())
+        return list(out)
+
+
+def digest_host(a):
+    """The digest JPEGB200_digestDevice computes, for a host array (include/jpegdec_b200.h)."""
+    b = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    if b.size % 8:
+        b = np.concatenate([b, np.zeros(8 - b.size % 8, dtype=np.uint8)])
+    w = b.view("<u8")
+    with np.errstate(over="ignore"):
+        z = w ^ (np.arange(w.size, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
 
 
 class Batch:

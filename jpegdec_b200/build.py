@@ -19,7 +19,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 C_SOURCES = ["jd_host.c", "jd_api.c"]
 CU_SOURCES = ["jd_device.cu"]
-HEADERS = ["jd_core.h", "jd_chunk.h", "jd_tokens.h", "jd_internal.h", "jd_kernels.cuh",
+HEADERS = ["jd_core.h", "jd_chunk.h", "jd_internal.h", "jd_kernels.cuh",
            os.path.join("..", "..", "include", "JPEGDEC.h"),
            os.path.join("..", "..", "include", "jpegdec_b200.h")]
 

@@ -115,13 +115,13 @@ typedef struct {
  *   blk_first : index (within the scan) of the first block that starts in this chunk
  *   next_entry: entry state of chunk ci+1 (where to snapshot the phase map), JD_CS_NONE for the last chunk
  *   blk_hdr   : headers of the scan (indexed by block index within the scan)
- *   rec/rec_index0/rec_cap: this chunk's record area
+ *   rec/rec_index0/rec_cap: this chunk's record area (rec_index0 = image-relative index of rec[0])
  *   slot      : phase slot id written into events (the stitch resolves the true phase per slot)
  *   blk0      : global index of the scan's first block (events) */
 template <typename EventSink>
 JD_HD void jd_chunk_emit(const JDScanIn &sc, const uint16_t *lut, const uint32_t *tposw, uint32_t ci, uint32_t entry,
                          uint32_t next_entry, uint32_t blk_first, jd_u64 *blk_hdr, uint16_t *rec, uint32_t rec_index0,
-                         uint32_t rec_cap, uint32_t slot, uint32_t blk0, EventSink &sink, JDChunkOut &out)
+                         uint32_t rec_cap, uint32_t slot, uint32_t blk0, uint32_t img, EventSink &sink, JDChunkOut &out)
 {
     out.jmap = JD_JW_INIT; out.dcsum[0] = out.dcsum[1] = out.dcsum[2] = 0; out.status = JD_SEG_OK; out.nown = 0;
     if (entry == JD_CS_NONE) return;
@@ -189,7 +189,7 @@ JD_HD void jd_chunk_emit(const JDScanIn &sc, const uint16_t *lut, const uint32_t
                         if (any) {
                             JDEvent ev;
                             ev.blk = blk0 + bi; ev.seg = slot; ev.j1 = j1; ev.field = (uint16_t)field;
-                            ev.s = (uint8_t)s; ev.p7 = (uint8_t)p7; ev.ord = ncoef;
+                            ev.s = (uint8_t)s; ev.p7 = (uint8_t)p7; ev.ord = ncoef; ev.img = img;
                             sink.push(ev);
                         }
                     }

@@ -32,9 +32,26 @@
 /* ------------------------------------------------------------------------- */
 #define JD_LUT_DC_SIZE 1152
 #define JD_LUT_AC_SIZE 2048
+#define JD_LUT_ACF_SIZE 1024
 #define JD_LUT_DC(t) ((t) * JD_LUT_DC_SIZE)
 #define JD_LUT_AC(t) (2 * JD_LUT_DC_SIZE + (t) * JD_LUT_AC_SIZE)
-#define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE) /* 6400 u16 = 12800 B */
+/* Fast AC table t (what the hot loop of jd_decode_segment reads): indexed by the next 10 bits alone.
+ *   entry = RARE << 15 | len << 8 | RS ;  len == 0: the code is longer than 10 bits (look it up in the second half of
+ *   JD_LUT_AC(t)) or invalid.  RARE = the symbol needs one of the exact checks of the store path: SSSS >= 10 (pair records /
+ *   not baseline) or len + SSSS >= 18 (a window-truncated read is possible). */
+#define JD_LUT_ACF(t) (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE + (t) * JD_LUT_ACF_SIZE)
+#define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE + 2 * JD_LUT_ACF_SIZE) /* 8448 u16 = 16896 B */
+#define JD_ACF_RARE 0x8000u
+
+/* Coefficient records of stream slot `slot` (restart segment, or chunk of a restart-free scan) that starts at byte offset
+ * `byte_off` of the batch buffer live at record index JD_REC_INDEX(byte_off, slot): no prefix sum between the stages.
+ * A stored coefficient costs at least 3 bits of stream (2-bit code + 1 magnitude bit) and at most two records (pair form),
+ * so 6 records per byte cover every valid stream; the 128 extra per slot let the decoder test the capacity once per block
+ * (a block stores at most 63 coefficients = 126 records) instead of once per coefficient. */
+#define JD_REC_PER_BYTE 6u
+#define JD_REC_SLOT_SLACK 128u
+#define JD_REC_INDEX(byte_off, slot) (JD_REC_PER_BYTE * (uint32_t)(byte_off) + JD_REC_SLOT_SLACK * (uint32_t)(slot))
+#define JD_REC_BLOCK_MAX 126u
 
 /* Block header written by the entropy kernel, read by the IDCT kernels (8 B):    */
 /*   bits  0..31 : index of the block's first AC record in the record array     */
@@ -108,6 +125,7 @@ typedef struct {
     uint8_t s;          /* SSSS */
     uint8_t p7;         /* (P + len) & 7 */
     uint32_t ord;       /* ordinal of the coefficient among the block's stored coefficients */
+    uint32_t img;       /* image index in the batch (record indices are image-relative) */
 } JDEvent;
 
 /* where the value of coefficient `ord` of a block lives, and how to rewrite it */
@@ -150,6 +168,7 @@ typedef struct {
     uint32_t seg;         /* global segment index (for events) */
     uint32_t blk0;        /* global index of this segment's first block (for events) */
     uint32_t al;          /* progressive DC scan: point transform (DC_ONLY instantiation) */
+    uint32_t img;         /* image index in the batch (for events) */
 } JDSegIn;
 
 typedef struct {
@@ -190,7 +209,7 @@ JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u 
 #define JD_MODE_PARSE_AC 2
 #define JD_MODE_STORE_LOW 3
 template <typename EventSink, int MODE = JD_MODE_BASELINE>
-JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
+JD_HD void jd_decode_segment_flat(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
                              const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
                              EventSink &sink, JDSegOut &out)
@@ -345,6 +364,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                             ev.s = (uint8_t)s;
                             ev.p7 = (uint8_t)p7;
                             ev.ord = (cnt >> 16) & 63u;
+                            ev.img = in.img;
                             sink.push(ev);
                         }
                     }
@@ -407,6 +427,278 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
          * block ended with EOB; then the bit offset is rounded up to a byte without a reload. */
         if (!last_was_eob) jw = jd_jw_ckpt(jw);
         if (P & 7) jw += JD_JW_ONES;
+    }
+    out.jmap = jw;
+    out.nrec = (uint32_t)(rp - rec);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Per-segment entropy decode, block-synchronous form (the one the kernels run).  */
+/*                                                                             */
+/* Same outputs as jd_decode_segment_flat above, organised for a warp whose 32   */
+/* lanes each walk their own restart segment: the walk is a loop over blocks     */
+/* with the DC symbol decoded at the top, an inner loop over the block's AC      */
+/* symbols, and the header written at the bottom.  The lanes of a warp therefore */
+/* re-converge at every block: inside the AC loop all active lanes execute the   */
+/* same ~50 instructions per symbol (lanes whose block is shorter idle until the */
+/* longest block of the warp ends; measured on the benchmark images that costs   */
+/* 1.29-1.35x the mean symbol count), instead of the union of the DC / AC / EOB / */
+/* block-end paths that a flat state machine executes for every symbol.          */
+/* The hot loop reads the 10-bit fast AC table (JD_LUT_ACF); everything rare --   */
+/* codes > 10 bits, magnitudes >= 10 bits, possibly truncated reads -- hangs off  */
+/* one flag bit of the table entry.  Record capacity is tested once per block     */
+/* (JD_REC_INDEX leaves room for a whole block).                                  */
+/* CLEAN = the input was un-stuffed by jdk_unstuff_segs: [start, end) holds the    */
+/* segment's entropy bytes only, start is 4-byte aligned, zeros follow.            */
+/* ------------------------------------------------------------------------- */
+JD_HD uint32_t jd_bswap32(uint32_t w)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(w, 0, 0x0123);
+#else
+    return __builtin_bswap32(w);
+#endif
+}
+
+/* the S extra bits at the top of x as a JPEG magnitude (T.81 F.2.2.1 EXTEND); s = 0 gives 0 */
+JD_HD int jd_extend_top(uint32_t x, uint32_t s)
+{
+    const uint32_t neg = ~(uint32_t)((int)x >> 31);          /* all ones when the first extra bit is 0: negative value */
+    const uint32_t y = x ^ neg;                              /* ~x for negative values: (~x) >> (32 - s) = -v */
+#ifdef __CUDA_ARCH__
+    const uint32_t mag = s ? __funnelshift_r(y, 0u, 32u - s) : 0u;
+#else
+    const uint32_t mag = s ? (y >> (32u - s)) : 0u;
+#endif
+    return (int)((mag ^ neg) - neg);
+}
+
+template <typename EventSink, int MODE = JD_MODE_BASELINE, bool CLEAN = false>
+JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
+                             const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
+                             jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
+                             EventSink &sink, JDSegOut &out)
+{
+    /* ---- bit reader: aligned 32-bit words, one word prefetched ahead of use ---- */
+    const uint32_t *words = (const uint32_t *)in.data;
+    const uint32_t endw = (in.end + 3u) >> 2;    /* first word index past the data */
+    uint32_t wi = in.start >> 2;                 /* index of the next word to consume */
+    uint32_t wnext = (wi < endw) ? words[wi] : 0u;
+    uint32_t skip = CLEAN ? 0u : (in.start & 3u); /* bytes of the first word that precede the segment */
+    uint32_t ffp = 0;                            /* previous byte was 0xFF (stuffing / marker undecided) */
+    uint32_t eos = 0;                            /* marker or end of data reached: zeros from here on */
+    jd_u64 bb = 0;                               /* bit buffer, MSB first */
+    int nb = 0;                                  /* valid bits in bb */
+
+    /* keeps >= 32 valid bits in bb */
+    auto refill = [&]() {
+        if (CLEAN) {
+            if (nb <= 32) {
+                const uint32_t w = wnext;
+                wi++;
+                wnext = (wi < endw) ? words[wi] : 0u;
+                bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
+                nb += 32;
+            }
+        } else
+        while (nb <= 32) {
+            const uint32_t w = wnext;
+            wi++;
+            wnext = (wi < endw) ? words[wi] : 0u;
+            if ((((((~w) - 0x01010101u) & w & 0x80808080u)) | skip | ffp | eos) == 0u) {
+                bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
+                nb += 32;
+            } else if (eos) {
+                nb = 64;                          /* bb's low bits are zero: the stream continues as zeros */
+            } else {
+                /* byte path: FF00 -> FF; FFxx (xx != 0) = marker: this segment's data ends (JPEGFilter :1519-1538) */
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t c = (w >> (8 * i)) & 0xFFu;
+                    if (skip) { skip--; continue; }
+                    if (eos) break;
+                    if (wi - 1u == (in.end >> 2) && (uint32_t)i >= (in.end & 3u)) { eos = 1; break; } /* past the file */
+                    if (ffp) {
+                        ffp = 0;
+                        if (c != 0u) { eos = 1; break; }
+                        bb |= (jd_u64)0xFFu << (56 - nb);
+                        nb += 8;
+                        continue;
+                    }
+                    if (c == 0xFFu) { ffp = 1; continue; }
+                    bb |= (jd_u64)c << (56 - nb);
+                    nb += 8;
+                }
+                if (wi >= endw && !eos && nb <= 32) eos = 1;
+            }
+        }
+    };
+
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    uint32_t jw = JD_JW_INIT;                    /* window-phase candidates (six nibbles) */
+    uint32_t p7 = 0;                             /* bits consumed in this segment, mod 8 */
+    uint16_t *rp = rec;                          /* next record slot */
+    uint16_t *const rend = rec + in.rec_cap;
+    int err = -1;
+    bool last_was_eob = true;
+
+    const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
+    const uint32_t nblk_total = in.nmcu * in.bpm;
+    /* per-MCU block schedule, one nibble per block: component (2 bits) | DC table << 2 | AC table << 3 */
+    uint32_t sched = 0;
+    for (uint32_t i = 0; i < in.bpm && i < 8u; i++) {
+        const uint32_t c = (i < nluma) ? 0u : (i - nluma + 1u);
+        sched |= (c | (((in.tsel >> (2 * c)) & 1u) << 2) | (((in.tsel >> (2 * c + 1)) & 1u) << 3)) << (4 * i);
+    }
+    const uint32_t bsh_end = 4u * in.bpm;
+    uint32_t bsh = 0;                            /* 4 * (block index inside the MCU) */
+    const uint32_t rec_lo = (uint32_t)(uintptr_t)rec;
+    constexpr uint32_t LIMIT = (MODE == JD_MODE_STORE_LOW) ? 5u : 64u;
+    uint32_t b = 0;                              /* blocks finished */
+
+    for (; b < nblk_total; b++) {
+        const uint32_t cur = (sched >> bsh) & 15u;
+        /* ---- DC symbol (jpeg.inl:2128-2165) ---- */
+        refill();
+        jw = jd_jw_ckpt(jw);                     /* R1 at block entry (also the previous block's R4) */
+        int dcval;
+        {
+            const uint16_t *tdc = lut + JD_LUT_DC((cur >> 2) & 1u);
+            const uint32_t w16 = (uint32_t)(bb >> 48);
+            const uint32_t e = tdc[(w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)];
+            if (e == 0u) { err = JD_SEG_BADCODE; break; }
+            const uint32_t len = e >> 8, s = e & 15u;
+            bb <<= len;
+            const int v = jd_extend_top((uint32_t)(bb >> 32), s);
+            bb <<= s;
+            nb -= (int)(len + s);
+            /* window reload R2 (:2149) only when the reference's LUT has no precomputed difference,
+             * i.e. not (SSSS != 0 && len + SSSS <= 6) (:1132) */
+            uint32_t t = p7 + len;
+            jw += (t >> 3) * JD_JW_ONES;
+            if (s != 0u && len + s > 6u) jw = jd_jw_ckpt(jw);
+            t = (t & 7u) + s;
+            jw += (t >> 3) * JD_JW_ONES;
+            p7 = t & 7u;
+            const uint32_t comp = cur & 3u;
+            const int pv = ((comp == 0u) ? pred0 : ((comp == 1u) ? pred1 : pred2)) + ((MODE == JD_MODE_DC_SCAN) ? (int)((uint32_t)v << in.al) : v);
+            pred0 = (comp == 0u) ? pv : pred0;
+            pred1 = (comp == 1u) ? pv : pred1;
+            pred2 = (comp >= 2u) ? pv : pred2;
+            dcval = pv;
+        }
+        uint16_t *const rec0 = rp;               /* this block's first record */
+        uint32_t bflags = 0, bigm = 0;           /* OR of the tposw words; JD_ACF_RARE once the block's records are pairs */
+        if (MODE != JD_MODE_DC_SCAN) {
+            if (MODE != JD_MODE_PARSE_AC && (uint32_t)(rend - rp) < JD_REC_BLOCK_MAX) { err = JD_SEG_OVERFLOW; break; }
+            /* ---- AC symbols (jpeg.inl:2225-2264) ---- */
+            const uint16_t *tac = lut + JD_LUT_ACF(cur >> 3);
+            uint32_t k = 1;
+            do {
+                refill();
+                jw = jd_jw_ckpt(jw);             /* R3 at the loop top (also the previous symbol's R4) */
+                const uint32_t hi = (uint32_t)(bb >> 32);
+                uint32_t e = tac[hi >> 22];
+                uint32_t len = (e >> 8) & 31u;
+                if (len == 0u) {
+                    /* code longer than 10 bits (first 6 bits are ones) or invalid */
+                    e = (hi >= 0xFC000000u) ? lut[JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)] : 0u;
+                    if (e == 0u) { err = JD_SEG_BADCODE; break; }
+                    len = e >> 8;
+                    e |= JD_ACF_RARE;
+                }
+                const uint32_t rs = e & 0xFFu, s = rs & 15u;
+                bb <<= len;
+                const uint32_t x = (uint32_t)(bb >> 32);
+                const int v = jd_extend_top(x, s);
+                bb <<= s;
+                nb -= (int)(len + s);
+                k = (rs == 0u) ? 128u : k + (rs >> 4);   /* EOB (:2241-2244) ends the block */
+                if (MODE != JD_MODE_PARSE_AC && s != 0u && k < LIMIT) {
+                    /* stored coefficient (jpeg.inl:2247-2256) */
+                    const uint32_t tw = tposw[k];
+                    bflags |= tw;
+                    if (((e | bigm) & JD_ACF_RARE) != 0u) {
+                        if (s > 11u) { err = JD_SEG_BADSIZE; break; }
+                        if (len + s >= 18u) {
+                            /* possibly a truncated read for some start phases */
+                            const uint32_t t1 = p7 + len;
+                            const uint32_t j1 = jw + (t1 >> 3) * JD_JW_ONES;
+                            const int q7 = (int)(t1 & 7u);
+                            if (((j1 + 0x222222u) & 0x888888u) != 0u) {
+                                bool any = false;
+                                for (int c = 0; c < 6; c++) {
+                                    const int jc = (int)((j1 >> (4 * c)) & 15u);
+                                    if (8 * jc + q7 + (int)s > 64) any = true;
+                                }
+                                if (any) {
+                                    JDEvent ev;
+                                    ev.blk = in.blk0 + b;
+                                    ev.seg = in.seg;
+                                    ev.j1 = j1;
+                                    ev.field = (uint16_t)(x >> (32u - s));
+                                    ev.s = (uint8_t)s;
+                                    ev.p7 = (uint8_t)q7;
+                                    ev.ord = bigm ? (uint32_t)(rp - rec0) >> 1 : (uint32_t)(rp - rec0);
+                                    ev.img = in.img;
+                                    sink.push(ev);
+                                }
+                            }
+                        }
+                        if (s >= 10u && !bigm) {
+                            /* first >= 10-bit magnitude of this block: switch its records to (t, value) pairs */
+                            const uint32_t ncoef = (uint32_t)(rp - rec0);
+                            for (uint32_t i = ncoef; i-- > 0u;) {
+                                const uint32_t r = rec0[i];
+                                rec0[2u * i] = (uint16_t)(r >> 10);
+                                rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
+                            }
+                            rp += ncoef;
+                            bigm = JD_ACF_RARE;
+                        }
+                        if (bigm) {
+                            rp[0] = (uint16_t)(tw & 63u);
+                            rp[1] = (uint16_t)(int16_t)v;
+                            rp += 2;
+                        } else {
+                            *rp++ = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+                        }
+                    } else {
+                        *rp++ = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+                    }
+                }
+                {
+                    const uint32_t t = p7 + len + s;
+                    jw += (t >> 3) * JD_JW_ONES;
+                    p7 = t & 7u;
+                }
+                k++;
+            } while (k < 64u);
+            if (err >= 0) break;
+            last_was_eob = (k == 129u);
+        }
+        /* ---- block finished: header = first record | dc << 32 | count << 48 | BIG << 54 | rows-4..7 << 55 | columns << 56 ---- */
+        {
+            const uint32_t nrec = (uint32_t)(rp - rec0);
+            const uint32_t cnt = (bigm ? ((nrec >> 1) << 16) | (1u << 22) : (nrec << 16));
+            const uint32_t ridx0 = in.rec_index0 + (((uint32_t)(uintptr_t)rec0 - rec_lo) >> 1);
+            blk_hdr[b] = (jd_u64)ridx0 | ((jd_u64)((bflags & JD_BF_MASK) | cnt | ((uint32_t)dcval & 0xFFFFu)) << 32);
+        }
+        /* next block of the MCU: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
+        bsh += 4u;
+        if (bsh == bsh_end) bsh = 0u;
+    }
+    if (err >= 0) {
+        /* undecodable from here: later stages must still find well-formed (empty) headers */
+        out.err_mcu = (int32_t)(b / in.bpm);
+        for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
+    }
+    out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
+    if (err < 0) {
+        out.err_mcu = -1;
+        /* end of restart interval (jpeg.inl:5337-5347): R4 already happened unless the last
+         * block ended with EOB; then the bit offset is rounded up to a byte without a reload. */
+        if (!last_was_eob) jw = jd_jw_ckpt(jw);
+        if (p7) jw += JD_JW_ONES;
     }
     out.jmap = jw;
     out.nrec = (uint32_t)(rp - rec);

@@ -10,6 +10,9 @@
 #include <string.h>
 #include <vector>
 #include <new>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 #include "jd_kernels.cuh"
 
@@ -22,7 +25,8 @@
         }                                                                                          \
     } while (0)
 
-static char g_err[256];
+/* error text of the calling thread (two host threads driving two contexts never share it) */
+static thread_local char g_err[256];
 
 /* Device allocations are recycled through the context: a decode job borrows buffers and hands them
  * back on destroy, so steady-state batches do no cudaMalloc/cudaFree (both synchronise the device). */
@@ -78,9 +82,11 @@ struct JPEGB200_CTX {
     JDPool pool;
     JDPinPool pinpool;
     int64_t last_counters[JPEGB200_NUM_COUNTERS]; /* summed over the jobs of the last JPEGB200_decodeBatch */
+    float last_ms[JPEGB200_NUM_TIMINGS];          /* CUDA-event stage times summed over those jobs */
+    int last_jobs;
+    int numa_node;                                /* host NUMA node the GPU hangs off (-1 unknown) */
+    int pipe_depth;                               /* jobs in flight inside JPEGB200_decodeBatch (0 = default) */
 };
-
-static JDPool *g_cur_pool = nullptr; /* pool of the context whose batch is being set up (calls are serialised per context) */
 
 template <typename T>
 struct DevBuf {
@@ -88,11 +94,11 @@ struct DevBuf {
     size_t n = 0;
     size_t bytes = 0;
     JDPool *pool = nullptr;
-    cudaError_t alloc(size_t count)
+    cudaError_t alloc(JDPool *from, size_t count)
     {
         if (count <= n && p) return cudaSuccess;
         release();
-        pool = g_cur_pool;
+        pool = from;
         size_t need = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
         void *q = nullptr;
         cudaError_t e = pool ? pool->get(need, &q, &bytes) : cudaMalloc(&q, bytes = need);
@@ -133,7 +139,9 @@ struct JPEGB200_BATCH {
     DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
     DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
     DevBuf<uint32_t> d_err_off, d_dprog;
-    DevBuf<uint32_t> d_tok, d_blk_tok, d_seg_errblk;   /* opt-in two-phase entropy stage (jd_tokens.h) */
+    DevBuf<uint8_t> d_clean;       /* un-stuffed restart segments (jdk_unstuff_segs) */
+    DevBuf<uint32_t> d_seg_clen;
+    uint64_t rec_total;            /* coefficient records the batch may need (JD_REC_INDEX layout) */
     DevBuf<uint4> d_dbands;        /* dither: (image, band, warp of the band above, -) per warp */
     std::vector<uint4> dbands;
     JDImageDesc *descs_dl;             /* descriptors read back (status, err_mcu); pinned, from ctx->pinpool */
@@ -157,7 +165,7 @@ struct JPEGB200_BATCH {
     bool have_ev;
     float ms[JPEGB200_NUM_TIMINGS];
     int64_t counters[JPEGB200_NUM_COUNTERS];
-    uint32_t *h_counters;              /* 4 words at the end of the descs_dl block */
+    uint32_t *h_counters;              /* 8 words at the end of the descs_dl block */
 };
 
 static char *ctx_err() { return g_err; }
@@ -198,6 +206,19 @@ extern "C" JPEGB200_CTX *JPEGB200_create(int device, int arith_mode)
     c->has_shared = false;
     c->shared_hits = 0;
     memset(c->last_counters, 0, sizeof(c->last_counters));
+    memset(c->last_ms, 0, sizeof(c->last_ms));
+    c->last_jobs = 0;
+    c->pipe_depth = 0;
+    c->numa_node = -1;
+    {   /* which host NUMA node is this GPU attached to?  (/sys/bus/pci/devices/<domain:bus:dev.fn>/numa_node) */
+        char bus[32] = {0}, path[96];
+        if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) == cudaSuccess) {
+            for (char *q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+            snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+            FILE *f = fopen(path, "r");
+            if (f) { int node = -1; if (fscanf(f, "%d", &node) == 1) c->numa_node = node; fclose(f); }
+        } else cudaGetLastError();
+    }
     return c;
 }
 
@@ -221,6 +242,152 @@ extern "C" void *JPEGB200_hostAlloc(size_t bytes)
 }
 
 extern "C" void JPEGB200_hostFree(void *p) { if (p) cudaFreeHost(p); }
+
+/* ---- host placement: the pixels of a batch leave the GPU over PCIe into pinned host memory; on a two-socket box that
+ * memory (and the thread that drives the copies) should sit on the socket the GPU hangs off, or every byte crosses the
+ * inter-socket link as well.  Nothing here is required for correctness. ---- */
+extern "C" int JPEGB200_numaNode(JPEGB200_CTX *ctx) { return ctx ? ctx->numa_node : -1; }
+
+/* parse "0-3,8,10-11" */
+static int jd_parse_cpulist(const char *txt, cpu_set_t *set)
+{
+    int n = 0;
+    CPU_ZERO(set);
+    const char *q = txt;
+    while (*q) {
+        char *e;
+        long a = strtol(q, &e, 10);
+        if (e == q) break;
+        long b2 = a;
+        if (*e == '-') { q = e + 1; b2 = strtol(q, &e, 10); }
+        for (long c = a; c <= b2 && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); n++; }
+        q = e;
+        while (*q == ',' || *q == ' ' || *q == '\n') q++;
+    }
+    return n;
+}
+
+/* Pins the CALLING thread (and the threads it creates later) to the CPUs of the context's NUMA node -- intersected with
+ * the CPUs the process may use -- and makes that node the preferred one for its allocations; pinned memory allocated
+ * afterwards (JPEGB200_hostAlloc) lands there.  Returns the number of CPUs in the new mask, 0 if nothing was changed. */
+extern "C" int JPEGB200_bindHostToDevice(JPEGB200_CTX *ctx)
+{
+    if (!ctx || ctx->numa_node < 0) return 0;
+    char path[96], txt[4096];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", ctx->numa_node);
+    FILE *f = fopen(path, "r");
+    if (!f) return 0;
+    const size_t got = fread(txt, 1, sizeof(txt) - 1, f);
+    fclose(f);
+    txt[got] = 0;
+    cpu_set_t node, cur, both;
+    if (jd_parse_cpulist(txt, &node) == 0) return 0;
+    if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 0;
+    CPU_AND(&both, &node, &cur);
+    const int n = CPU_COUNT(&both);
+    if (n == 0) return 0;
+    if (sched_setaffinity(0, sizeof(both), &both) != 0) return 0;
+#ifdef SYS_set_mempolicy
+    {   /* MPOL_PREFERRED = 1: fall back to other nodes rather than fail when the node is full */
+        unsigned long mask[16] = {0};
+        if (ctx->numa_node < (int)(8 * sizeof(mask))) {
+            mask[ctx->numa_node / (8 * sizeof(unsigned long))] |= 1ul << (ctx->numa_node % (8 * sizeof(unsigned long)));
+            (void)syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(8 * sizeof(mask)));
+        }
+    }
+#endif
+    return n;
+}
+
+extern "C" void *JPEGB200_deviceAlloc(JPEGB200_CTX *ctx, size_t bytes)
+{
+    if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void JPEGB200_deviceFree(JPEGB200_CTX *ctx, void *p)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFree(p);
+}
+
+extern "C" int JPEGB200_deviceRead(JPEGB200_CTX *ctx, void *host_dst, const void *dev_src, size_t bytes)
+{
+    if (!ctx) return 0;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+    return 1;
+}
+
+/* ---- digests of device-resident pixels: lets a caller (bench / tests) verify a whole device-resident batch against
+ * reference digests without moving the pixels to the host.  digest = sum over 8-byte words i of mix64(word ^ i * K)
+ * mod 2^64 (mix64 = the splitmix64 finaliser); order independent, so it reduces in parallel. ---- */
+__device__ __forceinline__ unsigned long long jd_mix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256) jdk_digest(const uint8_t *const *ptrs, const int64_t *lens, unsigned long long *out)
+{
+    const uint32_t img = blockIdx.y;
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(ptrs[img]);
+    const int64_t nbytes = lens[img], nfull = nbytes >> 3;
+    unsigned long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nfull; i += (int64_t)gridDim.x * blockDim.x)
+        acc += jd_mix64(w[i] ^ ((unsigned long long)i * 0x9E3779B97F4A7C15ull));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (nbytes & 7)) {   /* tail bytes, zero padded */
+        unsigned long long t = 0;
+        const uint8_t *q = ptrs[img] + (nfull << 3);
+        for (int k = 0; k < (int)(nbytes & 7); k++) t |= (unsigned long long)q[k] << (8 * k);
+        acc += jd_mix64(t ^ ((unsigned long long)nfull * 0x9E3779B97F4A7C15ull));
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    __shared__ unsigned long long s_part[8];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < 8; k++) t += s_part[k];
+        atomicAdd(out + img, t);
+    }
+}
+
+/* digests of n device byte ranges (8-byte aligned starts); synchronous */
+extern "C" int JPEGB200_digestDevice(JPEGB200_CTX *ctx, const void *const *dev_ptrs, const int64_t *lengths, int n, uint64_t *digests)
+{
+    if (!ctx || n <= 0 || !dev_ptrs || !lengths || !digests) return 0;
+    for (int i = 0; i < n; i++) if (((uintptr_t)dev_ptrs[i] & 7u) || lengths[i] < 0) { snprintf(g_err, sizeof(g_err), "digest ranges must start 8-byte aligned"); return 0; }
+    CK(cudaSetDevice(ctx->device));
+    void *d = nullptr;
+    const size_t pb = (size_t)n * 8;
+    CK(cudaMalloc(&d, 3 * pb));
+    uint8_t *dp = (uint8_t *)d;
+    int ok = 1;
+    if (cudaMemcpy(dp, dev_ptrs, pb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dp + pb, lengths, pb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(dp + 2 * pb, 0, pb) != cudaSuccess) ok = 0;
+    if (ok) {
+        for (int i0 = 0; i0 < n; i0 += 32768) {
+            const int cnt = (n - i0 < 32768) ? n - i0 : 32768;
+            jdk_digest<<<dim3(64, cnt), 256>>>((const uint8_t *const *)dp + i0, (const int64_t *)(dp + pb) + i0, (unsigned long long *)(dp + 2 * pb) + i0);
+        }
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(digests, dp + 2 * pb, pb, cudaMemcpyDeviceToHost) != cudaSuccess) ok = 0;
+    }
+    if (!ok) snprintf(g_err, sizeof(g_err), "digest failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d);
+    return ok;
+}
+
+extern "C" int JPEGB200_setPipelineDepth(JPEGB200_CTX *ctx, int jobs_in_flight)
+{
+    if (!ctx || jobs_in_flight < 0 || jobs_in_flight > 16) return 0;
+    ctx->pipe_depth = jobs_in_flight;
+    return 1;
+}
 
 /* ---- shared table blob ---- */
 extern "C" int JPEGB200_exportTables(const uint8_t *jpeg, int size, uint8_t *blob)
@@ -300,15 +467,16 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         if (!contig) off += ((size_t)sizes[i] + 15) & ~(size_t)15;
     }
     b->comp_total = contig ? (size_t)(datas[n - 1] + sizes[n - 1] - datas[0]) : off;
-    if (b->comp_total >= (1ull << 30)) {
-        snprintf(g_err, sizeof(g_err), "batch holds %zu compressed bytes; limit is 1 GiB per batch (split it)", b->comp_total);
+    if (b->comp_total >= (3ull << 30)) {
+        /* byte offsets into the batch buffer (and into the un-stuffed copy, which adds 32 bytes per segment) are 32-bit */
+        snprintf(g_err, sizeof(g_err), "batch holds %zu compressed bytes; one job takes at most 3 GiB (JPEGB200_decodeBatch splits larger batches)", b->comp_total);
         delete b;
         return nullptr;
     }
 
     std::vector<uint64_t> lut_hash;
     uint32_t seg = 0;
-    uint64_t blk = 0;
+    uint64_t blk = 0, rec_total = 0;
     size_t out_total = 0, gray_total = 0;
     for (int i = 0; i < n; i++) {
         JDInfo &inf = b->infos[i];
@@ -331,6 +499,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         } else if (ok && inf.mode != 0xC0) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; }
         if (ok && !inf.tables_ok) { ok = 0; st = JPEG_DECODE_ERROR; }           /* jpeg.inl:2166 */
         if (ok && inf.ncomp == 1 && pixel_type == RGB8888) { ok = 0; st = JPEG_INVALID_PARAMETER; }
+        if (ok && (uint64_t)sizes[i] >= (512ull << 20)) { ok = 0; st = JPEG_UNSUPPORTED_FEATURE; }   /* image-relative record indices are 32-bit */
         b->parse_status[i] = st;
         if (!ok) { /* keep a harmless empty descriptor */
             d.nseg = 0; d.seg_base = seg; d.blk_base = (uint32_t)blk; d.status = (uint32_t)st;
@@ -375,6 +544,11 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         d.seg_base = seg;
         d.blk_base = (uint32_t)blk;
         d.lutset = li;
+        /* coefficient records: image-relative indices (jd_core.h JD_REC_INDEX), one slot per restart segment and per chunk */
+        d.comp_off = (uint32_t)b->comp_off[i];
+        d.rec_base = rec_total;
+        rec_total += (uint64_t)JD_REC_PER_BYTE * (uint64_t)(((size_t)sizes[i] + 15) & ~(size_t)15) + (uint64_t)JD_REC_SLOT_SLACK * (d.nseg + d.nch + 1u);
+
         const int s = b->sshift;
         d.out_w = (uint32_t)((inf.width + (1 << s) - 1) >> s);
         d.out_h = (uint32_t)((inf.height + (1 << s) - 1) >> s);
@@ -397,6 +571,12 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
         if (blk >= (1ull << 32)) { snprintf(g_err, sizeof(g_err), "batch too large (block count)"); delete b; return nullptr; }
     }
     b->nseg = seg; b->nblk = blk; b->nlut = (uint32_t)lut_hash.size();
+    b->rec_total = rec_total;
+    if ((uint64_t)b->comp_total + 32ull * seg + 4096ull >= (1ull << 32)) {
+        snprintf(g_err, sizeof(g_err), "batch too large (%zu compressed bytes in %u restart segments)", b->comp_total, seg);
+        delete b;
+        return nullptr;
+    }
     b->out_total = out_total; b->gray_total = gray_total;
     /* work list: CTAs of 128 segments sharing one LUT set */
     b->seg_img.resize(seg ? seg : 1);
@@ -419,7 +599,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
-    b->d_tok.release(); b->d_blk_tok.release(); b->d_seg_errblk.release();
+    b->d_clean.release(); b->d_seg_clen.release();
     b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
@@ -465,7 +645,6 @@ extern "C" int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int6
 
 static int batch_stream(JPEGB200_BATCH *b)
 {
-    g_cur_pool = &b->ctx->pool;
     CK(cudaSetDevice(b->ctx->device));
     if (!b->stream) CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     if (!b->have_ev) {
@@ -480,9 +659,8 @@ extern "C" void *JPEGB200_batchStream(JPEGB200_BATCH *b) { if (!b || !batch_stre
 extern "C" int JPEGB200_batchAllocDeviceOutput(JPEGB200_BATCH *b)
 {
     if (!b) return 0;
-    g_cur_pool = &b->ctx->pool;
     CK(cudaSetDevice(b->ctx->device));
-    CK(b->d_out.alloc(b->out_total + 256));
+    CK(b->d_out.alloc(&b->ctx->pool, b->out_total + 256));
     b->arena_owned = true;
     return 1;
 }
@@ -510,27 +688,27 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
     if (!b) return 0;
     if (!batch_stream(b)) return 0;
     const int n = b->n;
-    CK(b->d_comp.alloc(b->comp_total + 256));
-    CK(b->d_descs.alloc(n));
-    CK(b->d_quant.alloc((size_t)n * 192));
-    CK(b->d_luts.alloc(b->luts.size() ? b->luts.size() : 1));
-    CK(b->d_work.alloc(b->work.size() ? b->work.size() : 1));
-    CK(b->d_cta_lut.alloc(b->cta_lut.size() ? b->cta_lut.size() : 1));
-    CK(b->d_seg_img.alloc(b->seg_img.size()));
+    CK(b->d_comp.alloc(&b->ctx->pool, b->comp_total + 256));
+    CK(b->d_descs.alloc(&b->ctx->pool, n));
+    CK(b->d_quant.alloc(&b->ctx->pool, (size_t)n * 192));
+    CK(b->d_luts.alloc(&b->ctx->pool, b->luts.size() ? b->luts.size() : 1));
+    CK(b->d_work.alloc(&b->ctx->pool, b->work.size() ? b->work.size() : 1));
+    CK(b->d_cta_lut.alloc(&b->ctx->pool, b->cta_lut.size() ? b->cta_lut.size() : 1));
+    CK(b->d_seg_img.alloc(&b->ctx->pool, b->seg_img.size()));
     const size_t ns = b->nseg ? b->nseg : 1;
-    CK(b->d_seg_start.alloc(ns + 1)); CK(b->d_seg_jmap.alloc(ns)); CK(b->d_seg_status.alloc(ns));
-    CK(b->d_seg_nrec.alloc(ns)); CK(b->d_seg_phase.alloc(ns + b->nchunks));
+    CK(b->d_seg_start.alloc(&b->ctx->pool, ns + 1)); CK(b->d_seg_jmap.alloc(&b->ctx->pool, ns)); CK(b->d_seg_status.alloc(&b->ctx->pool, ns));
+    CK(b->d_seg_nrec.alloc(&b->ctx->pool, ns)); CK(b->d_seg_phase.alloc(&b->ctx->pool, ns + b->nchunks));
     if (b->nchunks) {
         const size_t nc = b->nchunks;
-        CK(b->d_filt.alloc(b->comp_total + 512));
-        CK(b->d_cimg_list.alloc(b->cimg_list.size())); CK(b->d_chunk_img.alloc(nc)); CK(b->d_flen.alloc(n));
-        CK(b->d_E0.alloc(nc + 1)); CK(b->d_E1.alloc(nc + 1)); CK(b->d_cn.alloc(nc)); CK(b->d_cpre.alloc(nc)); CK(b->d_cjmap.alloc(nc));
-        CK(b->d_cstatus.alloc(nc)); CK(b->d_cnown.alloc(nc)); CK(b->d_cdcs.alloc(3 * nc)); CK(b->d_cpe.alloc(3 * nc));
+        CK(b->d_filt.alloc(&b->ctx->pool, b->comp_total + 512));
+        CK(b->d_cimg_list.alloc(&b->ctx->pool, b->cimg_list.size())); CK(b->d_chunk_img.alloc(&b->ctx->pool, nc)); CK(b->d_flen.alloc(&b->ctx->pool, n));
+        CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
+        CK(b->d_cstatus.alloc(&b->ctx->pool, nc)); CK(b->d_cnown.alloc(&b->ctx->pool, nc)); CK(b->d_cdcs.alloc(&b->ctx->pool, 3 * nc)); CK(b->d_cpe.alloc(&b->ctx->pool, 3 * nc));
     }
-    CK(b->d_counters.alloc(4));
-    CK(b->d_blk_hdr.alloc(b->nblk ? b->nblk : 1));
-    CK(b->d_rec.alloc(4 * b->comp_total + 1024));
-    CK(b->d_events.alloc(JD_EVENT_CAP));
+    CK(b->d_counters.alloc(&b->ctx->pool, 8));
+    CK(b->d_blk_hdr.alloc(&b->ctx->pool, b->nblk ? b->nblk : 1));
+    CK(b->d_rec.alloc(&b->ctx->pool, b->rec_total + 1024));
+    CK(b->d_events.alloc(&b->ctx->pool, JD_EVENT_CAP));
     cudaStream_t st = b->stream;
     CK(cudaEventRecord(b->ev[0], st));
     /* zero the tail padding so word loads past the last file read zeros */
@@ -646,6 +824,9 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     if (b->out_device && !b->arena_owned) {
         user_dev_out = true;
         for (int i = 0; i < n; i++) if (!b->outs[i] && b->parse_status[i] == JPEG_SUCCESS) user_dev_out = false;
+        bool any_ptr = false;
+        for (int i = 0; i < n; i++) if (b->outs[i]) any_ptr = true;
+        if (!user_dev_out && any_ptr) { snprintf(g_err, sizeof(g_err), "device output pointers given for some images only"); return 0; }
     }
     uint8_t *out_base = nullptr;
     if (user_dev_out) {
@@ -658,7 +839,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             b->descs[i].out_pitch = (uint32_t)b->pitches[i];
         }
     } else {
-        if (!b->d_out.p) { CK(b->d_out.alloc(b->out_total + 256)); b->arena_owned = true; }
+        if (!b->d_out.p) { CK(b->d_out.alloc(&b->ctx->pool, b->out_total + 256)); b->arena_owned = true; }
         out_base = b->d_out.p;
         for (int i = 0; i < n; i++) b->descs[i].out_off = b->arena_off[i];
     }
@@ -667,7 +848,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     std::vector<uint32_t> err_off;
     std::vector<JDImageDesc> descs_stage = b->descs;
     if (b->dither_bits) {
-        CK(b->d_gray.alloc(b->gray_total + 256));
+        CK(b->d_gray.alloc(&b->ctx->pool, b->gray_total + 256));
         size_t go = 0, eo = 0;
         gray_off.resize(2 * (size_t)n); err_off.resize(n);
         b->errinit.clear();
@@ -689,9 +870,9 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             memcpy(&b->errinit[eo], inf.p.huffvals + 2, cp);
             eo += el;
         }
-        CK(b->d_errline.alloc(eo + 16));
+        CK(b->d_errline.alloc(&b->ctx->pool, eo + 16));
         CK(cudaMemcpyAsync(b->d_errline.p, b->errinit.data(), eo, cudaMemcpyHostToDevice, st));
-        CK(b->d_gray_off.alloc(2 * (size_t)n)); CK(b->d_err_off.alloc(n));
+        CK(b->d_gray_off.alloc(&b->ctx->pool, 2 * (size_t)n)); CK(b->d_err_off.alloc(&b->ctx->pool, n));
         /* pageable sources: the runtime stages them before returning, so the vectors may go out of scope */
         CK(cudaMemcpyAsync(b->d_gray_off.p, gray_off.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->d_err_off.p, err_off.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -711,12 +892,12 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
                     prevpos[i] = pos;
                 }
         }
-        CK(b->d_dbands.alloc(b->dbands.size() ? b->dbands.size() : 1)); CK(b->d_dprog.alloc(b->dbands.size() + 1));
+        CK(b->d_dbands.alloc(&b->ctx->pool, b->dbands.size() ? b->dbands.size() : 1)); CK(b->d_dprog.alloc(&b->ctx->pool, b->dbands.size() + 1));
         if (!b->dbands.empty()) CK(cudaMemcpyAsync(b->d_dbands.p, b->dbands.data(), b->dbands.size() * sizeof(uint4), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(b->d_dprog.p, 0, (b->dbands.size() + 1) * 4, st));
     }
     CK(cudaMemcpyAsync(b->d_descs.p, descs_stage.data(), sizeof(JDImageDesc) * n, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(b->d_counters.p, 0, 16, st));
+    CK(cudaMemsetAsync(b->d_counters.p, 0, 32, st));
     if (b->nchunks) CK(cudaMemsetAsync(b->d_blk_hdr.p, 0, (size_t)b->nblk * 8, st)); /* blocks a truncated restart-free scan never reaches stay empty */
 
     CK(cudaEventRecord(b->ev[2], st));
@@ -727,24 +908,25 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         JDEntropyArgs ea;
         ea.data = b->d_comp.p; ea.imgs = b->d_descs.p; ea.luts = b->d_luts.p; ea.work = b->d_work.p; ea.cta_lut = b->d_cta_lut.p;
         ea.seg_img = b->d_seg_img.p; ea.seg_start = b->d_seg_start.p; ea.blk_hdr = b->d_blk_hdr.p; ea.rec = b->d_rec.p;
-        ea.rec_total = (uint32_t)(4 * b->comp_total + 1024);
         ea.seg_jmap = b->d_seg_jmap.p; ea.seg_status = b->d_seg_status.p; ea.seg_nrec = b->d_seg_nrec.p;
         ea.events = b->d_events.p; ea.event_count = b->d_counters.p; ea.event_cap = JD_EVENT_CAP;
-        ea.nwork = (uint32_t)b->work.size(); ea.data_base = 0; ea.dc_output = (b->sshift == 3) ? 1u : (b->sshift == 2) ? 2u : 0u;
-        static int use_tokens = -1;   /* JPEGDEC_B200_ENTROPY=tokens: two-phase stage (prototype, baseline full / half size only) */
-        if (use_tokens < 0) { const char *e = getenv("JPEGDEC_B200_ENTROPY"); use_tokens = (e && strcmp(e, "tokens") == 0) ? 1 : 0; }
-        bool any_prog = false;
-        for (int i = 0; i < n; i++) if (b->descs[i].prog & 1u) any_prog = true;
-        if (use_tokens && !any_prog && b->sshift < 2) {
-            JDTokenArgs ta;
-            ta.e = ea;
-            CK(b->d_tok.alloc(4 * b->comp_total + 64 * (size_t)b->nseg + 1024)); CK(b->d_blk_tok.alloc(b->nblk ? b->nblk : 1)); CK(b->d_seg_errblk.alloc(b->nseg ? b->nseg : 1));
-            ta.tok = b->d_tok.p; ta.tok_total = (uint32_t)(4 * b->comp_total + 64 * (size_t)b->nseg + 1024); ta.blk_tok = b->d_blk_tok.p; ta.seg_errblk = b->d_seg_errblk.p;
-            jdk_tokens_parse<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ta);
-            jdk_tokens_materialize<<<(unsigned)((b->work.size() * 32 + 127) / 128), 128, 0, st>>>(ta);
+        ea.nwork = (uint32_t)b->work.size(); ea.dc_output = (b->sshift == 3) ? 1u : (b->sshift == 2) ? 2u : 0u;
+        /* JPEGDEC_B200_ENTROPY=raw: the entropy kernel un-stuffs in its bit reader; default ("clean"): jdk_unstuff_segs
+         * first, so that the reader is a plain word stream */
+        static int use_clean = -1;
+        if (use_clean < 0) { const char *e = getenv("JPEGDEC_B200_ENTROPY"); use_clean = (e && strcmp(e, "raw") == 0) ? 0 : 1; }
+        const unsigned egrid = (unsigned)(b->work.size() / JD_ENTROPY_THREADS);
+        if (use_clean) {
+            CK(b->d_clean.alloc(&b->ctx->pool, b->comp_total + 32 * (size_t)b->nseg + 4096));
+            CK(b->d_seg_clen.alloc(&b->ctx->pool, b->nseg ? b->nseg : 1));
+            jdk_unstuff_segs<<<(b->nseg * 32u + JD_UNSTUFF_WARPS * 32u - 1u) / (JD_UNSTUFF_WARPS * 32u), JD_UNSTUFF_WARPS * 32, 0, st>>>(
+                b->d_comp.p, b->d_descs.p, b->d_seg_img.p, b->d_seg_start.p, b->nseg, b->d_clean.p, b->d_seg_clen.p);
+            ea.clean = b->d_clean.p; ea.seg_clen = b->d_seg_clen.p;
+            jdk_entropy<true><<<egrid, JD_ENTROPY_THREADS, 0, st>>>(ea);
             launches += 2;
         } else {
-            jdk_entropy<<<(unsigned)(b->work.size() / JD_ENTROPY_THREADS), JD_ENTROPY_THREADS, 0, st>>>(ea);
+            ea.clean = nullptr; ea.seg_clen = nullptr;
+            jdk_entropy<false><<<egrid, JD_ENTROPY_THREADS, 0, st>>>(ea);
             launches++;
         }
     }
@@ -756,7 +938,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ca.chunk_img = b->d_chunk_img.p; ca.nchunks = b->nchunks;
         ca.cn = b->d_cn.p; ca.cpre = b->d_cpre.p; ca.cjmap = b->d_cjmap.p; ca.cstatus = b->d_cstatus.p; ca.cnown = b->d_cnown.p;
         ca.cdcs = b->d_cdcs.p; ca.cpe = b->d_cpe.p; ca.changed = b->d_counters.p + 2;
-        ca.blk_hdr = b->d_blk_hdr.p; ca.rec = b->d_rec.p; ca.rec_total = (uint32_t)(4 * b->comp_total + 1024);
+        ca.blk_hdr = b->d_blk_hdr.p; ca.rec = b->d_rec.p;
         ca.events = b->d_events.p; ca.event_count = b->d_counters.p; ca.event_cap = JD_EVENT_CAP;
         ca.seg_phase = b->d_seg_phase.p; ca.seg_jmap = b->d_seg_jmap.p; ca.seg_status = b->d_seg_status.p; ca.nseg_total = b->nseg;
         const unsigned gc = (b->nchunks + 127) / 128, gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
@@ -785,8 +967,9 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         launches += 4;
     }
     CK(cudaEventRecord(b->ev[4], st));
-    jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p);
-    jdk_patch<<<32, 256, 0, st>>>(b->d_events.p, b->d_counters.p, JD_EVENT_CAP, b->d_seg_phase.p, b->d_blk_hdr.p, b->d_rec.p, b->d_counters.p + 1);
+    jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p, b->d_seg_nrec.p,
+                                               reinterpret_cast<unsigned long long *>(b->d_counters.p + 4));
+    jdk_patch<<<32, 256, 0, st>>>(b->d_descs.p, b->d_events.p, b->d_counters.p, JD_EVENT_CAP, b->d_seg_phase.p, b->d_blk_hdr.p, b->d_rec.p, b->d_counters.p + 1);
     launches += 2;
     CK(cudaEventRecord(b->ev[5], st));
     /* IDCT + colour: one launch per run of images with the same geometry class */
@@ -870,8 +1053,11 @@ extern "C" int JPEGB200_batchDownload(JPEGB200_BATCH *b)
             if ((uint8_t *)b->outs[i] - (uint8_t *)b->outs[0] != (ptrdiff_t)b->arena_off[i]) mirror = false;
             if (b->pitches[i] != (int64_t)b->descs[i].out_pitch) mirror = false;
         }
-        if (mirror && b->parse_status[0] == JPEG_SUCCESS) {
-            size_t span = b->arena_off[n - 1] + (size_t)b->descs[n - 1].out_pitch * b->descs[n - 1].out_h;
+        int last_ok = -1;
+        for (int i = n - 1; i >= 0 && last_ok < 0; i--) if (b->parse_status[i] == JPEG_SUCCESS) last_ok = i;
+        if (mirror && last_ok >= 0 && b->parse_status[0] == JPEG_SUCCESS) {
+            /* up to the end of the last image that has pixels (a rejected file owns no arena space) */
+            size_t span = b->arena_off[last_ok] + (size_t)b->descs[last_ok].out_pitch * b->descs[last_ok].out_h;
             CK(cudaMemcpyAsync(b->outs[0], b->d_out.p, span, cudaMemcpyDeviceToHost, st));
             bytes = (int64_t)span;
         } else {
@@ -885,14 +1071,14 @@ extern "C" int JPEGB200_batchDownload(JPEGB200_BATCH *b)
         }
     }
     if (!b->descs_dl) {
-        b->descs_dl = (JDImageDesc *)b->ctx->pinpool.get(sizeof(JDImageDesc) * b->n + 16, &b->descs_dl_bytes);
+        b->descs_dl = (JDImageDesc *)b->ctx->pinpool.get(sizeof(JDImageDesc) * b->n + 32, &b->descs_dl_bytes);
         if (!b->descs_dl) { snprintf(g_err, sizeof(g_err), "pinned status buffer allocation failed"); return 0; }
         b->h_counters = (uint32_t *)(b->descs_dl + b->n);
     }
     CK(cudaMemcpyAsync(b->descs_dl, b->d_descs.p, sizeof(JDImageDesc) * b->n, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(b->h_counters, b->d_counters.p, 32, cudaMemcpyDeviceToHost, st));
     b->downloaded = true;
-    bytes += (int64_t)sizeof(JDImageDesc) * b->n + 16;
+    bytes += (int64_t)sizeof(JDImageDesc) * b->n + 32;
     CK(cudaEventRecord(b->ev[9], st));
     b->counters[JPEGB200_C_D2H_BYTES] = bytes;
     return 1;
@@ -905,13 +1091,22 @@ extern "C" int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status)
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaGetLastError());
     int all_ok = 1;
+    /* more window-truncation events than the event buffer holds: some coefficients of this job were not patched, so its
+     * pixels may differ from the reference's -- report that instead of returning them as good */
+    const bool ev_overflow = b->downloaded && b->h_counters[0] > JD_EVENT_CAP;
+    if (ev_overflow) snprintf(g_err, sizeof(g_err), "%u window-truncation events exceed the event buffer (%u): job rejected", b->h_counters[0], JD_EVENT_CAP);
     for (int i = 0; i < b->n; i++) {
         int st = b->parse_status[i];
         if (st == JPEG_SUCCESS && b->downloaded && b->descs_dl[i].status != 0) st = JPEG_DECODE_ERROR; /* jpeg.inl:5354 */
+        if (st == JPEG_SUCCESS && ev_overflow) st = JPEG_DECODE_ERROR;
         if (status) status[i] = st;
         if (st != JPEG_SUCCESS) all_ok = 0;
     }
-    if (b->downloaded) b->counters[JPEGB200_C_EVENTS] = b->h_counters[1];
+    if (b->downloaded) {
+        b->counters[JPEGB200_C_EVENTS] = b->h_counters[1];            /* truncated reads the reference would have made */
+        b->counters[JPEGB200_C_EVENT_CANDIDATES] = b->h_counters[0];  /* reads that are truncated for SOME start phase */
+        b->counters[JPEGB200_C_RECORD_BYTES] = 2 * (int64_t)(((uint64_t)b->h_counters[5] << 32) | b->h_counters[4]);
+    }
     float t;
     auto el = [&](int a, int c) { t = 0; cudaEventElapsedTime(&t, b->ev[a], b->ev[c]); return t; };
     b->ms[JPEGB200_T_H2D] = el(0, 1);
@@ -947,44 +1142,68 @@ extern "C" int JPEGB200_batchGetCounters(JPEGB200_BATCH *b, int64_t *counters)
     return 1;
 }
 
-/* One call for a whole batch.  With host outputs the batch is cut into jobs of JD_PIPE_IMAGES images, each on its own
- * stream, all enqueued before the first wait: job k's pixels cross PCIe while job k+1's kernels run and job k+2's
- * compressed bytes go up, so the call costs about one D2H of the pixels instead of H2D + kernels + D2H. */
+/* One call for a whole batch of any size.  The batch is cut into jobs, each on its own stream, all enqueued before the
+ * first wait, so that job k's pixels cross PCIe (host outputs) or its IDCT runs (device outputs) while job k+1's entropy
+ * kernel runs and job k+2's compressed bytes go up.  Host outputs: jobs of JD_PIPE_IMAGES images (more when the images are
+ * small), so the call costs about one D2H of the pixels instead of H2D + kernels + D2H.  Device outputs: jobs of up to
+ * JD_JOB_COMP_BYTES compressed bytes, which bounds the transient coefficient records (12 B per compressed byte) however
+ * large the batch is; the pixels go straight to the caller's device pointers. */
 #define JD_PIPE_IMAGES 64
 #define JD_PIPE_MIN_BYTES ((int64_t)64 << 20)
 #define JD_PIPE_INFLIGHT 6
+#define JD_JOB_COMP_BYTES ((int64_t)192 << 20)
+#define JD_JOB_MAX_IMAGES 4096
+#define JD_PIPE_INFLIGHT_DEVICE 3
 extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *datas, const int32_t *sizes, int n,
                                     int pixel_type, int options, void *const *outs, const int64_t *pitches,
                                     int flags, int32_t *status)
 {
     if (!ctx || n <= 0) return 0;
+    const bool dev_out = (flags & JPEGB200_OUT_DEVICE) != 0;
+    if (dev_out && !outs) { snprintf(g_err, sizeof(g_err), "JPEGB200_decodeBatch with JPEGB200_OUT_DEVICE needs the caller's device pointers"); return 0; }
     memset(ctx->last_counters, 0, sizeof(ctx->last_counters));
+    memset(ctx->last_ms, 0, sizeof(ctx->last_ms));
+    ctx->last_jobs = 0;
     std::vector<JPEGB200_BATCH *> jobs;
     std::vector<int> first;
     int rc = 1, all = 1;
     size_t retired = 0;
+    const size_t depth = ctx->pipe_depth ? (size_t)ctx->pipe_depth : (size_t)(dev_out ? JD_PIPE_INFLIGHT_DEVICE : JD_PIPE_INFLIGHT);
     /* jobs complete in order; retiring one = wait + per-image status + counters + buffers back to the context's pools */
     auto retire = [&](size_t k) {
         if (rc) {
             const int r = JPEGB200_batchWait(jobs[k], status ? status + first[k] : nullptr);
             if (r == 0) all = 0; else if (r == 2 && all == 1) all = 2;
             for (int c = 0; c < JPEGB200_NUM_COUNTERS; c++) ctx->last_counters[c] += jobs[k]->counters[c];
+            for (int c = 0; c < JPEGB200_NUM_TIMINGS; c++) ctx->last_ms[c] += jobs[k]->ms[c];
+            ctx->last_jobs++;
         }
         JPEGB200_batchDestroy(jobs[k]);
         jobs[k] = nullptr;
     };
     for (int i0 = 0; i0 < n && rc;) {
-        int cnt = n - i0;
-        if (!(flags & JPEGB200_OUT_DEVICE) && cnt > JD_PIPE_IMAGES) cnt = JD_PIPE_IMAGES;
+        /* how many images the next job takes */
+        int cnt = 0;
+        int64_t cb = 0;
+        const int maxcnt = dev_out ? JD_JOB_MAX_IMAGES : JD_PIPE_IMAGES;
+        while (i0 + cnt < n && cnt < maxcnt) {
+            const int64_t sz = sizes[i0 + cnt] > 0 ? sizes[i0 + cnt] : 0;
+            if (cnt > 0 && cb + sz > JD_JOB_COMP_BYTES) break;
+            cb += sz; cnt++;
+        }
         JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas + i0, sizes + i0, cnt, pixel_type, options);
         if (!b) { rc = 0; break; }
-        if (!(flags & JPEGB200_OUT_DEVICE) && i0 + cnt < n) {
+        if (!dev_out && i0 + cnt < n && cnt == JD_PIPE_IMAGES) {
             int64_t ob = 0;
             for (int i = 0; i < cnt; i++) { int64_t pb = 0; ob += JPEGB200_batchOutputBytes(b, i, &pb); }
             if (ob < JD_PIPE_MIN_BYTES) { /* small images: redo with a job big enough to keep the kernels efficient */
                 int64_t per = ob > 0 ? (ob + cnt - 1) / cnt : 1;
                 int64_t want = (JD_PIPE_MIN_BYTES + per - 1) / per;
                 int cnt2 = (int)(want < (int64_t)(n - i0) ? want : (int64_t)(n - i0));
+                if (cnt2 > JD_JOB_MAX_IMAGES) cnt2 = JD_JOB_MAX_IMAGES;
+                int64_t cb2 = 0; int c3 = 0;
+                while (c3 < cnt2 && (c3 == 0 || cb2 + sizes[i0 + c3] <= JD_JOB_COMP_BYTES)) { cb2 += sizes[i0 + c3] > 0 ? sizes[i0 + c3] : 0; c3++; }
+                cnt2 = c3;
                 if (cnt2 > cnt) {
                     JPEGB200_batchDestroy(b);
                     cnt = cnt2;
@@ -997,11 +1216,19 @@ extern "C" int JPEGB200_decodeBatch(JPEGB200_CTX *ctx, const uint8_t *const *dat
         for (int i = 0; i < cnt; i++) JPEGB200_batchSetOutput(b, i, outs ? outs[i0 + i] : nullptr, pitches ? pitches[i0 + i] : 0);
         rc = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, flags) && JPEGB200_batchDownload(b);
         i0 += cnt;
-        /* bound the device memory of a very large batch: at most JD_PIPE_INFLIGHT jobs hold buffers at a time */
-        while (rc && jobs.size() - retired > JD_PIPE_INFLIGHT) retire(retired++);
+        /* bound the device memory of a very large batch: at most `depth` jobs hold buffers at a time */
+        while (rc && jobs.size() - retired > depth) retire(retired++);
     }
     while (retired < jobs.size()) retire(retired++);
     return rc ? all : 0;
+}
+
+extern "C" int JPEGB200_lastCallTimings(JPEGB200_CTX *ctx, float *ms, int *jobs)
+{
+    if (!ctx || !ms) return 0;
+    memcpy(ms, ctx->last_ms, sizeof(ctx->last_ms));
+    if (jobs) *jobs = ctx->last_jobs;
+    return 1;
 }
 
 extern "C" int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters)

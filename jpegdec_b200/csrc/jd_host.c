@@ -324,6 +324,28 @@ void jd_build_lut(const JDInfo *info, uint16_t *lut)
             cc <<= 1;
         }
     }
+    /* fast AC tables (jd_core.h JD_LUT_ACF): the next 10 bits alone decide.  Prefixes 111111xxxx belong to the long-code
+     * half of the table above; such a prefix gets a direct entry when all of its 64 extensions are one code of <= 10 bits,
+     * else len = 0 = "look in the long-code half".  Invalid prefixes are len = 0 too (the decoder tells them apart). */
+    for (int t = 0; t < 2; t++) {
+        const uint16_t *L = lut + 2 * 1152 + t * 2048;
+        uint16_t *F = lut + 2 * 1152 + 2 * 2048 + t * 1024;
+        for (unsigned idx = 0; idx < 1024; idx++) {
+            uint16_t e = 0;
+            if ((idx >> 4) != 0x3F) e = L[idx];
+            else {
+                const uint16_t *x = L + 1024 + ((idx & 15u) << 6);
+                e = x[0];
+                for (int j = 1; j < 64; j++) if (x[j] != e) e = 0;
+                if ((e >> 8) > 10) e = 0;
+            }
+            if (e) {
+                const unsigned len = e >> 8, s = e & 15u;
+                if (s >= 10 || len + s >= 18) e |= 0x8000u;
+            }
+            F[idx] = e;
+        }
+    }
 }
 
 /* AAN prescale factors 16384 * s[r] * s[c], s[0] = 1, s[k] = cos(k*pi/16) * sqrt(2)

@@ -13,7 +13,7 @@
 extern "C" {
 #endif
 
-#define JD_LUT_ENTRIES_H 6400 /* == JD_LUT_ENTRIES in jd_core.h */
+#define JD_LUT_ENTRIES_H 8448 /* == JD_LUT_ENTRIES in jd_core.h */
 
 /* Host-side result of parsing one JPEG header (all the per-image facts the GPU needs). */
 typedef struct {
@@ -43,7 +43,7 @@ void jd_build_quant(const JDInfo *info, int16_t *q /* [3][64] natural order, per
 uint64_t jd_tables_hash(const JDInfo *info);
 const int *jd_aan_table(void);
 
-/* Device-visible per-image descriptor (80 B). */
+/* Device-visible per-image descriptor (96 B). */
 typedef struct {
     uint32_t scan_off;      /* absolute offset of first entropy byte in the batch buffer */
     uint32_t scan_end;      /* absolute end of this file's bytes */
@@ -64,6 +64,10 @@ typedef struct {
     uint32_t err_mcu;
     uint32_t chunk_base;    /* restart-free scans decoded in parallel chunks: first global chunk index ... */
     uint32_t nch;           /* ... and number of chunks (0 = the scan is decoded per restart segment) */
+    uint32_t comp_off;      /* offset of this file's first byte in the batch buffer */
+    uint32_t pad_;
+    uint64_t rec_base;      /* index of this image's first coefficient record: block headers hold record indices relative
+                             * to it (jd_core.h JD_REC_INDEX with byte offsets relative to comp_off and image-local slots) */
 } JDImageDesc;
 
 #ifdef __cplusplus

@@ -20,7 +20,6 @@
 #include <stdint.h>
 #include "jd_core.h"
 #include "jd_chunk.h"
-#include "jd_tokens.h"
 #include "jd_internal.h"
 
 #define JD_NONE 0xFFFFFFFFu
@@ -108,7 +107,6 @@ struct JDEntropyArgs {
     const uint32_t *seg_start;    /* from prescan */
     jd_u64 *blk_hdr;
     uint16_t *rec;
-    uint32_t rec_total;           /* capacity of rec */
     uint32_t *seg_jmap;
     uint32_t *seg_status;         /* 0 ok, else (code << 28) | local err mcu */
     uint32_t *seg_nrec;
@@ -116,26 +114,25 @@ struct JDEntropyArgs {
     uint32_t *event_count;
     uint32_t event_cap;
     uint32_t nwork;
-    uint32_t data_base;           /* byte offset subtracted when sizing the record area */
     uint32_t dc_output;           /* 1: 1/8-scale job, only DC values are consumed downstream; 2: 1/4-scale job, zigzag 1..4 */
+    const uint8_t *clean;         /* un-stuffed segments (jdk_unstuff_segs) and their lengths, when that stage ran */
+    const uint32_t *seg_clen;
 };
 
-__global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
+/* Un-stuffed copy of a restart segment (JD_ENTROPY_CLEAN pipeline): segment `seg` whose raw bytes start at `start` is
+ * written at this 16-byte aligned offset of the clean buffer; consecutive segments are at least (raw length + 19) apart,
+ * which covers the un-stuffed bytes rounded down to 16 plus one zero-padded 16-byte chunk. */
+__host__ __device__ __forceinline__ uint32_t jd_clean_off(uint32_t start, uint32_t seg) { return (start & ~15u) + 32u * seg; }
+
+template <bool CLEAN>
+__device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const uint16_t *s_lut, const uint32_t *s_tpos)
 {
-    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
-    __shared__ uint32_t s_tpos[64];
-    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
-        for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
-    }
-    __syncthreads();
     const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
     if (wi >= a.nwork) return;
     const uint32_t seg = a.work[wi];
     if (seg == JD_NONE) return;
-    const JDImageDesc &im = a.imgs[a.seg_img[seg]];
+    const uint32_t img = a.seg_img[seg];
+    const JDImageDesc &im = a.imgs[img];
     const uint32_t sl = seg - im.seg_base; /* local segment index */
     const uint32_t total_mcus = (uint32_t)im.mcus_x * im.mcus_y;
     const uint32_t m0 = sl * im.mcus_per_seg;
@@ -148,6 +145,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     in.ncomp = im.ncomp;
     in.tsel = im.tsel;
     in.seg = seg;
+    in.img = img;
     in.blk0 = im.blk_base + m0 * im.bpm;
     jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
     JDSegOut so;
@@ -159,183 +157,165 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
         a.seg_nrec[seg] = 0;
         return;
     }
-    /* record area: 4 records per compressed byte of this segment (+64), located at 4x the
-     * segment's byte offset so no prefix sum over segments is needed */
+    /* record area of this segment (jd_core.h JD_REC_INDEX): no prefix sum over segments is needed */
     const uint32_t next = (sl + 1 < im.nseg) ? a.seg_start[seg + 1] : JD_NONE;
     const uint32_t seg_end = (next != JD_NONE) ? next : im.scan_end;
-    in.rec_index0 = 4u * (in.start - a.data_base) ;
-    uint32_t cap = 4u * (seg_end > in.start ? seg_end - in.start : 0u) ;
-    if ((uint64_t)in.rec_index0 + cap > a.rec_total) cap = (in.rec_index0 < a.rec_total) ? a.rec_total - in.rec_index0 : 0u;
-    in.rec_cap = cap;
+    in.rec_index0 = JD_REC_INDEX(in.start - im.comp_off, sl);
+    in.rec_cap = JD_REC_PER_BYTE * (seg_end > in.start ? seg_end - in.start : 0u) + JD_REC_SLOT_SLACK;
+    uint16_t *rec = a.rec + im.rec_base + in.rec_index0;
+    if (CLEAN) {
+        in.data = a.clean;
+        in.start = jd_clean_off(in.start, seg);     /* the host keeps the clean buffer below 4 GiB */
+        in.end = in.start + a.seg_clen[seg];
+    }
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     in.al = (im.prog >> 8) & 15u;
-    if (im.prog & 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_DC_SCAN>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
-    else if (a.dc_output == 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_PARSE_AC>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
-    else if (a.dc_output == 2u) jd_decode_segment<JDEventSinkDev, JD_MODE_STORE_LOW>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
-    else jd_decode_segment<JDEventSinkDev, JD_MODE_BASELINE>(in, s_lut, s_tpos, hdr, a.rec + in.rec_index0, sink, so);
+#ifdef JD_ENTROPY_V1
+    if (im.prog & 1u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_DC_SCAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else if (a.dc_output == 1u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_PARSE_AC>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else if (a.dc_output == 2u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_STORE_LOW>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else jd_decode_segment_flat<JDEventSinkDev, JD_MODE_BASELINE>(in, s_lut, s_tpos, hdr, rec, sink, so);
+#else
+    if (im.prog & 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_DC_SCAN, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else if (a.dc_output == 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_PARSE_AC, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else if (a.dc_output == 2u) jd_decode_segment<JDEventSinkDev, JD_MODE_STORE_LOW, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
+    else jd_decode_segment<JDEventSinkDev, JD_MODE_BASELINE, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
+#endif
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
     a.seg_nrec[seg] = so.nrec;
 }
 
-/* ------------------------------------------------------------------------------------ */
-/* two-phase entropy stage (jd_tokens.h) -- OPT-IN (JPEGDEC_B200_ENTROPY=tokens), not yet measured on a B200:      */
-/*   jdk_tokens_parse        1 thread per restart segment, one instruction stream per symbol, emits tokens          */
-/*   jdk_tokens_materialize  1 warp per restart segment, lane = block: DC predictors and record indices as warp      */
-/*                           scans carried over 32-block chunks, then records + headers exactly as jdk_entropy       */
-/* ------------------------------------------------------------------------------------ */
-struct JDTokenArgs {
-    JDEntropyArgs e;
-    uint32_t *tok;            /* tokens: a segment's tokens live at 4 x its byte offset + 64 x its index (u32 units): room for
-                               * 4 tokens per compressed byte plus one whole block, without a prefix sum over segments */
-    uint32_t tok_total;
-    uint32_t *blk_tok;        /* per block: tokens of its segment up to and including it */
-    uint32_t *seg_errblk;     /* per segment: first block without complete tokens; JD_NONE = segment missing */
-};
-
-__device__ __forceinline__ bool jd_token_seg_setup(const JDTokenArgs &a, uint32_t seg, JDSegIn &in, uint32_t &tok_index0, uint32_t &tok_cap)
-{
-    const JDImageDesc &im = a.e.imgs[a.e.seg_img[seg]];
-    const uint32_t sl = seg - im.seg_base;
-    const uint32_t total_mcus = (uint32_t)im.mcus_x * im.mcus_y;
-    const uint32_t m0 = sl * im.mcus_per_seg;
-    in.data = a.e.data;
-    in.start = a.e.seg_start[seg];
-    in.end = im.scan_end;
-    in.nmcu = (m0 + im.mcus_per_seg <= total_mcus) ? im.mcus_per_seg : total_mcus - m0;
-    in.bpm = im.bpm; in.ncomp = im.ncomp; in.tsel = im.tsel; in.seg = seg; in.al = 0;
-    in.blk0 = im.blk_base + m0 * im.bpm;
-    if (in.start == JD_NONE || in.start < im.scan_off || in.start > im.scan_end) return false;
-    const uint32_t next = (sl + 1 < im.nseg) ? a.e.seg_start[seg + 1] : JD_NONE;
-    const uint32_t seg_end = (next != JD_NONE) ? next : im.scan_end;
-    const uint32_t len = seg_end > in.start ? seg_end - in.start : 0u;
-    in.rec_index0 = 4u * (in.start - a.e.data_base);
-    uint32_t cap = 4u * len;
-    if ((uint64_t)in.rec_index0 + cap > a.e.rec_total) cap = (in.rec_index0 < a.e.rec_total) ? a.e.rec_total - in.rec_index0 : 0u;
-    in.rec_cap = cap;
-    tok_index0 = in.rec_index0 + 64u * seg;
-    tok_cap = 4u * len + 64u;
-    if ((uint64_t)tok_index0 + tok_cap > a.tok_total) tok_cap = (tok_index0 < a.tok_total) ? a.tok_total - tok_index0 : 0u;
-    return true;
-}
-
-__global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_tokens_parse(const JDTokenArgs a)
+template <bool CLEAN>
+__global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntropyArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    __shared__ uint32_t s_tpos[64];
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.e.luts + (size_t)a.e.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
         for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
-    if (wi >= a.e.nwork) return;
-    const uint32_t seg = a.e.work[wi];
-    if (seg == JD_NONE) return;
-    JDSegIn in;
-    uint32_t tok_cap = 0, tok_index0 = 0;
-    if (!jd_token_seg_setup(a, seg, in, tok_index0, tok_cap)) {
-        a.e.seg_jmap[seg] = JD_JW_INIT;
-        a.e.seg_status[seg] = ((uint32_t)JD_SEG_MISSING << 28);
-        a.seg_errblk[seg] = JD_NONE;
-        return;
-    }
-    JDEventSinkDev sink{a.e.events, a.e.event_count, a.e.event_cap};
-    JDParseOut po;
-    jd_parse_segment_uniform(in, s_lut, a.tok + tok_index0, tok_cap, a.blk_tok + in.blk0, sink, po);
-    a.e.seg_jmap[seg] = po.jmap;
-    a.e.seg_status[seg] = (po.status == JD_SEG_OK) ? 0u : ((po.status << 28) | ((po.err_blk / in.bpm) & 0x0FFFFFFFu));
-    a.seg_errblk[seg] = po.err_blk;
+    jd_entropy_body<CLEAN>(a, s_lut, s_tpos);
 }
 
-__device__ __forceinline__ uint32_t jd_warp_incl_scan(uint32_t v, uint32_t lane)
+/* ------------------------------------------------------------------------------------ */
+/* un-stuff the restart segments (JPEGFilter, src/jpeg.inl:1431-1540: FF00 -> FF, the stream    */
+/* of a segment ends at the first FFxx marker) so that the entropy kernel's bit reader is a     */
+/* plain word stream.  One warp per segment: 512 raw bytes per iteration (16 per lane, aligned  */
+/* 16-byte loads), kept bytes compacted through a shared-memory staging line and written out as */
+/* aligned 16-byte stores.                                                                      */
+/* ------------------------------------------------------------------------------------ */
+#define JD_UNSTUFF_WARPS 4
+__global__ void __launch_bounds__(JD_UNSTUFF_WARPS * 32) jdk_unstuff_segs(const uint8_t *__restrict__ data, const JDImageDesc *__restrict__ imgs,
+                                                                         const uint32_t *__restrict__ seg_img, const uint32_t *__restrict__ seg_start,
+                                                                         uint32_t nseg, uint8_t *__restrict__ clean, uint32_t *__restrict__ seg_clen)
 {
+    __shared__ __align__(16) uint8_t s_stage[JD_UNSTUFF_WARPS][512 + 32];
+    const uint32_t seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (seg >= nseg) return;
+    const JDImageDesc &im = imgs[seg_img[seg]];
+    if (im.nch != 0u || im.nseg == 0u) return;           /* restart-free scans take the chunk path; rejected headers own nothing */
+    const uint32_t sl = seg - im.seg_base;
+    const uint32_t start = seg_start[seg];
+    if (start == JD_NONE || start < im.scan_off || start > im.scan_end) { if (lane == 0) seg_clen[seg] = 0; return; }
+    const uint32_t next = (sl + 1 < im.nseg) ? seg_start[seg + 1] : JD_NONE;
+    /* the RSTn marker that ends the segment sits in the two bytes before the next segment's start */
+    const uint32_t end = (next != JD_NONE && next >= start + 2u) ? next - 2u : im.scan_end;
+    uint8_t *stage = s_stage[threadIdx.x >> 5];
+    uint8_t *dst = clean + jd_clean_off(start, seg);
+    uint32_t fill = 0, outpos = 0;
+    uint32_t carry_ff = 0;                               /* the byte before this iteration's first byte was a kept 0xFF */
+    bool done = false;
+    for (uint32_t p0 = start & ~15u; p0 < end && !done; p0 += 512u) {
+        const uint32_t p = p0 + lane * 16u;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (p < end) v = *reinterpret_cast<const uint4 *>(data + p);    /* the batch buffer is padded past its last file */
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        /* byte after my 16 (the next lane's first; lane 31 reads it) and byte before (the previous lane's last) */
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1) & 0xFFu;
+        if (lane == 31) nxt = (p + 16u < end) ? (uint32_t)data[p + 16u] : 0xD9u;
+        uint32_t prv = __shfl_up_sync(0xffffffffu, v.w, 1) >> 24;
+        if (lane == 0) prv = carry_ff ? 0xFFu : 0u;
+        uint32_t keep = 0, endpos = JD_NONE;
+        if (p < end && p + 16u > start) {
+            const uint32_t ffm = (((~w[0]) - 0x01010101u) & w[0] & 0x80808080u) | (((~w[1]) - 0x01010101u) & w[1] & 0x80808080u) |
+                                 (((~w[2]) - 0x01010101u) & w[2] & 0x80808080u) | (((~w[3]) - 0x01010101u) & w[3] & 0x80808080u);
+            if (ffm == 0u && prv != 0xFFu && p >= start && p + 16u <= end) {
+                keep = 0xFFFFu;                          /* no 0xFF in sight: every byte is data (has-zero-byte test on ~w is exact for "any") */
+            } else {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (uint32_t)d) v += t; }
-    return v;
-}
-
-__global__ void __launch_bounds__(128) jdk_tokens_materialize(const JDTokenArgs a)
-{
-    __shared__ uint32_t s_tpos[64];
-    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
-    __syncthreads();
-    const uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (wi >= a.e.nwork) return;
-    const uint32_t seg = a.e.work[wi];
-    if (seg == JD_NONE) return;
-    JDSegIn in;
-    uint32_t tok_cap = 0, tok_index0 = 0;
-    const bool present = jd_token_seg_setup(a, seg, in, tok_index0, tok_cap);
-    const uint32_t nblk = in.nmcu * in.bpm;
-    jd_u64 *hdr = a.e.blk_hdr + in.blk0;
-    if (!present) {                       /* restart marker missing: empty headers, as jdk_entropy */
-        for (uint32_t b = lane; b < nblk; b += 32) hdr[b] = 0ull;
-        if (lane == 0) a.e.seg_nrec[seg] = 0;
-        return;
-    }
-    const uint32_t errblk = a.seg_errblk[seg];
-    const uint32_t *tok = a.tok + tok_index0;
-    const uint32_t *btok = a.blk_tok + in.blk0;
-    uint16_t *rec = a.e.rec + in.rec_index0;
-    const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
-    int pred0 = 0, pred1 = 0, pred2 = 0;  /* carried over the chunks, identical in every lane */
-    uint32_t ri = 0, overflow_blk = JD_NONE;
-    for (uint32_t base = 0; base < nblk; base += 32) {
-        const uint32_t b = base + lane;
-        const bool inseg = b < nblk;
-        bool valid = inseg && b < errblk;
-        const uint32_t t0 = (valid && b) ? btok[b - 1] : 0u, t1 = valid ? btok[b] : 0u;
-        const uint32_t ncoef = valid ? t1 - t0 - 1u : 0u;
-        const int diff = valid ? JD_TOK_VAL(tok[t0]) : 0;
-        uint32_t big = 0;
-        for (uint32_t i = 0; i < ncoef; i++) { const int v = JD_TOK_VAL(tok[t0 + 1 + i]); if (v > 511 || v < -511) big = 1; }
-        const uint32_t nrec = big ? 2 * ncoef : ncoef;
-        const uint32_t bim = inseg ? b % in.bpm : 0u, comp = (bim < nluma) ? 0u : (bim - nluma + 1u);
-        /* prefix sums over the 32 blocks of this chunk */
-        const uint32_t s0 = jd_warp_incl_scan((uint32_t)((comp == 0u) ? diff : 0), lane);
-        const uint32_t s1 = jd_warp_incl_scan((uint32_t)((comp == 1u) ? diff : 0), lane);
-        const uint32_t s2 = jd_warp_incl_scan((uint32_t)((comp == 2u) ? diff : 0), lane);
-        const uint32_t sr = jd_warp_incl_scan(nrec, lane);
-        const int dc = (comp == 0u) ? pred0 + (int)s0 : (comp == 1u) ? pred1 + (int)s1 : pred2 + (int)s2;
-        const uint32_t rstart = ri + sr - nrec;
-        if (valid && rstart + nrec > in.rec_cap) valid = false;      /* record area exhausted: this block and all later ones */
-        const uint32_t firstbad = __ballot_sync(0xffffffffu, inseg && b < errblk && !valid);
-        if (firstbad && overflow_blk == JD_NONE) overflow_blk = base + (uint32_t)__ffs((int)firstbad) - 1u;
-        if (valid) {
-            uint32_t bflags = 0;
-            for (uint32_t i = 0; i < ncoef; i++) {
-                const uint32_t t = tok[t0 + 1 + i], tw = s_tpos[JD_TOK_K(t)];
-                const int v = JD_TOK_VAL(t);
-                bflags |= tw;
-                if (big) { rec[rstart + 2 * i] = (uint16_t)(tw & 63u); rec[rstart + 2 * i + 1] = (uint16_t)(int16_t)v; }
-                else rec[rstart + i] = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t pos = p + (uint32_t)i;
+                    const uint32_t b0 = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+                    const uint32_t bn = (i < 15) ? ((w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFFu) : nxt;
+                    const uint32_t bp = (i > 0) ? ((w[(i - 1) >> 2] >> (((i - 1) & 3) * 8)) & 0xFFu) : prv;
+                    if (pos < start || pos >= end) continue;
+                    const bool after_ff = (bp == 0xFFu) && (pos > start);
+                    if (b0 == 0xFFu && !after_ff) {
+                        /* FF00 keeps the FF; FF + anything else (or FF as the last byte) ends the data */
+                        if (pos + 1u < end && bn == 0u) keep |= 1u << i; else if (endpos == JD_NONE) endpos = pos;
+                    } else if (!(after_ff && b0 == 0u)) {
+                        /* an FF directly after a kept FF00 pair's zero is handled above (after_ff is false for it:
+                         * the byte before it is 00); a byte after an FF that is not 00 never gets here (stream ended) */
+                        keep |= 1u << i;
+                    }
+                }
             }
-            hdr[b] = jd_pack_hdr(in.rec_index0 + rstart, dc, ncoef, big, JD_BF_HI(bflags), JD_BF_COLMASK(bflags));
-        } else if (inseg) {
-            hdr[b] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
         }
-        pred0 += (int)__shfl_sync(0xffffffffu, s0, 31); pred1 += (int)__shfl_sync(0xffffffffu, s1, 31);
-        pred2 += (int)__shfl_sync(0xffffffffu, s2, 31); ri += __shfl_sync(0xffffffffu, sr, 31);
+        const uint32_t stop = __reduce_min_sync(0xffffffffu, endpos);
+        if (stop != JD_NONE) {
+            done = true;
+#pragma unroll
+            for (int i = 0; i < 16; i++) if (p + (uint32_t)i >= stop) keep &= ~(1u << i);
+        }
+        /* does the next iteration start right after a kept 0xFF?  (only lane 31's last byte matters) */
+        carry_ff = __shfl_sync(0xffffffffu, ((keep >> 15) & 1u) & (uint32_t)((v.w >> 24) == 0xFFu), 31);
+        const uint32_t cnt = __popc(keep);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+        uint32_t o = fill + x - cnt;
+#pragma unroll
+        for (int i = 0; i < 16; i++) if (keep & (1u << i)) stage[o++] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+        const uint32_t total = fill + __shfl_sync(0xffffffffu, x, 31);
+        __syncwarp();
+        const uint32_t nflush = total >> 4;
+        uint4 chunk = make_uint4(0, 0, 0, 0);
+        if (lane < nflush) chunk = *reinterpret_cast<const uint4 *>(stage + 16u * lane);
+        uint32_t rem_b = 0;
+        const uint32_t rem = total & 15u;
+        if (lane < rem) rem_b = stage[16u * nflush + lane];
+        __syncwarp();
+        if (lane < nflush) *reinterpret_cast<uint4 *>(dst + outpos + 16u * lane) = chunk;
+        if (lane < rem) stage[lane] = (uint8_t)rem_b;
+        __syncwarp();
+        outpos += 16u * nflush;
+        fill = rem;
     }
-    if (lane == 0) {
-        a.e.seg_nrec[seg] = ri;
-        if (overflow_blk != JD_NONE && a.e.seg_status[seg] == 0u)
-            a.e.seg_status[seg] = ((uint32_t)JD_SEG_OVERFLOW << 28) | ((overflow_blk / in.bpm) & 0x0FFFFFFFu);
-    }
+    /* tail: the last partial chunk, zero padded (the reader's last word must end in zeros) */
+    if (lane >= fill && lane < 16u) stage[lane] = 0;
+    __syncwarp();
+    if (lane == 0u) *reinterpret_cast<uint4 *>(dst + outpos) = *reinterpret_cast<const uint4 *>(stage);
+    if (lane == 0) seg_clen[seg] = outpos + fill;
 }
 
 /* ------------------------------------------------------------------------------------ */
 /* stitch + patch                                                                          */
 /* ------------------------------------------------------------------------------------ */
 __global__ void jdk_stitch(JDImageDesc *imgs, uint32_t nimg, const uint32_t *__restrict__ seg_jmap,
-                           const uint32_t *__restrict__ seg_status, uint32_t *__restrict__ seg_phase)
+                           const uint32_t *__restrict__ seg_status, uint32_t *__restrict__ seg_phase,
+                           const uint32_t *__restrict__ seg_nrec, unsigned long long *__restrict__ rec_count)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nimg) return;
     JDImageDesc &im = imgs[i];
     uint32_t c = 0, status = 0, err_mcu = 0;
+    unsigned long long nrec = 0;
     for (uint32_t s = 0; s < im.nseg; s++) {
+        if (im.nch == 0u) nrec += seg_nrec[im.seg_base + s];
         const uint32_t g = im.seg_base + s;
         seg_phase[g] = c;
         const uint32_t j = (seg_jmap[g] >> (4 * c)) & 15u;
@@ -345,9 +325,10 @@ __global__ void jdk_stitch(JDImageDesc *imgs, uint32_t nimg, const uint32_t *__r
     }
     im.status = status;
     im.err_mcu = err_mcu;
+    if (nrec) atomicAdd(rec_count, nrec);
 }
 
-__global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__restrict__ event_count, uint32_t cap,
+__global__ void jdk_patch(const JDImageDesc *__restrict__ imgs, const JDEvent *__restrict__ events, const uint32_t *__restrict__ event_count, uint32_t cap,
                           const uint32_t *__restrict__ seg_phase, const jd_u64 *__restrict__ blk_hdr, uint16_t *__restrict__ rec,
                           uint32_t *__restrict__ applied)
 {
@@ -357,7 +338,7 @@ __global__ void jdk_patch(const JDEvent *__restrict__ events, const uint32_t *__
         const JDEvent e = events[i];
         const uint32_t jc = (e.j1 >> (4 * seg_phase[e.seg])) & 15u;
         if (8 * (int)jc + e.p7 + e.s > 64) {
-            jd_patch_record(rec, blk_hdr[e.blk], e.ord, jd_event_value(&e, jc));
+            jd_patch_record(rec + imgs[e.img].rec_base, blk_hdr[e.blk], e.ord, jd_event_value(&e, jc));
             atomicAdd(applied, 1u);
         }
     }
@@ -382,7 +363,6 @@ struct JDChunkArgs {
     uint32_t *changed;
     jd_u64 *blk_hdr;
     uint16_t *rec;
-    uint32_t rec_total;
     JDEvent *events;
     uint32_t *event_count;
     uint32_t event_cap;
@@ -487,13 +467,13 @@ __global__ void __launch_bounds__(64) jdk_chunk_emit(const JDChunkArgs a)
     const JDScanIn sc = jd_scan_of(a, im, ii);
     const uint32_t entry = a.E_in[g];
     const uint32_t next = (c + 1 < im.nch) ? a.E_in[g + 1] : JD_CS_NONE;
-    uint32_t ri0 = 4u * (im.scan_off + c * JD_CHUNK_BYTES);
-    uint32_t cap = 4u * JD_CHUNK_BYTES;
-    if ((uint64_t)ri0 + cap > a.rec_total) cap = (ri0 < a.rec_total) ? a.rec_total - ri0 : 0u;
+    /* image-relative record slot: the scan's one "segment" owns slot 0..nseg-1, its chunks follow */
+    const uint32_t ri0 = JD_REC_INDEX(im.scan_off - im.comp_off + c * JD_CHUNK_BYTES, im.nseg + c);
+    const uint32_t cap = JD_REC_PER_BYTE * JD_CHUNK_BYTES + JD_REC_SLOT_SLACK;
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     JDChunkOut co;
     jd_chunk_emit(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,
-                  a.rec + ri0, ri0, cap, a.nseg_total + g, im.blk_base, sink, co);
+                  a.rec + im.rec_base + ri0, ri0, cap, a.nseg_total + g, im.blk_base, ii, sink, co);
     a.cjmap[g] = co.jmap;
     a.cstatus[g] = co.status;
     a.cnown[g] = co.nown;
@@ -777,6 +757,7 @@ jdk_idct_color(const JDIdctArgs a)
     jd_u64 h = 0;
     /* (block order inside an MCU in the stream = luma blocks, Cb, Cr = our blk numbering) */
     if (mx < a.mcus_x) h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
+    const uint16_t *const irec = a.rec + im.rec_base;
     const uint32_t ri = JD_HDR_REC(h);
     const int dc = JD_HDR_DC(h);
     const uint32_t ncoef = JD_HDR_NCOEF(h);
@@ -792,17 +773,17 @@ jdk_idct_color(const JDIdctArgs a)
         const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
         __syncwarp();
         if (!JD_HDR_BIG(h)) {
-            const uint16_t *rp = a.rec + ri + c;
+            const uint16_t *rp = irec + ri + c;
             if (c < ncoef) { const uint32_t r = __ldg(rp); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
             if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
             for (uint32_t i = c + 16; i < ncoef; i += 8) {
-                const uint32_t r = __ldg(a.rec + ri + i);
+                const uint32_t r = __ldg(irec + ri + i);
                 tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
             }
         } else {
             for (uint32_t i = c; i < ncoef; i += 8) {
-                const uint32_t t = __ldg(a.rec + ri + 2 * i) & 63u;
-                tile[t] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+                const uint32_t t = __ldg(irec + ri + 2 * i) & 63u;
+                tile[t] = (int16_t)__ldg(irec + ri + 2 * i + 1);
             }
         }
         __syncwarp();
@@ -962,6 +943,7 @@ jdk_idct_tb(const JDIdctArgs a)
     const JDImageDesc &im = a.imgs[img_i];
     const uint32_t strip = blockIdx.x, my = blockIdx.y;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint16_t *const irec = a.rec + im.rec_base;
 
     /* ---- headers + binning.  Thread-per-block classes: coefficients in columns 0-3 only (3-4 columns occupied), split by
      * whether rows 4-7 are empty (the reference picks its reduced column pass on that flag, jpeg.inl:2330): class 0 = rows
@@ -1022,7 +1004,7 @@ jdk_idct_tb(const JDIdctArgs a)
             /* the first 10 halfwords that cover the records come in as five independent aligned 32-bit loads (one round
              * trip instead of a chain of 2-byte loads); longer blocks finish in the loop below */
             const uint32_t off = ri & 1u, total = off + ncoef;
-            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(a.rec + (ri - off));
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(irec + (ri - off));
             uint32_t v[5];
 #pragma unroll
             for (int w = 0; w < 5; w++) v[w] = ((uint32_t)(2 * w) < total) ? __ldg(w32 + w) : 0u;
@@ -1033,9 +1015,9 @@ jdk_idct_tb(const JDIdctArgs a)
                     tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
                 }
             }
-            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
         } else {
-            for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+            for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
         }
         int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
         if (r47) {
@@ -1125,9 +1107,9 @@ jdk_idct_tb(const JDIdctArgs a)
                     const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
                     __syncwarp();
                     if (!JD_HDR_BIG(h)) {
-                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(a.rec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
                     } else {
-                        for (uint32_t i = c; i < ncoef; i += 8) tile[__ldg(a.rec + ri + 2 * i) & 63u] = (int16_t)__ldg(a.rec + ri + 2 * i + 1);
+                        for (uint32_t i = c; i < ncoef; i += 8) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
                     }
                     __syncwarp();
                     int m[8], o[8];
@@ -1196,7 +1178,7 @@ struct JDScaledArgs {
     uint32_t padded;
 };
 
-__device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h, const int32_t *q, bool eighth, uint32_t px[4])
+__device__ __forceinline__ void jd_scaled_block(const uint16_t *irec, jd_u64 h, const int32_t *q, bool eighth, uint32_t px[4])
 {
     const int dc = JD_HDR_DC(h);
     const int q0 = q[0];
@@ -1208,8 +1190,8 @@ __device__ __forceinline__ void jd_scaled_block(const JDScaledArgs &a, jd_u64 h,
      * tile positions 8, 1, 2, 9; jpeg.inl:2117-2119) come first */
     for (uint32_t i = 0; i < ncoef; i++) {
         uint32_t t; int v;
-        if (big) { t = a.rec[ri + 2 * i] & 63u; v = (int)(short)a.rec[ri + 2 * i + 1]; }
-        else { const uint32_t r = a.rec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
+        if (big) { t = irec[ri + 2 * i] & 63u; v = (int)(short)irec[ri + 2 * i + 1]; }
+        else { const uint32_t r = irec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
         if (t == 8u) m1 = v; else if (t == 1u) m8 = v; else if (t == 9u) m9 = v; else if (t != 2u) break;
         any = true;
     }
@@ -1236,12 +1218,13 @@ __global__ void __launch_bounds__(128) jdk_scaled(const JDScaledArgs a)
     const int32_t *q = a.quant + (size_t)img_i * 192;
     const jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m * im.bpm;
     uint32_t ypx[4][4], cb[4], cr[4];
-    for (uint32_t b = 0; b < nluma; b++) jd_scaled_block(a, hdr[b], q, eighth, ypx[b]);
+    const uint16_t *const irec = a.rec + im.rec_base;
+    for (uint32_t b = 0; b < nluma; b++) jd_scaled_block(irec, hdr[b], q, eighth, ypx[b]);
     const bool gray_out = a.pixel_type >= EIGHT_BIT_GRAYSCALE;
     const bool colour = (im.ncomp == 3) && !gray_out;
     if (colour) {
-        jd_scaled_block(a, hdr[nluma], q + 64, eighth, cb);
-        jd_scaled_block(a, hdr[nluma + 1], q + 128, eighth, cr);
+        jd_scaled_block(irec, hdr[nluma], q + 64, eighth, cb);
+        jd_scaled_block(irec, hdr[nluma + 1], q + 128, eighth, cr);
     }
     const uint32_t shift = eighth ? 3u : 2u;
     const uint32_t W = a.padded ? (uint32_t)im.mcus_x * hs * bs : (((uint32_t)im.width + (1u << shift) - 1u) >> shift);

@@ -74,11 +74,14 @@ def hostsim():
     return _sim
 
 
-def hostsim_decode(data, pt, opt, arith, w, h, chunked=False):
-    """chunked=True forces the restart-free chunk-parallel path (jd_chunk.h) for scans without restart markers."""
+def hostsim_decode(data, pt, opt, arith, w, h, chunked=False, clean=False):
+    """chunked=True forces the restart-free chunk-parallel path (jd_chunk.h) for scans without restart markers;
+    clean=True un-stuffs each restart segment first and decodes it with the CLEAN bit reader (the GPU default)."""
     oh, pitch = tight_shape(w, h, pt, opt)
     if chunked:
         opt |= 0x20000
+    if clean:
+        opt |= 0x40000
     out = np.zeros((oh, pitch), dtype=np.uint8)
     v = [C.c_int() for _ in range(4)]
     rc = hostsim().hostsim_decode(data, len(data), pt, opt, arith, out.ctypes.data, pitch, *[C.byref(x) for x in v])

@@ -19,7 +19,7 @@ int main(int argc,char**argv){
       for(int j=0;j<k;j++){ int lim = m<2200?m:2200; int off=rand_r(&seed)%lim; buf[off]=(uint8_t)rand_r(&seed);}  /* header area */
       JDInfo info; memset(&info,0,sizeof(info));
       int r=jd_parse_header(buf,m,0,&info); tot++;
-      if(r){ ok++; uint16_t *lut=malloc(6400*2); jd_build_lut(&info,lut); int16_t q[192]; jd_build_quant(&info,q); (void)jd_tables_hash(&info); free(lut);
+      if(r){ ok++; uint16_t *lut=malloc(JD_LUT_ENTRIES_H*2); jd_build_lut(&info,lut); int16_t q[192]; jd_build_quant(&info,q); (void)jd_tables_hash(&info); free(lut);
              if(info.has_thumb && info.thumb_data>0){ JDInfo t; memset(&t,0,sizeof(t)); jd_parse_header(buf,m,info.thumb_data,&t);} }
       free(buf);
     }

@@ -36,6 +36,20 @@ struct Planes {
     std::vector<uint8_t> Y, Cb, Cr;
 };
 
+/* serial statement of what jdk_unstuff_segs writes for one restart segment: FF00 -> FF, the data ends at the first other
+ * FFxx (or at `end`); zero padded; the un-stuffed length is stored in the vector's last word */
+static void hostsim_unstuff(const uint8_t *data, uint32_t start, uint32_t end, std::vector<uint32_t> &out)
+{
+    out.assign((end - start) / 4 + 16, 0);
+    uint8_t *o = (uint8_t *)out.data();
+    uint32_t n = 0;
+    for (uint32_t p = start; p < end; p++) {
+        if (data[p] == 0xFF) { if (p + 1 < end && data[p + 1] == 0) { o[n++] = 0xFF; p++; } else break; }
+        else o[n++] = data[p];
+    }
+    out[out.size() - 1] = n;
+}
+
 extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int options, int arith,
                               uint8_t *out, int out_pitch, int *out_w, int *out_h, int *n_events,
                               int *err)
@@ -85,8 +99,11 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
 
     const int nblk = total_mcus * info.bpm;
     std::vector<jd_u64> hdr(nblk, 0);
-    std::vector<uint16_t> rec((size_t)size * 4 + 1024, 0);
+    /* records: JD_REC_INDEX layout, byte offsets relative to the file start, one slot per segment and per chunk */
+    std::vector<uint16_t> rec((size_t)size * JD_REC_PER_BYTE + (size_t)JD_REC_SLOT_SLACK * ((size_t)nseg + (size_t)size / JD_CHUNK_BYTES + 4) + 1024, 0);
     std::vector<uint32_t> jmap(nseg, 0);
+    const bool clean = (options & 0x40000) != 0;   /* test hook: un-stuff first, CLEAN bit reader (the GPU default) */
+    std::vector<uint32_t> cbuf;
     VecSink sink;
     int bad = 0;
     for (int i = 0; i < 64; i++) kTposW[i] = jd_tposw(kTpos[i]);
@@ -124,9 +141,9 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         { uint32_t run = 0; for (uint32_t c = 0; c < nch; c++) { pre[c] = run; run += nst[c]; } }
         std::vector<JDChunkOut> co(nch);
         for (uint32_t c = 0; c < nch; c++) {
-            const uint32_t ri0 = 4u * (c * JD_CHUNK_BYTES);
+            const uint32_t ri0 = JD_REC_INDEX((uint32_t)info.scan_offset + c * JD_CHUNK_BYTES, 1u + c);
             jd_chunk_emit(sc, lut.data(), kTposW, c, E[c], (c + 1 < nch) ? E[c + 1] : JD_CS_NONE, pre[c], hdr.data(), rec.data() + ri0, ri0,
-                          4u * JD_CHUNK_BYTES, c, 0u, sink, co[c]);
+                          JD_REC_PER_BYTE * JD_CHUNK_BYTES + JD_REC_SLOT_SLACK, c, 0u, 0u, sink, co[c]);
             if (co[c].status != JD_SEG_OK) bad = 1;
         }
         /* stitch over chunks: true phase per chunk, DC predictor at each chunk entry */
@@ -160,16 +177,28 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.ncomp = (uint32_t)info.ncomp;
         in.tsel = (uint32_t)info.tsel;
         if (in.start == 0xFFFFFFFFu) { bad = 1; break; }
-        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset);
-        in.rec_cap = 4u * ((sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu ? seg_start[sgi + 1] : (uint32_t)size) - in.start) + 64u;
+        const uint32_t seg_end = (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] : (uint32_t)size;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi);
+        in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
         in.seg = (uint32_t)sgi;
+        in.img = 0;
         in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         in.al = prog ? (uint32_t)(info.approx & 15) : 0u;
-        if (prog) jd_decode_segment<VecSink, JD_MODE_DC_SCAN>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
-        else if (sshift == 3) jd_decode_segment<VecSink, JD_MODE_PARSE_AC>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
-        else if (sshift == 2) jd_decode_segment<VecSink, JD_MODE_STORE_LOW>(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
-        else jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
+        jd_u64 *hp = hdr.data() + (size_t)m0 * info.bpm;
+        uint16_t *rp0 = rec.data() + in.rec_index0;
+        if (clean) {
+            hostsim_unstuff(cdata, in.start, (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] - 2u : (uint32_t)size, cbuf);
+            in.data = (const uint8_t *)cbuf.data(); in.end = cbuf[cbuf.size() - 1]; in.start = 0;
+            if (prog) jd_decode_segment<VecSink, JD_MODE_DC_SCAN, true>(in, lut.data(), kTposW, hp, rp0, sink, so);
+            else if (sshift == 3) jd_decode_segment<VecSink, JD_MODE_PARSE_AC, true>(in, lut.data(), kTposW, hp, rp0, sink, so);
+            else if (sshift == 2) jd_decode_segment<VecSink, JD_MODE_STORE_LOW, true>(in, lut.data(), kTposW, hp, rp0, sink, so);
+            else jd_decode_segment<VecSink, JD_MODE_BASELINE, true>(in, lut.data(), kTposW, hp, rp0, sink, so);
+        }
+        else if (prog) jd_decode_segment<VecSink, JD_MODE_DC_SCAN>(in, lut.data(), kTposW, hp, rp0, sink, so);
+        else if (sshift == 3) jd_decode_segment<VecSink, JD_MODE_PARSE_AC>(in, lut.data(), kTposW, hp, rp0, sink, so);
+        else if (sshift == 2) jd_decode_segment<VecSink, JD_MODE_STORE_LOW>(in, lut.data(), kTposW, hp, rp0, sink, so);
+        else jd_decode_segment(in, lut.data(), kTposW, hp, rp0, sink, so);
         jmap[sgi] = so.jmap;
         if (so.err_mcu >= 0) { bad = 1; break; }
     }
@@ -405,13 +434,13 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     memcpy(padded.data(), data, (size_t)size);
     const int nblk = total_mcus * info.bpm;
     std::vector<jd_u64> hdr(nblk, 0);
-    std::vector<uint16_t> rec((size_t)size * 4 + 1024, 0);
+    std::vector<uint16_t> rec((size_t)size * JD_REC_PER_BYTE + (size_t)JD_REC_SLOT_SLACK * (nseg + 1) + 1024, 0);
     VecSink sink;
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in; in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
         int m0 = sgi * mps; in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
-        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
-        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset); in.rec_cap = 1u << 30; in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
+        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.rec_cap = JD_REC_PER_BYTE * ((uint32_t)size - in.start) + JD_REC_SLOT_SLACK; in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
     }
@@ -431,9 +460,10 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     return nblk;
 }
 
-/* ---- two-phase entropy prototype (jd_tokens.h) against the single walk (jd_core.h): returns the number of mismatches ---- */
-#include "../../jpegdec_b200/csrc/jd_tokens.h"
-extern "C" int hostsim_tokens_check(const uint8_t *data, int size, int *n_segments, int *n_tokens, int *n_events, int *n_bad_segments)
+/* ---- the block-synchronous walk the kernels run (jd_decode_segment, raw and CLEAN reader) against the flat state-machine
+ * form of the same walk (jd_decode_segment_flat): headers, records, window-phase map, events, status and failing MCU must be
+ * identical.  Returns the number of mismatches. ---- */
+extern "C" int hostsim_walk_check(const uint8_t *data, int size, int *n_segments, int *n_records, int *n_events, int *n_bad_segments)
 {
     JDInfo info;
     if (!jd_parse_header(data, size, 0, &info) || info.mode != 0xC0 || !info.tables_ok) return -1;
@@ -446,13 +476,13 @@ extern "C" int hostsim_tokens_check(const uint8_t *data, int size, int *n_segmen
     std::vector<uint32_t> seg_start(nseg, 0xFFFFFFFFu);
     seg_start[0] = (uint32_t)info.scan_offset;
     { int k = 1; for (int i = info.scan_offset; i + 1 < size && k < nseg; i++) if (data[i] == 0xFF && data[i + 1] >= 0xD0 && data[i + 1] <= 0xD7) { seg_start[k++] = (uint32_t)(i + 2); i++; } }
-    std::vector<uint32_t> padded((size + 64) / 4 + 16, 0);
+    std::vector<uint32_t> padded((size + 64) / 4 + 16, 0), cbuf;
     memcpy(padded.data(), data, (size_t)size);
     const int nblk = total_mcus * info.bpm;
-    std::vector<jd_u64> hdrA(nblk, 0), hdrB(nblk, 0);
-    std::vector<uint16_t> recA((size_t)size * 4 + 4096, 0), recB((size_t)size * 4 + 4096, 0);
-    std::vector<uint32_t> tok((size_t)size * 8 + 4096), blk_tok(nblk, 0);
-    int bad = 0, ntok = 0, nev = 0, nbadseg = 0;
+    const size_t nrec_cap = (size_t)size * JD_REC_PER_BYTE + (size_t)JD_REC_SLOT_SLACK * (nseg + 1) + 4096;
+    std::vector<jd_u64> hdrA(nblk, 0), hdrB(nblk, 0), hdrC(nblk, 0);
+    std::vector<uint16_t> recA(nrec_cap, 0), recB(nrec_cap, 0), recC(nrec_cap, 0);
+    int bad = 0, nrec = 0, nev = 0, nbadseg = 0;
     for (int sgi = 0; sgi < nseg; sgi++) {
         if (seg_start[sgi] == 0xFFFFFFFFu) break;
         JDSegIn in;
@@ -460,35 +490,45 @@ extern "C" int hostsim_tokens_check(const uint8_t *data, int size, int *n_segmen
         const int m0 = sgi * mps;
         in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
         in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
-        in.rec_index0 = 4u * (in.start - (uint32_t)info.scan_offset); in.seg = (uint32_t)sgi;
-        in.rec_cap = (uint32_t)(recA.size() - in.rec_index0 - 64);
+        const uint32_t seg_end = (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] : (uint32_t)size;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.seg = (uint32_t)sgi; in.img = 0;
+        in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
         in.blk0 = (uint32_t)(m0 * info.bpm); in.al = 0;
         const uint32_t nb = in.nmcu * in.bpm;
-        VecSink sA, sB;
-        JDSegOut so;
-        jd_decode_segment(in, lut.data(), kTposW, hdrA.data() + in.blk0, recA.data() + in.rec_index0, sA, so);
-        JDParseOut po;
-        if (getenv("HOSTSIM_TOKENS_UNIFORM")) jd_parse_segment_uniform(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
-        else jd_parse_segment(in, lut.data(), tok.data(), (uint32_t)tok.size(), blk_tok.data() + in.blk0, sB, po);
-        uint32_t nrecB = 0;
-        if (jd_materialize_segment(in, kTposW, tok.data(), blk_tok.data() + in.blk0, po.err_blk, hdrB.data() + in.blk0, recB.data() + in.rec_index0, &nrecB) != JD_SEG_OK) po.status = JD_SEG_OVERFLOW;
-        ntok += (int)po.ntok; nev += (int)sA.ev.size();
-        if (so.status == JD_SEG_OVERFLOW || po.status == JD_SEG_OVERFLOW) { nbadseg++; continue; }   /* capacities differ between the two forms */
-        if (so.status != po.status) bad++;
-        if (so.status != JD_SEG_OK) nbadseg++;
-        if (so.status == JD_SEG_OK && (so.jmap != po.jmap || so.nrec != nrecB || po.err_blk != nb)) bad++;
-        if (so.status != JD_SEG_OK && (int32_t)(po.err_blk / in.bpm) != so.err_mcu) bad++;
-        if (sA.ev.size() != sB.ev.size()) bad++;
-        else for (size_t e = 0; e < sA.ev.size(); e++) if (memcmp(&sA.ev[e], &sB.ev[e], sizeof(JDEvent)) != 0) { bad++; break; }
-        for (uint32_t b = 0; b < nb; b++) {
-            const jd_u64 ha = hdrA[in.blk0 + b], hb = hdrB[in.blk0 + b];
-            if (ha != hb) { bad++; continue; }
-            const uint32_t n = JD_HDR_NCOEF(ha) * (JD_HDR_BIG(ha) ? 2u : 1u);
-            if (n && memcmp(recA.data() + JD_HDR_REC(ha), recB.data() + JD_HDR_REC(hb), n * 2u) != 0) bad++;
+        VecSink sA, sB, sC;
+        JDSegOut oA, oB, oC;
+        jd_decode_segment_flat(in, lut.data(), kTposW, hdrA.data() + in.blk0, recA.data() + in.rec_index0, sA, oA);
+        jd_decode_segment(in, lut.data(), kTposW, hdrB.data() + in.blk0, recB.data() + in.rec_index0, sB, oB);
+        JDSegIn ic = in;
+        hostsim_unstuff((const uint8_t *)padded.data(), in.start, (seg_end == (uint32_t)size) ? seg_end : seg_end - 2u, cbuf);
+        ic.data = (const uint8_t *)cbuf.data(); ic.start = 0; ic.end = cbuf[cbuf.size() - 1];
+        jd_decode_segment<VecSink, JD_MODE_BASELINE, true>(ic, lut.data(), kTposW, hdrC.data() + in.blk0, recC.data() + in.rec_index0, sC, oC);
+        nrec += (int)oA.nrec; nev += (int)sA.ev.size();
+        if (oA.status != JD_SEG_OK) nbadseg++;
+        const JDSegOut *os[2] = {&oB, &oC};
+        const VecSink *ss[2] = {&sB, &sC};
+        const std::vector<jd_u64> *hs[2] = {&hdrB, &hdrC};
+        const std::vector<uint16_t> *rs[2] = {&recB, &recC};
+        for (int v = 0; v < 2; v++) {
+            /* the flat form tests the record capacity per coefficient, the block form per block: an overflow may be reported
+             * one block earlier, everything else must agree */
+            if (oA.status == JD_SEG_OVERFLOW || os[v]->status == JD_SEG_OVERFLOW) { if (oA.status != os[v]->status) bad++; continue; }
+            if (oA.status != os[v]->status || oA.err_mcu != os[v]->err_mcu) { bad++; continue; }
+            if (oA.status == JD_SEG_OK && (oA.jmap != os[v]->jmap || oA.nrec != os[v]->nrec)) bad++;
+            if (sA.ev.size() != ss[v]->ev.size()) bad++;
+            else for (size_t e = 0; e < sA.ev.size(); e++) if (memcmp(&sA.ev[e], &ss[v]->ev[e], sizeof(JDEvent)) != 0) { bad++; break; }
+            const uint32_t ngood = (oA.status == JD_SEG_OK) ? nb : (uint32_t)oA.err_mcu * in.bpm;   /* whole MCUs before the failing one */
+            for (uint32_t b = 0; b < nb; b++) {
+                const jd_u64 ha = hdrA[in.blk0 + b], hb = (*hs[v])[in.blk0 + b];
+                if (b >= ngood && b < ngood + in.bpm) continue;   /* blocks of the failing MCU before the error: both forms finish the same ones, checked by err_mcu */
+                if (ha != hb) { bad++; continue; }
+                const uint32_t n = JD_HDR_NCOEF(ha) * (JD_HDR_BIG(ha) ? 2u : 1u);
+                if (n && memcmp(recA.data() + JD_HDR_REC(ha), rs[v]->data() + JD_HDR_REC(hb), n * 2u) != 0) bad++;
+            }
         }
     }
     if (n_segments) *n_segments = nseg;
-    if (n_tokens) *n_tokens = ntok;
+    if (n_records) *n_records = nrec;
     if (n_events) *n_events = nev;
     if (n_bad_segments) *n_bad_segments = nbadseg;
     return bad;

@@ -37,6 +37,9 @@ def test_kernel_stepper_matches_reference_digests(name):
                 rc, out, nev = T.hostsim_decode(data, pt, opt, arith, w, h)
                 assert rc == want["rc"]
                 assert T.sha(out) == want["sha"], (name, mode, ptn, sn)
+                if pt == 0:      # the un-stuffed (CLEAN) reader of the same walk
+                    rc, out, nev = T.hostsim_decode(data, pt, opt, arith, w, h, clean=True)
+                    assert rc == want["rc"] and T.sha(out) == want["sha"], (name, mode, ptn, sn, "clean")
 
 
 def test_window_quirk_events_are_needed():
@@ -220,19 +223,21 @@ def test_seeded_random_sweep_vs_live_reference():
     assert checked == 120
 
 
-def test_two_phase_entropy_equals_the_single_walk():
-    """jd_tokens.h (prototype of a two-phase entropy stage: a minimal sequential parse that emits tokens, then a per-block
-    materialisation): headers, records, window-phase maps and truncation events must equal jd_decode_segment's on every
-    baseline fixture, on synthetic files of every sampling, and on corrupted scans (same status, same failing MCU)."""
+def test_block_synchronous_walk_equals_the_flat_walk():
+    """jd_decode_segment (jd_core.h: the block-synchronous entropy walk the kernels run, with the raw and with the un-stuffed
+    CLEAN bit reader, fast 10-bit AC table, per-block capacity test) against jd_decode_segment_flat (one flat state machine per
+    symbol): headers, records, window-phase maps, truncation events, status and failing MCU must be equal on every baseline
+    fixture, on synthetic files of every sampling, and on corrupted scans."""
     import ctypes as C
     import glob
     import os
     from tests import synth
     L = T.hostsim()
-    L.hostsim_tokens_check.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+    L.hostsim_walk_check.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 4
     files = {os.path.basename(f): open(f, "rb").read() for f in sorted(glob.glob(os.path.join(T.GOLD, "images", "*.jpg")))}
     files["hd"] = synth.synth_jpeg(1920, 1080, 3, 75)
     files["q98"] = synth.synth_jpeg(320, 240, 4, 98, restart_rows=0)
+    files["q100"] = synth.synth_jpeg(160, 120, 8, 100)
     files["s422"] = synth.synth_jpeg(333, 251, 5, 85, subsampling="4:2:2", restart_rows=2)
     files["s444"] = synth.synth_jpeg(333, 251, 6, 60, subsampling="4:4:4")
     files["gray"] = synth.synth_jpeg(640, 360, 7, 75, gray=True)
@@ -242,18 +247,12 @@ def test_two_phase_entropy_equals_the_single_walk():
         for _ in range(3):
             b[int(rng.integers(700, len(b) - 2))] = int(rng.integers(0, 256))
         files["corrupt_scan_%d" % k] = bytes(b)
-    for uniform in (False, True):            # the branchy parse and its one-instruction-stream form
-        if uniform:
-            os.environ["HOSTSIM_TOKENS_UNIFORM"] = "1"
-        else:
-            os.environ.pop("HOSTSIM_TOKENS_UNIFORM", None)
-        checked = tokens = events = badsegs = 0
-        for name, data in files.items():
-            v = [C.c_int() for _ in range(4)]
-            r = L.hostsim_tokens_check(data, len(data), *[C.byref(x) for x in v])
-            if r == -1:
-                continue                          # header rejected / progressive: not this path
-            assert r == 0, (name, r, uniform)
-            checked += 1; tokens += v[1].value; events += v[2].value; badsegs += v[3].value
-        assert checked >= 55 and tokens > 1000000 and events > 50 and badsegs > 0
-    os.environ.pop("HOSTSIM_TOKENS_UNIFORM", None)
+    checked = records = events = badsegs = 0
+    for name, data in files.items():
+        v = [C.c_int() for _ in range(4)]
+        r = L.hostsim_walk_check(data, len(data), *[C.byref(x) for x in v])
+        if r == -1:
+            continue                          # header rejected / progressive: not this path
+        assert r == 0, (name, r)
+        checked += 1; records += v[1].value; events += v[2].value; badsegs += v[3].value
+    assert checked >= 55 and records > 1000000 and events > 50 and badsegs > 0
