@@ -41,8 +41,51 @@ WORKLOADS = {
                        desc="512 x 3840x2160 4:2:0 q85 -> RGB565 at JPEG_SCALE_EIGHTH (BASELINE.json configs[3]); MP = source pixels"),
     "dither444": dict(n=256, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=6, subsampling="4:4:4",
                       desc="256 x 2048x1536 4:4:4 colour q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4], colour variant)"),
+    "uhd10k": dict(n=1250, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2, coef_bpp=3, unique=32, verify_all=True,
+                   desc="BASELINE.json configs[2]: 10 000 x 3840x2160 4:2:0 q85 -> RGB565 sharded over 8 GPUs = 1250 images per GPU "
+                        "(32 unique seeds per GPU = 256 over 8 ranks, cycled); every image's device-resident pixels are verified "
+                        "by digest against the reference"),
     "tiny": dict(n=16, w=640, h=480, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, desc="16 x 640x480 (smoke)"),
 }
+
+
+def host_cpu_facts():
+    """What the process may actually use (the judge's round-1 finding: os.cpu_count() said 128 on a lease with ~16)."""
+    facts = {"os_cpu_count": os.cpu_count()}
+    try:
+        facts["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        facts["affinity"] = None
+    quota = None
+    try:
+        txt = open("/sys/fs/cgroup/cpu.max").read().split()
+        if txt and txt[0] != "max":
+            quota = float(txt[0]) / float(txt[1])
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    facts["cgroup_cpu_quota"] = quota
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                facts["model"] = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        facts["model"] = None
+    try:
+        facts["numa_nodes"] = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        facts["numa_nodes"] = None
+    usable = facts["affinity"] or facts["os_cpu_count"] or 1
+    if quota:
+        usable = max(1, min(usable, int(quota + 0.5)))
+    facts["usable"] = usable
+    return facts
 
 
 def load_peaks():
@@ -56,14 +99,19 @@ def load_peaks():
 
 
 def load_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload's kernel
+    instance (profiles/roofline_traffic.json: {workload: {"bytes": dram read + write, "kernel": instance, "from": summary file}});
+    None when no capture of this build's instance is committed."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            e = json.load(open(p)).get(workload)
+            if isinstance(e, dict):
+                return e.get("bytes"), e
+            return None, None
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
 class ClockSampler:
@@ -161,7 +209,7 @@ def make_images(wl, rank, unique):
     from tests import synth
     # every rank generates its own images at the same time: share the host cores between the ranks
     world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
-    workers = max(2, min(64, (os.cpu_count() or 8) // world))
+    workers = max(2, min(64, host_cpu_facts()["usable"] // world))
     jp = synth.synth_set(unique, wl["w"], wl["h"], quality=wl["q"], seed0=rank * unique, gray=wl.get("gray", False),
                          restart_rows=wl.get("restart_rows", 1), subsampling=wl.get("subsampling", "4:2:0"), workers=workers)
     return jp
@@ -204,14 +252,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     W = max(args.warmup, 0)
     K = max(args.steps, 1)
-    threads = os.cpu_count() or 1
+    cpu_facts = host_cpu_facts()
+    threads = cpu_facts["usable"]
     n_img = wl["n"]
+    if "unique" in wl:
+        args.unique = wl["unique"]
     mp_per_step_rank = n_img * wl["w"] * wl["h"] / 1e6
     config = {"workload": wl["desc"], "images_per_gpu": n_img, "width": wl["w"], "height": wl["h"],
               "quality": wl["q"], "subsampling": "4:2:0", "restart_interval": "1 MCU row",
               "pixel_type": wl["pt"], "arith_mode": "SSE2-build parity", "parallelism": "images sharded, dp%d" % world,
               "l2_policy": "inputs_exceed_l2 (per step: %.0f MB compressed + %.1f GB pixels >> 126 MB L2)" % (
-                  n_img * 0.29 if args.workload == "hd1024" else n_img * 1.6, n_img * wl["w"] * wl["h"] * wl["bpp_out"] / 1e9)}
+                  n_img * 0.29 if args.workload == "hd1024" else n_img * 1.6, n_img * wl["w"] * wl["h"] * wl["bpp_out"] / 1e9),
+              "value_excludes": "H2D of the compressed bytes (resident in HBM before the timed region; its time is stages_ms.h2d) and any D2H; e2e includes both"}
 
     import jpegdec_b200 as J
     pixel_type = getattr(J, wl["pt"])
@@ -240,7 +292,7 @@ def main():
             "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_total / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32 (SSE2 build)", "data": "synthetic",
             "config": dict(config, note="reference CPU path, all host threads; each step is a bounded sample of the workload"),
-            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "reference", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "reference", "sample": sample, "host": cpu_facts},
             "e2e": {"value": v, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -269,6 +321,11 @@ def main():
     unique = min(args.unique, n_img)
     jpegs = make_images(wl, rank, unique)
     ctx = J.Context(local_rank, J.JPEG_ARITH_SSE2)
+    # pinned host buffers and the thread that drives the copies go next to this rank's GPU (two-socket hosts: GPU0-3 on
+    # node 0, GPU4-7 on node 1); the CPU baseline below restores the full mask first
+    full_affinity = os.sched_getaffinity(0)
+    bound_cpus = 0 if os.environ.get("JPEGDEC_B200_NO_BIND") else ctx.bind_host_to_device()
+    numa = {"gpu_node": ctx.numa_node(), "bound_cpus": bound_cpus}
     # shared Huffman/quant table blob: rank 0 exports, NCCL broadcast, every rank imports
     blob = torch.zeros(J.TABLE_BLOB_BYTES, dtype=torch.uint8, device="cuda")
     if rank == 0:
@@ -324,35 +381,105 @@ def main():
     value = world * mp_per_step_rank / (ms_step / 1e3)
     idct_ms = stage["idct"] / K
     entropy_ms = stage["entropy"] / K
-    # ---- bit-exactness spot check of what was just timed (first unique images vs reference) ----
-    parity = None
-    try:
+    # ---- bit-exactness of what was just timed: a sample for most workloads, EVERY image for verify_all workloads ----
+    def reference_pixels(i):
+        """tight reference image of unique image i: the compiled reference when it travelled, else the C restatement"""
         from oracle import refdrv
-        if refdrv.available("sse") and rank == 0 and pixel_type <= J.EIGHT_BIT_GRAYSCALE:
+        if refdrv.available("sse"):
             ref = refdrv.Ref("sse")
-            nchk = min(4, unique)
-            outs_h, st_h, _, _ = J.decode_batch_to_host(ctx, jpegs[:nchk], pixel_type, opt)
-            okc = 0
-            for i in range(nchk):
+            if pixel_type > J.EIGHT_BIT_GRAYSCALE:
+                rc, err, img, _ = ref.decode_dither(jpegs[i], pixel_type, opt)
+            else:
                 rc, err, img, _ = ref.decode_cb(jpegs[i], pixel_type, opt, want_log=False)
-                okc += int(rc == 1 and st_h[i] == 0 and img.shape == outs_h[i].shape and np.array_equal(img, outs_h[i]))
-            parity = "%d/%d sampled images bit-exact vs reference (SSE2 build)" % (okc, nchk)
+            return (img if rc == 1 else None), "reference (oracle/_ref SSE2 build)"
+        from tests import common as T
+        rc, img = T.oracle_decode(jpegs[i], pixel_type, opt, 0, wl["w"], wl["h"])
+        return (img if rc == 1 else None), "C restatement (oracle/jpegdec_oracle.c)"
+
+    parity, parity_all = None, None
+    sh0 = {2: 1, 4: 2, 8: 3}.get(opt & 14, 0)
+    ow0, oh0 = (wl["w"] + (1 << sh0) - 1) >> sh0, (wl["h"] + (1 << sh0) - 1) >> sh0
+    row_bytes = (ow0 * J.bits_per_pixel(pixel_type) + 7) // 8     # bytes of a row that hold image pixels (dithered rows are MCU-padded)
+    try:
+        if rank == 0:
+            nchk = min(4, unique)
+            okc, src = 0, ""
+            for i in range(nchk):
+                want, src = reference_pixels(i)
+                got = b.read_output(i)
+                okc += int(want is not None and got.shape[0] == oh0 and np.array_equal(got[:, :row_bytes], want[:oh0, :row_bytes]))
+            parity = "%d/%d sampled images of the timed batch bit-exact vs %s" % (okc, nchk, src)
+        if wl.get("verify_all"):
+            # digests on the device (JPEGB200_digestDevice) of every image of this rank's batch vs digests of the reference's pixels
+            want_d = []
+            for i in range(unique):
+                img, src = reference_pixels(i)
+                want_d.append(J.digest_host(img[:oh0, :row_bytes]) if img is not None else None)
+            devp = [b.device_output(i)[0] for i in range(n_img)]
+            got_d = ctx.digest_device(devp, [oh0 * row_bytes] * n_img)
+            good = sum(1 for i in range(n_img) if got_d[i] == want_d[i % unique])
+            tot = torch.tensor([good, n_img], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tot)
+            parity_all = {"verified": int(tot[0].item()), "images": int(tot[1].item()), "against": src,
+                          "how": "64-bit digest of each image's device-resident pixels (JPEGB200_digestDevice) == digest of the reference's pixels for that seed"}
     except Exception as e:  # parity is asserted in tests/; here it is informational
         parity = "not checked: %r" % (e,)
     table_hits = ctx.shared_table_hits()
     b.close()
 
+    # ---- one call per step, device outputs (verify_all workloads): JPEGB200_decodeBatch cuts the rank's slice into jobs ----
+    one_call = None
+    if wl.get("verify_all"):
+        per = oh0 * row_bytes
+        stride = (per + 255) & ~255
+        dev = ctx.device_alloc(stride * n_img)
+        douts = [dev + i * stride for i in range(n_img)]
+
+        def dev_call():
+            rc, s2, c2 = J.decode_batch(ctx, ptrs, sizes, pixel_type, opt, douts, None, J.JPEGB200_OUT_DEVICE)
+            if rc != 1:
+                raise SystemExit("decodeBatch(OUT_DEVICE) failed: rc=%d %s" % (rc, s2[:8]))
+            return c2
+        for _ in range(max(1, min(W, 2))):
+            dev_call()
+        barrier()
+        t0 = time.time()
+        for _ in range(K):
+            c2 = dev_call()
+        barrier()
+        t1 = time.time()
+        oc_ms = max_over_ranks(1e3 * (t1 - t0) / K)
+        tms, njobs = ctx.last_call_timings()
+        got_d = ctx.digest_device(douts, [per] * n_img)
+        good = sum(1 for i in range(n_img) if got_d[i] == want_d[i % unique])
+        tot = torch.tensor([good, n_img], dtype=torch.int64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot)
+        one_call = {"value": world * mp_per_step_rank / (oc_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": oc_ms, "jobs_per_call": njobs,
+                    "h2d_bytes_per_step": int(c2["h2d_bytes"]), "verified": int(tot[0].item()), "images": int(tot[1].item()),
+                    "note": "ONE JPEGB200_decodeBatch(JPEGB200_OUT_DEVICE) call per rank and step: compressed files in pinned host memory "
+                            "(H2D inside the timed region), pixels written to the caller's device buffer; wall clock, max over ranks"}
+        ctx.device_free(dev)
+
     # ---- end to end through the public C ABI with host buffers (`e2e`) ----
     e2e = None
     if not args.no_e2e:
-        out_bytes = int(wl["w"] * wl["h"] * wl["bpp_out"])
+        out_bytes = oh0 * row_bytes
         stride = (out_bytes + 255) & ~255
-        out_ptr = L.JPEGB200_hostAlloc(stride * n_img + 256)
+        n_e2e = n_img
+        try:   # the pinned output of every rank must fit the host (uhd10k: 20.7 GB per rank)
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+            while n_e2e > 64 and stride * n_e2e * world > 0.5 * avail:
+                n_e2e //= 2
+        except Exception:
+            pass
+        out_ptr = L.JPEGB200_hostAlloc(stride * n_e2e + 256)
         if out_ptr:
-            outs = [out_ptr + i * stride for i in range(n_img)]
+            outs = [out_ptr + i * stride for i in range(n_e2e)]
 
             def one_call():
-                rc, s2, c2 = J.decode_batch(ctx, ptrs, sizes, pixel_type, opt, outs)
+                rc, s2, c2 = J.decode_batch(ctx, ptrs[:n_e2e], sizes[:n_e2e], pixel_type, opt, outs)
                 if rc != 1:
                     raise SystemExit("e2e decodeBatch failed: rc=%d %s" % (rc, s2[:8]))
                 return s2, c2
@@ -365,9 +492,9 @@ def main():
             barrier()
             t1 = time.time()
             e_ms = max_over_ranks(1e3 * (t1 - t0) / K)
-            e2e = {"value": world * mp_per_step_rank / (e_ms / 1e3), "unit": "Mpixels/s",
+            e2e = {"value": world * (mp_per_step_rank * n_e2e / n_img) / (e_ms / 1e3), "unit": "Mpixels/s",
                    "h2d_bytes_per_step": int(c2["h2d_bytes"]), "d2h_bytes_per_step": int(c2["d2h_bytes"]),
-                   "ms_per_step": e_ms,
+                   "ms_per_step": e_ms, "images_per_gpu": n_e2e, "d2h_gb_per_s_per_gpu": float(c2["d2h_bytes"]) / (e_ms / 1e3) / 1e9,
                    "note": "one JPEGB200_decodeBatch C-ABI call per step, host buffers both sides (pinned): host parse + H2D + kernels + D2H of all pixels + status, run inside the call as a pipeline of 64-image jobs on separate streams"}
             L.JPEGB200_hostFree(out_ptr)
         else:
@@ -379,23 +506,34 @@ def main():
     alg_bytes = int(n_img * wl["w"] * wl["h"] * (wl["bpp_out"] + wl["coef_bpp"]))
     achieved = alg_bytes / (idct_ms / 1e3) / 1e9
     out_gbs = n_img * wl["w"] * wl["h"] * wl["bpp_out"] / (idct_ms / 1e3) / 1e9
+    traffic, traffic_src = load_traffic(args.workload)
     roofline = {"bound": "hbm", "kernel": wl.get("kernel", "jdk_idct_tb / jdk_idct_color (fused expand + dequant + IDCT + colour)"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": load_traffic(args.workload), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": idct_ms,
-                "write_only_gbs": out_gbs, "write_frac": out_gbs / peak}
+                "write_only_gbs": out_gbs, "write_frac": out_gbs / peak,
+                "kernel_share_of_step": idct_ms / (dev_ms / K) if dev_ms > 0 else None,
+                "dominant": bool(idct_ms >= entropy_ms),
+                "note": "achieved = SURVEY 8(d) algorithmic bytes (output + 2 B x samples per source pixel) / CUDA-event time of the launch; "
+                        "write_frac = output bytes only (the north-star's 0.40 target); traffic = ncu dram read + write of the named capture"}
+    # the whole step against the same roof: compressed bytes in + pixels out (SURVEY 8(d) whole-pipeline figure)
+    step_bytes = float(cnt["compressed_bytes"]) + float(cnt["output_bytes"])
+    step_roofline = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / ((dev_ms / K) / 1e3) / 1e9, "unit": "GB/s",
+                     "frac": step_bytes / ((dev_ms / K) / 1e3) / 1e9 / peak,
+                     "entropy_stage_ms": entropy_ms, "entropy_share_of_step": entropy_ms / (dev_ms / K) if dev_ms > 0 else None}
 
     # ---- CPU baseline beside it (rank 0, N=1 only, bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and pixel_type <= J.EIGHT_BIT_GRAYSCALE:
         try:
             from oracle import refdrv
+            os.sched_setaffinity(0, full_affinity)      # the reference gets every CPU the process may use, not just the GPU's node
             if refdrv.available("sse"):
                 n_sample = max(threads * 8, 256)
                 v, secs = cpu_reference_run(wl, jpegs, pixel_type, n_sample, threads, passes=3)
                 v1, secs1 = cpu_reference_run(wl, jpegs, pixel_type, 32, 1, passes=2)
                 cpu = {"value": v, "unit": "Mpixels/s", "cores": threads, "kind": "reference",
                        "sample": "%d images (%d unique cycled), best of 3, framebuffer mode, oracle/_ref SSE2 build" % (n_sample, unique),
-                       "single_thread_value": v1}
+                       "single_thread_value": v1, "host": cpu_facts}
         except Exception as e:
             cpu = {"value": None, "unit": "Mpixels/s", "cores": threads, "kind": "reference", "sample": "failed: %r" % (e,)}
 
@@ -412,7 +550,9 @@ def main():
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms": {k: v / K for k, v in stage.items()}, "wall_ms_per_step": wall_ms_step,
             "entropy_symbol_stage_ms": entropy_ms, "quirk_events_per_step": int(cnt["events"]),
-            "shared_table_hits": table_hits, "parity_spot_check": parity}
+            "shared_table_hits": table_hits, "parity_spot_check": parity, "parity_all": parity_all, "one_call_device": one_call,
+            "step_roofline": step_roofline, "numa": numa,
+            "entropy_pipeline": os.environ.get("JPEGDEC_B200_ENTROPY", "clean (jdk_unstuff_segs + word reader)")}
         try:   # the entropy stage is reported as compressed MB/s; scaled workloads also as output pixels
             comp_mb = float(cnt["compressed_bytes"]) / 1e6
             line["entropy_compressed_mb_per_s"] = world * comp_mb / (entropy_ms / 1e3) if entropy_ms > 0 else None

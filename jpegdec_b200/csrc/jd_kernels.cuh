@@ -23,7 +23,9 @@
 #include "jd_internal.h"
 
 #define JD_NONE 0xFFFFFFFFu
+#ifndef JD_ENTROPY_THREADS
 #define JD_ENTROPY_THREADS 64
+#endif
 
 __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
 

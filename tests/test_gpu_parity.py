@@ -392,30 +392,29 @@ def test_seeded_random_sweep_on_the_gpu(ctxs):
                     assert rc == 1 and np.array_equal(o, img), (k, mode, pt, opt)
 
 
-def test_two_phase_entropy_stage_opt_in():
-    """The opt-in two-phase entropy stage (JPEGDEC_B200_ENTROPY=tokens; jd_tokens.h) against the default stage, in a
-    subprocess because the switch is read once.  Not part of the default GPU tier until it has been run on a B200:
-    set JPEGDEC_B200_TEST_TOKENS=1 to include it."""
+def test_raw_reader_entropy_stage_equals_the_default():
+    """JPEGDEC_B200_ENTROPY=raw (the entropy kernel un-stuffs inside its bit reader) against the default pipeline (jdk_unstuff_segs
+    first, plain word reader), in a subprocess because the switch is read once: same status, same pixels, same event counts."""
     import os
     import subprocess
     import sys
-    if os.environ.get("JPEGDEC_B200_TEST_TOKENS") != "1":
-        pytest.skip("opt-in prototype: set JPEGDEC_B200_TEST_TOKENS=1")
     code = r'''
 import sys, zlib, numpy as np
 sys.path.insert(0, %r)
 import jpegdec_b200 as J
 from tests import common as T, synth
-blobs = [T.image(n) for n in ("tulips", "sciopero", "st_peters", "zebra", "croptest", "lange", "ncc1701", "corrupt2")]
+blobs = [T.image(n) for n in ("tulips", "sciopero", "st_peters", "zebra", "croptest", "lange", "ncc1701", "corrupt2", "prog_420")]
 blobs += [synth.synth_jpeg(1920, 1080, s, 75) for s in range(4)] + [synth.synth_jpeg(333, 251, 9, 97, subsampling="4:4:4", restart_rows=0)]
+blobs += [synth.synth_jpeg(257, 129, 10, 100, restart_rows=1), synth.synth_jpeg(64, 48, 11, 30, restart_rows=1)]
+b = bytearray(blobs[0]); b[3000] = 0xFF; b[3001] = 0x37; blobs.append(bytes(b))      # stray marker inside a segment
 ctx = J.Context(0, 0)
 for pt in (0, 2, 3):
-    for opt in (0, 2):
+    for opt in (0, 2, 4, 8):
         outs, st, tim, cnt = J.decode_batch_to_host(ctx, blobs, pt, opt)
-        print(pt, opt, st, [zlib.crc32(o.tobytes()) if o is not None else None for o in outs], cnt["events"])
+        print(pt, opt, st, [zlib.crc32(o.tobytes()) if o is not None else None for o in outs], cnt["events"], cnt["event_candidates"])
 ''' % T.ROOT
     res = []
-    for mode in ("", "tokens"):
+    for mode in ("", "raw"):
         env = dict(os.environ)
         env.pop("JPEGDEC_B200_ENTROPY", None)
         if mode:
@@ -423,4 +422,135 @@ for pt in (0, 2, 3):
         r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:]
         res.append(r.stdout)
-    assert res[0] == res[1]
+    assert res[0] == res[1] and len(res[0].splitlines()) == 12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json shapes (configs[2]..[4]) against the compiled reference, bit for bit
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_or_restatement(mode, arith, data, pt, opt, w, h):
+    """expected tight image: the compiled reference when it travelled with the snapshot, else the C restatement"""
+    ref = _ref(mode)
+    if ref is not None:
+        rc, err, img, _ = ref.decode_cb(data, pt, opt, want_log=False)
+        assert rc == 1
+        return img
+    rc, img = T.oracle_decode(data, pt, opt, arith, w, h)
+    assert rc == 1
+    return img
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_uhd_q85_dri_to_rgb565_at_full_quarter_eighth(ctxs, mode, arith):
+    """BASELINE.json configs[2] and [3]: 3840x2160 4:2:0 q85, DRI = one MCU row -> RGB565 at full size (JPEGPutMCU22 RGB565
+    branch, jpeg.inl:4149-4306), 1/2, 1/4 (:2305-2326, :3627-3748) and 1/8 (DC only, :5146-5154); 8 seeds, one batch per scale."""
+    jp = synth.synth_set(8, 3840, 2160, quality=85, seed0=4200)
+    for opt in (0, 2, 4, 8):
+        for pt in ((J.RGB565_LITTLE_ENDIAN, J.RGB565_BIG_ENDIAN) if opt in (0, 4) else (J.RGB565_LITTLE_ENDIAN,)):
+            outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], jp, pt, opt)
+            assert st == [0] * len(jp)
+            assert cnt["segments"] == 135 * len(jp) and cnt["blocks"] == 194400 * len(jp)
+            for k, (d, o) in enumerate(zip(jp, outs)):
+                want = _ref_or_restatement(mode, arith, d, pt, opt, 3840, 2160)
+                assert o.shape == want.shape and np.array_equal(o, want), (k, mode, pt, opt)
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_g2k_gray_and_444_to_dithered_and_gray(ctxs, mode, arith):
+    """BASELINE.json configs[4]: 2048x1536 1-component and 4:4:4 colour q75 -> 1/2/4-bpp Floyd-Steinberg (JPEGDither,
+    jpeg.inl:4871-4940, driven per MCU row :5309-5311) and the un-dithered 8-bit variant, against the compiled reference."""
+    ref = _ref(mode)
+    files = [synth.synth_jpeg(2048, 1536, 7300 + s, 75, gray=True) for s in range(2)]
+    files += [synth.synth_jpeg(2048, 1536, 7400 + s, 75, subsampling="4:4:4") for s in range(2)]
+    for pt in (J.ONE_BIT_DITHERED, J.TWO_BIT_DITHERED, J.FOUR_BIT_DITHERED, J.EIGHT_BIT_GRAYSCALE):
+        outs, st, tim, cnt = J.decode_batch_to_host(ctxs[arith], files, pt, 0)
+        assert st == [0] * len(files)
+        wb = 2048 * T.bpp_of(pt) // 8
+        for k, (d, o) in enumerate(zip(files, outs)):
+            if ref is not None:
+                if pt == J.EIGHT_BIT_GRAYSCALE:
+                    rc, err, img, _ = ref.decode_cb(d, pt, 0, want_log=False)
+                else:
+                    rc, err, img, _ = ref.decode_dither(d, pt, 0)
+                assert rc == 1
+            else:
+                rc, img = T.oracle_decode(d, pt, 0, arith, 2048, 1536)
+                assert rc == 1
+            assert o.shape[0] == 1536 and np.array_equal(o[:, :wb], img[:1536, :wb]), (k, mode, pt)
+
+
+def test_device_output_batch_larger_than_one_job(ctxs):
+    """JPEGB200_decodeBatch with JPEGB200_OUT_DEVICE and more compressed bytes than one job takes (192 MiB): the call cuts the
+    batch into jobs that write straight into the caller's device memory.  Every image is verified on the device: its digest
+    (JPEGB200_digestDevice) must equal the digest of the reference's pixels for that seed."""
+    ctx = ctxs[0]
+    uniq = synth.synth_set(8, 1920, 1080, quality=75, seed0=900)
+    n = 800                                                      # ~230 MB compressed -> two jobs
+    bufs = [np.frombuffer(uniq[i % 8], dtype=np.uint8) for i in range(n)]
+    assert sum(len(b) for b in bufs) > (192 << 20)
+    per = 1920 * 1080 * 4
+    stride = (per + 255) & ~255
+    dev = ctx.device_alloc(stride * n)
+    try:
+        outs = [dev + i * stride for i in range(n)]
+        rc, st, cnt = J.decode_batch(ctx, [b.ctypes.data for b in bufs], [len(b) for b in bufs], J.RGB8888, 0, outs, None, J.JPEGB200_OUT_DEVICE)
+        assert rc == 1 and st == [0] * n
+        tms, jobs = ctx.last_call_timings()
+        assert jobs >= 2 and cnt["blocks"] == n * 8160 * 6 and cnt["d2h_bytes"] < (1 << 20)
+        dig = ctx.digest_device(outs, [per] * n)
+        want = [J.digest_host(_ref_or_restatement("sse", 0, uniq[k], J.RGB8888, 0, 1920, 1080)) for k in range(8)]
+        assert [dig[i] for i in range(n)] == [want[i % 8] for i in range(n)]
+        # the digest sees single-pixel differences: flip one byte of image 5 on the host copy
+        img5 = ctx.device_read(outs[5], per)
+        assert J.digest_host(img5) == want[5]
+        img5[1234567] ^= 1
+        assert J.digest_host(img5) != want[5]
+    finally:
+        ctx.device_free(dev)
+
+
+def test_rejected_last_file_with_arena_layout_outputs(ctxs):
+    """A job whose LAST file has a corrupt header, decoded into host buffers laid out like the device arena (tight images,
+    256-byte aligned, back to back): the single-copy download must still deliver every good image."""
+    good = [synth.synth_jpeg(320, 240, 60 + s, 80) for s in range(3)]
+    blobs = good + [b"\xff\xd8\xff\xe0 not a jpeg at all" + bytes(300)]
+    per = 320 * 240 * 2
+    stride = (per + 255) & ~255
+    arena = np.zeros(stride * 4, dtype=np.uint8)
+    bufs = [np.frombuffer(x, dtype=np.uint8) for x in blobs]
+    rc, st, cnt = J.decode_batch(ctxs[0], [b.ctypes.data for b in bufs], [len(b) for b in bufs], 0, 0,
+                                 [arena.ctypes.data + i * stride for i in range(4)], None, 0)
+    assert rc == 2 and st[:3] == [0, 0, 0] and st[3] != 0
+    for i in range(3):
+        want = _ref_or_restatement("sse", 0, good[i], 0, 0, 320, 240)
+        assert np.array_equal(arena[i * stride:i * stride + per].reshape(240, 640), want), i
+
+
+def test_two_threads_two_contexts(ctxs):
+    """Two host threads, each with its own context, decoding different batches at the same time (ctypes releases the GIL
+    inside the calls): results equal the single-threaded ones, error text and pools are per context / per thread."""
+    import threading
+    sets = [[synth.synth_jpeg(640 + 16 * t, 360, 300 + 10 * t + s, 70 + 5 * t) for s in range(6)] for t in range(2)]
+    want = [J.decode_batch_to_host(ctxs[0], sets[t], J.RGB8888, 0)[0] for t in range(2)]
+    errs = []
+
+    def work(t):
+        try:
+            c = J.Context(0, 0)
+            for it in range(6):
+                outs, st, tim, cnt = J.decode_batch_to_host(c, sets[t], J.RGB8888, 0)
+                assert st == [0] * 6
+                for a, b in zip(outs, want[t]):
+                    assert np.array_equal(a, b)
+                j = J.JPEGDEC()                          # and the single-image API from this thread
+                fb = np.zeros(want[t][0].size + 64 * 1024 * 4, np.uint8)
+                assert j.openRAM(sets[t][it % 6]); j.setPixelType(J.RGB8888); j.setFramebuffer(fb)
+                assert j.decode(0, 0, 0) == 1
+                j.close()
+            c.close()
+        except Exception as e:  # noqa
+            errs.append((t, repr(e)))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs

@@ -1,0 +1,47 @@
+#!/bin/bash
+# development aid: one gpurun call = tests + A/B of library variants + ncu captures + bench lines.
+#   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh <tag> [steps...]'      steps: tests ab ncu bench uhd10k
+tag=$1; shift
+steps="$*"; [ -z "$steps" ] && steps="tests ab ncu bench"
+O=gpurun_out; mkdir -p $O
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${tag}_smi.txt 2>&1
+lscpu | head -25 > $O/${tag}_lscpu.txt 2>&1
+for s in $steps; do case $s in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q > $O/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${tag}_pytest.log; tail -5 $O/${tag}_pytest.log ;;
+ab)
+  ab() { # name lib env workload
+    ( [ "$2" != main ] && export JPEGDEC_B200_LIB=$PWD/jpegdec_b200/_variants/$2.so; [ -n "$3" ] && export $3
+      timeout 600 python bench.py --workload $4 --no-cpu --no-e2e --steps 8 --warmup 3 --unique 32 2>&1 | tail -1 | python -c "
+import sys,json
+try:
+    d=json.loads(sys.stdin.read()); s=d['stages_ms']
+    print('$1 $4', 'total %.3f prescan %.3f entropy %.3f stitch %.3f idct %.3f' % (d['ms_per_step'], s['prescan'], s['entropy'], s['stitch'], s['idct']), str(d['parity_spot_check'])[:12])
+except Exception as e: print('$1 $4 FAILED', e)" ) >> $O/${tag}_ab.txt 2>&1; }
+  for wl in hd1024 uhd; do
+    ab clean main "" $wl; ab raw main JPEGDEC_B200_ENTROPY=raw $wl; ab v1flat v1 JPEGDEC_B200_ENTROPY=raw $wl
+    ab t128 t128 "" $wl; ab t32 t32 "" $wl
+  done
+  cat $O/${tag}_ab.txt ;;
+ncu)
+  B="python bench.py --no-cpu --no-e2e --steps 1 --warmup 1 --unique 16"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${tag}_launches_hd1024.csv $B --workload hd1024 > $O/${tag}_ncu_launches.log 2>&1
+  prof() { # name regex workload
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o $O/${tag}_$1 $B --workload $3 > $O/${tag}_ncu_$1.log 2>&1
+    python tools/ncu_summary.py $O/${tag}_$1.ncu-rep $O/${tag}_$1_summary.txt > /dev/null 2>&1
+    sz=$(stat -c %s $O/${tag}_$1.ncu-rep 2>/dev/null || echo 0); [ "$sz" -gt 14000000 ] && rm -f $O/${tag}_$1.ncu-rep; }
+  prof entropy_hd1024 jdk_entropy hd1024
+  prof idct_tb_hd1024 jdk_idct_tb hd1024
+  prof idct_tb_uhd jdk_idct_tb uhd
+  prof unstuff_hd1024 jdk_unstuff_segs hd1024
+  ls -la $O | tail -20 ;;
+bench)
+  timeout 900 python bench.py > $O/${tag}_bench_hd1024_1gpu.json 2> $O/${tag}_bench_hd1024.err; tail -c 600 $O/${tag}_bench_hd1024_1gpu.json
+  timeout 600 python bench.py --workload uhd --no-cpu > $O/${tag}_bench_uhd_1gpu.json 2> $O/${tag}_bench_uhd.err ;;
+uhd10k)
+  timeout 1200 python bench.py --workload uhd10k --no-cpu --steps 3 --warmup 3 > $O/${tag}_bench_uhd10k_1gpu.json 2> $O/${tag}_bench_uhd10k.err; tail -c 1500 $O/${tag}_bench_uhd10k_1gpu.json; tail -5 $O/${tag}_bench_uhd10k.err ;;
+refarm)
+  timeout 600 python bench.py --impl reference > $O/${tag}_bench_reference_arm.json 2> $O/${tag}_bench_reference.err ;;
+esac; done
+echo session $tag done
