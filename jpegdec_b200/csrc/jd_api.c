@@ -18,18 +18,66 @@
 
 #define JPEGB200_OPT_PADDED 0x10000 /* internal option bit: write the whole MCU-aligned frame */
 
+/* One context per (device, arithmetic build), created on first use.  g_lock guards this table and the staging pool; the GPU
+ * work of a decode holds only its context's lock (a context is driven by one thread at a time); the host replay of the
+ * delivery rules -- which runs the user's callback -- holds no lock at all, so a callback may decode another image and
+ * decodes on different GPUs do not serialise each other (the reference is re-entrant per handle). */
+#define JD_MAX_DEVICES 64
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-static JPEGB200_CTX *g_ctx[64][2];
-static uint8_t *g_stage;
-static size_t g_stage_bytes;
+static JPEGB200_CTX *g_ctx[JD_MAX_DEVICES][2];
+static pthread_mutex_t g_ctx_lock[JD_MAX_DEVICES][2];
+static int g_ctx_lock_init;
 
-static JPEGB200_CTX *get_ctx(int device, int arith)
+/* pinned staging frames, recycled (allocating pinned memory costs far more than a small decode) */
+#define JD_STAGE_SLOTS 8
+static struct { uint8_t *p; size_t bytes; } g_stage[JD_STAGE_SLOTS];
+
+static uint8_t *stage_get(size_t need, size_t *got)
 {
-    int d = device;
-    if (d < 0) d = 0; /* slot for "current device" */
-    if (d >= 64) return NULL;
-    if (!g_ctx[d][arith ? 1 : 0]) g_ctx[d][arith ? 1 : 0] = JPEGB200_create(device, arith);
-    return g_ctx[d][arith ? 1 : 0];
+    uint8_t *p = NULL;
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < JD_STAGE_SLOTS; i++)
+        if (g_stage[i].p && g_stage[i].bytes >= need) { p = g_stage[i].p; *got = g_stage[i].bytes; g_stage[i].p = NULL; break; }
+    pthread_mutex_unlock(&g_lock);
+    if (p) return p;
+    *got = need + (1u << 20);
+    return (uint8_t *)JPEGB200_hostAlloc(*got);
+}
+
+static void stage_put(uint8_t *p, size_t bytes)
+{
+    if (!p) return;
+    pthread_mutex_lock(&g_lock);
+    int slot = -1;
+    for (int i = 0; i < JD_STAGE_SLOTS; i++) {
+        if (!g_stage[i].p) { slot = i; break; }
+        if (slot < 0 || g_stage[i].bytes < g_stage[slot].bytes) slot = i;
+    }
+    uint8_t *drop = NULL;
+    if (g_stage[slot].p) { if (g_stage[slot].bytes >= bytes) { drop = p; p = NULL; } else drop = g_stage[slot].p; }
+    if (p) { g_stage[slot].p = p; g_stage[slot].bytes = bytes; }
+    pthread_mutex_unlock(&g_lock);
+    if (drop) JPEGB200_hostFree(drop);
+}
+
+extern int JPEGB200_currentDevice(void);
+
+/* returns the context and its lock for (device, arith); device < 0 = the calling thread's current CUDA device */
+static JPEGB200_CTX *get_ctx(int device, int arith, pthread_mutex_t **lock)
+{
+    if (device < 0) device = JPEGB200_currentDevice();
+    if (device < 0 || device >= JD_MAX_DEVICES) return NULL;
+    const int a = arith ? 1 : 0;
+    pthread_mutex_lock(&g_lock);
+    if (!g_ctx_lock_init) {
+        for (int d = 0; d < JD_MAX_DEVICES; d++) { pthread_mutex_init(&g_ctx_lock[d][0], NULL); pthread_mutex_init(&g_ctx_lock[d][1], NULL); }
+        g_ctx_lock_init = 1;
+    }
+    if (!g_ctx[device][a]) g_ctx[device][a] = JPEGB200_create(device, arith);
+    JPEGB200_CTX *c = g_ctx[device][a];
+    pthread_mutex_unlock(&g_lock);
+    *lock = &g_ctx_lock[device][a];
+    return c;
 }
 
 static void fill_from_info(JPEGIMAGE *p, const JDInfo *inf)
@@ -236,15 +284,153 @@ static int bits_per_pixel(int pt)
     }
 }
 
-/* copies one scaled MCU (mw x mh pixels of `bypp` bytes) out of the decoded frame */
-static void copy_mcu(uint8_t *dst, int dst_pitch_bytes, const uint8_t *frame, int frame_pitch, int mx, int my, int mw, int mh,
-                     int bypp, int max_cols)
+/* ------------------------------------------------------------------------------------------------------------------
+ * Delivery.  The GPU decodes the whole MCU-aligned frame; what remains of DecodeJPEG (src/jpeg.inl:5008-5127, :5300-5336)
+ * is WHICH pixels go WHERE.  That is pure geometry, so it is computed first, as a list of draw items, and only then
+ * executed: a draw item = a run of consecutive MCUs of one MCU row that the reference hands to the callback in one call.
+ * The reference's rules (kept, quirks included, because callers see them):
+ *   - MCU column x of row y is skipped when the row starts above the crop (y * mcuH < cropY) or when x * mcuW lies outside
+ *     [cropX, cropX + cropW] -- both ends inclusive, so one MCU past the crop's right edge is still delivered (:5111, :5135);
+ *   - a group is flushed when it is full or when the row's last MCU column has just been placed (:5300); a row whose last
+ *     column is skipped never flushes a partial group;
+ *   - after a flush the next group's width shrinks to what is left of the crop or of the row, rounded up to whole MCUs
+ *     (:5327-5335); the width the callback may use is trimmed at the scaled image's right edge, else at the crop (:5313-5317);
+ *   - with crop x scale the tests above compare SCALED MCU positions with the unscaled crop rectangle: the
+ *     outcome (e.g. no callbacks at all at 1/4 and 1/8) is reproduced literally.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int width, height;                  /* image size (full scale) */
+    int crop_x, crop_y, crop_w, crop_h;
+    int x_off, y_off;                   /* JPEG_decode placement */
+    int subsample, pixel_type, options, max_mcus;
+} JDDeliveryGeom;
+
+typedef struct {
+    int32_t mcu_row, mcu_col0, n_mcus;  /* the MCUs this call carries: n_mcus consecutive columns from mcu_col0 */
+    int32_t x, y, w, h, w_used;         /* JPEGDRAW fields (w = iWidth = pitch of the block group in pixels) */
+    int32_t buf;                        /* JPEG_USES_DMA: which half of the pixel buffer (0 / 1) */
+} JDDrawItem;
+
+static int scale_shift_of(int options)
 {
-    const uint8_t *src = frame + (size_t)my * mh * frame_pitch + (size_t)mx * mw * bypp;
-    int cols = mw;
-    if (max_cols < cols) cols = max_cols;
-    if (cols <= 0) return;
-    for (int r = 0; r < mh; r++) memcpy(dst + (size_t)r * dst_pitch_bytes, src + (size_t)r * frame_pitch, (size_t)cols * bypp);
+    return (options & JPEG_SCALE_HALF) ? 1 : (options & JPEG_SCALE_QUARTER) ? 2 : (options & JPEG_SCALE_EIGHTH) ? 3 : 0;
+}
+
+/* Fills items[] (at most cap) and returns the number of draw calls the reference makes for this geometry; exported for
+ * the CPU test tier, which compares it with the reference's own callback log (no GPU needed). */
+int jd_delivery_schedule(const JDDeliveryGeom *g, JDDrawItem *items, int cap)
+{
+    const int shift = scale_shift_of(g->options);
+    int mw, mh;
+    mcu_size(g->subsample, &mw, &mh);
+    const int cols = (g->width + mw - 1) / mw;
+    const int rows = (g->crop_y + g->crop_h + mh - 1) / mh;      /* unscaled MCU height (:5014-5037) */
+    mw >>= shift; mh >>= shift;
+    const int pt = g->pixel_type;
+    /* MCUs per draw call (:5062-5084) */
+    int group = MAX_BUFFERED_PIXELS / (mw * mh);
+    if (pt == RGB8888) group /= 2;
+    if (pt == EIGHT_BIT_GRAYSCALE) group *= 2;
+    if (group > cols) group = cols;
+    int halves = 0;
+    if (group > g->max_mcus) group = g->max_mcus;
+    else if (g->options & JPEG_USES_DMA) { group /= 2; halves = 1; }
+    if (pt > EIGHT_BIT_GRAYSCALE) group = cols;
+    if (g->crop_w != g->width && group * mw > g->crop_w) group = g->crop_w / mw;
+    if (group < 1) group = 1;
+    const int round = (1 << shift) - 1;
+    const int out_w = (g->width + round) >> shift, out_h = (g->height + round) >> shift;
+    int n = 0, buf = 0;
+    int h = mh;                                                   /* once trimmed it stays trimmed (jd.iHeight is never reset) */
+    for (int r = 0; r < rows; r++) {
+        const int row_above_crop = (r * mh < g->crop_y);
+        int pitch = group * mw, filled = 0, first = -1;
+        int x_px = g->x_off;
+        for (int c = 0; c < cols; c++) {
+            const int skip = row_above_crop || c * mw < g->crop_x || c * mw > g->crop_x + g->crop_w;
+            if (skip) continue;
+            if (filled == 0) first = c;
+            filled += mw;
+            if (filled != pitch && c != cols - 1) continue;
+            /* flush */
+            JDDrawItem it;
+            it.mcu_row = r; it.mcu_col0 = first; it.n_mcus = filled / mw;
+            it.x = x_px; it.w = it.w_used = pitch;
+            if ((x_px - g->x_off) + pitch > out_w) it.w_used = out_w - (x_px - g->x_off);
+            else if ((x_px - g->x_off) + pitch > g->crop_w) it.w_used = g->crop_w - (x_px - g->x_off);
+            it.y = g->y_off + r * mh - g->crop_y;
+            if ((it.y - g->y_off + mh) > out_h) h = out_h - (it.y - g->y_off);
+            it.h = h;
+            it.buf = buf;
+            if (n < cap) items[n] = it;
+            n++;
+            if (halves) buf ^= 1;
+            x_px += pitch;
+            if (g->crop_w != cols * mw && (pitch + x_px) > (g->crop_x + g->crop_w)) pitch = g->crop_w - (x_px - g->x_off);
+            else if ((cols - 1 - c) < group) pitch = (cols - 1 - c) * mw;
+            if (pitch & (mw - 1)) pitch = (pitch + (mw - 1)) & ~(mw - 1);
+            if (pitch < 0) pitch = 0;
+            filled = 0;
+        }
+    }
+    return n;
+}
+
+static void geom_of(const JPEGIMAGE *p, JDDeliveryGeom *g)
+{
+    g->width = p->iWidth; g->height = p->iHeight;
+    g->crop_x = p->iCropX; g->crop_y = p->iCropY; g->crop_w = p->iCropCX; g->crop_h = p->iCropCY;
+    g->x_off = p->iXOffset; g->y_off = p->iYOffset;
+    g->subsample = p->ucSubSample; g->pixel_type = p->ucPixelType; g->options = p->iOptions; g->max_mcus = p->iMaxMCUs;
+}
+
+/* framebuffer mode (:5114-5124): every non-skipped MCU goes to (x_mcu - first kept column, y - cropY) of a frame whose pitch
+ * is the crop width; no callback */
+static void deliver_framebuffer(const JPEGIMAGE *p, const uint8_t *frame, int frame_pitch, int bypp, int last_mcu)
+{
+    const int shift = scale_shift_of(p->iOptions);
+    int mw, mh;
+    mcu_size(p->ucSubSample, &mw, &mh);
+    const int cols = (p->iWidth + mw - 1) / mw;
+    const int rows = (p->iCropY + p->iCropCY + mh - 1) / mh;
+    mw >>= shift; mh >>= shift;
+    const int out_h = (p->iHeight + (1 << shift) - 1) >> shift;
+    const int pitch_px = p->iCropCX;
+    const int pt = p->ucPixelType;
+    /* the reference's SSE2 colour paths store whole MCUs with no edge clipping (jpeg.inl:3409, :4006): the right-edge MCU runs
+     * on into the start of the next line (and is partly overwritten later, in MCU order), the bottom MCU row continues below
+     * the image -- which is why the caller's buffer must cover whole MCU rows (c_cmdline/main.c:180).  Same writes, same
+     * order; clipped only at the end of that MCU-row-aligned buffer.  Every other path clips at the image edges
+     * (:3520-3524, :4311-4332). */
+    const int whole_mcus = p->ucArithMode == JPEG_ARITH_SSE2 && shift == 0 && p->ucNumComponents == 3 && pt <= RGB8888 &&
+                           (p->ucSubSample == 0x11 || p->ucSubSample == 0x22);
+    const size_t fb_px = (size_t)pitch_px * (size_t)(rows * mh - p->iCropY);
+    for (int r = 0; r < rows; r++) {
+        if (r * mh < p->iCropY) continue;
+        const int ty = r * mh - p->iCropY;
+        int xoff = 0;
+        for (int c = 0; c < cols; c++) {
+            if (last_mcu >= 0 && r * cols + c > last_mcu) return;       /* decode error: the loops stop after the failing MCU (:5128) */
+            if (c * mw < p->iCropX || c * mw > p->iCropX + p->iCropCX) continue;
+            const uint8_t *src = frame + (size_t)r * mh * frame_pitch + (size_t)c * mw * bypp;
+            if (whole_mcus) {
+                for (int l = 0; l < mh; l++) {
+                    const size_t at = (size_t)(ty + l) * pitch_px + xoff;
+                    size_t n = (size_t)mw;
+                    if (at >= fb_px) break;
+                    if (at + n > fb_px) n = fb_px - at;
+                    memcpy((uint8_t *)p->pFramebuffer + at * bypp, src + (size_t)l * frame_pitch, n * bypp);
+                }
+            } else {
+                int lines = mh, px = pitch_px - xoff;
+                if (r * mh + lines > out_h) lines = out_h - r * mh;
+                if (px > mw) px = mw;
+                for (int l = 0; l < lines && px > 0; l++)
+                    memcpy((uint8_t *)p->pFramebuffer + ((size_t)(ty + l) * pitch_px + xoff) * bypp, src + (size_t)l * frame_pitch, (size_t)px * bypp);
+            }
+            xoff += mw;
+        }
+    }
 }
 
 static int decode_common(JPEGIMAGE *p)
@@ -255,7 +441,7 @@ static int decode_common(JPEGIMAGE *p)
     if (options & JPEG_EXIF_THUMBNAIL) {
         if (p->iThumbData == 0 || p->iThumbWidth == 0) { p->iError = JPEG_INVALID_PARAMETER; return 0; } /* jpeg.inl:4969 */
     }
-    int shift = (options & JPEG_SCALE_HALF) ? 1 : (options & JPEG_SCALE_QUARTER) ? 2 : (options & JPEG_SCALE_EIGHTH) ? 3 : 0;
+    const int shift = scale_shift_of(options);
     if ((options & JPEG_LUMA_ONLY) && p->ucPixelType < EIGHT_BIT_GRAYSCALE) p->ucPixelType = EIGHT_BIT_GRAYSCALE; /* :4991 */
     if (p->ucPixelType >= INVALID_PIXEL_TYPE) { p->iError = JPEG_INVALID_PARAMETER; return 0; }
     const int pt = p->ucPixelType;
@@ -263,143 +449,95 @@ static int decode_common(JPEGIMAGE *p)
     if (dither && !p->pDitherBuffer) { p->iError = JPEG_INVALID_PARAMETER; return 0; }
     if (!p->pFramebuffer && !p->pfnDraw) { p->iError = JPEG_INVALID_PARAMETER; return 0; }
 
-    pthread_mutex_lock(&g_lock);
-    JPEGB200_CTX *ctx = get_ctx(p->iDevice, p->ucArithMode);
-    if (!ctx) { pthread_mutex_unlock(&g_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
+    /* ---- the GPU part: whole MCU-aligned frame into a pinned staging buffer (holds the context's lock only) ---- */
+    pthread_mutex_t *ctx_lock = NULL;
+    JPEGB200_CTX *ctx = get_ctx(p->iDevice, p->ucArithMode, &ctx_lock);
+    if (!ctx) { p->iError = JPEG_ERROR_MEMORY; return 0; }
+    pthread_mutex_lock(ctx_lock);
     const uint8_t *datas[1] = {p->pFileData};
     int32_t sizes[1] = {p->iFileSize};
     JPEGB200_BATCH *b = JPEGB200_batchCreate(ctx, datas, sizes, 1, pt, (options & 0xFF) | JPEGB200_OPT_PADDED);
-    if (!b) { pthread_mutex_unlock(&g_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
+    if (!b) { pthread_mutex_unlock(ctx_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
     int32_t w = 0, h = 0, sub = 0, fw = 0, fh = 0, st = 0;
     JPEGB200_batchImageInfo(b, 0, &w, &h, &sub, &fw, &fh, &st);
-    if (st != JPEG_SUCCESS) { JPEGB200_batchDestroy(b); pthread_mutex_unlock(&g_lock); p->iError = st; return 0; }
+    if (st != JPEG_SUCCESS) { JPEGB200_batchDestroy(b); pthread_mutex_unlock(ctx_lock); p->iError = st; return 0; }
     if (options & JPEG_EXIF_THUMBNAIL) { /* the reference re-parses into the same state (:4975) */
         p->iWidth = p->iCropCX = w; p->iHeight = p->iCropCY = h; p->iCropX = p->iCropY = 0; p->ucSubSample = (uint8_t)sub;
     }
     int64_t fpitch = 0;
-    int64_t fbytes = JPEGB200_batchOutputBytes(b, 0, &fpitch);
-    if ((size_t)fbytes + 64 > g_stage_bytes) {
-        if (g_stage) JPEGB200_hostFree(g_stage);
-        g_stage_bytes = (size_t)fbytes + 64 + (1u << 20);
-        g_stage = (uint8_t *)JPEGB200_hostAlloc(g_stage_bytes);
-        if (!g_stage) { g_stage_bytes = 0; JPEGB200_batchDestroy(b); pthread_mutex_unlock(&g_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
-    }
-    JPEGB200_batchSetOutput(b, 0, g_stage, 0);
+    const int64_t fbytes = JPEGB200_batchOutputBytes(b, 0, &fpitch);
+    size_t stage_bytes = 0;
+    uint8_t *stage = stage_get((size_t)fbytes + 64, &stage_bytes);
+    if (!stage) { JPEGB200_batchDestroy(b); pthread_mutex_unlock(ctx_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
+    JPEGB200_batchSetOutput(b, 0, stage, 0);
     int32_t dst_status = 0;
-    int ok = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, 0) && JPEGB200_batchDownload(b);
-    int wrc = ok ? JPEGB200_batchWait(b, &dst_status) : 0;
-    extern int JPEGB200_batchErrMcu(JPEGB200_BATCH * b, int i);
-    int err_mcu = wrc ? JPEGB200_batchErrMcu(b, 0) : -1;
+    const int ok = JPEGB200_batchUpload(b) && JPEGB200_batchDecode(b, 0) && JPEGB200_batchDownload(b);
+    const int wrc = ok ? JPEGB200_batchWait(b, &dst_status) : 0;
+    const int err_mcu = wrc ? JPEGB200_batchErrMcu(b, 0) : -1;
     JPEGB200_batchDestroy(b);
-    if (!wrc) { pthread_mutex_unlock(&g_lock); p->iError = JPEG_ERROR_MEMORY; return 0; }
-    const int decode_failed = (dst_status != JPEG_SUCCESS);
+    pthread_mutex_unlock(ctx_lock);
+    if (!wrc) { stage_put(stage, stage_bytes); p->iError = JPEG_ERROR_MEMORY; return 0; }
+    int decode_failed = (dst_status != JPEG_SUCCESS);
+    int last_mcu = (decode_failed && err_mcu >= 0) ? err_mcu : -1;   /* MCUs after the failing one are never delivered */
+    {   /* a crop that reaches below the image (JPEG_setCropArea does not prevent it for small images) makes the reference walk
+         * MCU rows that do not exist: it runs out of data and fails with JPEG_DECODE_ERROR after the real rows were delivered */
+        int fmw, fmh;
+        mcu_size(p->ucSubSample, &fmw, &fmh);
+        const int cols0 = (p->iWidth + fmw - 1) / fmw, rows0 = (p->iHeight + fmh - 1) / fmh;
+        if ((p->iCropY + p->iCropCY + fmh - 1) / fmh > rows0) {
+            decode_failed = 1;
+            if (last_mcu < 0 || last_mcu > rows0 * cols0 - 1) last_mcu = rows0 * cols0 - 1;
+        }
+    }
 
-    /* ---- delivery: geometry of DecodeJPEG (jpeg.inl:5008-5127, :5300-5336) ---- */
+    /* ---- delivery (no lock held: the callback may call back into the library) ---- */
     int mw, mh;
     mcu_size(p->ucSubSample, &mw, &mh);
-    const int cx = (p->iWidth + mw - 1) / mw;
-    const int cy = (p->iCropY + p->iCropCY + mh - 1) / mh;
+    const int cols = (p->iWidth + mw - 1) / mw;
     mw >>= shift; mh >>= shift;
     const int bpp = bits_per_pixel(pt);
     const int bypp = bpp >= 8 ? bpp / 8 : 1;
-    const uint8_t *frame = g_stage;
     const int frame_pitch = (int)fpitch;
-    int per_cb = MAX_BUFFERED_PIXELS / (mw * mh);
-    if (pt == RGB8888) per_cb /= 2;
-    int dma_size = 0, dma_off = 0;
-    if (pt == EIGHT_BIT_GRAYSCALE) per_cb *= 2;
-    if (per_cb > cx) per_cb = cx;
-    if (per_cb > p->iMaxMCUs) per_cb = p->iMaxMCUs;
-    else if (options & JPEG_USES_DMA) { per_cb /= 2; dma_size = MAX_BUFFERED_PIXELS / 2; }
-    if (dither) per_cb = cx;
-    if (p->iCropCX != p->iWidth && per_cb * mw > p->iCropCX) per_cb = p->iCropCX / mw;
-    if (per_cb < 1) per_cb = 1;
-    const int adj = (1 << shift) - 1;
-    const int cur_w = (p->iWidth + adj) >> shift, cur_h = (p->iHeight + adj) >> shift;
-    /* pixel staging the callbacks see: same size as the reference's usPixels (2048 px + slack), 16-byte aligned */
-    uint16_t pixbuf_raw[MAX_BUFFERED_PIXELS + 64];
-    uint16_t *pixbuf = (uint16_t *)(((uintptr_t)pixbuf_raw + 15) & ~(uintptr_t)15);
-    JPEGDRAW jd;
-    memset(&jd, 0, sizeof(jd));
-    jd.iBpp = bpp;
-    jd.iHeight = mh;
-    int keep_going = 1;
-    const int sse_mcu_writes = p->pFramebuffer && p->ucArithMode == JPEG_ARITH_SSE2 && shift == 0 && p->ucNumComponents == 3 &&
-                               pt <= RGB8888 && (p->ucSubSample == 0x11 || p->ucSubSample == 0x22);
-    const int dpitch = dither ? (cx * mw * bpp + 7) / 8 : 0;
-    for (int y = 0; y < cy && keep_going; y++) {
-        const int skip_row = (y * mh < p->iCropY);
-        int pitch_px, xoff = 0;
-        uint8_t *rowbase = NULL;
-        jd.x = p->iXOffset;
-        if (p->pFramebuffer) {
-            pitch_px = p->iCropCX;
-            const int ty = y * mh - p->iCropY;
-            rowbase = (uint8_t *)p->pFramebuffer + (ptrdiff_t)ty * pitch_px * bypp;
-        } else {
-            pitch_px = per_cb * mw;
-        }
-        for (int x = 0; x < cx && keep_going; x++) {
-            const int skip = skip_row || x * mw < p->iCropX || x * mw > p->iCropX + p->iCropCX;
-            const int mcu_index = y * cx + x;
-            if (decode_failed && err_mcu >= 0 && mcu_index > err_mcu) { keep_going = 0; break; } /* loops stop after the failing MCU (:5128) */
-            if (!skip) {
-                if (dither) {
-                    /* packed rows come from the dither kernel; nothing to gather per MCU */
-                } else if (p->pFramebuffer) {
-                    int rows = mh;
-                    const uint8_t *src = frame + (size_t)y * mh * frame_pitch + (size_t)x * mw * bypp;
-                    if (sse_mcu_writes) {
-                        /* the reference's SSE2 colour paths store whole MCUs with no edge clipping (jpeg.inl:3409, :4006):
-                         * the right-edge MCU runs on into the start of the next line (and is partly overwritten later, in
-                         * MCU order), the bottom MCU row continues below the image -- which is why the caller's buffer
-                         * must cover whole MCU rows (c_cmdline/main.c:180).  Same writes, same order; clipped only at the
-                         * end of that MCU-row-aligned buffer. */
-                        const size_t fb_px = (size_t)pitch_px * (size_t)(cy * mh - p->iCropY);
-                        for (int r = 0; r < rows; r++) {
-                            const size_t at = (size_t)(y * mh - p->iCropY + r) * pitch_px + xoff;
-                            size_t n = (size_t)mw;
-                            if (at >= fb_px) break;
-                            if (at + n > fb_px) n = fb_px - at;
-                            memcpy((uint8_t *)p->pFramebuffer + at * bypp, src + (size_t)r * frame_pitch, n * bypp);
-                        }
-                    } else {
-                        if (y * mh + rows > cur_h) rows = cur_h - y * mh; /* scalar paths clip at the image edges (:3520-3524, :4311-4332) */
-                        if (rows > 0) {
-                            int cols = pitch_px - xoff; if (cols > mw) cols = mw;
-                            for (int r = 0; r < rows && cols > 0; r++)
-                                memcpy(rowbase + ((size_t)r * pitch_px + xoff) * bypp, src + (size_t)r * frame_pitch, (size_t)cols * bypp);
-                        }
-                    }
-                } else {
-                    uint8_t *dst = (uint8_t *)(pixbuf + dma_off) + (size_t)xoff * bypp;
-                    copy_mcu(dst, pitch_px * bypp, frame, frame_pitch, x, y, mw, mh, bypp, pitch_px > 0 ? mw : 0);
-                }
-                xoff += mw;
+    if (p->pFramebuffer) {
+        deliver_framebuffer(p, stage, frame_pitch, bypp, last_mcu);
+    } else {
+        JDDeliveryGeom g;
+        geom_of(p, &g);
+        const int n_items = jd_delivery_schedule(&g, NULL, 0);
+        JDDrawItem *items = (JDDrawItem *)malloc(sizeof(JDDrawItem) * (size_t)(n_items > 0 ? n_items : 1));
+        if (!items) { stage_put(stage, stage_bytes); p->iError = JPEG_ERROR_MEMORY; return 0; }
+        jd_delivery_schedule(&g, items, n_items);
+        /* the pixel block the callback sees: same size as the reference's usPixels (2048 px + slack), 16-byte aligned; with
+         * JPEG_USES_DMA the two halves alternate (:5073-5076, :5326) */
+        uint16_t pixbuf_raw[MAX_BUFFERED_PIXELS + 64];
+        uint16_t *pixbuf = (uint16_t *)(((uintptr_t)pixbuf_raw + 15) & ~(uintptr_t)15);
+        const int dpitch = dither ? (cols * mw * bpp + 7) / 8 : 0;
+        JPEGDRAW jd;
+        memset(&jd, 0, sizeof(jd));
+        jd.iBpp = bpp;
+        jd.pUser = p->pUser;
+        for (int i = 0; i < n_items; i++) {
+            const JDDrawItem *it = &items[i];
+            /* a decode error ends the MCU loops after the failing MCU (:5128): a group is delivered only if its last MCU was reached */
+            if (last_mcu >= 0 && it->mcu_row * cols + it->mcu_col0 + it->n_mcus - 1 > last_mcu) break;
+            if (dither) {
+                /* packed rows come from the dither kernel: one whole MCU row per call, in the caller's dither buffer */
+                memcpy(p->pDitherBuffer, stage + (size_t)it->mcu_row * mh * frame_pitch, (size_t)dpitch * mh);
+                jd.pPixels = (uint16_t *)p->pDitherBuffer;
+            } else {
+                uint8_t *dst = (uint8_t *)(pixbuf + (it->buf ? MAX_BUFFERED_PIXELS / 2 : 0));
+                const uint8_t *src = stage + (size_t)it->mcu_row * mh * frame_pitch + (size_t)it->mcu_col0 * mw * bypp;
+                int px = it->n_mcus * mw;
+                if (px > it->w) px = it->w;
+                for (int l = 0; l < mh && px > 0; l++) memcpy(dst + (size_t)l * it->w * bypp, src + (size_t)l * frame_pitch, (size_t)px * bypp);
+                jd.pPixels = (uint16_t *)dst;
             }
-            if (!p->pFramebuffer && (xoff == pitch_px || x == cx - 1) && !skip) {
-                jd.iWidth = jd.iWidthUsed = pitch_px;
-                jd.pUser = p->pUser;
-                if ((jd.x - p->iXOffset) + pitch_px > cur_w) jd.iWidthUsed = cur_w - (jd.x - p->iXOffset);
-                else if ((jd.x - p->iXOffset) + pitch_px > p->iCropCX) jd.iWidthUsed = p->iCropCX - (jd.x - p->iXOffset);
-                jd.y = p->iYOffset + y * mh - p->iCropY;
-                if ((jd.y - p->iYOffset + mh) > cur_h) jd.iHeight = cur_h - (jd.y - p->iYOffset);
-                if (dither) {
-                    memcpy(p->pDitherBuffer, frame + (size_t)y * mh * frame_pitch, (size_t)dpitch * mh);
-                    jd.pPixels = (uint16_t *)p->pDitherBuffer;
-                } else jd.pPixels = pixbuf + dma_off;
-                keep_going = (*p->pfnDraw)(&jd);
-                dma_off ^= dma_size;
-                jd.x += pitch_px;
-                if (p->iCropCX != cx * mw && (pitch_px + jd.x) > (p->iCropX + p->iCropCX)) pitch_px = p->iCropCX - (jd.x - p->iXOffset);
-                else if ((cx - 1 - x) < per_cb) pitch_px = (cx - 1 - x) * mw;
-                xoff = 0;
-                if (pitch_px & (mw - 1)) pitch_px = (pitch_px + (mw - 1)) & ~(mw - 1);
-                if (pitch_px < 0) pitch_px = 0;
-            }
+            jd.x = it->x; jd.y = it->y; jd.iWidth = it->w; jd.iWidthUsed = it->w_used; jd.iHeight = it->h;
+            if (!(*p->pfnDraw)(&jd)) break;
         }
+        free(items);
     }
-    pthread_mutex_unlock(&g_lock);
+    stage_put(stage, stage_bytes);
     if (decode_failed) { p->iError = JPEG_DECODE_ERROR; return 0; }
     return 1;
 }

@@ -179,6 +179,14 @@ extern "C" int JPEGB200_deviceCount(void)
     return n;
 }
 
+/* the calling thread's current CUDA device (-1 without CUDA) */
+extern "C" int JPEGB200_currentDevice(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+
 extern "C" JPEGB200_CTX *JPEGB200_create(int device, int arith_mode)
 {
     int n = 0;

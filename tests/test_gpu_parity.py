@@ -554,3 +554,44 @@ def test_two_threads_two_contexts(ctxs):
     [x.start() for x in th]
     [x.join() for x in th]
     assert not errs, errs
+
+
+@pytest.mark.parametrize("mode,arith", MODES)
+def test_crop_times_scale_callbacks_and_framebuffer(mode, arith):
+    """setCropArea combined with 1/2, 1/4, 1/8 (the reference compares scaled MCU positions with the unscaled
+    crop rectangle) through the callback and into a framebuffer: same callback sequence, same pixels as the live reference
+    (src/jpeg.inl:5111-5137, :5114-5124); the geometry alone is pinned on the CPU in tests/test_host.py."""
+    ref = _ref(mode)
+    if ref is None:
+        pytest.skip("oracle/_ref not present")
+    for name, crops in (("tulips", [(96, 64, 256, 192), (50, 50, 125, 170), (0, 0, 64, 64)]), ("zebra", [(32, 16, 128, 96)])):
+        data = T.image(name)
+        for crop in crops:
+            for pt in (0, 2, 3):
+                for opt in (0, 2, 4, 8):
+                    rc_r, err_r, img_r, log_r = ref.decode_cb(data, pt, opt, crop=crop)
+                    j = J.JPEGDEC(); draw, log, blocks = _collect(j, pt, opt)
+                    assert j.openRAM(data, draw); j.setArithMode(arith); j.setPixelType(pt); j.setCropArea(*crop)
+                    assert j.decode(0, 0, opt) == rc_r == 1
+                    assert log == [tuple(r[:6]) for r in log_r], (name, crop, pt, opt)
+                    out = np.zeros_like(img_r)
+                    for (x, y, w, h, wu, bpp), buf in zip(log, blocks):
+                        a = np.frombuffer(buf, dtype=np.uint8).reshape(h, w * bpp // 8)
+                        bw, x0 = wu * bpp // 8, x * bpp // 8
+                        ys = slice(max(y, 0), min(y + h, out.shape[0]))
+                        if x0 < 0 or ys.start >= ys.stop:
+                            continue
+                        out[ys, x0:x0 + bw] = a[ys.start - y:ys.stop - y, :bw][:, :out.shape[1] - x0]
+                    assert np.array_equal(out, img_r), (name, crop, pt, opt)
+                    j.close()
+                    if opt == 0 or arith == 1:
+                        # framebuffer + crop (pitch = crop width, :5116); at full scale in the SSE2 build the reference's colour
+                        # paths store whole MCUs past the right edge -- the same stores are made here
+                        rc_f, err_f, fb_r = ref.decode_fb(data, pt, opt, crop=crop)
+                        j = J.JPEGDEC(); assert j.openRAM(data); j.setArithMode(arith); j.setPixelType(pt); j.setCropArea(*crop)
+                        fb = np.zeros_like(fb_r); j.setFramebuffer(fb)
+                        assert j.decode(0, 0, opt) == rc_f == 1
+                        cx, cy, cw, ch = j.getCropArea()
+                        nvis = cw * (ch >> {0: 0, 2: 1, 4: 2, 8: 3}[opt]) * T.bpp_of(pt) // 8
+                        assert np.array_equal(fb[:nvis], fb_r[:nvis]), (name, crop, pt, opt, "framebuffer")
+                        j.close()

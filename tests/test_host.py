@@ -111,3 +111,68 @@ def test_table_blob_roundtrip_host_side():
     assert blob[:8].tobytes() != b"\0" * 8
     # standard Huffman tables in both files -> same LUT hash, different quant
     assert (blob[:8] == blob2[:8]).all() == (blob[16:16 + 12800] == blob2[16:16 + 12800]).all()
+
+
+class _Geom(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "crop_x", "crop_y", "crop_w", "crop_h", "x_off", "y_off",
+                                       "subsample", "pixel_type", "options", "max_mcus")]
+
+
+class _Item(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("mcu_row", "mcu_col0", "n_mcus", "x", "y", "w", "h", "w_used", "buf")]
+
+
+def _schedule(geom):
+    L = J.lib()
+    L.jd_delivery_schedule.argtypes = [C.POINTER(_Geom), C.POINTER(_Item), C.c_int]
+    n = L.jd_delivery_schedule(C.byref(geom), None, 0)
+    items = (_Item * max(n, 1))()
+    assert L.jd_delivery_schedule(C.byref(geom), items, n) == n
+    return [(it.x, it.y, it.w, it.h, it.w_used, it.buf) for it in items[:n]]
+
+
+def test_delivery_schedule_equals_the_reference_callback_sequence():
+    """The draw-callback geometry (jd_api.c jd_delivery_schedule: which MCUs go into which call, x / y / iWidth / iHeight /
+    iWidthUsed, the JPEG_USES_DMA half) against the callback log of the compiled reference, WITHOUT a GPU: every fixture
+    sampling x pixel type x scale x decode offset x setMaxOutputSize x crop -- including crop x scale, where the reference
+    compares scaled MCU positions with the unscaled crop rectangle (fewer rows at 1/2, no callbacks at 1/4
+    and 1/8); reproduced literally (src/jpeg.inl:5062-5084, :5111, :5135, :5300-5336)."""
+    from oracle import refdrv
+    if not refdrv.available("sse"):
+        pytest.skip("oracle/_ref not built here")
+    ref = refdrv.Ref("sse")
+    rng = np.random.default_rng(5)
+    checked = with_crop_scaled = 0
+    for name in ("tulips", "zebra", "ncc1701", "sciopero", "lange", "croptest", "octocat_small"):
+        data = T.image(name)
+        j = J.JPEGDEC()
+        assert j.openRAM(data)
+        w, h, sub = j.getWidth(), j.getHeight(), j.getSubSample()
+        crops = [None, (50, 50, 125, 170), (96, 64, 256, 192), (0, 0, 64, 64), (16, 32, 100, 40)]
+        crops += [(int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(1, w)), int(rng.integers(1, h))) for _ in range(4)]
+        for crop in crops:
+            if crop is not None and (crop[0] + 16 >= w or crop[1] + 16 >= h):
+                continue
+            for pt in (0, 2, 3):
+                for opt in (0, 2, 4, 8, J.JPEG_USES_DMA, 2 | J.JPEG_USES_DMA):
+                    for (xo, yo, maxm) in ((0, 0, 0), (7, 3, 0), (0, 0, 3)):
+                        if crop is not None and (xo or maxm) and opt:
+                            continue
+                        rc, err, img, log = ref.decode_cb(data, pt, opt, xoff=xo, yoff=yo, crop=crop, max_mcus=maxm)
+                        assert rc in (0, 1)     # 0: the crop reaches below the image and the reference runs out of data
+                        j2 = J.JPEGDEC()
+                        assert j2.openRAM(data)
+                        if crop is not None:
+                            j2.setCropArea(*crop)
+                        cx, cy, cw, ch = j2.getCropArea()
+                        g = _Geom(w, h, cx, cy, cw, ch, xo, yo, sub, pt, opt, maxm if maxm else 1000)
+                        got = _schedule(g)
+                        want = [(r[0], r[1], r[2], r[3], r[4], r[6]) for r in log]
+                        if rc == 0:
+                            assert err == J.JPEG_DECODE_ERROR and cy + ch > h
+                            got = got[:len(want)]     # the calls made before the reference failed
+                        assert got == want, (name, crop, pt, opt, xo, yo, maxm, got[:3], want[:3])
+                        checked += 1
+                        with_crop_scaled += int(crop is not None and (opt & 14) != 0)
+        j.close()
+    assert checked > 1500 and with_crop_scaled > 300
