@@ -161,6 +161,8 @@ struct JPEGB200_BATCH {
     DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
     DevBuf<int32_t> d_cdcs, d_cpe;
     uint32_t h_changed;
+    bool chunk_iterate;            /* restart-free scans: iterate the entry states with a host check (fallback mode) */
+    int decode_flags;
     cudaEvent_t ev[JPEGB200_NUM_TIMINGS + 2];
     bool have_ev;
     float ms[JPEGB200_NUM_TIMINGS];
@@ -171,6 +173,7 @@ struct JPEGB200_BATCH {
 static char *ctx_err() { return g_err; }
 
 #define JD_EVENT_CAP (1u << 20)
+#define JD_CHUNK_PASSES 6     /* restart-free scans: entry-state passes per decode (the last one verifies) */
 
 extern "C" int JPEGB200_deviceCount(void)
 {
@@ -446,7 +449,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
     b->dither_bits = (pixel_type == FOUR_BIT_DITHERED) ? 4 : (pixel_type == TWO_BIT_DITHERED) ? 2 : (pixel_type == ONE_BIT_DITHERED) ? 1 : 0;
     b->stream = nullptr;
     b->descs_dl = nullptr; b->descs_dl_bytes = 0; b->downloaded = false; b->h_counters = nullptr;
-    b->nchunks = 0;
+    b->nchunks = 0; b->chunk_iterate = false; b->decode_flags = 0;
     b->uploaded = false; b->out_device = false; b->arena_owned = false; b->have_ev = false;
     memset(b->ms, 0, sizeof(b->ms));
     memset(b->counters, 0, sizeof(b->counters));
@@ -826,6 +829,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     cudaStream_t st = b->stream;
     const int n = b->n;
     b->out_device = (flags & JPEGB200_OUT_DEVICE) != 0;
+    b->decode_flags = flags;
     int launches = 0;
     /* output placement */
     bool user_dev_out = false;
@@ -955,14 +959,23 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         launches++;
         uint32_t *Ein = b->d_E0.p, *Eout = b->d_E1.p;
         int passes = 0;
+        /* The entry states reach their fix point in 2-4 passes on real streams (a chunk re-synchronises well inside its 512
+         * bytes).  Normal mode: JD_CHUNK_PASSES passes back to back, the last one only verifying (it raises a flag if an entry
+         * state still moved) -- no host round trip, so jobs of JPEGB200_decodeBatch stay in flight; batchWait re-runs the job
+         * in the iterating mode below if the flag came back set. */
+        static int fixed_passes = -1;   /* JPEGDEC_B200_CHUNK_PASSES=n: test hook (n = 1 forces the fallback) */
+        if (fixed_passes < 0) { const char *e = getenv("JPEGDEC_B200_CHUNK_PASSES"); fixed_passes = (e && atoi(e) > 0) ? atoi(e) : JD_CHUNK_PASSES; }
+        const int fixed = b->chunk_iterate ? 0 : fixed_passes;
         for (;;) {
-            for (int k = 0; k < 3; k++) {
-                if (k == 2) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
+            const int burst = fixed ? fixed : 3;
+            for (int k = 0; k < burst; k++) {
+                if (k == burst - 1) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
                 ca.E_in = Ein; ca.E_out = Eout;
                 jdk_chunk_parse<<<gc, 128, 0, st>>>(ca);
                 launches++; passes++;
                 uint32_t *tmp = Ein; Ein = Eout; Eout = tmp;
             }
+            if (fixed) break;
             CK(cudaMemcpyAsync(&b->h_changed, b->d_counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (!b->h_changed || passes > (int)b->nchunks + 8) break;
@@ -1098,6 +1111,16 @@ extern "C" int JPEGB200_batchWait(JPEGB200_BATCH *b, int32_t *status)
     CK(cudaSetDevice(b->ctx->device));
     CK(cudaStreamSynchronize(b->stream));
     CK(cudaGetLastError());
+    if (b->nchunks && b->downloaded && !b->chunk_iterate && b->h_counters[2] != 0u) {
+        /* a restart-free scan whose chunk entry states had not settled after the fixed passes: decode the job again,
+         * iterating to the fix point */
+        b->chunk_iterate = true;
+        const int again = JPEGB200_batchDecode(b, b->decode_flags) && JPEGB200_batchDownload(b);
+        b->chunk_iterate = false;
+        if (!again) return 0;
+        CK(cudaStreamSynchronize(b->stream));
+        CK(cudaGetLastError());
+    }
     int all_ok = 1;
     /* more window-truncation events than the event buffer holds: some coefficients of this job were not patched, so its
      * pixels may differ from the reference's -- report that instead of returning them as good */

@@ -392,7 +392,7 @@ def test_seeded_random_sweep_on_the_gpu(ctxs):
                     assert rc == 1 and np.array_equal(o, img), (k, mode, pt, opt)
 
 
-def test_raw_reader_entropy_stage_equals_the_default():
+def test_pipeline_switches_give_the_default_result():
     """JPEGDEC_B200_ENTROPY=raw (the entropy kernel un-stuffs inside its bit reader) against the default pipeline (jdk_unstuff_segs
     first, plain word reader), in a subprocess because the switch is read once: same status, same pixels, same event counts."""
     import os
@@ -414,15 +414,16 @@ for pt in (0, 2, 3):
         print(pt, opt, st, [zlib.crc32(o.tobytes()) if o is not None else None for o in outs], cnt["events"], cnt["event_candidates"])
 ''' % T.ROOT
     res = []
-    for mode in ("", "raw"):
+    # third run: restart-free scans with a single entry-state pass, which forces batchWait's iterate-to-the-fix-point fallback
+    for extra in ({}, {"JPEGDEC_B200_ENTROPY": "raw"}, {"JPEGDEC_B200_CHUNK_PASSES": "1"}):
         env = dict(os.environ)
         env.pop("JPEGDEC_B200_ENTROPY", None)
-        if mode:
-            env["JPEGDEC_B200_ENTROPY"] = mode
+        env.pop("JPEGDEC_B200_CHUNK_PASSES", None)
+        env.update(extra)
         r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=900)
         assert r.returncode == 0, r.stdout[-2000:]
         res.append(r.stdout)
-    assert res[0] == res[1] and len(res[0].splitlines()) == 12
+    assert res[0] == res[1] == res[2] and len(res[0].splitlines()) == 12
 
 
 # ---------------------------------------------------------------------------------------------------------------------
