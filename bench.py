@@ -429,7 +429,7 @@ def main():
     b.close()
 
     # ---- one call per step, device outputs (verify_all workloads): JPEGB200_decodeBatch cuts the rank's slice into jobs ----
-    one_call = None
+    dev_one_call = None
     if wl.get("verify_all"):
         per = oh0 * row_bytes
         stride = (per + 255) & ~255
@@ -456,7 +456,7 @@ def main():
         tot = torch.tensor([good, n_img], dtype=torch.int64, device="cuda")
         if world > 1:
             dist.all_reduce(tot)
-        one_call = {"value": world * mp_per_step_rank / (oc_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": oc_ms, "jobs_per_call": njobs,
+        dev_one_call = {"value": world * mp_per_step_rank / (oc_ms / 1e3), "unit": "Mpixels/s", "ms_per_step": oc_ms, "jobs_per_call": njobs,
                     "h2d_bytes_per_step": int(c2["h2d_bytes"]), "verified": int(tot[0].item()), "images": int(tot[1].item()),
                     "note": "ONE JPEGB200_decodeBatch(JPEGB200_OUT_DEVICE) call per rank and step: compressed files in pinned host memory "
                             "(H2D inside the timed region), pixels written to the caller's device buffer; wall clock, max over ranks"}
@@ -550,7 +550,7 @@ def main():
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
             "stages_ms": {k: v / K for k, v in stage.items()}, "wall_ms_per_step": wall_ms_step,
             "entropy_symbol_stage_ms": entropy_ms, "quirk_events_per_step": int(cnt["events"]),
-            "shared_table_hits": table_hits, "parity_spot_check": parity, "parity_all": parity_all, "one_call_device": one_call,
+            "shared_table_hits": table_hits, "parity_spot_check": parity, "parity_all": parity_all, "one_call_device": dev_one_call,
             "step_roofline": step_roofline, "numa": numa,
             "entropy_pipeline": os.environ.get("JPEGDEC_B200_ENTROPY", "clean (jdk_unstuff_segs + word reader)")}
         try:   # the entropy stage is reported as compressed MB/s; scaled workloads also as output pixels
@@ -562,7 +562,7 @@ def main():
                 line["output_mpixels_per_s"] = value * (ow * oh) / float(wl["w"] * wl["h"])
         except Exception:
             pass
-        print(json.dumps(line))
+        print(json.dumps(line, default=str))
     return 0
 
 

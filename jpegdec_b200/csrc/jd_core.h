@@ -14,6 +14,7 @@
 #define JD_CORE_H
 
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define JD_HD __host__ __device__ __forceinline__
@@ -473,30 +474,75 @@ JD_HD int jd_extend_top(uint32_t x, uint32_t s)
     return (int)((mag ^ neg) - neg);
 }
 
+/* 16 bytes of the un-stuffed stream */
+typedef struct { uint32_t x, y, z, w; } jd_u128;
+JD_HD jd_u128 jd_ld128(const uint8_t *p)
+{
+    jd_u128 r;
+#ifdef __CUDA_ARCH__
+    const uint4 v = *reinterpret_cast<const uint4 *>(p);
+    r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+#else
+    memcpy(&r, p, 16);
+#endif
+    return r;
+}
+
+/* Table reads of the entropy walk.  On the device both tables live in the CTA's shared memory (jdk_entropy): reading them
+ * through 32-bit shared-window addresses keeps the generic-to-shared conversion out of the per-symbol loop. */
+#ifdef __CUDA_ARCH__
+struct JDTab16 {
+    uint32_t base;
+    /* the empty asm makes the address opaque: it stays in a register instead of being re-derived in the loop */
+    __device__ __forceinline__ JDTab16(const uint16_t *p) : base((uint32_t)__cvta_generic_to_shared(p)) { asm volatile("" : "+r"(base)); }
+    __device__ __forceinline__ uint32_t at(uint32_t i) const { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * i)); return v; }
+};
+struct JDTab32 {
+    uint32_t base;
+    __device__ __forceinline__ JDTab32(const uint32_t *p) : base((uint32_t)__cvta_generic_to_shared(p)) { asm volatile("" : "+r"(base)); }
+    __device__ __forceinline__ uint32_t at(uint32_t i) const { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * i)); return v; }
+};
+#else
+struct JDTab16 { const uint16_t *p; JDTab16(const uint16_t *q) : p(q) {} uint32_t at(uint32_t i) const { return p[i]; } };
+struct JDTab32 { const uint32_t *p; JDTab32(const uint32_t *q) : p(q) {} uint32_t at(uint32_t i) const { return p[i]; } };
+#endif
+
 template <typename EventSink, int MODE = JD_MODE_BASELINE, bool CLEAN = false>
 JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_ENTRIES, shared/global */,
                              const uint32_t *tposw /* 64 words: jd_tposw(JD_TPOS[k]), shared/global */,
                              jd_u64 *blk_hdr /* nmcu*bpm headers */, uint16_t *rec /* this segment's records */,
                              EventSink &sink, JDSegOut &out)
 {
-    /* ---- bit reader: aligned 32-bit words, one word prefetched ahead of use ---- */
+    /* ---- bit reader.  Raw input: aligned 32-bit words, one word prefetched ahead of use, un-stuffing on the fly.
+     * CLEAN input: 16-byte chunks (the segment starts 16-byte aligned and ends in zeros), one chunk prefetched ahead:
+     * a lane touches global memory once per ~24 symbols and the data is on its way ~24 symbols before it is needed
+     * (with 4-byte loads the walk stalled on L2 / DRAM latency: 53 % of the stall samples of the round-2 first build). ---- */
     const uint32_t *words = (const uint32_t *)in.data;
     const uint32_t endw = (in.end + 3u) >> 2;    /* first word index past the data */
     uint32_t wi = in.start >> 2;                 /* index of the next word to consume */
-    uint32_t wnext = (wi < endw) ? words[wi] : 0u;
+    uint32_t wnext = (!CLEAN && wi < endw) ? words[wi] : 0u;
     uint32_t skip = CLEAN ? 0u : (in.start & 3u); /* bytes of the first word that precede the segment */
     uint32_t ffp = 0;                            /* previous byte was 0xFF (stuffing / marker undecided) */
     uint32_t eos = 0;                            /* marker or end of data reached: zeros from here on */
     jd_u64 bb = 0;                               /* bit buffer, MSB first */
     int nb = 0;                                  /* valid bits in bb */
+    const uint8_t *const cbase = in.data + in.start;
+    const uint32_t nchunk = CLEAN ? ((in.end - in.start + 15u) >> 4) : 0u;
+    const jd_u128 zero128 = {0u, 0u, 0u, 0u};
+    jd_u128 cq = (nchunk > 0u) ? jd_ld128(cbase) : zero128;          /* words not yet consumed, cq.x first */
+    jd_u128 cn = (nchunk > 1u) ? jd_ld128(cbase + 16) : zero128;     /* the chunk after it */
+    uint32_t cleft = 4u, ci = 1u;                                    /* words left in cq; index of the chunk in cn */
 
     /* keeps >= 32 valid bits in bb */
     auto refill = [&]() {
         if (CLEAN) {
             if (nb <= 32) {
-                const uint32_t w = wnext;
-                wi++;
-                wnext = (wi < endw) ? words[wi] : 0u;
+                const uint32_t w = cq.x;
+                cq.x = cq.y; cq.y = cq.z; cq.z = cq.w;
+                if (--cleft == 0u) {
+                    cq = cn; cleft = 4u; ci++;
+                    cn = (ci < nchunk) ? jd_ld128(cbase + 16u * ci) : zero128;
+                }
                 bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
                 nb += 32;
             }
@@ -536,10 +582,20 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     int pred0 = 0, pred1 = 0, pred2 = 0;
     uint32_t jw = JD_JW_INIT;                    /* window-phase candidates (six nibbles) */
     uint32_t p7 = 0;                             /* bits consumed in this segment, mod 8 */
-    uint16_t *rp = rec;                          /* next record slot */
-    uint16_t *const rend = rec + in.rec_cap;
+    uint32_t ro = 0;                             /* next record slot (index into rec) */
+#ifdef __CUDA_ARCH__
+    /* one opaque register pair for the record base (else it is re-derived from its parts at every store); records are
+     * written with st.global through it */
+    size_t rec_g = __cvta_generic_to_global(rec);
+    asm volatile("" : "+l"(rec_g));
+#define JD_REC_ST(i, val) asm volatile("st.global.u16 [%0], %1;" ::"l"(rec_g + 2ull * (i)), "h"((uint16_t)(val)) : "memory")
+#else
+#define JD_REC_ST(i, val) (rec[(i)] = (uint16_t)(val))
+#endif
     int err = -1;
     bool last_was_eob = true;
+    const JDTab16 T(lut);
+    const JDTab32 TP(tposw);
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
     const uint32_t nblk_total = in.nmcu * in.bpm;
@@ -551,7 +607,6 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     }
     const uint32_t bsh_end = 4u * in.bpm;
     uint32_t bsh = 0;                            /* 4 * (block index inside the MCU) */
-    const uint32_t rec_lo = (uint32_t)(uintptr_t)rec;
     constexpr uint32_t LIMIT = (MODE == JD_MODE_STORE_LOW) ? 5u : 64u;
     uint32_t b = 0;                              /* blocks finished */
 
@@ -562,9 +617,8 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         jw = jd_jw_ckpt(jw);                     /* R1 at block entry (also the previous block's R4) */
         int dcval;
         {
-            const uint16_t *tdc = lut + JD_LUT_DC((cur >> 2) & 1u);
             const uint32_t w16 = (uint32_t)(bb >> 48);
-            const uint32_t e = tdc[(w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)];
+            const uint32_t e = T.at(JD_LUT_DC((cur >> 2) & 1u) + ((w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)));
             if (e == 0u) { err = JD_SEG_BADCODE; break; }
             const uint32_t len = e >> 8, s = e & 15u;
             bb <<= len;
@@ -586,36 +640,40 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             pred2 = (comp >= 2u) ? pv : pred2;
             dcval = pv;
         }
-        uint16_t *const rec0 = rp;               /* this block's first record */
+        const uint32_t r0 = ro;                  /* this block's first record */
         uint32_t bflags = 0, bigm = 0;           /* OR of the tposw words; JD_ACF_RARE once the block's records are pairs */
         if (MODE != JD_MODE_DC_SCAN) {
-            if (MODE != JD_MODE_PARSE_AC && (uint32_t)(rend - rp) < JD_REC_BLOCK_MAX) { err = JD_SEG_OVERFLOW; break; }
+            if (MODE != JD_MODE_PARSE_AC && in.rec_cap - ro < JD_REC_BLOCK_MAX) { err = JD_SEG_OVERFLOW; break; }
             /* ---- AC symbols (jpeg.inl:2225-2264) ---- */
-            const uint16_t *tac = lut + JD_LUT_ACF(cur >> 3);
+            const uint32_t tacf = JD_LUT_ACF(cur >> 3);
             uint32_t k = 1;
             do {
                 refill();
                 jw = jd_jw_ckpt(jw);             /* R3 at the loop top (also the previous symbol's R4) */
                 const uint32_t hi = (uint32_t)(bb >> 32);
-                uint32_t e = tac[hi >> 22];
+                uint32_t e = T.at(tacf + (hi >> 22));
                 uint32_t len = (e >> 8) & 31u;
                 if (len == 0u) {
                     /* code longer than 10 bits (first 6 bits are ones) or invalid */
-                    e = (hi >= 0xFC000000u) ? lut[JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)] : 0u;
+                    e = (hi >= 0xFC000000u) ? T.at(JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)) : 0u;
                     if (e == 0u) { err = JD_SEG_BADCODE; break; }
                     len = e >> 8;
                     e |= JD_ACF_RARE;
                 }
                 const uint32_t rs = e & 0xFFu, s = rs & 15u;
-                bb <<= len;
-                const uint32_t x = (uint32_t)(bb >> 32);
+                /* the S bits after the code, at the top of a word; then one shift past code + extra bits */
+#ifdef __CUDA_ARCH__
+                const uint32_t x = __funnelshift_l((uint32_t)bb, hi, len);
+#else
+                const uint32_t x = (uint32_t)((bb << len) >> 32);
+#endif
                 const int v = jd_extend_top(x, s);
-                bb <<= s;
+                bb <<= (len + s);
                 nb -= (int)(len + s);
                 k = (rs == 0u) ? 128u : k + (rs >> 4);   /* EOB (:2241-2244) ends the block */
                 if (MODE != JD_MODE_PARSE_AC && s != 0u && k < LIMIT) {
                     /* stored coefficient (jpeg.inl:2247-2256) */
-                    const uint32_t tw = tposw[k];
+                    const uint32_t tw = TP.at(k);
                     bflags |= tw;
                     if (((e | bigm) & JD_ACF_RARE) != 0u) {
                         if (s > 11u) { err = JD_SEG_BADSIZE; break; }
@@ -638,7 +696,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                                     ev.field = (uint16_t)(x >> (32u - s));
                                     ev.s = (uint8_t)s;
                                     ev.p7 = (uint8_t)q7;
-                                    ev.ord = bigm ? (uint32_t)(rp - rec0) >> 1 : (uint32_t)(rp - rec0);
+                                    ev.ord = bigm ? (ro - r0) >> 1 : (ro - r0);
                                     ev.img = in.img;
                                     sink.push(ev);
                                 }
@@ -646,24 +704,27 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                         }
                         if (s >= 10u && !bigm) {
                             /* first >= 10-bit magnitude of this block: switch its records to (t, value) pairs */
-                            const uint32_t ncoef = (uint32_t)(rp - rec0);
+                            const uint32_t ncoef = ro - r0;
+                            uint16_t *const rec0 = rec + r0;
                             for (uint32_t i = ncoef; i-- > 0u;) {
                                 const uint32_t r = rec0[i];
                                 rec0[2u * i] = (uint16_t)(r >> 10);
                                 rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
                             }
-                            rp += ncoef;
+                            ro += ncoef;
                             bigm = JD_ACF_RARE;
                         }
                         if (bigm) {
-                            rp[0] = (uint16_t)(tw & 63u);
-                            rp[1] = (uint16_t)(int16_t)v;
-                            rp += 2;
+                            JD_REC_ST(ro, tw & 63u);
+                            JD_REC_ST(ro + 1u, (uint32_t)v & 0xFFFFu);
+                            ro += 2u;
                         } else {
-                            *rp++ = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+                            JD_REC_ST(ro, (tw << 10) | ((uint32_t)v & 0x3FFu));
+                            ro++;
                         }
                     } else {
-                        *rp++ = (uint16_t)((tw << 10) | ((uint32_t)v & 0x3FFu));
+                        JD_REC_ST(ro, (tw << 10) | ((uint32_t)v & 0x3FFu));
+                        ro++;
                     }
                 }
                 {
@@ -678,9 +739,9 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         }
         /* ---- block finished: header = first record | dc << 32 | count << 48 | BIG << 54 | rows-4..7 << 55 | columns << 56 ---- */
         {
-            const uint32_t nrec = (uint32_t)(rp - rec0);
+            const uint32_t nrec = ro - r0;
             const uint32_t cnt = (bigm ? ((nrec >> 1) << 16) | (1u << 22) : (nrec << 16));
-            const uint32_t ridx0 = in.rec_index0 + (((uint32_t)(uintptr_t)rec0 - rec_lo) >> 1);
+            const uint32_t ridx0 = in.rec_index0 + r0;
             blk_hdr[b] = (jd_u64)ridx0 | ((jd_u64)((bflags & JD_BF_MASK) | cnt | ((uint32_t)dcval & 0xFFFFu)) << 32);
         }
         /* next block of the MCU: luma blocks first, then Cb, Cr (jpeg.inl:5138-5275) */
@@ -701,7 +762,8 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         if (p7) jw += JD_JW_ONES;
     }
     out.jmap = jw;
-    out.nrec = (uint32_t)(rp - rec);
+    out.nrec = ro;
+#undef JD_REC_ST
 }
 
 /* ------------------------------------------------------------------------- */

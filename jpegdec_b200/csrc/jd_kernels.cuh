@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     __shared__ uint32_t s_tpos[64];
-    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
+    for (int i = threadIdx.x; i < 64; i += JD_ENTROPY_THREADS) s_tpos[i] = jd_tposw(c_tpos[i]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
         uint4 *dst = reinterpret_cast<uint4 *>(s_lut);

@@ -20,8 +20,8 @@ try:
     print('$1 $4', 'total %.3f prescan %.3f entropy %.3f stitch %.3f idct %.3f' % (d['ms_per_step'], s['prescan'], s['entropy'], s['stitch'], s['idct']), str(d['parity_spot_check'])[:12])
 except Exception as e: print('$1 $4 FAILED', e)" ) >> $O/${tag}_ab.txt 2>&1; }
   for wl in hd1024 uhd; do
-    ab clean main "" $wl; ab raw main JPEGDEC_B200_ENTROPY=raw $wl; ab v1flat v1 JPEGDEC_B200_ENTROPY=raw $wl
-    ab t128 t128 "" $wl; ab t32 t32 "" $wl
+    ab clean main "" $wl; ab raw main JPEGDEC_B200_ENTROPY=raw $wl
+    for v in $ABVARIANTS; do ab $v $v "" $wl; done
   done
   cat $O/${tag}_ab.txt ;;
 ncu)
