@@ -511,6 +511,9 @@ static int decode_common(JPEGIMAGE *p)
          * JPEG_USES_DMA the two halves alternate (:5073-5076, :5326) */
         uint16_t pixbuf_raw[MAX_BUFFERED_PIXELS + 64];
         uint16_t *pixbuf = (uint16_t *)(((uintptr_t)pixbuf_raw + 15) & ~(uintptr_t)15);
+        /* a group that ends at the image's right edge before it is full (crop x scale) leaves the rest of the block unwritten:
+         * stale bytes in the reference, zeros here */
+        memset(pixbuf_raw, 0, sizeof(pixbuf_raw));
         const int dpitch = dither ? (cols * mw * bpp + 7) / 8 : 0;
         JPEGDRAW jd;
         memset(&jd, 0, sizeof(jd));

@@ -61,9 +61,9 @@
 /*   bit  54     : BIG -- some magnitude needs >= 10 bits: records are pairs     */
 /*   bit  55     : a stored coefficient lies in rows 4-7 (u16MCUFlags & 0x2000)  */
 /*   bits 56..63 : occupied-column mask (low byte of u16MCUFlags, jpeg.inl:2253) */
-/* AC record (u16), normal blocks: (t << 10) | (value & 0x3FF), |value| <= 511,  */
-/*   t = position in the column-major coefficient tile = (n & 7) * 8 + (n >> 3)  */
-/*   for natural index n.  BIG blocks: two u16 per coefficient: t, then value.   */
+/* AC record (u16), normal blocks: (n << 10) | (value & 0x3FF), |value| <= 511,  */
+/*   n = natural (row-major) index of the coefficient = row * 8 + column.        */
+/*   BIG blocks: two u16 per coefficient: n, then value.                         */
 /* Only stored coefficients get a record (no ZRL / EOB records).                 */
 typedef unsigned long long jd_u64;
 
@@ -79,14 +79,10 @@ JD_HD jd_u64 jd_pack_hdr(uint32_t rec_index, int dc, uint32_t ncoef, uint32_t bi
 #define JD_HDR_HI(h) ((uint32_t)((h) >> 55) & 1u)
 #define JD_HDR_COLMASK(h) ((uint32_t)((h) >> 56) & 0xFFu)
 
-/* zigzag index k -> tile position t (column-major: t = (n & 7) * 8 + (n >> 3), n = de-zigzag(k)) */
-#define JD_TPOS_INIT { \
-    0, 8, 1, 2, 9, 16, 24, 17, 10, 3, 4, 11, 18, 25, 32, 40, \
-    33, 26, 19, 12, 5, 6, 13, 20, 27, 34, 41, 48, 56, 49, 42, 35, \
-    28, 21, 14, 7, 15, 22, 29, 36, 43, 50, 57, 58, 51, 44, 37, 30, \
-    23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63 }
-
-/* de-zigzag: zigzag index k -> natural (row-major) index (ITU T.81 Figure 5). */
+/* de-zigzag: zigzag index k -> natural (row-major) index n (ITU T.81 Figure 5): the position a record carries. */
+#define JD_TPOS_INIT JD_DEZIGZAG_INIT
+/* natural index <-> position in a column-major 8x8 tile (the same bit swap both ways) */
+#define JD_TRANSPOSE6(x) ((((x) & 7u) << 3) | ((x) >> 3))
 #define JD_DEZIGZAG_INIT { \
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, \
     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, \
@@ -192,9 +188,9 @@ typedef struct {
 #define JD_LD8(p) (*(p))
 #endif
 
-/* zigzag k -> packed word: tile position t | rows-4..7 bit << 23 | column bit (1 << (t >> 3)) << 24 -- the flag bits sit
+/* zigzag k -> packed word: natural index n | rows-4..7 bit << 23 | column bit (1 << (n & 7)) << 24 -- the flag bits sit
  * where the block header's high word keeps them, so OR-ing the words of a block's coefficients builds that word */
-JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u << (t >> 3)) << 24); }
+JD_HD uint32_t jd_tposw(uint32_t n) { return n | (((n >> 5) & 1u) << 23) | ((1u << (n & 7u)) << 24); }
 #define JD_BF_HI(bf) (((bf) >> 23) & 1u)
 #define JD_BF_COLMASK(bf) ((bf) >> 24)
 #define JD_BF_MASK 0xFF800000u
@@ -956,6 +952,173 @@ JD_HD void jd_row(const int p[8], uint32_t colmask, uint32_t o[8])
     int t[8];
     jd_row_raw(p, colmask, t);
     for (int i = 0; i < 8; i++) o[i] = jd_range(t[i]);
+}
+
+/* ------------------------------------------------------------------------- */
+/* One THREAD per 8x8 block, SSE2-build arithmetic, two columns per register.    */
+/*                                                                             */
+/* The reference's SSE2 column pass (jpeg.inl:2327-2440) works on eight int16    */
+/* lanes = the eight columns of the block, every operation wrapping at 16 bits.  */
+/* A GPU thread that owns a whole block keeps the block as 8 rows x 4 registers,  */
+/* each register = two adjacent columns of one row (low half = the even column): */
+/* adds and subtracts are then one packed instruction for two columns            */
+/* (VIADD.16x2), only the five high multiplies per column work on the halves     */
+/* separately.  The column pass runs in place, pair by pair, so the block never   */
+/* leaves the registers between the passes (no transpose through shared memory,  */
+/* no warp synchronisation).  The row pass (jpeg.inl:2681-2797) is 32-bit         */
+/* arithmetic on the sign-extended halves, except its last butterflies + clamp    */
+/* which are exact in 16-bit lanes again (only bits 5..14 of a row output reach   */
+/* the range table).                                                             */
+/* ------------------------------------------------------------------------- */
+JD_HD uint32_t jd_perm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const jd_u64 v = ((jd_u64)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+JD_HD uint32_t jd_add2(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __vadd2(a, b);
+#else
+    return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16);
+#endif
+}
+JD_HD uint32_t jd_sub2(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __vsub2(a, b);
+#else
+    return ((a - b) & 0xFFFFu) | (((a >> 16) - (b >> 16)) << 16);
+#endif
+}
+/* per half: max(min(a + b, c), 0), signed 16-bit lanes (VIADDMNMX.S16x2.RELU) */
+JD_HD uint32_t jd_addmin2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+#ifdef __CUDA_ARCH__
+    return __viaddmin_s16x2_relu(a, b, c);
+#else
+    uint32_t r = 0;
+    for (int h = 0; h < 2; h++) {
+        int v = (int)(int16_t)(uint16_t)((a >> (16 * h)) + (b >> (16 * h)));
+        const int m = (int)(int16_t)(uint16_t)(c >> (16 * h));
+        v = v < m ? v : m;
+        v = v < 0 ? 0 : v;
+        r |= ((uint32_t)v & 0xFFFFu) << (16 * h);
+    }
+    return r;
+#endif
+}
+/* both halves: _mm_mulhi_epi16(_mm_slli_epi16(x, 2), K) */
+JD_HD uint32_t jd_mh2p(uint32_t x, int K)
+{
+    const int lo = ((int)(x << 18) >> 16) * K;
+    const int hi = ((int)((x & 0xFFFF0000u) << 2) >> 16) * K;
+    return jd_perm((uint32_t)lo, (uint32_t)hi, 0x7632);
+}
+
+/* column pass of one column pair, in place: d[r] = row r (rows 4..7 are not read when HI is false, jpeg.inl:2330-2367) */
+template <bool HI>
+JD_HD void jd_colpass_pair(uint32_t d[8])
+{
+    uint32_t T0, T1, T2, T3, T4, T5, T6, T7;
+    if (!HI) {
+        uint32_t t12 = jd_mh2p(d[2], JD_K0414);
+        T0 = jd_add2(d[0], d[2]); T3 = jd_sub2(d[0], d[2]); T1 = jd_add2(d[0], t12); T2 = jd_sub2(d[0], t12);
+        T7 = jd_add2(d[1], d[3]);
+        const uint32_t e = jd_sub2(d[1], d[3]);
+        const uint32_t t11 = jd_mh2p(e, JD_K1414);
+        const uint32_t z5 = jd_mh2p(e, JD_K1847);
+        t12 = jd_mh2p(d[3], JD_K2613);
+        t12 = jd_add2(jd_add2(t12, t12), z5);
+        T6 = jd_sub2(t12, T7);
+        T5 = jd_sub2(t11, T6);
+        T4 = jd_add2(jd_sub2(jd_mh2p(d[1], JD_K1082), z5), T5);
+    } else {
+        const uint32_t t10 = jd_add2(d[0], d[4]), t11a = jd_sub2(d[0], d[4]);
+        const uint32_t t13 = jd_add2(d[2], d[6]);
+        uint32_t t12 = jd_sub2(jd_mh2p(jd_sub2(d[2], d[6]), JD_K1414), t13);
+        T0 = jd_add2(t10, t13); T3 = jd_sub2(t10, t13); T1 = jd_add2(t11a, t12); T2 = jd_sub2(t11a, t12);
+        const uint32_t z13 = jd_add2(d[5], d[3]), z10 = jd_sub2(d[5], d[3]);
+        const uint32_t z11 = jd_add2(d[1], d[7]), z12 = jd_sub2(d[1], d[7]);
+        T7 = jd_add2(z11, z13);
+        const uint32_t t11 = jd_mh2p(jd_sub2(z11, z13), JD_K1414);
+        const uint32_t z5 = jd_mh2p(jd_add2(z10, z12), JD_K1847);
+        t12 = jd_mh2p(z10, -JD_K2613);
+        t12 = jd_add2(jd_add2(t12, t12), z5);
+        T6 = jd_sub2(t12, T7);
+        T5 = jd_sub2(t11, T6);
+        T4 = jd_add2(jd_sub2(jd_mh2p(z12, JD_K1082), z5), T5);
+    }
+    d[0] = jd_add2(T0, T7); d[1] = jd_add2(T1, T6); d[2] = jd_add2(T2, T5); d[3] = jd_sub2(T3, T4);
+    d[4] = jd_add2(T3, T4); d[5] = jd_sub2(T2, T5); d[6] = jd_sub2(T1, T6); d[7] = jd_sub2(T0, T7);
+}
+
+/* The 8 butterflies that end a row pass + the ucRangeTable clamp, two pixels per instruction.  Only bits 5..14 of a row
+ * output reach the range table (10-bit index, jpeg.inl:2721-2797), so 16-bit lanes are exact.  The caller has added
+ * JD_ROW_BIAS = (128 + 384) << 5 to the block's DC term (it enters every output with weight 1), which makes the 10-bit
+ * field non-negative: pixel = clamp(field - 384, 0, 255) -- one VIADDMNMX.S16x2.RELU per pixel pair.
+ * Returns the 8 pixel bytes of the row in *lo (pixels 0..3) and *hi (pixels 4..7). */
+#define JD_ROW_BIAS 16384
+JD_HD uint32_t jd_clamp2(uint32_t v)
+{
+    return jd_addmin2_relu((v >> 5) & 0x03FF03FFu, 0xFE80FE80u, 0x00FF00FFu);
+}
+JD_HD void jd_row_finish2(const int t[8], uint32_t *lo, uint32_t *hi)
+{
+    const uint32_t a01 = jd_perm((uint32_t)t[0], (uint32_t)t[1], 0x5410), a23 = jd_perm((uint32_t)t[2], (uint32_t)t[3], 0x5410);
+    const uint32_t b76 = jd_perm((uint32_t)t[7], (uint32_t)t[6], 0x5410), b54 = jd_perm((uint32_t)t[5], (uint32_t)(-t[4]), 0x5410);
+    const uint32_t s01 = jd_clamp2(jd_add2(a01, b76)), s23 = jd_clamp2(jd_add2(a23, b54)); /* o0,o1 | o2,o3 */
+    const uint32_t d76 = jd_clamp2(jd_sub2(a01, b76)), d54 = jd_clamp2(jd_sub2(a23, b54)); /* o7,o6 | o5,o4 */
+    *lo = jd_perm(s01, s23, 0x6420);
+    *hi = jd_perm(d54, d76, 0x4602);
+}
+
+/* Whole block: x[r][q] = row r, columns 2q (low half) and 2q+1 of the DEQUANTISED coefficients (int16 wrap of coefficient x
+ * quant, JD_ROW_BIAS added to the DC term), NP = column pairs that can hold coefficients (2: columns 0-3, 4: all).  hi =
+ * some coefficient lies in rows 4-7 (u16MCUFlags & 0x2000), colmask = occupied columns.  px[r] receives row r's 8 bytes. */
+template <int NP>
+JD_HD void jd_idct_block_packed(uint32_t x[8][NP], bool hi, uint32_t colmask, uint32_t px[8][2])
+{
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int q = 0; q < NP; q++) {
+        uint32_t d[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int r = 0; r < 8; r++) d[r] = x[r][q];
+        if (hi) jd_colpass_pair<true>(d); else jd_colpass_pair<false>(d);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int r = 0; r < 8; r++) x[r][q] = d[r];
+    }
+    /* rows: 1-2 columns = the reference's approximation (:2688-2697), else the 4-column or the general formula -- the
+     * general one with columns 4-7 zero gives the 4-column result exactly, so NP alone may pick it */
+    const uint32_t rowmask = ((colmask & 0xFCu) == 0u) ? 0x03u : ((NP == 2) ? 0x0Fu : 0xFFu);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int r = 0; r < 8; r++) {
+        int p[8], t[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; q++) {
+            const uint32_t w = (q < NP) ? x[r][q < NP ? q : 0] : 0u;
+            p[2 * q] = (int)(short)(uint16_t)(w & 0xFFFFu);
+            p[2 * q + 1] = (int)w >> 16;
+        }
+        jd_row_terms(p, rowmask, t);
+        jd_row_finish2(t, &px[r][0], &px[r][1]);
+    }
 }
 
 /* ------------------------------------------------------------------------- */

@@ -776,16 +776,16 @@ jdk_idct_color(const JDIdctArgs a)
         __syncwarp();
         if (!JD_HDR_BIG(h)) {
             const uint16_t *rp = irec + ri + c;
-            if (c < ncoef) { const uint32_t r = __ldg(rp); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
-            if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            if (c < ncoef) { const uint32_t r = __ldg(rp); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
+            if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
             for (uint32_t i = c + 16; i < ncoef; i += 8) {
                 const uint32_t r = __ldg(irec + ri + i);
-                tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
+                tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22);
             }
         } else {
             for (uint32_t i = c; i < ncoef; i += 8) {
                 const uint32_t t = __ldg(irec + ri + 2 * i) & 63u;
-                tile[t] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+                tile[JD_TRANSPOSE6(t)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
             }
         }
         __syncwarp();
@@ -907,22 +907,12 @@ __device__ __forceinline__ void jd_unpack4(const uint2 v, int m[4])
     m[2] = (int)(short)(v.y & 0xFFFF); m[3] = (int)v.y >> 16;
 }
 
-/* The 8 butterflies that end a row pass + the ucRangeTable clamp, two pixels per instruction.  Only bits 5..14 of a row
- * output reach the range table (10-bit index, jpeg.inl:2721-2797), so 16-bit lanes are exact.  The caller has added
- * JD_ROW_BIAS = (128 + 384) << 5 to the row's DC term (it enters every output with weight 1), which makes the 10-bit
- * field non-negative: pixel = clamp(field - 384, 0, 255) -- one VIADDMNMX.S16x2.RELU per pixel pair. */
-#define JD_ROW_BIAS 16384
-__device__ __forceinline__ uint32_t jd_clamp2(uint32_t v)
-{
-    return __viaddmin_s16x2_relu((v >> 5) & 0x03FF03FFu, 0xFE80FE80u, 0x00FF00FFu);
-}
+/* the 8 butterflies that end a row pass + the ucRangeTable clamp, two pixels per instruction: jd_core.h jd_row_finish2 */
 __device__ __forceinline__ uint2 jd_row_finish_packed(const int t[8])
 {
-    const uint32_t a01 = __byte_perm((uint32_t)t[0], (uint32_t)t[1], 0x5410), a23 = __byte_perm((uint32_t)t[2], (uint32_t)t[3], 0x5410);
-    const uint32_t b76 = __byte_perm((uint32_t)t[7], (uint32_t)t[6], 0x5410), b54 = __byte_perm((uint32_t)t[5], (uint32_t)(-t[4]), 0x5410);
-    const uint32_t s01 = jd_clamp2(__vadd2(a01, b76)), s23 = jd_clamp2(__vadd2(a23, b54)); /* o0,o1 | o2,o3 */
-    const uint32_t d76 = jd_clamp2(__vsub2(a01, b76)), d54 = jd_clamp2(__vsub2(a23, b54)); /* o7,o6 | o5,o4 */
-    return make_uint2(__byte_perm(s01, s23, 0x6420), __byte_perm(d54, d76, 0x4602));
+    uint2 r;
+    jd_row_finish2(t, &r.x, &r.y);
+    return r;
 }
 
 #ifndef JD_TB_MINB
@@ -1014,12 +1004,12 @@ jdk_idct_tb(const JDIdctArgs a)
             for (int hh = 0; hh < 10; hh++) {
                 if ((uint32_t)hh >= off && (uint32_t)hh < total) {
                     const uint32_t r = (hh & 1) ? (v[hh >> 1] >> 16) : (v[hh >> 1] & 0xFFFFu);
-                    tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
+                    tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22);
                 }
             }
-            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(irec + ri + i); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
         } else {
-            for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+            for (uint32_t i = 0; i < ncoef; i++) tile[JD_TRANSPOSE6(__ldg(irec + ri + 2 * i) & 63u)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
         }
         int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
         if (r47) {
@@ -1109,9 +1099,9 @@ jdk_idct_tb(const JDIdctArgs a)
                     const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
                     __syncwarp();
                     if (!JD_HDR_BIG(h)) {
-                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(irec + ri + i); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
                     } else {
-                        for (uint32_t i = c; i < ncoef; i += 8) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+                        for (uint32_t i = c; i < ncoef; i += 8) tile[JD_TRANSPOSE6(__ldg(irec + ri + 2 * i) & 63u)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
                     }
                     __syncwarp();
                     int m[8], o[8];
@@ -1188,13 +1178,13 @@ __device__ __forceinline__ void jd_scaled_block(const uint16_t *irec, jd_u64 h, 
     const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h), big = JD_HDR_BIG(h);
     int m1 = 0, m8 = 0, m9 = 0;
     bool any = false;
-    /* records are in zigzag order: the ones the 1/4 path keeps (zigzag 1..4 = natural 1, 8, 16, 9 =
-     * tile positions 8, 1, 2, 9; jpeg.inl:2117-2119) come first */
+    /* records are in zigzag order: the ones the 1/4 path keeps (zigzag 1..4 = natural 1, 8, 16, 9;
+     * jpeg.inl:2117-2119) come first */
     for (uint32_t i = 0; i < ncoef; i++) {
         uint32_t t; int v;
         if (big) { t = irec[ri + 2 * i] & 63u; v = (int)(short)irec[ri + 2 * i + 1]; }
         else { const uint32_t r = irec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
-        if (t == 8u) m1 = v; else if (t == 1u) m8 = v; else if (t == 9u) m9 = v; else if (t != 2u) break;
+        if (t == 1u) m1 = v; else if (t == 8u) m8 = v; else if (t == 9u) m9 = v; else if (t != 16u) break;
         any = true;
     }
     if (!any) { px[0] = px[1] = px[2] = px[3] = jd_range(dc * q0); return; }

@@ -253,7 +253,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
                 uint32_t t; int v;
                 if (bigb) { t = rec[ri + 2 * i] & 63u; v = (int16_t)rec[ri + 2 * i + 1]; }
                 else { const uint32_t r = rec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
-                const int n = (int)((t & 7u) * 8u + (t >> 3));
+                const int n = (int)t;   /* records carry the natural index */
                 /* 1/4 and 1/8 scale keep only zigzag 1..4 = natural 1, 8, 16, 9 (jpeg.inl:2117-2119) */
                 if (sshift >= 2 && !(n == 1 || n == 8 || n == 16 || n == 9)) continue;
                 tile[n] = (int16_t)v;
@@ -414,6 +414,42 @@ extern "C" void hostsim_idct(const int16_t *coef, const int16_t *quant, unsigned
         jd_row(p, flags & 0xFFu, o);
         for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)o[c];
     }
+}
+
+/* one block through the packed thread-per-block code of jdk_idct_p (jd_core.h jd_idct_block_packed, SSE2-build arithmetic) */
+extern "C" void hostsim_idct_packed(const int16_t *coef, const int16_t *quant, unsigned flags, uint8_t *out)
+{
+    const bool hi = (flags & 0x2000u) != 0;
+    const uint32_t colmask = flags & 0xFFu;
+    uint16_t d[64];
+    for (int n = 0; n < 64; n++) d[n] = (uint16_t)(coef[n] * quant[n]);
+    d[0] = (uint16_t)(d[0] + JD_ROW_BIAS);
+    uint32_t px[8][2];
+    if ((colmask & 0xF0u) == 0u) {
+        uint32_t x[8][2];
+        for (int r = 0; r < 8; r++) for (int q = 0; q < 2; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
+        jd_idct_block_packed<2>(x, hi, colmask, px);
+    } else {
+        uint32_t x[8][4];
+        for (int r = 0; r < 8; r++) for (int q = 0; q < 4; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
+        jd_idct_block_packed<4>(x, hi, colmask, px);
+    }
+    for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)(px[r][c >> 2] >> (8 * (c & 3)));
+}
+
+/* the same block with the 4-column lanes forced through the general (8-column) instantiation, as happens in a warp that
+ * mixes both kinds */
+extern "C" void hostsim_idct_packed_general(const int16_t *coef, const int16_t *quant, unsigned flags, uint8_t *out)
+{
+    const bool hi = (flags & 0x2000u) != 0;
+    const uint32_t colmask = flags & 0xFFu;
+    uint16_t d[64];
+    for (int n = 0; n < 64; n++) d[n] = (uint16_t)(coef[n] * quant[n]);
+    d[0] = (uint16_t)(d[0] + JD_ROW_BIAS);
+    uint32_t px[8][2], x[8][4];
+    for (int r = 0; r < 8; r++) for (int q = 0; q < 4; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
+    jd_idct_block_packed<4>(x, hi, colmask, px);
+    for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)(px[r][c >> 2] >> (8 * (c & 3)));
 }
 
 /* statistics of the block classes the IDCT kernel branches on (development aid) */

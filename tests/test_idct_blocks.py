@@ -64,6 +64,12 @@ def test_idct_blocks_reference_restatement_kernelcode():
             orc.oracle_idct(coef.ctypes.data, quant.ctypes.data, fl, arith, 0, o_or.ctypes.data)
             sim.hostsim_idct(coef.ctypes.data, quant.ctypes.data, fl, arith, o_sim.ctypes.data)
             assert np.array_equal(o_or, o_sim), (arith, hex(fl))
+            if arith == 0:      # the packed thread-per-block code of jdk_idct_p, both instantiations
+                o_p = np.zeros(64, np.uint8); o_g = np.zeros(64, np.uint8)
+                sim.hostsim_idct_packed(coef.ctypes.data, quant.ctypes.data, fl, o_p.ctypes.data)
+                sim.hostsim_idct_packed_general(coef.ctypes.data, quant.ctypes.data, fl, o_g.ctypes.data)
+                assert np.array_equal(o_or, o_p), ("packed", hex(fl))
+                assert np.array_equal(o_or, o_g), ("packed general", hex(fl))
             if refs[arith] is not None:
                 o_ref = np.zeros(64, np.uint8)
                 refs[arith].ref_idct(coef.ctypes.data, quant.ctypes.data, fl, 0, o_ref.ctypes.data)
