@@ -166,6 +166,7 @@ typedef struct {
     uint32_t blk0;        /* global index of this segment's first block (for events) */
     uint32_t al;          /* progressive DC scan: point transform (DC_ONLY instantiation) */
     uint32_t img;         /* image index in the batch (for events) */
+    uint32_t *ring;       /* CLEAN reader: this walker's 32-word stream ring (16-byte aligned; shared memory on the device) */
 } JDSegIn;
 
 typedef struct {
@@ -510,9 +511,12 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                              EventSink &sink, JDSegOut &out)
 {
     /* ---- bit reader.  Raw input: aligned 32-bit words, one word prefetched ahead of use, un-stuffing on the fly.
-     * CLEAN input: 16-byte chunks (the segment starts 16-byte aligned and ends in zeros), one chunk prefetched ahead:
-     * a lane touches global memory once per ~24 symbols and the data is on its way ~24 symbols before it is needed
-     * (with 4-byte loads the walk stalled on L2 / DRAM latency: 53 % of the stall samples of the round-2 first build). ---- */
+     * CLEAN input (the segment starts 16-byte aligned and ends in zeros): the stream is staged through a 32-word ring per
+     * walker in shared memory.  The ring is topped up at WARP-SYNCHRONOUS ticks: every 8th symbol all lanes that are in the
+     * loop first park the 32 bytes they requested at the previous tick, then request the next 32 if there is room.  Global
+     * loads are therefore only issued at ticks and only consumed at the following tick, >= 8 symbols later.  (Scoreboards
+     * are per warp register, not per lane: with a per-lane prefetch register, any lane's pending load stalled every other
+     * lane that touched the same register name -- 48 % of the stall samples in the first round-2 builds.) ---- */
     const uint32_t *words = (const uint32_t *)in.data;
     const uint32_t endw = (in.end + 3u) >> 2;    /* first word index past the data */
     uint32_t wi = in.start >> 2;                 /* index of the next word to consume */
@@ -525,20 +529,47 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     const uint8_t *const cbase = in.data + in.start;
     const uint32_t nchunk = CLEAN ? ((in.end - in.start + 15u) >> 4) : 0u;
     const jd_u128 zero128 = {0u, 0u, 0u, 0u};
-    jd_u128 cq = (nchunk > 0u) ? jd_ld128(cbase) : zero128;          /* words not yet consumed, cq.x first */
-    jd_u128 cn = (nchunk > 1u) ? jd_ld128(cbase + 16) : zero128;     /* the chunk after it */
-    uint32_t cleft = 4u, ci = 1u;                                    /* words left in cq; index of the chunk in cn */
+    uint32_t *const ring = in.ring;
+    uint32_t rd = 0, wr = 0, gi = 0, tick = 0;   /* words read / written so far; next chunk to request; symbols since the last tick */
+    jd_u128 pa = zero128, pb = zero128;          /* the 32 bytes requested at the last tick */
+    bool pend = false;
+    auto ring_put = [&](uint32_t at, const jd_u128 &v) {
+#ifdef __CUDA_ARCH__
+        *reinterpret_cast<uint4 *>(ring + at) = make_uint4(v.x, v.y, v.z, v.w);
+#else
+        ring[at] = v.x; ring[at + 1] = v.y; ring[at + 2] = v.z; ring[at + 3] = v.w;
+#endif
+    };
+    auto chunk = [&](uint32_t i) { return (i < nchunk) ? jd_ld128(cbase + 16u * i) : zero128; };   /* zeros follow the data */
+    auto topup = [&]() {
+        if (pend) { ring_put(wr & 31u, pa); ring_put((wr + 4u) & 31u, pb); wr += 8u; }
+        pend = (32u - (wr - rd)) >= 8u;
+        if (pend) { pa = chunk(gi); pb = chunk(gi + 1u); gi += 2u; }
+    };
+    if (CLEAN) {
+        /* start: 64 bytes in the ring, 32 more on their way */
+        for (uint32_t i = 0; i < 4u; i++) ring_put(4u * i, chunk(i));
+        wr = 16u; gi = 4u;
+        topup();
+    }
+    /* one symbol consumed: top the ring up every 8th symbol, all lanes of the warp at the same instruction */
+    auto tick1 = [&]() {
+        if (CLEAN) {
+            tick++;
+#ifdef __CUDA_ARCH__
+            if (__any_sync(__activemask(), (tick & 7u) == 0u)) { topup(); tick = 0; }
+#else
+            if ((tick & 7u) == 0u) { topup(); tick = 0; }
+#endif
+        }
+    };
 
     /* keeps >= 32 valid bits in bb */
     auto refill = [&]() {
         if (CLEAN) {
             if (nb <= 32) {
-                const uint32_t w = cq.x;
-                cq.x = cq.y; cq.y = cq.z; cq.z = cq.w;
-                if (--cleft == 0u) {
-                    cq = cn; cleft = 4u; ci++;
-                    cn = (ci < nchunk) ? jd_ld128(cbase + 16u * ci) : zero128;
-                }
+                const uint32_t w = ring[rd & 31u];
+                rd++;
                 bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
                 nb += 32;
             }
@@ -636,6 +667,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             pred2 = (comp >= 2u) ? pv : pred2;
             dcval = pv;
         }
+        tick1();
         const uint32_t r0 = ro;                  /* this block's first record */
         uint32_t bflags = 0, bigm = 0;           /* OR of the tposw words; JD_ACF_RARE once the block's records are pairs */
         if (MODE != JD_MODE_DC_SCAN) {
@@ -728,6 +760,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                     jw += (t >> 3) * JD_JW_ONES;
                     p7 = t & 7u;
                 }
+                tick1();
                 k++;
             } while (k < 64u);
             if (err >= 0) break;
@@ -1081,9 +1114,10 @@ JD_HD void jd_row_finish2(const int t[8], uint32_t *lo, uint32_t *hi)
 
 /* Whole block: x[r][q] = row r, columns 2q (low half) and 2q+1 of the DEQUANTISED coefficients (int16 wrap of coefficient x
  * quant, JD_ROW_BIAS added to the DC term), NP = column pairs that can hold coefficients (2: columns 0-3, 4: all).  hi =
- * some coefficient lies in rows 4-7 (u16MCUFlags & 0x2000), colmask = occupied columns.  px[r] receives row r's 8 bytes. */
+ * some coefficient lies in rows 4-7 (u16MCUFlags & 0x2000; rows 4-7 of x are not read otherwise), colmask = occupied
+ * columns.  Row r's 8 pixel bytes go to out + r * stride (8-byte aligned). */
 template <int NP>
-JD_HD void jd_idct_block_packed(uint32_t x[8][NP], bool hi, uint32_t colmask, uint32_t px[8][2])
+JD_HD void jd_idct_block_packed(uint32_t x[8][NP], bool hi, uint32_t colmask, uint8_t *out, uint32_t stride)
 {
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -1117,7 +1151,14 @@ JD_HD void jd_idct_block_packed(uint32_t x[8][NP], bool hi, uint32_t colmask, ui
             p[2 * q + 1] = (int)w >> 16;
         }
         jd_row_terms(p, rowmask, t);
-        jd_row_finish2(t, &px[r][0], &px[r][1]);
+        uint32_t lo, hi8;
+        jd_row_finish2(t, &lo, &hi8);
+#ifdef __CUDA_ARCH__
+        *reinterpret_cast<uint2 *>(out + r * stride) = make_uint2(lo, hi8);
+#else
+        uint32_t *o = (uint32_t *)(out + (size_t)r * stride);
+        o[0] = lo; o[1] = hi8;
+#endif
     }
 }
 

@@ -779,6 +779,49 @@ static void launch_idct_tb(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
     else jdk_idct_tb<HS, VS, NC, MPB, PT, JPEG_ARITH_SCALAR><<<grid, G::THREADS, 0, st>>>(a);
 }
 
+/* SSE2-build arithmetic: the packed thread-per-block kernel for every sampling / pixel type, full and half size */
+template <int HS, int VS, int NC, int MPB, int PT>
+static void launch_idct_p(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, bool half, cudaStream_t st)
+{
+    dim3 grid((mcus_x + MPB - 1) / MPB, mcus_y, nimg);
+    static bool carveout_set = false;   /* 7-8 CTAs of ~27 KB static shared memory per SM need the large carveout */
+    if (!carveout_set) {
+        cudaFuncSetAttribute(jdk_idct_p<HS, VS, NC, MPB, PT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(jdk_idct_p<HS, VS, NC, MPB, PT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
+    if (half) jdk_idct_p<HS, VS, NC, MPB, PT, true><<<grid, 128, 0, st>>>(a);
+    else jdk_idct_p<HS, VS, NC, MPB, PT, false><<<grid, 128, 0, st>>>(a);
+}
+
+template <int HS, int VS>
+static int launch_idct_packed(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, int ncomp, int ptclass, bool half, cudaStream_t st)
+{
+    constexpr int MPB1 = 128 / (HS * VS);            /* luma only: HS * VS blocks per MCU */
+    constexpr int MPB3 = (HS * VS == 4) ? 20 : (HS * VS == 2) ? 30 : 40;
+    if (ptclass == JD_PT_GRAY) { launch_idct_p<HS, VS, 1, MPB1, JD_PT_GRAY>(a, mcus_x, mcus_y, nimg, half, st); return 1; }
+    if (ncomp == 1) {
+        if (HS != 1 || VS != 1 || ptclass != JD_PT_565) return 0;
+        launch_idct_p<1, 1, 1, 128, JD_PT_565>(a, mcus_x, mcus_y, nimg, half, st);
+        return 1;
+    }
+    if (HS == 2 && VS == 2) {
+        /* strips of 20 MCUs (320 px) unless strips of 16 waste fewer MCU slots (1920 and 3840 px divide evenly by 320) */
+        const uint32_t pad16 = (mcus_x + 15) / 16 * 16 - mcus_x, pad20 = (mcus_x + 19) / 20 * 20 - mcus_x;
+        if (pad20 <= pad16) {
+            if (ptclass == JD_PT_565) launch_idct_p<2, 2, 3, 20, JD_PT_565>(a, mcus_x, mcus_y, nimg, half, st);
+            else launch_idct_p<2, 2, 3, 20, JD_PT_8888>(a, mcus_x, mcus_y, nimg, half, st);
+        } else {
+            if (ptclass == JD_PT_565) launch_idct_p<2, 2, 3, 16, JD_PT_565>(a, mcus_x, mcus_y, nimg, half, st);
+            else launch_idct_p<2, 2, 3, 16, JD_PT_8888>(a, mcus_x, mcus_y, nimg, half, st);
+        }
+        return 1;
+    }
+    if (ptclass == JD_PT_565) launch_idct_p<HS, VS, 3, MPB3, JD_PT_565>(a, mcus_x, mcus_y, nimg, half, st);
+    else launch_idct_p<HS, VS, 3, MPB3, JD_PT_8888>(a, mcus_x, mcus_y, nimg, half, st);
+    return 1;
+}
+
 template <int HS, int VS, int MPB3, int MPB1>
 static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y, uint32_t nimg, int ncomp, int ptclass,
                            int arith, bool half, cudaStream_t st)
@@ -1025,6 +1068,16 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             ia.bpm = (uint32_t)f.bpm;
             int ok = 0;
             const int ar = b->ctx->arith;
+            static int use_packed = -1;   /* JPEGDEC_B200_IDCT=lanes|tb: the round-1 kernels also for the SSE2-build arithmetic (A/B) */
+            if (use_packed < 0) { const char *e = getenv("JPEGDEC_B200_IDCT"); use_packed = (e && (strcmp(e, "lanes") == 0 || strcmp(e, "tb") == 0)) ? 0 : 1; }
+            if (ar == JPEG_ARITH_SSE2 && use_packed) {
+                switch (f.subsample) {
+                    case 0x00: case 0x11: ok = launch_idct_packed<1, 1>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;
+                    case 0x21: ok = launch_idct_packed<2, 1>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;
+                    case 0x12: ok = launch_idct_packed<1, 2>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;
+                    case 0x22: ok = launch_idct_packed<2, 2>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;
+                }
+            } else
             switch (f.subsample) {
                 case 0x00: case 0x11: ok = launch_idct_geo<1, 1, 16, 32>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;
                 case 0x21: ok = launch_idct_geo<2, 1, 8, 16>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, ar, half, st); break;

@@ -26,6 +26,7 @@
 #ifndef JD_ENTROPY_THREADS
 #define JD_ENTROPY_THREADS 64
 #endif
+#define JD_RING_STRIDE 36   /* words between two walkers' rings: 32 + 4 keeps 16-byte alignment and spreads the banks */
 
 __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
 
@@ -127,7 +128,7 @@ struct JDEntropyArgs {
 __host__ __device__ __forceinline__ uint32_t jd_clean_off(uint32_t start, uint32_t seg) { return (start & ~15u) + 32u * seg; }
 
 template <bool CLEAN>
-__device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const uint16_t *s_lut, const uint32_t *s_tpos)
+__device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const uint16_t *s_lut, const uint32_t *s_tpos, uint32_t *s_ring)
 {
     const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
     if (wi >= a.nwork) return;
@@ -148,6 +149,7 @@ __device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const ui
     in.tsel = im.tsel;
     in.seg = seg;
     in.img = img;
+    in.ring = s_ring + threadIdx.x * JD_RING_STRIDE;
     in.blk0 = im.blk_base + m0 * im.bpm;
     jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
     JDSegOut so;
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     __shared__ uint32_t s_tpos[64];
+    __shared__ __align__(16) uint32_t s_ring[CLEAN ? JD_ENTROPY_THREADS * JD_RING_STRIDE : 4];   /* per-walker stream rings (jd_core.h) */
     for (int i = threadIdx.x; i < 64; i += JD_ENTROPY_THREADS) s_tpos[i] = jd_tposw(c_tpos[i]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
         for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    jd_entropy_body<CLEAN>(a, s_lut, s_tpos);
+    jd_entropy_body<CLEAN>(a, s_lut, s_tpos, s_ring);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -737,6 +740,50 @@ __device__ __forceinline__ void jd_phase_c_full(const JDIdctArgs &a, const uint8
     }
 }
 
+/* Phase C at 1/2 scale: 2x2 luma sums; scalar colour code in both builds (jpeg.inl:3297-3322, :3577-3626) */
+template <int HS, int VS, int NC, int PT, int WCTA, int HCTA, int YSTRIDE, int CSTRIDE, int NTHREADS>
+__device__ __forceinline__ void jd_phase_c_half(const JDIdctArgs &a, const uint8_t *s_y, const uint8_t *s_cb, const uint8_t *s_cr,
+                                                uint32_t strip, uint32_t my, uint32_t tid, uint32_t W, uint32_t H,
+                                                uint8_t *outbase, uint32_t pitch)
+{
+    constexpr int BYPP = (PT == JD_PT_565) ? 2 : (PT == JD_PT_8888 ? 4 : 1);
+    const uint32_t OW = (W + 1) >> 1, OH = (H + 1) >> 1;
+    constexpr int OWC = WCTA / 2, OHC = HCTA / 2;
+    for (uint32_t it = tid; it < (uint32_t)(OWC * OHC); it += NTHREADS) {
+        const uint32_t oy = it / OWC, ox = it - oy * OWC;
+        const uint32_t gy = my * OHC + oy, gx = strip * OWC + ox;
+        if (gy >= OH || gx >= OW) continue;
+        const uint8_t *yp = s_y + (2 * oy) * YSTRIDE + 2 * ox;
+        const int sum = yp[0] + yp[1] + yp[YSTRIDE] + yp[YSTRIDE + 1];
+        uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
+        if (PT == JD_PT_GRAY) {
+            *dst = (uint8_t)((sum + 2) >> 2);
+        } else if (NC == 1) {
+            uint32_t v = jd_gray565((uint32_t)((sum + 2) >> 2));
+            if (a.big_endian) v = jd_bswap16(v);
+            *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+        } else {
+            int Cb, Cr;
+            if (HS == 2 && VS == 2) {
+                Cb = s_cb[oy * CSTRIDE + ox]; Cr = s_cr[oy * CSTRIDE + ox];
+            } else if (HS == 1 && VS == 1) {
+                const uint8_t *p1 = s_cb + (2 * oy) * CSTRIDE + 2 * ox, *p2 = s_cr + (2 * oy) * CSTRIDE + 2 * ox;
+                Cb = (p1[0] + p1[1] + p1[CSTRIDE] + p1[CSTRIDE + 1] + 2) >> 2;
+                Cr = (p2[0] + p2[1] + p2[CSTRIDE] + p2[CSTRIDE + 1] + 2) >> 2;
+            } else if (HS == 2) {
+                Cb = (s_cb[(2 * oy) * CSTRIDE + ox] + s_cb[(2 * oy + 1) * CSTRIDE + ox] + 1) >> 1;
+                Cr = (s_cr[(2 * oy) * CSTRIDE + ox] + s_cr[(2 * oy + 1) * CSTRIDE + ox] + 1) >> 1;
+            } else {
+                Cb = (s_cb[oy * CSTRIDE + 2 * ox] + s_cb[oy * CSTRIDE + 2 * ox + 1] + 1) >> 1;
+                Cr = (s_cr[oy * CSTRIDE + 2 * ox] + s_cr[oy * CSTRIDE + 2 * ox + 1] + 1) >> 1;
+            }
+            const uint32_t v = jd_pixel_scalar<PT>(sum << 10, Cb - 128, Cr - 128, a.big_endian != 0u);
+            if (PT == JD_PT_8888) *reinterpret_cast<uint32_t *>(dst) = v;
+            else *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
+        }
+    }
+}
+
 template <int HS, int VS, int NC, int MPB, int PT, int ARITH, bool HALF>
 __global__ void __launch_bounds__(JDGeo<HS, VS, NC, MPB>::THREADS)
 jdk_idct_color(const JDIdctArgs a)
@@ -837,42 +884,7 @@ jdk_idct_color(const JDIdctArgs a)
     if (!HALF) {
         jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
     } else {
-        /* 1/2 scale: 2x2 luma sums; scalar colour code in both builds (jpeg.inl:3297-3322, :3577-3626) */
-        const uint32_t OW = (W + 1) >> 1, OH = (H + 1) >> 1;
-        constexpr int OWC = G::WCTA / 2, OHC = G::HCTA / 2;
-        for (uint32_t it = tid; it < (uint32_t)(OWC * OHC); it += G::THREADS) {
-            const uint32_t oy = it / OWC, ox = it - oy * OWC;
-            const uint32_t gy = my * OHC + oy, gx = strip * OWC + ox;
-            if (gy >= OH || gx >= OW) continue;
-            const uint8_t *yp = s_y + (2 * oy) * G::YSTRIDE + 2 * ox;
-            const int sum = yp[0] + yp[1] + yp[G::YSTRIDE] + yp[G::YSTRIDE + 1];
-            uint8_t *dst = outbase + (size_t)gy * pitch + (size_t)gx * BYPP;
-            if (PT == JD_PT_GRAY) {
-                *dst = (uint8_t)((sum + 2) >> 2);
-            } else if (NC == 1) {
-                uint32_t v = jd_gray565((uint32_t)((sum + 2) >> 2));
-                if (a.big_endian) v = jd_bswap16(v);
-                *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
-            } else {
-                int Cb, Cr;
-                if (HS == 2 && VS == 2) {
-                    Cb = s_cb[oy * G::CSTRIDE + ox]; Cr = s_cr[oy * G::CSTRIDE + ox];
-                } else if (HS == 1 && VS == 1) {
-                    const uint8_t *p1 = s_cb + (2 * oy) * G::CSTRIDE + 2 * ox, *p2 = s_cr + (2 * oy) * G::CSTRIDE + 2 * ox;
-                    Cb = (p1[0] + p1[1] + p1[G::CSTRIDE] + p1[G::CSTRIDE + 1] + 2) >> 2;
-                    Cr = (p2[0] + p2[1] + p2[G::CSTRIDE] + p2[G::CSTRIDE + 1] + 2) >> 2;
-                } else if (HS == 2) {
-                    Cb = (s_cb[(2 * oy) * G::CSTRIDE + ox] + s_cb[(2 * oy + 1) * G::CSTRIDE + ox] + 1) >> 1;
-                    Cr = (s_cr[(2 * oy) * G::CSTRIDE + ox] + s_cr[(2 * oy + 1) * G::CSTRIDE + ox] + 1) >> 1;
-                } else {
-                    Cb = (s_cb[oy * G::CSTRIDE + 2 * ox] + s_cb[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
-                    Cr = (s_cr[oy * G::CSTRIDE + 2 * ox] + s_cr[oy * G::CSTRIDE + 2 * ox + 1] + 1) >> 1;
-                }
-                const uint32_t v = jd_pixel_scalar<PT>(sum << 10, Cb - 128, Cr - 128, a.big_endian != 0u);
-                if (PT == JD_PT_8888) *reinterpret_cast<uint32_t *>(dst) = v;
-                else *reinterpret_cast<uint16_t *>(dst) = (uint16_t)v;
-            }
-        }
+        jd_phase_c_half<HS, VS, NC, PT, G::WCTA, G::HCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
     }
 }
 
@@ -1153,6 +1165,191 @@ jdk_idct_tb(const JDIdctArgs a)
         jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, true>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H, outbase, pitch);
     else
         jd_phase_c_full<HS, VS, NC, PT, ARITH, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, false>(a, s_y, s_c, s_c + 8 * G::CSTRIDE, strip, my, tid, W, H, outbase, pitch);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* fused expand + dequant + IDCT + colour, one THREAD per 8x8 block, two columns per         */
+/* register (SSE2-build arithmetic; every sampling, full and half size).                     */
+/*                                                                                          */
+/* CTA = a strip of MPB MCUs of one MCU row, at most 128 blocks, one per thread.  The blocks */
+/* are first binned inside the CTA -- rows 4-7 empty / populated (the reference's two column  */
+/* pass variants, jpeg.inl:2330) x coefficients within columns 0-3 / beyond -- so that the    */
+/* lanes of a warp mostly run the same code.  A thread then expands its block's records into  */
+/* a private row-major tile in shared memory, dequantising on the way (int16 wrap, like the   */
+/* reference's _mm_mullo_epi16), pulls the tile into registers as 8 rows x 2 or 4 column       */
+/* pairs, and runs jd_idct_block_packed (jd_core.h): packed column pass in place, row pass,   */
+/* pixels into the CTA's planes.  No transpose through shared memory, no warp                 */
+/* synchronisation.  A warp that holds only blocks confined to columns 0-3 uses the           */
+/* two-pair instantiation (half the registers and column passes); a mixed warp takes the       */
+/* four-pair one for all its lanes, which gives identical results.  Colour phase as in the    */
+/* other fused kernels.                                                                       */
+/* ------------------------------------------------------------------------------------ */
+template <int HS, int VS, int NC, int MPB>
+struct JDGeoP {
+    static constexpr int BPMEFF = HS * VS + (NC == 3 ? 2 : 0);
+    static constexpr int NB = MPB * BPMEFF;                       /* blocks per CTA (<= THREADS) */
+    static constexpr int THREADS = 128;
+    static constexpr int WCTA = MPB * HS * 8;
+    static constexpr int HCTA = VS * 8;
+    static constexpr int YSTRIDE = WCTA + 16;
+    static constexpr int CSTRIDE = MPB * 8 + 8;
+    static constexpr int TWORDS = 36;                             /* words per private tile: 32 + 4 (conflict-free LDS.128 per quarter warp) */
+};
+
+#ifndef JD_P_MINB
+#define JD_P_MINB 7
+#endif
+template <int HS, int VS, int NC, int MPB, int PT, bool HALF>
+__global__ void __launch_bounds__(128, JD_P_MINB)
+jdk_idct_p(const JDIdctArgs a)
+{
+    using G = JDGeoP<HS, VS, NC, MPB>;
+    static_assert(G::NB <= G::THREADS, "one thread per block");
+    __shared__ __align__(16) uint32_t s_tile[G::NB * G::TWORDS];
+    __shared__ __align__(16) uint8_t s_y[G::HCTA * G::YSTRIDE];
+    __shared__ __align__(16) uint8_t s_c[(NC == 3 ? 2 : 1) * 8 * G::CSTRIDE];
+    __shared__ jd_u64 s_hdr[G::NB];
+    __shared__ __align__(16) uint32_t s_wc[4][4];
+    __shared__ uint16_t s_q[3 * 64];                              /* prescaled quant, natural order, low 16 bits */
+    __shared__ uint8_t s_perm[G::THREADS];
+
+    const uint32_t img_i = a.img0 + blockIdx.z;
+    const JDImageDesc &im = a.imgs[img_i];
+    const uint32_t strip = blockIdx.x, my = blockIdx.y;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    const uint16_t *const irec = a.rec + im.rec_base;
+
+    /* ---- headers, quant, binning: bin 0 = rows 4-7 empty & columns 0-3, 1 = rows 4-7 populated & columns 0-3,
+     * 2 = populated & beyond column 3, 3 = empty & beyond column 3 (one boundary between the 2-pair and the 4-pair blocks,
+     * two between the column-pass variants) ---- */
+    uint32_t key = 4;
+    if (tid < (uint32_t)G::NB) {
+        const uint32_t ml = jd_div_small<G::BPMEFF>(tid), blk = tid - ml * G::BPMEFF;
+        const uint32_t mx = strip * MPB + ml;
+        if (mx < a.mcus_x) {
+            const jd_u64 h = __ldg(a.blk_hdr + im.blk_base + (my * a.mcus_x + mx) * a.bpm + blk);
+            s_hdr[tid] = h;
+            const uint32_t wide = (JD_HDR_COLMASK(h) & 0xF0u) != 0u, hi = JD_HDR_HI(h);
+            key = wide ? (hi ? 2u : 3u) : hi;
+        }
+    }
+    for (uint32_t i = tid; i < (NC == 3 ? 192u : 64u); i += G::THREADS) {
+        const uint32_t n = i & 63u;
+        s_q[i] = (uint16_t)__ldg(a.quant + (size_t)img_i * 192 + (i & ~63u) + (n & 7u) * 8u + (n >> 3));   /* stored column-major */
+    }
+    uint32_t bal[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) bal[k] = __ballot_sync(0xffffffffu, key == (uint32_t)k);
+    if (lane < 4u) s_wc[lane][wid] = __popc(lane == 0u ? bal[0] : lane == 1u ? bal[1] : lane == 2u ? bal[2] : bal[3]);
+    __syncthreads();
+    uint32_t nbin[4], pre = 0;
+    {
+        uint32_t before = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint4 c = *reinterpret_cast<const uint4 *>(s_wc[k]);
+            nbin[k] = c.x + c.y + c.z + c.w;
+            const uint32_t inwarps = (wid > 0u ? c.x : 0u) + (wid > 1u ? c.y : 0u) + (wid > 2u ? c.z : 0u);
+            if (key == (uint32_t)k) pre = before + inwarps + __popc(bal[k] & ((1u << lane) - 1u));
+            before += nbin[k];
+        }
+    }
+    if (key < 4u) s_perm[pre] = (uint8_t)tid;
+    __syncthreads();
+    const uint32_t n2 = nbin[0] + nbin[1], nall = n2 + nbin[2] + nbin[3];
+
+    /* ---- this thread's block ---- */
+    const bool have = tid < nall;
+    const bool wide = have && tid >= n2;
+    const bool wide_any = __any_sync(0xffffffffu, wide);
+    if (have) {
+        const uint32_t pb = s_perm[tid];
+        const jd_u64 h = s_hdr[pb];
+        const uint32_t ml = jd_div_small<G::BPMEFF>(pb), blk = pb - ml * G::BPMEFF;
+        const uint32_t comp = (blk < (uint32_t)(HS * VS)) ? 0u : blk - HS * VS + 1u;
+        const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h);
+        const bool hi = JD_HDR_HI(h) != 0u;
+        const uint16_t *q = s_q + comp * 64u;
+        uint32_t *tile = s_tile + tid * G::TWORDS;
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(tile);
+        uint8_t *prow;  /* first output row of this block in the staged plane */
+        uint32_t pstride;
+        if (comp == 0) {
+            const uint32_t lx = (HS == 2) ? (blk & 1u) : 0u;
+            const uint32_t ly = (HS == 2 && VS == 2) ? (blk >> 1) : ((VS == 2) ? blk : 0u);
+            prow = s_y + (ly * 8) * G::YSTRIDE + (ml * HS + lx) * 8; pstride = G::YSTRIDE;
+        } else {
+            prow = s_c + ((comp - 1) * 8) * G::CSTRIDE + ml * 8; pstride = G::CSTRIDE;
+        }
+        /* expand + dequantise: d = (int16)(coefficient * quant) like _mm_mullo_epi16 (jpeg.inl:2338) */
+        const uint4 z4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < 4; r++) *reinterpret_cast<uint4 *>(tile + 4 * r) = z4;
+        if (hi) {
+#pragma unroll
+            for (int r = 4; r < 8; r++) *reinterpret_cast<uint4 *>(tile + 4 * r) = z4;
+        }
+        if (!JD_HDR_BIG(h)) {
+            /* the first 10 halfwords that cover the records come in as five independent aligned 32-bit loads (one round
+             * trip instead of a chain of 2-byte loads); longer blocks finish in the loop below */
+            const uint32_t off = ri & 1u, total = off + ncoef;
+            const uint32_t *w32 = reinterpret_cast<const uint32_t *>(irec + (ri - off));
+            uint32_t v[5];
+#pragma unroll
+            for (int w = 0; w < 5; w++) v[w] = ((uint32_t)(2 * w) < total) ? __ldg(w32 + w) : 0u;
+#pragma unroll
+            for (int hh = 0; hh < 10; hh++) {
+                if ((uint32_t)hh >= off && (uint32_t)hh < total) {
+                    const uint32_t r = (hh & 1) ? (v[hh >> 1] >> 16) : (v[hh >> 1] & 0xFFFFu);
+                    const uint32_t n = r >> 10;
+                    t16[n] = (uint16_t)(((int)(r << 22) >> 22) * (int)q[n]);
+                }
+            }
+            for (uint32_t i = 10u - off; i < ncoef; i++) {
+                const uint32_t r = __ldg(irec + ri + i), n = r >> 10;
+                t16[n] = (uint16_t)(((int)(r << 22) >> 22) * (int)q[n]);
+            }
+        } else {
+            for (uint32_t i = 0; i < ncoef; i++) {
+                const uint32_t n = __ldg(irec + ri + 2 * i) & 63u;
+                t16[n] = (uint16_t)((int)(short)__ldg(irec + ri + 2 * i + 1) * (int)q[n]);
+            }
+        }
+        t16[0] = (uint16_t)(JD_HDR_DC(h) * (int)q[0] + JD_ROW_BIAS);
+        const uint32_t cm = JD_HDR_COLMASK(h);
+        if (!wide_any) {
+            uint32_t x[8][2];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (r < 4 || hi) { const uint2 w = *reinterpret_cast<const uint2 *>(tile + 4 * r); x[r][0] = w.x; x[r][1] = w.y; }
+                else { x[r][0] = 0u; x[r][1] = 0u; }
+            }
+            jd_idct_block_packed<2>(x, hi, cm, prow, pstride);
+        } else {
+            uint32_t x[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (r < 4 || hi) { const uint4 w = *reinterpret_cast<const uint4 *>(tile + 4 * r); x[r][0] = w.x; x[r][1] = w.y; x[r][2] = w.z; x[r][3] = w.w; }
+                else { x[r][0] = 0u; x[r][1] = 0u; x[r][2] = 0u; x[r][3] = 0u; }
+            }
+            jd_idct_block_packed<4>(x, hi, cm, prow, pstride);
+        }
+    }
+    __syncthreads();
+
+    /* ---- phase C ---- */
+    const uint32_t W = a.padded ? a.mcus_x * HS * 8 : a.width;
+    const uint32_t H = a.padded ? a.mcus_y * VS * 8 : a.height;
+    uint8_t *outbase = a.out + im.out_off;
+    const uint32_t pitch = im.out_pitch;
+    const uint8_t *s_cb = s_c, *s_cr = s_c + 8 * G::CSTRIDE;
+    if (HALF) {
+        jd_phase_c_half<HS, VS, NC, PT, G::WCTA, G::HCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
+    } else if ((strip + 1) * G::WCTA <= W && (my + 1) * G::HCTA <= H && ((reinterpret_cast<uintptr_t>(outbase) | pitch) & 15u) == 0u) {
+        jd_phase_c_full<HS, VS, NC, PT, JPEG_ARITH_SSE2, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, true>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
+    } else {
+        jd_phase_c_full<HS, VS, NC, PT, JPEG_ARITH_SSE2, G::WCTA, G::YSTRIDE, G::CSTRIDE, G::THREADS, false>(a, s_y, s_cb, s_cr, strip, my, tid, W, H, outbase, pitch);
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */

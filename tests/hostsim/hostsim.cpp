@@ -19,6 +19,8 @@
 #include "../../jpegdec_b200/csrc/jd_chunk.h"
 #include "../../jpegdec_b200/csrc/jd_internal.h"
 
+static uint32_t g_ring[64];   /* stream ring of the CLEAN reader (one walker at a time here) */
+
 struct VecSink {
     std::vector<JDEvent> ev;
     void push(const JDEvent &e) { ev.push_back(e); }
@@ -182,6 +184,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
         in.seg = (uint32_t)sgi;
         in.img = 0;
+        in.ring = g_ring;
         in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         in.al = prog ? (uint32_t)(info.approx & 15) : 0u;
@@ -424,17 +427,17 @@ extern "C" void hostsim_idct_packed(const int16_t *coef, const int16_t *quant, u
     uint16_t d[64];
     for (int n = 0; n < 64; n++) d[n] = (uint16_t)(coef[n] * quant[n]);
     d[0] = (uint16_t)(d[0] + JD_ROW_BIAS);
-    uint32_t px[8][2];
+    uint32_t px[16];
     if ((colmask & 0xF0u) == 0u) {
         uint32_t x[8][2];
         for (int r = 0; r < 8; r++) for (int q = 0; q < 2; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
-        jd_idct_block_packed<2>(x, hi, colmask, px);
+        jd_idct_block_packed<2>(x, hi, colmask, (uint8_t *)px, 8);
     } else {
         uint32_t x[8][4];
         for (int r = 0; r < 8; r++) for (int q = 0; q < 4; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
-        jd_idct_block_packed<4>(x, hi, colmask, px);
+        jd_idct_block_packed<4>(x, hi, colmask, (uint8_t *)px, 8);
     }
-    for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)(px[r][c >> 2] >> (8 * (c & 3)));
+    memcpy(out, px, 64);
 }
 
 /* the same block with the 4-column lanes forced through the general (8-column) instantiation, as happens in a warp that
@@ -446,10 +449,10 @@ extern "C" void hostsim_idct_packed_general(const int16_t *coef, const int16_t *
     uint16_t d[64];
     for (int n = 0; n < 64; n++) d[n] = (uint16_t)(coef[n] * quant[n]);
     d[0] = (uint16_t)(d[0] + JD_ROW_BIAS);
-    uint32_t px[8][2], x[8][4];
+    uint32_t px[16], x[8][4];
     for (int r = 0; r < 8; r++) for (int q = 0; q < 4; q++) x[r][q] = (uint32_t)d[r * 8 + 2 * q] | ((uint32_t)d[r * 8 + 2 * q + 1] << 16);
-    jd_idct_block_packed<4>(x, hi, colmask, px);
-    for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) out[r * 8 + c] = (uint8_t)(px[r][c >> 2] >> (8 * (c & 3)));
+    jd_idct_block_packed<4>(x, hi, colmask, (uint8_t *)px, 8);
+    memcpy(out, px, 64);
 }
 
 /* statistics of the block classes the IDCT kernel branches on (development aid) */
@@ -475,7 +478,7 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in; in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
         int m0 = sgi * mps; in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
-        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0;
+        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0; in.ring = g_ring;
         in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.rec_cap = JD_REC_PER_BYTE * ((uint32_t)size - in.start) + JD_REC_SLOT_SLACK; in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
@@ -527,7 +530,7 @@ extern "C" int hostsim_walk_check(const uint8_t *data, int size, int *n_segments
         in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
         in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
         const uint32_t seg_end = (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] : (uint32_t)size;
-        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.seg = (uint32_t)sgi; in.img = 0;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.seg = (uint32_t)sgi; in.img = 0; in.ring = g_ring;
         in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
         in.blk0 = (uint32_t)(m0 * info.bpm); in.al = 0;
         const uint32_t nb = in.nmcu * in.bpm;

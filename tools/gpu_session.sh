@@ -3,6 +3,7 @@
 #   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh <tag> [steps...]'      steps: tests ab ncu bench uhd10k
 tag=$1; shift
 steps="$*"; [ -z "$steps" ] && steps="tests ab ncu bench"
+: ${ABWORKLOADS:="hd1024 uhd"}
 O=gpurun_out; mkdir -p $O
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${tag}_smi.txt 2>&1
@@ -19,8 +20,9 @@ try:
     d=json.loads(sys.stdin.read()); s=d['stages_ms']
     print('$1 $4', 'total %.3f prescan %.3f entropy %.3f stitch %.3f idct %.3f' % (d['ms_per_step'], s['prescan'], s['entropy'], s['stitch'], s['idct']), str(d['parity_spot_check'])[:12])
 except Exception as e: print('$1 $4 FAILED', e)" ) >> $O/${tag}_ab.txt 2>&1; }
-  for wl in hd1024 uhd; do
-    ab clean main "" $wl; ab raw main JPEGDEC_B200_ENTROPY=raw $wl
+  for wl in $ABWORKLOADS; do
+    ab default main "" $wl
+    for e in $ABENVS; do ab $e main $e $wl; done
     for v in $ABVARIANTS; do ab $v $v "" $wl; done
   done
   cat $O/${tag}_ab.txt ;;
@@ -31,10 +33,9 @@ ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o $O/${tag}_$1 $B --workload $3 > $O/${tag}_ncu_$1.log 2>&1
     python tools/ncu_summary.py $O/${tag}_$1.ncu-rep $O/${tag}_$1_summary.txt > /dev/null 2>&1
     sz=$(stat -c %s $O/${tag}_$1.ncu-rep 2>/dev/null || echo 0); [ "$sz" -gt 14000000 ] && rm -f $O/${tag}_$1.ncu-rep; }
-  prof entropy_hd1024 jdk_entropy hd1024
-  prof idct_tb_hd1024 jdk_idct_tb hd1024
-  prof idct_tb_uhd jdk_idct_tb uhd
-  prof unstuff_hd1024 jdk_unstuff_segs hd1024
+  for spec in ${NCUSPECS:-entropy_hd1024:jdk_entropy:hd1024 idct_p_hd1024:jdk_idct_p:hd1024 idct_p_uhd:jdk_idct_p:uhd}; do
+    IFS=: read n rx w <<< "$spec"; prof $n $rx $w
+  done
   ls -la $O | tail -20 ;;
 bench)
   timeout 900 python bench.py > $O/${tag}_bench_hd1024_1gpu.json 2> $O/${tag}_bench_hd1024.err; tail -c 600 $O/${tag}_bench_hd1024_1gpu.json
