@@ -424,9 +424,17 @@ static void deliver_framebuffer(const JPEGIMAGE *p, const uint8_t *frame, int fr
             } else {
                 int lines = mh, px = pitch_px - xoff;
                 if (r * mh + lines > out_h) lines = out_h - r * mh;
-                if (px > mw) px = mw;
-                for (int l = 0; l < lines && px > 0; l++)
-                    memcpy((uint8_t *)p->pFramebuffer + ((size_t)(ty + l) * pitch_px + xoff) * bypp, src + (size_t)l * frame_pitch, (size_t)px * bypp);
+                /* inside the pitch an MCU is clipped at its end; the one MCU the inclusive crop test lets through past the
+                 * crop's right edge (:5111) lies beyond the pitch and is stored whole, i.e. it runs on into the next line
+                 * like in the reference (clipped only at the end of the MCU-row-aligned buffer) */
+                if (px > mw || px <= 0) px = mw;
+                for (int l = 0; l < lines; l++) {
+                    const size_t at = (size_t)(ty + l) * pitch_px + xoff;
+                    size_t n = (size_t)px;
+                    if (at >= fb_px) break;
+                    if (at + n > fb_px) n = fb_px - at;
+                    memcpy((uint8_t *)p->pFramebuffer + at * bypp, src + (size_t)l * frame_pitch, n * bypp);
+                }
             }
             xoff += mw;
         }

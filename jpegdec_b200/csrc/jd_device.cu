@@ -71,12 +71,19 @@ struct JDPinPool {
     void drain() { for (auto &s : free_) cudaFreeHost(s.p); free_.clear(); }
 };
 
+/* a job's stream and its timing events, recycled through the context (creating them costs more than a small decode) */
+struct JDStreamSet {
+    cudaStream_t stream;
+    cudaEvent_t ev[JPEGB200_NUM_TIMINGS + 2];
+};
+
 struct JPEGB200_CTX {
+    std::vector<JDStreamSet> free_streams;
     int device;
     int arith;
     char err[256];
     bool has_shared;
-    uint64_t shared_hash;
+    uint64_t shared_hash, shared_hash2;
     uint16_t shared_lut[JD_LUT_ENTRIES];
     int shared_hits;
     JDPool pool;
@@ -240,6 +247,7 @@ extern "C" void JPEGB200_destroy(JPEGB200_CTX *ctx)
     cudaDeviceSynchronize();
     ctx->pool.drain();
     ctx->pinpool.drain();
+    for (auto &ss : ctx->free_streams) { for (auto &e : ss.ev) cudaEventDestroy(e); cudaStreamDestroy(ss.stream); }
     delete ctx;
 }
 
@@ -406,9 +414,9 @@ extern "C" int JPEGB200_exportTables(const uint8_t *jpeg, int size, uint8_t *blo
     JDInfo *info = new JDInfo();
     int rc = jd_parse_header(jpeg, size, 0, info);
     if (rc) {
-        uint64_t h = jd_tables_hash(info);
+        const uint64_t h = jd_tables_hash(info), h2 = jd_tables_hash2(info);   /* 128-bit key of the DHT content */
         memcpy(blob, &h, 8);
-        memset(blob + 8, 0, 8);
+        memcpy(blob + 8, &h2, 8);
         jd_build_lut(info, (uint16_t *)(blob + 16));
         jd_build_quant(info, (int16_t *)(blob + 16 + JD_LUT_ENTRIES * 2));
     }
@@ -420,6 +428,7 @@ extern "C" int JPEGB200_setSharedTables(JPEGB200_CTX *ctx, const uint8_t *blob)
 {
     if (!ctx) return 0;
     memcpy(&ctx->shared_hash, blob, 8);
+    memcpy(&ctx->shared_hash2, blob + 8, 8);
     memcpy(ctx->shared_lut, blob + 16, JD_LUT_ENTRIES * 2);
     ctx->has_shared = true;
     ctx->shared_hits = 0;
@@ -486,6 +495,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
     }
 
     std::vector<uint64_t> lut_hash;
+    std::vector<int> lut_owner;      /* first image that defined each LUT set: a hash match is confirmed on the DHT bytes */
     uint32_t seg = 0;
     uint64_t blk = 0, rec_total = 0;
     size_t out_total = 0, gray_total = 0;
@@ -524,15 +534,17 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
                 for (int nn = 0; nn < 64; nn++) qt[cc * 64 + (nn & 7) * 8 + (nn >> 3)] = qn[cc * 64 + nn];
         }
         /* Huffman LUT set: dedupe on the raw DHT content */
-        uint64_t h = jd_tables_hash(&inf);
+        const uint64_t h = jd_tables_hash(&inf);
         uint32_t li = 0;
-        for (; li < lut_hash.size(); li++) if (lut_hash[li] == h) break;
+        for (; li < lut_hash.size(); li++) if (lut_hash[li] == h && jd_tables_equal(&inf, &b->infos[lut_owner[li]])) break;
+        const bool shared = ctx->has_shared && ctx->shared_hash == h && ctx->shared_hash2 == jd_tables_hash2(&inf);
         if (li == lut_hash.size()) {
-            lut_hash.push_back(h);
+            lut_hash.push_back(h); lut_owner.push_back(i);
             b->luts.resize((size_t)(li + 1) * JD_LUT_ENTRIES);
-            if (ctx->has_shared && ctx->shared_hash == h) { memcpy(&b->luts[(size_t)li * JD_LUT_ENTRIES], ctx->shared_lut, JD_LUT_ENTRIES * 2); ctx->shared_hits++; }
+            if (shared) memcpy(&b->luts[(size_t)li * JD_LUT_ENTRIES], ctx->shared_lut, JD_LUT_ENTRIES * 2);
             else jd_build_lut(&inf, &b->luts[(size_t)li * JD_LUT_ENTRIES]);
-        } else if (ctx->has_shared && ctx->shared_hash == h) ctx->shared_hits++;
+        }
+        if (shared) ctx->shared_hits++;
         const uint32_t total_mcus = (uint32_t)inf.mcus_x * inf.mcus_y;
         const uint32_t mps = inf.restart_interval ? (uint32_t)inf.restart_interval : total_mcus;
         d.scan_off = (uint32_t)(b->comp_off[i] + inf.scan_offset);
@@ -617,8 +629,15 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
     b->d_seg_jmap.release(); b->d_seg_status.release(); b->d_seg_nrec.release(); b->d_seg_phase.release();
     b->d_counters.release(); b->d_blk_hdr.release(); b->d_events.release();
-    if (b->have_ev) for (auto &e : b->ev) cudaEventDestroy(e);
-    if (b->stream) cudaStreamDestroy(b->stream);
+    if (b->stream && b->have_ev) {   /* back to the context for the next job */
+        JDStreamSet ss;
+        ss.stream = b->stream;
+        for (int i = 0; i < JPEGB200_NUM_TIMINGS + 2; i++) ss.ev[i] = b->ev[i];
+        b->ctx->free_streams.push_back(ss);
+    } else {
+        if (b->have_ev) for (auto &e : b->ev) cudaEventDestroy(e);
+        if (b->stream) cudaStreamDestroy(b->stream);
+    }
     if (b->descs_dl) b->ctx->pinpool.put(b->descs_dl, b->descs_dl_bytes);
     delete b;
 }
@@ -657,6 +676,13 @@ extern "C" int JPEGB200_batchSetOutput(JPEGB200_BATCH *b, int i, void *out, int6
 static int batch_stream(JPEGB200_BATCH *b)
 {
     CK(cudaSetDevice(b->ctx->device));
+    if (!b->stream && !b->have_ev && !b->ctx->free_streams.empty()) {
+        const JDStreamSet ss = b->ctx->free_streams.back();
+        b->ctx->free_streams.pop_back();
+        b->stream = ss.stream;
+        for (int i = 0; i < JPEGB200_NUM_TIMINGS + 2; i++) b->ev[i] = ss.ev[i];
+        b->have_ev = true;
+    }
     if (!b->stream) CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     if (!b->have_ev) {
         for (auto &e : b->ev) CK(cudaEventCreate(&e));
@@ -1372,8 +1398,13 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
            uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift,
            const uint4 *bands, uint32_t nbands, uint32_t *progress)
 {
-    const uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   /* global warp = band */
+    /* Bands are handed out through a ticket counter (progress[nbands]) in the order in which warps START, not by warp index:
+     * the list is band-major (band k of every image before band k + 1), so the band a warp waits on was always claimed by a
+     * warp that is already running -- forward progress does not depend on the order in which the hardware schedules CTAs. */
     const uint32_t lane = threadIdx.x & 31u;
+    uint32_t wg = 0;
+    if (lane == 0) wg = atomicAdd(progress + nbands, 1u);
+    wg = __shfl_sync(0xffffffffu, wg, 0);
     if (wg >= nbands) return;
     const uint4 bd = bands[wg];
     const uint32_t i = bd.x, bi = bd.y;

@@ -387,6 +387,38 @@ void jd_build_quant(const JDInfo *info, int16_t *q)
     }
 }
 
+/* 1 when both headers define the same Huffman tables (same table ids, same counts, same symbols) */
+int jd_tables_equal(const JDInfo *x, const JDInfo *y)
+{
+    if (x->p.huff_defined != y->p.huff_defined) return 0;
+    for (int t = 0; t < 8; t++) {
+        if (!(x->p.huff_defined & (1u << t))) continue;
+        const uint8_t *bx = x->p.huffvals + t * HUFF_TABLEN, *by = y->p.huffvals + t * HUFF_TABLEN;
+        int total = 0;
+        for (int i = 0; i < 16; i++) total += bx[i];
+        if (total > 256) total = 256;
+        if (memcmp(bx, by, (size_t)(16 + total)) != 0) return 0;
+    }
+    return 1;
+}
+
+/* second, independent 64-bit digest of the same bytes (keys the shared-table blob together with jd_tables_hash) */
+uint64_t jd_tables_hash2(const JDInfo *info)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    const uint8_t *hv = info->p.huffvals;
+    for (int t = 0; t < 8; t++) {
+        if (!(info->p.huff_defined & (1u << t))) continue;
+        const uint8_t *b = hv + t * HUFF_TABLEN;
+        int total = 0;
+        for (int i = 0; i < 16; i++) total += b[i];
+        if (total > 256) total = 256;
+        h = (h + (uint64_t)(t + 1)) * 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+        for (int i = 0; i < 16 + total; i++) { h = (h + b[i]) * 0xD6E8FEB86659FD93ull; h ^= h >> 29; }
+    }
+    return h;
+}
+
 uint64_t jd_tables_hash(const JDInfo *info)
 {
     /* FNV-1a over the defined DHT tables */

@@ -41,6 +41,8 @@ int jd_check_huffman(const JDInfo *info);                      /* 1 ok, 0 -> JPE
 void jd_build_lut(const JDInfo *info, uint16_t *lut /* JD_LUT_ENTRIES_H */);
 void jd_build_quant(const JDInfo *info, int16_t *q /* [3][64] natural order, per component */);
 uint64_t jd_tables_hash(const JDInfo *info);
+uint64_t jd_tables_hash2(const JDInfo *info);
+int jd_tables_equal(const JDInfo *x, const JDInfo *y);
 const int *jd_aan_table(void);
 
 /* Device-visible per-image descriptor (96 B). */
