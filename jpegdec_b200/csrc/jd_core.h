@@ -61,9 +61,9 @@
 /*   bit  54     : BIG -- some magnitude needs >= 10 bits: records are pairs     */
 /*   bit  55     : a stored coefficient lies in rows 4-7 (u16MCUFlags & 0x2000)  */
 /*   bits 56..63 : occupied-column mask (low byte of u16MCUFlags, jpeg.inl:2253) */
-/* AC record (u16), normal blocks: (n << 10) | (value & 0x3FF), |value| <= 511,  */
-/*   n = natural (row-major) index of the coefficient = row * 8 + column.        */
-/*   BIG blocks: two u16 per coefficient: n, then value.                         */
+/* AC record (u16), normal blocks: (t << 10) | (value & 0x3FF), |value| <= 511,  */
+/*   t = position in the column-major coefficient tile = (n & 7) * 8 + (n >> 3)  */
+/*   for natural index n.  BIG blocks: two u16 per coefficient: t, then value.   */
 /* Only stored coefficients get a record (no ZRL / EOB records).                 */
 typedef unsigned long long jd_u64;
 
@@ -79,10 +79,17 @@ JD_HD jd_u64 jd_pack_hdr(uint32_t rec_index, int dc, uint32_t ncoef, uint32_t bi
 #define JD_HDR_HI(h) ((uint32_t)((h) >> 55) & 1u)
 #define JD_HDR_COLMASK(h) ((uint32_t)((h) >> 56) & 0xFFu)
 
-/* de-zigzag: zigzag index k -> natural (row-major) index n (ITU T.81 Figure 5): the position a record carries. */
-#define JD_TPOS_INIT JD_DEZIGZAG_INIT
-/* natural index <-> position in a column-major 8x8 tile (the same bit swap both ways) */
+/* zigzag index k -> tile position t (column-major: t = (n & 7) * 8 + (n >> 3), n = de-zigzag(k)): what a record carries
+ * (the 4:2:0 thread-per-block kernel reads whole columns of its private tile with one load) */
+#define JD_TPOS_INIT { \
+    0, 8, 1, 2, 9, 16, 24, 17, 10, 3, 4, 11, 18, 25, 32, 40, \
+    33, 26, 19, 12, 5, 6, 13, 20, 27, 34, 41, 48, 56, 49, 42, 35, \
+    28, 21, 14, 7, 15, 22, 29, 36, 43, 50, 57, 58, 51, 44, 37, 30, \
+    23, 31, 38, 45, 52, 59, 60, 53, 46, 39, 47, 54, 61, 62, 55, 63 }
+/* tile position <-> natural (row-major) index (the same bit swap both ways) */
 #define JD_TRANSPOSE6(x) ((((x) & 7u) << 3) | ((x) >> 3))
+
+/* de-zigzag: zigzag index k -> natural (row-major) index (ITU T.81 Figure 5). */
 #define JD_DEZIGZAG_INIT { \
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, \
     12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28, \
@@ -189,9 +196,9 @@ typedef struct {
 #define JD_LD8(p) (*(p))
 #endif
 
-/* zigzag k -> packed word: natural index n | rows-4..7 bit << 23 | column bit (1 << (n & 7)) << 24 -- the flag bits sit
+/* zigzag k -> packed word: tile position t | rows-4..7 bit << 23 | column bit (1 << (t >> 3)) << 24 -- the flag bits sit
  * where the block header's high word keeps them, so OR-ing the words of a block's coefficients builds that word */
-JD_HD uint32_t jd_tposw(uint32_t n) { return n | (((n >> 5) & 1u) << 23) | ((1u << (n & 7u)) << 24); }
+JD_HD uint32_t jd_tposw(uint32_t t) { return t | (((t >> 2) & 1u) << 23) | ((1u << (t >> 3)) << 24); }
 #define JD_BF_HI(bf) (((bf) >> 23) & 1u)
 #define JD_BF_COLMASK(bf) ((bf) >> 24)
 #define JD_BF_MASK 0xFF800000u

@@ -1096,7 +1096,13 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             const int ar = b->ctx->arith;
             static int use_packed = -1;   /* JPEGDEC_B200_IDCT=lanes|tb: the round-1 kernels also for the SSE2-build arithmetic (A/B) */
             if (use_packed < 0) { const char *e = getenv("JPEGDEC_B200_IDCT"); use_packed = (e && (strcmp(e, "lanes") == 0 || strcmp(e, "tb") == 0)) ? 0 : 1; }
-            if (ar == JPEG_ARITH_SSE2 && use_packed) {
+            /* 4:2:0 colour at full size keeps jdk_idct_tb (measured faster there: 3.25 vs 3.95 ms on 1024 x HD -- packed
+             * 16-bit subtraction costs three instructions on this part, which eats what the packed adds save); every other
+             * sampling / pixel type / half scale takes the packed thread-per-block kernel instead of the 8-lanes-per-block one */
+            const bool tb_case = f.subsample == 0x22 && f.ncomp == 3 && b->ptclass != JD_PT_GRAY && !half;
+            static int force_packed = -1;
+            if (force_packed < 0) { const char *e = getenv("JPEGDEC_B200_IDCT"); force_packed = (e && strcmp(e, "packed") == 0) ? 1 : 0; }
+            if (ar == JPEG_ARITH_SSE2 && use_packed && (!tb_case || force_packed)) {
                 switch (f.subsample) {
                     case 0x00: case 0x11: ok = launch_idct_packed<1, 1>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;
                     case 0x21: ok = launch_idct_packed<2, 1>(ia, max_mx, max_my, nimg, f.ncomp, b->ptclass, half, st); break;

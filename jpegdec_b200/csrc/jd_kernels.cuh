@@ -823,16 +823,16 @@ jdk_idct_color(const JDIdctArgs a)
         __syncwarp();
         if (!JD_HDR_BIG(h)) {
             const uint16_t *rp = irec + ri + c;
-            if (c < ncoef) { const uint32_t r = __ldg(rp); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
-            if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
+            if (c < ncoef) { const uint32_t r = __ldg(rp); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
+            if (c + 8 < ncoef) { const uint32_t r = __ldg(rp + 8); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
             for (uint32_t i = c + 16; i < ncoef; i += 8) {
                 const uint32_t r = __ldg(irec + ri + i);
-                tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22);
+                tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
             }
         } else {
             for (uint32_t i = c; i < ncoef; i += 8) {
                 const uint32_t t = __ldg(irec + ri + 2 * i) & 63u;
-                tile[JD_TRANSPOSE6(t)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+                tile[t] = (int16_t)__ldg(irec + ri + 2 * i + 1);
             }
         }
         __syncwarp();
@@ -1016,12 +1016,12 @@ jdk_idct_tb(const JDIdctArgs a)
             for (int hh = 0; hh < 10; hh++) {
                 if ((uint32_t)hh >= off && (uint32_t)hh < total) {
                     const uint32_t r = (hh & 1) ? (v[hh >> 1] >> 16) : (v[hh >> 1] & 0xFFFFu);
-                    tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22);
+                    tile[r >> 10] = (int16_t)((int)(r << 22) >> 22);
                 }
             }
-            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(irec + ri + i); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
+            for (uint32_t i = 10u - off; i < ncoef; i++) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
         } else {
-            for (uint32_t i = 0; i < ncoef; i++) tile[JD_TRANSPOSE6(__ldg(irec + ri + 2 * i) & 63u)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+            for (uint32_t i = 0; i < ncoef; i++) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
         }
         int cr[8][4]; /* column-pass results (as int16 values), [row][column] */
         if (r47) {
@@ -1111,9 +1111,9 @@ jdk_idct_tb(const JDIdctArgs a)
                     const uint4 q1 = __ldg(reinterpret_cast<const uint4 *>(qg + c * 8 + 4));
                     __syncwarp();
                     if (!JD_HDR_BIG(h)) {
-                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(irec + ri + i); tile[JD_TRANSPOSE6(r >> 10)] = (int16_t)((int)(r << 22) >> 22); }
+                        for (uint32_t i = c; i < ncoef; i += 8) { const uint32_t r = __ldg(irec + ri + i); tile[r >> 10] = (int16_t)((int)(r << 22) >> 22); }
                     } else {
-                        for (uint32_t i = c; i < ncoef; i += 8) tile[JD_TRANSPOSE6(__ldg(irec + ri + 2 * i) & 63u)] = (int16_t)__ldg(irec + ri + 2 * i + 1);
+                        for (uint32_t i = c; i < ncoef; i += 8) tile[__ldg(irec + ri + 2 * i) & 63u] = (int16_t)__ldg(irec + ri + 2 * i + 1);
                     }
                     __syncwarp();
                     int m[8], o[8];
@@ -1301,17 +1301,17 @@ jdk_idct_p(const JDIdctArgs a)
             for (int hh = 0; hh < 10; hh++) {
                 if ((uint32_t)hh >= off && (uint32_t)hh < total) {
                     const uint32_t r = (hh & 1) ? (v[hh >> 1] >> 16) : (v[hh >> 1] & 0xFFFFu);
-                    const uint32_t n = r >> 10;
+                    const uint32_t n = JD_TRANSPOSE6(r >> 10);      /* records carry column-major positions */
                     t16[n] = (uint16_t)(((int)(r << 22) >> 22) * (int)q[n]);
                 }
             }
             for (uint32_t i = 10u - off; i < ncoef; i++) {
-                const uint32_t r = __ldg(irec + ri + i), n = r >> 10;
+                const uint32_t r = __ldg(irec + ri + i), n = JD_TRANSPOSE6(r >> 10);
                 t16[n] = (uint16_t)(((int)(r << 22) >> 22) * (int)q[n]);
             }
         } else {
             for (uint32_t i = 0; i < ncoef; i++) {
-                const uint32_t n = __ldg(irec + ri + 2 * i) & 63u;
+                const uint32_t t = __ldg(irec + ri + 2 * i) & 63u, n = JD_TRANSPOSE6(t);
                 t16[n] = (uint16_t)((int)(short)__ldg(irec + ri + 2 * i + 1) * (int)q[n]);
             }
         }
@@ -1375,13 +1375,13 @@ __device__ __forceinline__ void jd_scaled_block(const uint16_t *irec, jd_u64 h, 
     const uint32_t ri = JD_HDR_REC(h), ncoef = JD_HDR_NCOEF(h), big = JD_HDR_BIG(h);
     int m1 = 0, m8 = 0, m9 = 0;
     bool any = false;
-    /* records are in zigzag order: the ones the 1/4 path keeps (zigzag 1..4 = natural 1, 8, 16, 9;
-     * jpeg.inl:2117-2119) come first */
+    /* records are in zigzag order: the ones the 1/4 path keeps (zigzag 1..4 = natural 1, 8, 16, 9 =
+     * tile positions 8, 1, 2, 9; jpeg.inl:2117-2119) come first */
     for (uint32_t i = 0; i < ncoef; i++) {
         uint32_t t; int v;
         if (big) { t = irec[ri + 2 * i] & 63u; v = (int)(short)irec[ri + 2 * i + 1]; }
         else { const uint32_t r = irec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
-        if (t == 1u) m1 = v; else if (t == 8u) m8 = v; else if (t == 9u) m9 = v; else if (t != 16u) break;
+        if (t == 8u) m1 = v; else if (t == 1u) m8 = v; else if (t == 9u) m9 = v; else if (t != 2u) break;
         any = true;
     }
     if (!any) { px[0] = px[1] = px[2] = px[3] = jd_range(dc * q0); return; }

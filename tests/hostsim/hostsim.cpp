@@ -256,7 +256,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
                 uint32_t t; int v;
                 if (bigb) { t = rec[ri + 2 * i] & 63u; v = (int16_t)rec[ri + 2 * i + 1]; }
                 else { const uint32_t r = rec[ri + i]; t = r >> 10; v = (int)(r << 22) >> 22; }
-                const int n = (int)t;   /* records carry the natural index */
+                const int n = (int)((t & 7u) * 8u + (t >> 3));
                 /* 1/4 and 1/8 scale keep only zigzag 1..4 = natural 1, 8, 16, 9 (jpeg.inl:2117-2119) */
                 if (sshift >= 2 && !(n == 1 || n == 8 || n == 16 || n == 9)) continue;
                 tile[n] = (int16_t)v;
