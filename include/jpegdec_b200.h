@@ -140,7 +140,7 @@ int JPEGB200_lastCallTimings(JPEGB200_CTX *ctx, float *ms, int *jobs);
 int JPEGB200_setPipelineDepth(JPEGB200_CTX *ctx, int jobs_in_flight);
 
 /* ---- shared-table blob (multi-GPU: rank 0 exports, NCCL broadcast, other ranks import) ---- */
-#define JPEGB200_TABLE_BLOB_BYTES (8448 * 2 + 3 * 64 * 2 + 16)
+#define JPEGB200_TABLE_BLOB_BYTES (10496 * 2 + 3 * 64 * 2 + 16)
 int JPEGB200_exportTables(const uint8_t *jpeg, int size, uint8_t *blob /* JPEGB200_TABLE_BLOB_BYTES */);
 int JPEGB200_setSharedTables(JPEGB200_CTX *ctx, const uint8_t *blob);
 int JPEGB200_sharedTableHits(JPEGB200_CTX *ctx);

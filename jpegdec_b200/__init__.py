@@ -29,7 +29,7 @@ JPEGB200_OUT_DEVICE = 1
 TIMING_NAMES = ["h2d", "prescan", "entropy", "stitch", "idct", "dither", "d2h", "total"]
 COUNTER_NAMES = ["launches", "segments", "blocks", "events", "compressed_bytes", "output_bytes",
                  "record_bytes", "h2d_bytes", "d2h_bytes", "event_candidates"]
-TABLE_BLOB_BYTES = 8448 * 2 + 3 * 64 * 2 + 16
+TABLE_BLOB_BYTES = 10496 * 2 + 3 * 64 * 2 + 16
 
 
 class JPEGDRAW(C.Structure):

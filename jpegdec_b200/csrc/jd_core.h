@@ -33,16 +33,22 @@
 /* ------------------------------------------------------------------------- */
 #define JD_LUT_DC_SIZE 1152
 #define JD_LUT_AC_SIZE 2048
-#define JD_LUT_ACF_SIZE 1024
+#define JD_LUT_ACF_SIZE 2048    /* in u16 units: 1024 32-bit entries */
 #define JD_LUT_DC(t) ((t) * JD_LUT_DC_SIZE)
 #define JD_LUT_AC(t) (2 * JD_LUT_DC_SIZE + (t) * JD_LUT_AC_SIZE)
-/* Fast AC table t (what the hot loop of jd_decode_segment reads): indexed by the next 10 bits alone.
- *   entry = RARE << 15 | len << 8 | RS ;  len == 0: the code is longer than 10 bits (look it up in the second half of
- *   JD_LUT_AC(t)) or invalid.  RARE = the symbol needs one of the exact checks of the store path: SSSS >= 10 (pair records /
- *   not baseline) or len + SSSS >= 18 (a window-truncated read is possible). */
+/* Fast AC table t (what the hot loop of jd_decode_segment reads): 1024 32-bit entries indexed by the next 10 bits alone, with
+ * every field the loop needs already split out, one per byte:
+ *   byte 0 = len + SSSS (bits the symbol consumes), bit 7 = RARE;  byte 1 = len;  byte 2 = SSSS;
+ *   byte 3 = run + 1 (how far the zigzag index advances), 128 for EOB.
+ *   entry == 0: the code is longer than 10 bits (look it up in the second half of JD_LUT_AC(t)) or invalid.
+ *   RARE = the symbol needs one of the exact checks of the store path: SSSS >= 10 (pair records / not baseline) or
+ *   len + SSSS >= 18 (a window-truncated read is possible). */
 #define JD_LUT_ACF(t) (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE + (t) * JD_LUT_ACF_SIZE)
-#define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE + 2 * JD_LUT_ACF_SIZE) /* 8448 u16 = 16896 B */
-#define JD_ACF_RARE 0x8000u
+#define JD_LUT_ENTRIES (2 * JD_LUT_DC_SIZE + 2 * JD_LUT_AC_SIZE + 2 * JD_LUT_ACF_SIZE) /* 10496 u16 = 20992 B */
+#define JD_ACF_RARE 0x80u
+#define JD_ACF_PACK(len, rs) ((uint32_t)((len) + ((rs) & 15u)) | ((uint32_t)(len) << 8) | (((uint32_t)(rs) & 15u) << 16) | \
+                              ((((rs) == 0u) ? 128u : (((uint32_t)(rs) >> 4) + 1u)) << 24) | \
+                              (((((rs) & 15u) >= 10u) || ((len) + ((rs) & 15u) >= 18u)) ? JD_ACF_RARE : 0u))
 
 /* Coefficient records of stream slot `slot` (restart segment, or chunk of a restart-free scan) that starts at byte offset
  * `byte_off` of the batch buffer live at record index JD_REC_INDEX(byte_off, slot): no prefix sum between the stages.
@@ -519,11 +525,12 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
 {
     /* ---- bit reader.  Raw input: aligned 32-bit words, one word prefetched ahead of use, un-stuffing on the fly.
      * CLEAN input (the segment starts 16-byte aligned and ends in zeros): the stream is staged through a 32-word ring per
-     * walker in shared memory.  The ring is topped up at WARP-SYNCHRONOUS ticks: every 8th symbol all lanes that are in the
-     * loop first park the 32 bytes they requested at the previous tick, then request the next 32 if there is room.  Global
-     * loads are therefore only issued at ticks and only consumed at the following tick, >= 8 symbols later.  (Scoreboards
-     * are per warp register, not per lane: with a per-lane prefetch register, any lane's pending load stalled every other
-     * lane that touched the same register name -- 48 % of the stall samples in the first round-2 builds.) ---- */
+     * walker in shared memory.  The ring is topped up where the warp is CONVERGED, at the top of every block: each lane first
+     * parks the 32 bytes it requested one block earlier, then requests the next 32 if there is room.  Global loads are thus
+     * issued and consumed a whole block apart and by all lanes at the same instruction.  (Scoreboards are per warp
+     * register, not per lane: with a per-lane prefetch register, any lane's pending load stalled every other lane that
+     * touched the same register name -- 31 % of the stall samples of the first round-2 builds sat on that one instruction.)
+     * A block that swallows more than the ring holds (> ~100 bytes: rare) tops up on the spot. ---- */
     const uint32_t *words = (const uint32_t *)in.data;
     const uint32_t endw = (in.end + 3u) >> 2;    /* first word index past the data */
     uint32_t wi = in.start >> 2;                 /* index of the next word to consume */
@@ -537,7 +544,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     const uint32_t nchunk = CLEAN ? ((in.end - in.start + 15u) >> 4) : 0u;
     const jd_u128 zero128 = {0u, 0u, 0u, 0u};
     uint32_t *const ring = in.ring;
-    uint32_t rd = 0, wr = 0, gi = 0, tick = 0;   /* words read / written so far; next chunk to request; symbols since the last tick */
+    uint32_t rd = 0, wr = 0, gi = 0;             /* words read / written so far; next chunk to request */
     jd_u128 pa = zero128, pb = zero128;          /* the 32 bytes requested at the last tick */
     bool pend = false;
     auto ring_put = [&](uint32_t at, const jd_u128 &v) {
@@ -559,22 +566,11 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         wr = 16u; gi = 4u;
         topup();
     }
-    /* one symbol consumed: top the ring up every 8th symbol, all lanes of the warp at the same instruction */
-    auto tick1 = [&]() {
-        if (CLEAN) {
-            tick++;
-#ifdef __CUDA_ARCH__
-            if (__any_sync(__activemask(), (tick & 7u) == 0u)) { topup(); tick = 0; }
-#else
-            if ((tick & 7u) == 0u) { topup(); tick = 0; }
-#endif
-        }
-    };
-
     /* keeps >= 32 valid bits in bb */
     auto refill = [&]() {
         if (CLEAN) {
             if (nb <= 32) {
+                while (rd == wr) topup();        /* ring ran dry inside one block (rare) */
                 const uint32_t w = ring[rd & 31u];
                 rd++;
                 bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
@@ -629,6 +625,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     int err = -1;
     bool last_was_eob = true;
     const JDTab16 T(lut);
+    const JDTab32 T32((const uint32_t *)lut);    /* the fast AC tables are 32-bit entries inside the same set */
     const JDTab32 TP(tposw);
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
@@ -646,6 +643,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
 
     for (; b < nblk_total; b++) {
         const uint32_t cur = (sched >> bsh) & 15u;
+        if (CLEAN) topup();                      /* the warp is converged here */
         /* ---- DC symbol (jpeg.inl:2128-2165) ---- */
         refill();
         jw = jd_jw_ckpt(jw);                     /* R1 at block entry (also the previous block's R4) */
@@ -674,41 +672,41 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
             pred2 = (comp >= 2u) ? pv : pred2;
             dcval = pv;
         }
-        tick1();
         const uint32_t r0 = ro;                  /* this block's first record */
         uint32_t bflags = 0, bigm = 0;           /* OR of the tposw words; JD_ACF_RARE once the block's records are pairs */
         if (MODE != JD_MODE_DC_SCAN) {
             if (MODE != JD_MODE_PARSE_AC && in.rec_cap - ro < JD_REC_BLOCK_MAX) { err = JD_SEG_OVERFLOW; break; }
             /* ---- AC symbols (jpeg.inl:2225-2264) ---- */
-            const uint32_t tacf = JD_LUT_ACF(cur >> 3);
-            uint32_t k = 1;
+            const uint32_t tacf = JD_LUT_ACF(cur >> 3) >> 1;   /* 32-bit entries */
+            uint32_t k = 1;                      /* zigzag index of the next coefficient */
             do {
                 refill();
                 jw = jd_jw_ckpt(jw);             /* R3 at the loop top (also the previous symbol's R4) */
                 const uint32_t hi = (uint32_t)(bb >> 32);
-                uint32_t e = T.at(tacf + (hi >> 22));
-                uint32_t len = (e >> 8) & 31u;
-                if (len == 0u) {
+                uint32_t e = T32.at(tacf + (hi >> 22));
+                if (e == 0u) {
                     /* code longer than 10 bits (first 6 bits are ones) or invalid */
-                    e = (hi >= 0xFC000000u) ? T.at(JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)) : 0u;
-                    if (e == 0u) { err = JD_SEG_BADCODE; break; }
-                    len = e >> 8;
-                    e |= JD_ACF_RARE;
+                    const uint32_t e16 = (hi >= 0xFC000000u) ? T.at(JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)) : 0u;
+                    if (e16 == 0u) { err = JD_SEG_BADCODE; break; }
+                    e = JD_ACF_PACK(e16 >> 8, e16 & 0xFFu) | JD_ACF_RARE;
                 }
-                const uint32_t rs = e & 0xFFu, s = rs & 15u;
+                const uint32_t tot = e & 0x1Fu, len = (e >> 8) & 0xFFu, s = (e >> 16) & 0xFFu;
                 /* the S bits after the code, at the top of a word; then one shift past code + extra bits */
 #ifdef __CUDA_ARCH__
                 const uint32_t x = __funnelshift_l((uint32_t)bb, hi, len);
+                const uint32_t mag = __funnelshift_r(x, 0u, 32u - s);               /* s = 0: unused */
 #else
                 const uint32_t x = (uint32_t)((bb << len) >> 32);
+                const uint32_t mag = s ? (x >> (32u - s)) : 0u;
 #endif
-                const int v = jd_extend_top(x, s);
-                bb <<= (len + s);
-                nb -= (int)(len + s);
-                k = (rs == 0u) ? 128u : k + (rs >> 4);   /* EOB (:2241-2244) ends the block */
-                if (MODE != JD_MODE_PARSE_AC && s != 0u && k < LIMIT) {
-                    /* stored coefficient (jpeg.inl:2247-2256) */
-                    const uint32_t tw = TP.at(k);
+                /* EXTEND (T.81 F.2.2.1): first extra bit 0 = negative, value = field - (2^S - 1) */
+                const int v = (int)(mag - (~(uint32_t)((int)x >> 31) & ~(0xFFFFFFFFu << s)));
+                bb <<= tot;
+                nb -= (int)tot;
+                const uint32_t kn = k + (e >> 24);      /* index after this symbol; EOB adds 128 (:2241-2244) */
+                if (MODE != JD_MODE_PARSE_AC && s != 0u && kn <= LIMIT) {
+                    /* stored coefficient at zigzag kn - 1 (jpeg.inl:2247-2256) */
+                    const uint32_t tw = TP.at(kn - 1u);
                     bflags |= tw;
                     if (((e | bigm) & JD_ACF_RARE) != 0u) {
                         if (s > 11u) { err = JD_SEG_BADSIZE; break; }
@@ -763,15 +761,14 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                     }
                 }
                 {
-                    const uint32_t t = p7 + len + s;
+                    const uint32_t t = p7 + tot;
                     jw += (t >> 3) * JD_JW_ONES;
                     p7 = t & 7u;
                 }
-                tick1();
-                k++;
+                k = kn;
             } while (k < 64u);
             if (err >= 0) break;
-            last_was_eob = (k == 129u);
+            last_was_eob = (k >= 128u);
         }
         /* ---- block finished: header = first record | dc << 32 | count << 48 | BIG << 54 | rows-4..7 << 55 | columns << 56 ---- */
         {

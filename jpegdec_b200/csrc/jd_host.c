@@ -329,7 +329,7 @@ void jd_build_lut(const JDInfo *info, uint16_t *lut)
      * else len = 0 = "look in the long-code half".  Invalid prefixes are len = 0 too (the decoder tells them apart). */
     for (int t = 0; t < 2; t++) {
         const uint16_t *L = lut + 2 * 1152 + t * 2048;
-        uint16_t *F = lut + 2 * 1152 + 2 * 2048 + t * 1024;
+        uint16_t *F = lut + 2 * 1152 + 2 * 2048 + t * 2048;      /* 1024 32-bit entries (little endian halves) */
         for (unsigned idx = 0; idx < 1024; idx++) {
             uint16_t e = 0;
             if ((idx >> 4) != 0x3F) e = L[idx];
@@ -339,11 +339,14 @@ void jd_build_lut(const JDInfo *info, uint16_t *lut)
                 for (int j = 1; j < 64; j++) if (x[j] != e) e = 0;
                 if ((e >> 8) > 10) e = 0;
             }
+            uint32_t f = 0;
             if (e) {
-                const unsigned len = e >> 8, s = e & 15u;
-                if (s >= 10 || len + s >= 18) e |= 0x8000u;
+                const unsigned len = e >> 8, rs = e & 0xFFu, s = rs & 15u;
+                f = (len + s) | (len << 8) | (s << 16) | ((rs == 0 ? 128u : (rs >> 4) + 1u) << 24);
+                if (s >= 10 || len + s >= 18) f |= 0x80u;
             }
-            F[idx] = e;
+            F[2 * idx] = (uint16_t)(f & 0xFFFFu);
+            F[2 * idx + 1] = (uint16_t)(f >> 16);
         }
     }
 }

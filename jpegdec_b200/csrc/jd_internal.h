@@ -13,7 +13,7 @@
 extern "C" {
 #endif
 
-#define JD_LUT_ENTRIES_H 8448 /* == JD_LUT_ENTRIES in jd_core.h */
+#define JD_LUT_ENTRIES_H 10496 /* == JD_LUT_ENTRIES in jd_core.h */
 
 /* Host-side result of parsing one JPEG header (all the per-image facts the GPU needs). */
 typedef struct {

@@ -24,7 +24,7 @@
 
 #define JD_NONE 0xFFFFFFFFu
 #ifndef JD_ENTROPY_THREADS
-#define JD_ENTROPY_THREADS 64
+#define JD_ENTROPY_THREADS 128
 #endif
 #define JD_RING_STRIDE 36   /* words between two walkers' rings: 32 + 4 keeps 16-byte alignment and spreads the banks */
 
