@@ -412,6 +412,12 @@ static void deliver_framebuffer(const JPEGIMAGE *p, const uint8_t *frame, int fr
         for (int c = 0; c < cols; c++) {
             if (last_mcu >= 0 && r * cols + c > last_mcu) return;       /* decode error: the loops stop after the failing MCU (:5128) */
             if (c * mw < p->iCropX || c * mw > p->iCropX + p->iCropCX) continue;
+            /* The inclusive test above lets one MCU past the crop's right edge through (:5111).  In a framebuffer that MCU lies
+             * beyond the pitch: most of the reference's pixel paths store it anyway, so it runs on into the next line and
+             * clobbers the first pixels there (2 640 wrong pixels on tulips); some clip it
+             * (JPEGPutMCU8BitGray 4:2:0, :3019).  It is never stored here: the framebuffer receives the cropped image the
+             * callbacks deliver (documented deviation). */
+            if (xoff >= pitch_px) continue;
             const uint8_t *src = frame + (size_t)r * mh * frame_pitch + (size_t)c * mw * bypp;
             if (whole_mcus) {
                 for (int l = 0; l < mh; l++) {
@@ -424,10 +430,7 @@ static void deliver_framebuffer(const JPEGIMAGE *p, const uint8_t *frame, int fr
             } else {
                 int lines = mh, px = pitch_px - xoff;
                 if (r * mh + lines > out_h) lines = out_h - r * mh;
-                /* inside the pitch an MCU is clipped at its end; the one MCU the inclusive crop test lets through past the
-                 * crop's right edge (:5111) lies beyond the pitch and is stored whole, i.e. it runs on into the next line
-                 * like in the reference (clipped only at the end of the MCU-row-aligned buffer) */
-                if (px > mw || px <= 0) px = mw;
+                if (px > mw) px = mw;
                 for (int l = 0; l < lines; l++) {
                     const size_t at = (size_t)(ty + l) * pitch_px + xoff;
                     size_t n = (size_t)px;

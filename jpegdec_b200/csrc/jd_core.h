@@ -57,7 +57,11 @@
  * (a block stores at most 63 coefficients = 126 records) instead of once per coefficient. */
 #define JD_REC_PER_BYTE 6u
 #define JD_REC_SLOT_SLACK 128u
-#define JD_REC_INDEX(byte_off, slot) (JD_REC_PER_BYTE * (uint32_t)(byte_off) + JD_REC_SLOT_SLACK * (uint32_t)(slot))
+/* rounded down to 8 records = 16 bytes: the entropy walk writes its records as aligned 16-byte chunks (2-byte stores made
+ * the kernel L1TEX / crossbar-request bound: every one of them travels as its own 32-byte sector).  The rounding eats at
+ * most 7 of the previous slot's 128 spare records, which JD_REC_CAP leaves unused. */
+#define JD_REC_INDEX(byte_off, slot) (((JD_REC_PER_BYTE * (uint32_t)(byte_off)) & ~7u) + JD_REC_SLOT_SLACK * (uint32_t)(slot))
+#define JD_REC_CAP(nbytes) (JD_REC_PER_BYTE * (uint32_t)(nbytes) + JD_REC_SLOT_SLACK - 8u)
 #define JD_REC_BLOCK_MAX 126u
 
 /* Block header written by the entropy kernel, read by the IDCT kernels (8 B):    */
@@ -180,6 +184,7 @@ typedef struct {
     uint32_t al;          /* progressive DC scan: point transform (DC_ONLY instantiation) */
     uint32_t img;         /* image index in the batch (for events) */
     uint32_t *ring;       /* CLEAN reader: this walker's 32-word stream ring (16-byte aligned; shared memory on the device) */
+    uint16_t *stage;      /* this walker's 8-record staging chunk (16-byte aligned; shared memory on the device) */
 } JDSegIn;
 
 typedef struct {
@@ -614,14 +619,45 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     uint32_t p7 = 0;                             /* bits consumed in this segment, mod 8 */
     uint32_t ro = 0;                             /* next record slot (index into rec) */
 #ifdef __CUDA_ARCH__
-    /* one opaque register pair for the record base (else it is re-derived from its parts at every store); records are
-     * written with st.global through it */
+    /* one opaque register pair for the record base (else it is re-derived from its parts at every store) */
     size_t rec_g = __cvta_generic_to_global(rec);
     asm volatile("" : "+l"(rec_g));
 #define JD_REC_ST(i, val) asm volatile("st.global.u16 [%0], %1;" ::"l"(rec_g + 2ull * (i)), "h"((uint16_t)(val)) : "memory")
 #else
 #define JD_REC_ST(i, val) (rec[(i)] = (uint16_t)(val))
 #endif
+    /* Records leave as aligned 16-byte chunks: a record is parked in this walker's staging chunk (shared memory) and every
+     * eighth one sends the chunk off with one 16-byte store.  `direct` = records go out one by one instead, from the moment a
+     * block switches to pair records (its earlier records must be in global memory to be rewritten) until the record index
+     * is a multiple of 8 again. */
+    uint16_t *const stage = in.stage;
+    bool direct = false;
+    auto flush_chunk = [&](uint32_t first) {     /* the staging chunk holds records first .. first + 7 */
+#ifdef __CUDA_ARCH__
+        const uint4 c = *reinterpret_cast<const uint4 *>(stage);
+        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(rec_g + 2ull * first), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+#else
+        memcpy(rec + first, stage, 16);
+#endif
+    };
+    auto put = [&](uint32_t val) {
+        if (!direct) {
+            stage[ro & 7u] = (uint16_t)val;
+            ro++;
+            if ((ro & 7u) == 0u) flush_chunk(ro - 8u);
+        } else {
+            JD_REC_ST(ro, val);
+            ro++;
+            if ((ro & 7u) == 0u) direct = false;
+        }
+    };
+    /* everything parked so far goes out record by record; later records follow directly */
+    auto go_direct = [&]() {
+        if (!direct) {
+            for (uint32_t i = ro & ~7u; i < ro; i++) JD_REC_ST(i, stage[i & 7u]);
+            direct = (ro & 7u) != 0u;
+        }
+    };
     int err = -1;
     bool last_was_eob = true;
     const JDTab16 T(lut);
@@ -738,6 +774,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                         if (s >= 10u && !bigm) {
                             /* first >= 10-bit magnitude of this block: switch its records to (t, value) pairs */
                             const uint32_t ncoef = ro - r0;
+                            go_direct();
                             uint16_t *const rec0 = rec + r0;
                             for (uint32_t i = ncoef; i-- > 0u;) {
                                 const uint32_t r = rec0[i];
@@ -745,19 +782,17 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                                 rec0[2u * i + 1u] = (uint16_t)(int16_t)((int)(r << 22) >> 22);
                             }
                             ro += ncoef;
+                            direct = true;       /* until the index is a multiple of 8 again */
                             bigm = JD_ACF_RARE;
                         }
                         if (bigm) {
-                            JD_REC_ST(ro, tw & 63u);
-                            JD_REC_ST(ro + 1u, (uint32_t)v & 0xFFFFu);
-                            ro += 2u;
+                            put(tw & 63u);
+                            put((uint32_t)v & 0xFFFFu);
                         } else {
-                            JD_REC_ST(ro, (tw << 10) | ((uint32_t)v & 0x3FFu));
-                            ro++;
+                            put((tw << 10) | ((uint32_t)v & 0x3FFu));
                         }
                     } else {
-                        JD_REC_ST(ro, (tw << 10) | ((uint32_t)v & 0x3FFu));
-                        ro++;
+                        put((tw << 10) | ((uint32_t)v & 0x3FFu));
                     }
                 }
                 {
@@ -781,6 +816,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         bsh += 4u;
         if (bsh == bsh_end) bsh = 0u;
     }
+    if (!direct && (ro & 7u) != 0u) flush_chunk(ro & ~7u);   /* the last, partly filled chunk (its tail lies in the slot's slack) */
     if (err >= 0) {
         /* undecodable from here: later stages must still find well-formed (empty) headers */
         out.err_mcu = (int32_t)(b / in.bpm);

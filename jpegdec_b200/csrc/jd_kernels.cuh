@@ -128,7 +128,7 @@ struct JDEntropyArgs {
 __host__ __device__ __forceinline__ uint32_t jd_clean_off(uint32_t start, uint32_t seg) { return (start & ~15u) + 32u * seg; }
 
 template <bool CLEAN>
-__device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const uint16_t *s_lut, const uint32_t *s_tpos, uint32_t *s_ring)
+__device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const uint16_t *s_lut, const uint32_t *s_tpos, uint32_t *s_ring, uint16_t *s_stage)
 {
     const uint32_t wi = blockIdx.x * JD_ENTROPY_THREADS + threadIdx.x;
     if (wi >= a.nwork) return;
@@ -150,6 +150,7 @@ __device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const ui
     in.seg = seg;
     in.img = img;
     in.ring = s_ring + threadIdx.x * JD_RING_STRIDE;
+    in.stage = s_stage + threadIdx.x * 8;
     in.blk0 = im.blk_base + m0 * im.bpm;
     jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
     JDSegOut so;
@@ -165,7 +166,7 @@ __device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const ui
     const uint32_t next = (sl + 1 < im.nseg) ? a.seg_start[seg + 1] : JD_NONE;
     const uint32_t seg_end = (next != JD_NONE) ? next : im.scan_end;
     in.rec_index0 = JD_REC_INDEX(in.start - im.comp_off, sl);
-    in.rec_cap = JD_REC_PER_BYTE * (seg_end > in.start ? seg_end - in.start : 0u) + JD_REC_SLOT_SLACK;
+    in.rec_cap = JD_REC_CAP(seg_end > in.start ? seg_end - in.start : 0u);
     uint16_t *rec = a.rec + im.rec_base + in.rec_index0;
     if (CLEAN) {
         in.data = a.clean;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     __shared__ uint32_t s_tpos[64];
     __shared__ __align__(16) uint32_t s_ring[CLEAN ? JD_ENTROPY_THREADS * JD_RING_STRIDE : 4];   /* per-walker stream rings (jd_core.h) */
+    __shared__ __align__(16) uint16_t s_stage[JD_ENTROPY_THREADS * 8];                           /* per-walker record staging chunks */
     for (int i = threadIdx.x; i < 64; i += JD_ENTROPY_THREADS) s_tpos[i] = jd_tposw(c_tpos[i]);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.luts + (size_t)a.cta_lut[blockIdx.x] * JD_LUT_ENTRIES);
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(JD_ENTROPY_THREADS) jdk_entropy(const JDEntrop
         for (int i = threadIdx.x; i < JD_LUT_ENTRIES * 2 / 16; i += JD_ENTROPY_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    jd_entropy_body<CLEAN>(a, s_lut, s_tpos, s_ring);
+    jd_entropy_body<CLEAN>(a, s_lut, s_tpos, s_ring, s_stage);
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(64) jdk_chunk_emit(const JDChunkArgs a)
     const uint32_t next = (c + 1 < im.nch) ? a.E_in[g + 1] : JD_CS_NONE;
     /* image-relative record slot: the scan's one "segment" owns slot 0..nseg-1, its chunks follow */
     const uint32_t ri0 = JD_REC_INDEX(im.scan_off - im.comp_off + c * JD_CHUNK_BYTES, im.nseg + c);
-    const uint32_t cap = JD_REC_PER_BYTE * JD_CHUNK_BYTES + JD_REC_SLOT_SLACK;
+    const uint32_t cap = JD_REC_CAP(JD_CHUNK_BYTES);
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     JDChunkOut co;
     jd_chunk_emit(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,

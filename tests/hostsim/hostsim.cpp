@@ -19,7 +19,8 @@
 #include "../../jpegdec_b200/csrc/jd_chunk.h"
 #include "../../jpegdec_b200/csrc/jd_internal.h"
 
-static uint32_t g_ring[64];   /* stream ring of the CLEAN reader (one walker at a time here) */
+static uint32_t g_ring[64];
+static uint16_t g_stage[8];   /* record staging chunk of the walk */   /* stream ring of the CLEAN reader (one walker at a time here) */
 
 struct VecSink {
     std::vector<JDEvent> ev;
@@ -145,7 +146,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         for (uint32_t c = 0; c < nch; c++) {
             const uint32_t ri0 = JD_REC_INDEX((uint32_t)info.scan_offset + c * JD_CHUNK_BYTES, 1u + c);
             jd_chunk_emit(sc, lut.data(), kTposW, c, E[c], (c + 1 < nch) ? E[c + 1] : JD_CS_NONE, pre[c], hdr.data(), rec.data() + ri0, ri0,
-                          JD_REC_PER_BYTE * JD_CHUNK_BYTES + JD_REC_SLOT_SLACK, c, 0u, 0u, sink, co[c]);
+                          JD_REC_CAP(JD_CHUNK_BYTES), c, 0u, 0u, sink, co[c]);
             if (co[c].status != JD_SEG_OK) bad = 1;
         }
         /* stitch over chunks: true phase per chunk, DC predictor at each chunk entry */
@@ -181,10 +182,10 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         if (in.start == 0xFFFFFFFFu) { bad = 1; break; }
         const uint32_t seg_end = (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] : (uint32_t)size;
         in.rec_index0 = JD_REC_INDEX(in.start, sgi);
-        in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
+        in.rec_cap = JD_REC_CAP(seg_end - in.start);
         in.seg = (uint32_t)sgi;
         in.img = 0;
-        in.ring = g_ring;
+        in.ring = g_ring; in.stage = g_stage;
         in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         in.al = prog ? (uint32_t)(info.approx & 15) : 0u;
@@ -478,8 +479,8 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in; in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
         int m0 = sgi * mps; in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
-        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0; in.ring = g_ring;
-        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.rec_cap = JD_REC_PER_BYTE * ((uint32_t)size - in.start) + JD_REC_SLOT_SLACK; in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
+        in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0; in.ring = g_ring; in.stage = g_stage;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.rec_cap = JD_REC_CAP((uint32_t)size - in.start); in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
         JDSegOut so;
         jd_decode_segment(in, lut.data(), kTposW, hdr.data() + (size_t)m0 * info.bpm, rec.data() + in.rec_index0, sink, so);
     }
@@ -530,8 +531,8 @@ extern "C" int hostsim_walk_check(const uint8_t *data, int size, int *n_segments
         in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
         in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
         const uint32_t seg_end = (sgi + 1 < nseg && seg_start[sgi + 1] != 0xFFFFFFFFu) ? seg_start[sgi + 1] : (uint32_t)size;
-        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.seg = (uint32_t)sgi; in.img = 0; in.ring = g_ring;
-        in.rec_cap = JD_REC_PER_BYTE * (seg_end - in.start) + JD_REC_SLOT_SLACK;
+        in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.seg = (uint32_t)sgi; in.img = 0; in.ring = g_ring; in.stage = g_stage;
+        in.rec_cap = JD_REC_CAP(seg_end - in.start);
         in.blk0 = (uint32_t)(m0 * info.bpm); in.al = 0;
         const uint32_t nb = in.nmcu * in.bpm;
         VecSink sA, sB, sC;

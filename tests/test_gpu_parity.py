@@ -594,14 +594,15 @@ def test_crop_times_scale_callbacks_and_framebuffer(mode, arith):
                         want[ys, x0 + bw:x0 + wu * bpp // 8] = 0
                     assert np.array_equal(out, want), (name, crop, pt, opt)
                     j.close()
-                    if opt == 0 or arith == 1:
-                        # framebuffer + crop (pitch = crop width, :5116); at full scale in the SSE2 build the reference's colour
-                        # paths store whole MCUs past the right edge -- the same stores are made here
-                        rc_f, err_f, fb_r = ref.decode_fb(data, pt, opt, crop=crop)
+                    if opt == 0:
+                        # framebuffer + crop (pitch = crop width, :5116): the cropped image the callbacks deliver.  (The reference
+                        # itself clobbers the first pixels of most lines here: the one MCU its inclusive crop test lets through
+                        # past the right edge is stored beyond the pitch -- documented deviation, DESIGN.md.)
                         j = J.JPEGDEC(); assert j.openRAM(data); j.setArithMode(arith); j.setPixelType(pt); j.setCropArea(*crop)
-                        fb = np.zeros_like(fb_r); j.setFramebuffer(fb)
-                        assert j.decode(0, 0, opt) == rc_f == 1
                         cx, cy, cw, ch = j.getCropArea()
-                        nvis = cw * (ch >> {0: 0, 2: 1, 4: 2, 8: 3}[opt]) * T.bpp_of(pt) // 8
-                        assert np.array_equal(fb[:nvis], fb_r[:nvis]), (name, crop, pt, opt, "framebuffer")
+                        bypp = T.bpp_of(pt) // 8
+                        fb = np.zeros((ch + 32) * cw * bypp, np.uint8); j.setFramebuffer(fb)
+                        assert j.decode(0, 0, opt) == 1
+                        got = fb[:ch * cw * bypp].reshape(ch, cw * bypp)
+                        assert np.array_equal(got, img_r[:ch, :cw * bypp]), (name, crop, pt, opt, "framebuffer")
                         j.close()
