@@ -38,8 +38,21 @@ ncu)
   done
   ls -la $O | tail -20 ;;
 bench)
-  timeout 900 python bench.py > $O/${tag}_bench_hd1024_1gpu.json 2> $O/${tag}_bench_hd1024.err; tail -c 600 $O/${tag}_bench_hd1024_1gpu.json
-  timeout 600 python bench.py --workload uhd --no-cpu > $O/${tag}_bench_uhd_1gpu.json 2> $O/${tag}_bench_uhd.err ;;
+  timeout 900 python bench.py --pipelined > $O/${tag}_bench_hd1024_1gpu.json 2> $O/${tag}_bench_hd1024.err; tail -c 600 $O/${tag}_bench_hd1024_1gpu.json
+  timeout 600 python bench.py --workload uhd --no-cpu --pipelined > $O/${tag}_bench_uhd_1gpu.json 2> $O/${tag}_bench_uhd.err ;;
+others)
+  for wl in uhd_quarter uhd_eighth dither dither444 hd_norst; do
+    timeout 600 python bench.py --workload $wl --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_${wl}_1gpu.json 2> $O/${tag}_bench_${wl}.err
+    tail -c 300 $O/${tag}_bench_${wl}_1gpu.json; echo
+  done ;;
+multi)
+  # N-GPU lines (gpurun --gpus N): the north-star slice per GPU with every image verified, then the default workload with e2e
+  N=${NGPUS:-8}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+  nvidia-smi topo -m > $O/${tag}_topo.txt 2>&1
+  timeout 1500 $TR bench.py --gpus $N --workload uhd10k --steps 3 --warmup 3 --no-cpu > $O/${tag}_bench_uhd10k_${N}gpu.json 2> $O/${tag}_bench_uhd10k_${N}gpu.err; tail -c 1200 $O/${tag}_bench_uhd10k_${N}gpu.json
+  timeout 900 $TR bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > $O/${tag}_bench_hd1024_${N}gpu.json 2> $O/${tag}_bench_hd1024_${N}gpu.err; tail -c 900 $O/${tag}_bench_hd1024_${N}gpu.json
+  if [ -n "$NOBIND" ]; then JPEGDEC_B200_NO_BIND=1 timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu > $O/${tag}_bench_hd1024_${N}gpu_nobind.json 2> $O/${tag}_bench_hd1024_${N}gpu_nobind.err; fi ;;
 uhd10k)
   timeout 1200 python bench.py --workload uhd10k --no-cpu --steps 3 --warmup 3 > $O/${tag}_bench_uhd10k_1gpu.json 2> $O/${tag}_bench_uhd10k.err; tail -c 1500 $O/${tag}_bench_uhd10k_1gpu.json; tail -5 $O/${tag}_bench_uhd10k.err ;;
 refarm)
