@@ -573,6 +573,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     }
     /* keeps >= 32 valid bits in bb */
     auto refill = [&]() {
+#ifdef JD_REFILL_BRANCHY
         if (CLEAN) {
             if (nb <= 32) {
                 while (rd == wr) topup();        /* ring ran dry inside one block (rare) */
@@ -581,6 +582,19 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
                 bb |= (jd_u64)jd_bswap32(w) << (32 - nb);
                 nb += 32;
             }
+        } else
+#endif
+        if (CLEAN) {
+            /* straight-line: in a warp nearly every symbol sees SOME lane below 32 bits, so a branch would be taken (by a
+             * handful of lanes) almost every time; the ring word is read regardless and merged under a predicate */
+            const bool need = nb <= 32;
+            if (need && rd == wr) { do topup(); while (rd == wr); }   /* ring ran dry inside one block (rare) */
+            const uint32_t w = jd_bswap32(ring[rd & 31u]);
+            const uint32_t sh = need ? (uint32_t)(32 - nb) : 0u;
+            const jd_u64 add = (jd_u64)w << sh;
+            bb |= need ? add : 0ull;
+            rd += need ? 1u : 0u;
+            nb += need ? 32 : 0;
         } else
         while (nb <= 32) {
             const uint32_t w = wnext;
@@ -713,7 +727,10 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         if (MODE != JD_MODE_DC_SCAN) {
             if (MODE != JD_MODE_PARSE_AC && in.rec_cap - ro < JD_REC_BLOCK_MAX) { err = JD_SEG_OVERFLOW; break; }
             /* ---- AC symbols (jpeg.inl:2225-2264) ---- */
-            const uint32_t tacf = JD_LUT_ACF(cur >> 3) >> 1;   /* 32-bit entries */
+            uint32_t tacf = JD_LUT_ACF(cur >> 3) >> 1;         /* 32-bit entries */
+#if defined(__CUDA_ARCH__) && !defined(JD_NO_LAUNDER)
+            asm volatile("" : "+r"(tacf));                     /* keep it in a register: else re-derived per symbol */
+#endif
             uint32_t k = 1;                      /* zigzag index of the next coefficient */
             do {
                 refill();
