@@ -180,7 +180,7 @@ struct JPEGB200_BATCH {
 static char *ctx_err() { return g_err; }
 
 #define JD_EVENT_CAP (1u << 20)
-#define JD_CHUNK_PASSES 6     /* restart-free scans: entry-state passes per decode (the last one verifies) */
+#define JD_CHUNK_PASSES 4     /* restart-free scans: entry-state passes per decode (the last one verifies) */
 
 extern "C" int JPEGB200_deviceCount(void)
 {
