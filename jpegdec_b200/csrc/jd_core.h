@@ -18,8 +18,10 @@
 
 #ifdef __CUDACC__
 #define JD_HD __host__ __device__ __forceinline__
+#define JD_HDM __host__ __device__ __forceinline__   /* member functions */
 #else
 #define JD_HD static inline
+#define JD_HDM inline
 #endif
 
 /* ------------------------------------------------------------------------- */

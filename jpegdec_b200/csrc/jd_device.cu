@@ -163,9 +163,9 @@ struct JPEGB200_BATCH {
     std::vector<uint64_t> arena_off; /* per-image offset inside d_out */
     /* restart-free scans decoded chunk-parallel (jd_chunk.h) */
     std::vector<uint32_t> cimg_list, chunk_img;
-    uint32_t nchunks;
+    uint32_t nchunks, max_nch;
     DevBuf<uint8_t> d_filt;
-    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
+    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_Ep, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
     DevBuf<int32_t> d_cdcs, d_cpe;
     uint32_t h_changed;
     bool chunk_iterate;            /* restart-free scans: iterate the entry states with a host check (fallback mode) */
@@ -180,7 +180,7 @@ struct JPEGB200_BATCH {
 static char *ctx_err() { return g_err; }
 
 #define JD_EVENT_CAP (1u << 20)
-#define JD_CHUNK_PASSES 4     /* restart-free scans: entry-state passes per decode (the last one verifies) */
+#define JD_CHUNK_PASSES 6     /* restart-free scans: entry-state passes per decode (from the third on only moved chunks are parsed; the last one verifies) */
 
 extern "C" int JPEGB200_deviceCount(void)
 {
@@ -458,7 +458,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
     b->dither_bits = (pixel_type == FOUR_BIT_DITHERED) ? 4 : (pixel_type == TWO_BIT_DITHERED) ? 2 : (pixel_type == ONE_BIT_DITHERED) ? 1 : 0;
     b->stream = nullptr;
     b->descs_dl = nullptr; b->descs_dl_bytes = 0; b->downloaded = false; b->h_counters = nullptr;
-    b->nchunks = 0; b->chunk_iterate = false; b->decode_flags = 0;
+    b->nchunks = 0; b->max_nch = 0; b->chunk_iterate = false; b->decode_flags = 0;
     b->uploaded = false; b->out_device = false; b->arena_owned = false; b->have_ev = false;
     memset(b->ms, 0, sizeof(b->ms));
     memset(b->counters, 0, sizeof(b->counters));
@@ -561,6 +561,7 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
             d.chunk_base = b->nchunks;
             d.nch = ((uint32_t)(sizes[i] - inf.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;
             b->nchunks += d.nch;
+            if (d.nch > b->max_nch) b->max_nch = d.nch;
             b->cimg_list.push_back((uint32_t)i);
             for (uint32_t cc = 0; cc < d.nch; cc++) b->chunk_img.push_back((uint32_t)i);
         }
@@ -623,7 +624,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
     b->d_clean.release(); b->d_seg_clen.release();
-    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release();
+    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release(); b->d_Ep.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
@@ -739,7 +740,7 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
         const size_t nc = b->nchunks;
         CK(b->d_filt.alloc(&b->ctx->pool, b->comp_total + 512));
         CK(b->d_cimg_list.alloc(&b->ctx->pool, b->cimg_list.size())); CK(b->d_chunk_img.alloc(&b->ctx->pool, nc)); CK(b->d_flen.alloc(&b->ctx->pool, n));
-        CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
+        CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_Ep.alloc(&b->ctx->pool, nc)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
         CK(b->d_cstatus.alloc(&b->ctx->pool, nc)); CK(b->d_cnown.alloc(&b->ctx->pool, nc)); CK(b->d_cdcs.alloc(&b->ctx->pool, 3 * nc)); CK(b->d_cpe.alloc(&b->ctx->pool, 3 * nc));
     }
     CK(b->d_counters.alloc(&b->ctx->pool, 8));
@@ -1022,16 +1023,25 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ca.blk_hdr = b->d_blk_hdr.p; ca.rec = b->d_rec.p;
         ca.events = b->d_events.p; ca.event_count = b->d_counters.p; ca.event_cap = JD_EVENT_CAP;
         ca.seg_phase = b->d_seg_phase.p; ca.seg_jmap = b->d_seg_jmap.p; ca.seg_status = b->d_seg_status.p; ca.nseg_total = b->nseg;
-        const unsigned gc = (b->nchunks + 127) / 128, gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
-        CK(cudaMemsetAsync(b->d_E0.p, 0, (size_t)(b->nchunks + 1) * 4, st));    /* guess: every chunk starts a block at its first bit */
-        jdk_unstuff<<<gi, 128, 0, st>>>(ca);
-        launches++;
-        uint32_t *Ein = b->d_E0.p, *Eout = b->d_E1.p;
+        const unsigned gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
+        ca.max_nch = b->max_nch; ca.Ep = b->d_Ep.p;
+        const dim3 gchunks((b->max_nch + 127) / 128, (unsigned)b->cimg_list.size());
+        /* guess: every chunk starts a block at its first bit (exit state of every left neighbour = (0, 0, 0)); no chunk parsed yet */
+        CK(cudaMemsetAsync(b->d_E0.p, 0, (size_t)(b->nchunks + 1) * 4, st));
+        CK(cudaMemsetAsync(b->d_Ep.p, 0xFE, (size_t)b->nchunks * 4, st));
+        {
+            const dim3 gu(((b->max_nch * JD_CHUNK_BYTES + JD_UNSTUFF_PIECE - 1) / JD_UNSTUFF_PIECE + 3) / 4, (unsigned)b->cimg_list.size());
+            jdk_unstuff<false><<<gu, 128, 0, st>>>(ca);
+            jdk_unstuff<true><<<gu, 128, 0, st>>>(ca);
+        }
+        launches += 2;
+        uint32_t *Xin = b->d_E0.p, *Xout = b->d_E1.p;
         int passes = 0;
         /* The entry states reach their fix point in 2-4 passes on real streams (a chunk re-synchronises well inside its 512
-         * bytes).  Normal mode: JD_CHUNK_PASSES passes back to back, the last one only verifying (it raises a flag if an entry
-         * state still moved) -- no host round trip, so jobs of JPEGB200_decodeBatch stay in flight; batchWait re-runs the job
-         * in the iterating mode below if the flag came back set. */
+         * bytes), and from the third pass on only the chunks whose entry state moved are parsed again.  Normal mode:
+         * JD_CHUNK_PASSES passes back to back, the last one verifying (it raises a flag if an exit state still moved) -- no
+         * host round trip, so jobs of JPEGB200_decodeBatch stay in flight; batchWait re-runs the job in the iterating mode
+         * below if the flag came back set. */
         static int fixed_passes = -1;   /* JPEGDEC_B200_CHUNK_PASSES=n: test hook (n = 1 forces the fallback) */
         if (fixed_passes < 0) { const char *e = getenv("JPEGDEC_B200_CHUNK_PASSES"); fixed_passes = (e && atoi(e) > 0) ? atoi(e) : JD_CHUNK_PASSES; }
         const int fixed = b->chunk_iterate ? 0 : fixed_passes;
@@ -1039,22 +1049,21 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             const int burst = fixed ? fixed : 3;
             for (int k = 0; k < burst; k++) {
                 if (k == burst - 1) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
-                ca.E_in = Ein; ca.E_out = Eout;
-                jdk_chunk_parse<<<gc, 128, 0, st>>>(ca);
+                ca.X_in = Xin; ca.X_out = Xout;
+                jdk_chunk_parse<<<gchunks, 128, 0, st>>>(ca);
                 launches++; passes++;
-                uint32_t *tmp = Ein; Ein = Eout; Eout = tmp;
+                uint32_t *tmp = Xin; Xin = Xout; Xout = tmp;
             }
             if (fixed) break;
             CK(cudaMemcpyAsync(&b->h_changed, b->d_counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             if (!b->h_changed || passes > (int)b->nchunks + 8) break;
         }
-        ca.E_in = Ein; ca.E_out = Eout;
-        jdk_chunk_prefix<<<((unsigned)b->cimg_list.size() + 63) / 64, 64, 0, st>>>(ca);
-        jdk_chunk_emit<<<(b->nchunks + 63) / 64, 64, 0, st>>>(ca);
-        jdk_chunk_stitch<<<((unsigned)b->cimg_list.size() + 63) / 64, 64, 0, st>>>(ca);
-        jdk_chunk_dcfix<<<gc, 128, 0, st>>>(ca);
-        launches += 4;
+        ca.X_in = Xin; ca.X_out = Xout;
+        jdk_chunk_prefix<<<gi, 128, 0, st>>>(ca);
+        jdk_chunk_emit<<<gchunks, 128, 0, st>>>(ca);
+        jdk_chunk_stitch<<<gi, 128, 0, st>>>(ca);
+        launches += 3;
     }
     CK(cudaEventRecord(b->ev[4], st));
     jdk_stitch<<<(n + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_seg_jmap.p, b->d_seg_status.p, b->d_seg_phase.p, b->d_seg_nrec.p,

@@ -364,9 +364,11 @@ struct JDChunkArgs {
     uint32_t *flen;                /* per image: un-stuffed scan length */
     const uint32_t *chunk_img;     /* per chunk: image index */
     uint32_t nchunks;
-    uint32_t *E_in, *E_out;        /* entry states (double buffered across passes) */
+    uint32_t *X_in, *X_out;        /* exit state of every chunk = entry state of its right neighbour (double buffered across passes) */
+    uint32_t *Ep;                  /* entry state each chunk was last parsed from */
+    uint32_t max_nch;              /* chunks of the longest scan (grid x = ceil / 128) */
     uint32_t *cn, *cpre, *cjmap, *cstatus, *cnown;
-    int32_t *cdcs, *cpe;           /* per chunk x 3: DC sums / DC predictor at entry */
+    int32_t *cdcs, *cpe;           /* per chunk x 3: DC sums (parse pass) / DC predictors at the chunk's first block (prefix) */
     uint32_t *changed;
     jd_u64 *blk_hdr;
     uint16_t *rec;
@@ -377,20 +379,19 @@ struct JDChunkArgs {
     uint32_t nseg_total;           /* phase slot of chunk g = nseg_total + g */
 };
 
-/* one warp per restart-free scan: FF00 -> FF, stop at the first marker (JPEGFilter, jpeg.inl:1431-1540) */
-__global__ void __launch_bounds__(128) jdk_unstuff(const JDChunkArgs a)
+/* Restart-free scans: FF00 -> FF, stop at the first marker (JPEGFilter, jpeg.inl:1431-1540).  One warp per 4 KB piece of a
+ * scan, two passes: count the bytes each piece keeps (and whether a marker ends the scan inside it), then every piece sums
+ * the counts to its left and writes its kept bytes there.  (The first version walked a whole scan with one warp: 1.9 ms per
+ * 1024 HD images, all of it latency.) */
+#define JD_UNSTUFF_PIECE 4096u
+template <bool WRITE>
+__device__ __forceinline__ uint32_t jd_unstuff_piece(const uint8_t *__restrict__ src, uint32_t len, uint32_t p0, uint32_t p1, uint8_t *dst,
+                                                     uint32_t base, bool &stopped, uint32_t lane)
 {
-    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
-    if (w >= a.ncimg) return;
-    const uint32_t ii = a.cimg_list[w];
-    const JDImageDesc &im = a.imgs[ii];
-    const uint8_t *src = a.comp + im.scan_off;
-    uint8_t *dst = a.filt + im.scan_off;
-    const uint32_t len = im.scan_end - im.scan_off;
-    uint32_t base = 0;
-    bool done = false;
-    for (uint32_t p0 = 0; p0 < len && !done; p0 += 128) {
-        const uint32_t p = p0 + lane * 4;
+    uint32_t kept = 0;
+    stopped = false;
+    for (uint32_t q0 = p0; q0 < p1 && !stopped; q0 += 128) {
+        const uint32_t p = q0 + lane * 4;
         uint32_t b[6]; /* b[0] = byte before, b[1..4] = mine, b[5] = byte after */
 #pragma unroll
         for (int i = 0; i < 6; i++) {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128) jdk_unstuff(const JDChunkArgs a)
         }
         const uint32_t stop = __reduce_min_sync(0xffffffffu, endpos);
         if (stop != 0xFFFFFFFFu) {
-            done = true;
+            stopped = true;
 #pragma unroll
             for (int i = 0; i < 4; i++) if (p + (uint32_t)i >= stop) keep &= ~(1u << i);
         }
@@ -415,13 +416,51 @@ __global__ void __launch_bounds__(128) jdk_unstuff(const JDChunkArgs a)
         uint32_t x = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
-        uint32_t o = base + x - cnt;
+        if (WRITE) {
+            uint32_t o = base + kept + x - cnt;
 #pragma unroll
-        for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)b[i + 1];
-        base += __shfl_sync(0xffffffffu, x, 31);
+            for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)b[i + 1];
+        }
+        kept += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (lane < 24) dst[base + lane] = 0; /* reads run a few bytes past the end */
-    if (lane == 0) a.flen[ii] = base;
+    return kept;
+}
+
+/* grid: x = groups of 4 pieces, y = position in cimg_list; per piece scratch = cn / cpre at the piece's first chunk */
+template <bool WRITE>
+__global__ void __launch_bounds__(128) jdk_unstuff(const JDChunkArgs a)
+{
+    const uint32_t piece = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    const uint32_t ii = a.cimg_list[blockIdx.y];
+    const JDImageDesc &im = a.imgs[ii];
+    const uint32_t len = im.scan_end - im.scan_off;
+    const uint32_t p0 = piece * JD_UNSTUFF_PIECE;
+    if (p0 >= len && !(len == 0u && piece == 0u)) return;
+    const uint32_t p1 = (p0 + JD_UNSTUFF_PIECE < len) ? p0 + JD_UNSTUFF_PIECE : len;
+    const uint8_t *src = a.comp + im.scan_off;
+    uint8_t *dst = a.filt + im.scan_off;
+    const uint32_t slot = im.chunk_base + piece * (JD_UNSTUFF_PIECE / JD_CHUNK_BYTES);   /* nch >= len / 512 + 1 */
+    bool stopped;
+    if (!WRITE) {
+        const uint32_t kept = jd_unstuff_piece<false>(src, len, p0, p1, dst, 0u, stopped, lane);
+        if (lane == 0) { a.cn[slot] = kept; a.cpre[slot] = stopped ? 1u : 0u; }
+        return;
+    }
+    /* bytes kept to the left, and whether the scan already ended there */
+    uint32_t base = 0, ended = 0;
+    for (uint32_t q = lane; q < piece; q += 32u) {
+        const uint32_t sl = im.chunk_base + q * (JD_UNSTUFF_PIECE / JD_CHUNK_BYTES);
+        base += a.cn[sl]; ended |= a.cpre[sl];
+    }
+    base = __reduce_add_sync(0xffffffffu, base);
+    ended = __reduce_or_sync(0xffffffffu, ended);
+    if (ended) return;
+    const uint32_t kept = jd_unstuff_piece<true>(src, len, p0, p1, dst, base, stopped, lane);
+    if (stopped || p1 >= len) {
+        /* the scan ends in this piece: its un-stuffed length, and zeros for the reads that run a few bytes past the end */
+        if (lane < 24) dst[base + kept + lane] = 0;
+        if (lane == 0) a.flen[ii] = base + kept;
+    }
 }
 
 __device__ __forceinline__ JDScanIn jd_scan_of(const JDChunkArgs &a, const JDImageDesc &im, uint32_t ii)
@@ -433,95 +472,155 @@ __device__ __forceinline__ JDScanIn jd_scan_of(const JDChunkArgs &a, const JDIma
     return sc;
 }
 
-__global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
+/* The chunk kernels run one CTA per 128 consecutive chunks of ONE image (blockIdx.y = position in cimg_list), so the
+ * image's Huffman table set sits in shared memory like in jdk_entropy. */
+__device__ __forceinline__ void jd_load_lut_set(uint16_t *s_lut, const uint16_t *g_lut)
 {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.nchunks) return;
-    const uint32_t ii = a.chunk_img[g];
-    const JDImageDesc &im = a.imgs[ii];
-    const uint32_t c = g - im.chunk_base;
-    const JDScanIn sc = jd_scan_of(a, im, ii);
-    const uint32_t entry = (c == 0) ? JD_CS_PACK(0, 0, 0) : a.E_in[g];
-    uint32_t nstart, bad;
-    const uint32_t ex = jd_chunk_parse(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, c, entry, &nstart, &bad);
-    a.cn[g] = nstart;
-    if (c == 0) a.E_out[g] = JD_CS_PACK(0, 0, 0);
-    if (c + 1 < im.nch) {
-        a.E_out[g + 1] = ex;
-        if (ex != a.E_in[g + 1]) atomicOr(a.changed, 1u);
-    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(g_lut);
+    uint4 *dst = reinterpret_cast<uint4 *>(s_lut);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)(JD_LUT_ENTRIES / 8); i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-__global__ void jdk_chunk_prefix(const JDChunkArgs a)
+/* One speculative pass.  The entry state of chunk c is the exit state chunk c-1 produced in the previous pass (X_in);
+ * a chunk whose entry state is the one it was last parsed from keeps its results, so after the first two passes only the
+ * few chunks whose left neighbour had not re-synchronised are parsed again. */
+__global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    const uint32_t ii = a.cimg_list[blockIdx.y];
+    const JDImageDesc &im = a.imgs[ii];
+    const uint32_t c = blockIdx.x * 128u + threadIdx.x;
+    if (blockIdx.x * 128u >= im.nch) return;
+    const uint32_t g = im.chunk_base + c;
+    const bool live = c < im.nch;
+    uint32_t entry = 0;
+    bool need = false;
+    if (live) {
+        entry = (c == 0) ? JD_CS_PACK(0, 0, 0) : a.X_in[g - 1];
+        need = entry != a.Ep[g];
+        if (!need) a.X_out[g] = a.X_in[g];
+    }
+    if (!__syncthreads_or(need ? 1 : 0)) return;
+    jd_load_lut_set(s_lut, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES);
+    __syncthreads();
+    if (!need) return;
+    const JDScanIn sc = jd_scan_of(a, im, ii);
+    uint32_t nstart, bad;
+    int32_t dcs[3];
+    const uint32_t ex = jd_chunk_parse(sc, s_lut, c, entry, &nstart, &bad, dcs);
+    a.cn[g] = nstart;
+    a.cdcs[3 * g] = dcs[0]; a.cdcs[3 * g + 1] = dcs[1]; a.cdcs[3 * g + 2] = dcs[2];
+    a.Ep[g] = entry;
+    if (ex != a.X_in[g]) atomicOr(a.changed, 1u);
+    a.X_out[g] = ex;
+}
+
+/* per restart-free scan (one warp): blocks started before each chunk and the DC predictors at each chunk's first block */
+__global__ void __launch_bounds__(128) jdk_chunk_prefix(const JDChunkArgs a)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (w >= a.ncimg) return;
     const JDImageDesc &im = a.imgs[a.cimg_list[w]];
     uint32_t run = 0;
-    for (uint32_t c = 0; c < im.nch; c++) { a.cpre[im.chunk_base + c] = run; run += a.cn[im.chunk_base + c]; }
+    int r0 = 0, r1 = 0, r2 = 0;
+    for (uint32_t cb = 0; cb < im.nch; cb += 32u) {
+        const uint32_t c = cb + lane, g = im.chunk_base + c;
+        const bool live = c < im.nch;
+        const uint32_t n = live ? a.cn[g] : 0u;
+        const int d0 = live ? a.cdcs[3 * g] : 0, d1 = live ? a.cdcs[3 * g + 1] : 0, d2 = live ? a.cdcs[3 * g + 2] : 0;
+        uint32_t x = n;
+        int y0 = d0, y1 = d1, y2 = d2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t xv = __shfl_up_sync(0xffffffffu, x, d);
+            const int v0 = __shfl_up_sync(0xffffffffu, y0, d), v1 = __shfl_up_sync(0xffffffffu, y1, d), v2 = __shfl_up_sync(0xffffffffu, y2, d);
+            if (lane >= (uint32_t)d) { x += xv; y0 += v0; y1 += v1; y2 += v2; }
+        }
+        if (live) {
+            a.cpre[g] = run + x - n;
+            a.cpe[3 * g] = r0 + y0 - d0; a.cpe[3 * g + 1] = r1 + y1 - d1; a.cpe[3 * g + 2] = r2 + y2 - d2;
+        }
+        run += __shfl_sync(0xffffffffu, x, 31);
+        r0 += __shfl_sync(0xffffffffu, y0, 31); r1 += __shfl_sync(0xffffffffu, y1, 31); r2 += __shfl_sync(0xffffffffu, y2, 31);
+    }
 }
 
-__global__ void __launch_bounds__(64) jdk_chunk_emit(const JDChunkArgs a)
+__global__ void __launch_bounds__(128) jdk_chunk_emit(const JDChunkArgs a)
 {
+    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     __shared__ uint32_t s_tpos[64];
-    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
-    __syncthreads();
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.nchunks) return;
-    const uint32_t ii = a.chunk_img[g];
+    const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
-    const uint32_t c = g - im.chunk_base;
+    if (blockIdx.x * 128u >= im.nch) return;
+    if (threadIdx.x < 64) s_tpos[threadIdx.x] = jd_tposw(c_tpos[threadIdx.x]);
+    jd_load_lut_set(s_lut, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES);
+    __syncthreads();
+    const uint32_t c = blockIdx.x * 128u + threadIdx.x;
+    if (c >= im.nch) return;
+    const uint32_t g = im.chunk_base + c;
     const JDScanIn sc = jd_scan_of(a, im, ii);
-    const uint32_t entry = a.E_in[g];
-    const uint32_t next = (c + 1 < im.nch) ? a.E_in[g + 1] : JD_CS_NONE;
+    const uint32_t entry = (c == 0) ? JD_CS_PACK(0, 0, 0) : a.X_in[g - 1];
+    const uint32_t next = (c + 1 < im.nch) ? a.X_in[g] : JD_CS_NONE;
     /* image-relative record slot: the scan's one "segment" owns slot 0..nseg-1, its chunks follow */
     const uint32_t ri0 = JD_REC_INDEX(im.scan_off - im.comp_off + c * JD_CHUNK_BYTES, im.nseg + c);
     const uint32_t cap = JD_REC_CAP(JD_CHUNK_BYTES);
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     JDChunkOut co;
-    jd_chunk_emit(sc, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,
-                  a.rec + im.rec_base + ri0, ri0, cap, a.nseg_total + g, im.blk_base, ii, sink, co);
+    const int32_t pred_in[3] = {a.cpe[3 * g], a.cpe[3 * g + 1], a.cpe[3 * g + 2]};
+    jd_chunk_emit(sc, s_lut, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,
+                  a.rec + im.rec_base + ri0, ri0, cap, a.nseg_total + g, im.blk_base, ii, pred_in, sink, co);
     a.cjmap[g] = co.jmap;
     a.cstatus[g] = co.status;
     a.cnown[g] = co.nown;
-    a.cdcs[3 * g] = co.dcsum[0]; a.cdcs[3 * g + 1] = co.dcsum[1]; a.cdcs[3 * g + 2] = co.dcsum[2];
 }
 
-/* per restart-free scan: true window phase and DC predictors at each chunk entry; folds the chunk statuses */
-__global__ void jdk_chunk_stitch(const JDChunkArgs a)
+/* phase map composition: first `a`, then `b` (six nibbles: next phase for each current phase; both normalised to 0..5) */
+__device__ __forceinline__ uint32_t jd_jmap_compose(uint32_t a, uint32_t b)
 {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t r = 0;
+#pragma unroll
+    for (int p = 0; p < 6; p++) r |= ((b >> (4u * ((a >> (4 * p)) & 15u))) & 15u) << (4 * p);
+    return r;
+}
+
+/* per restart-free scan (one warp): true window phase at each chunk entry = the composition of the phase maps of the chunks
+ * to its left applied to phase 0 (a scan over the chunks, 32 at a time); folds the chunk statuses */
+__global__ void __launch_bounds__(128) jdk_chunk_stitch(const JDChunkArgs a)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (w >= a.ncimg) return;
     const JDImageDesc &im = a.imgs[a.cimg_list[w]];
-    uint32_t cur = 0, status = 0, err_mcu = 0;
-    int run0 = 0, run1 = 0, run2 = 0;
-    for (uint32_t c = 0; c < im.nch; c++) {
-        const uint32_t g = im.chunk_base + c;
-        a.seg_phase[a.nseg_total + g] = cur;
-        const uint32_t j = (a.cjmap[g] >> (4 * cur)) & 15u;
-        cur = (j >= 6u) ? 0u : j;
-        a.cpe[3 * g] = run0; a.cpe[3 * g + 1] = run1; a.cpe[3 * g + 2] = run2;
-        run0 += a.cdcs[3 * g]; run1 += a.cdcs[3 * g + 1]; run2 += a.cdcs[3 * g + 2];
-        if (a.cstatus[g] != 0u && status == 0u) { status = a.cstatus[g]; err_mcu = (a.cpre[g] + a.cnown[g]) / im.bpm; }
+    const uint32_t ident = 0x543210u;
+    uint32_t carry = ident;              /* composition of every chunk before this group of 32 */
+    uint32_t first_bad = 0xFFFFFFFFu;
+    for (uint32_t cb = 0; cb < im.nch; cb += 32u) {
+        const uint32_t c = cb + lane, g = im.chunk_base + c;
+        const bool live = c < im.nch;
+        const uint32_t m = live ? jd_jw_ckpt(a.cjmap[g]) : ident;      /* phases >= 6 restart at 0 */
+        uint32_t x = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x = jd_jmap_compose(y, x);
+        }
+        uint32_t excl = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) excl = ident;
+        if (live) {
+            a.seg_phase[a.nseg_total + g] = jd_jmap_compose(carry, excl) & 15u;
+            if (a.cstatus[g] != 0u && c < first_bad) first_bad = c;
+        }
+        carry = jd_jmap_compose(carry, __shfl_sync(0xffffffffu, x, 31));
     }
-    /* the scan is one "segment" for the per-image stitch (jdk_stitch) */
-    a.seg_jmap[im.seg_base] = JD_JW_INIT;
-    a.seg_status[im.seg_base] = status ? ((status << 28) | (err_mcu & 0x0FFFFFFFu)) : 0u;
-}
-
-__global__ void __launch_bounds__(128) jdk_chunk_dcfix(const JDChunkArgs a)
-{
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.nchunks) return;
-    const JDImageDesc &im = a.imgs[a.chunk_img[g]];
-    const uint32_t nl = (im.ncomp == 3) ? (uint32_t)im.bpm - 2u : (uint32_t)im.bpm;
-    jd_u64 *hdr = a.blk_hdr + im.blk_base;
-    const uint32_t b0 = a.cpre[g], b1 = b0 + a.cnown[g];
-    for (uint32_t bi = b0; bi < b1; bi++) {
-        const uint32_t bim = bi % im.bpm, comp = (bim < nl) ? 0u : bim - nl + 1u;
-        const jd_u64 h = hdr[bi];
-        const int dc = JD_HDR_DC(h) + a.cpe[3 * g + comp];
-        hdr[bi] = (h & ~((jd_u64)0xFFFFu << 32)) | ((jd_u64)(uint16_t)(int16_t)dc << 32);
+    first_bad = __reduce_min_sync(0xffffffffu, first_bad);
+    if (lane == 0) {
+        uint32_t status = 0, err_mcu = 0;
+        if (first_bad != 0xFFFFFFFFu) {
+            const uint32_t g = im.chunk_base + first_bad;
+            status = a.cstatus[g]; err_mcu = (a.cpre[g] + a.cnown[g]) / im.bpm;
+        }
+        /* the scan is one "segment" for the per-image stitch (jdk_stitch) */
+        a.seg_jmap[im.seg_base] = JD_JW_INIT;
+        a.seg_status[im.seg_base] = status ? ((status << 28) | (err_mcu & 0x0FFFFFFFu)) : 0u;
     }
 }
 

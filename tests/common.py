@@ -70,6 +70,7 @@ def hostsim():
         L.hostsim_decode.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
         L.hostsim_open.argtypes = [C.c_char_p, C.c_int] + [C.POINTER(C.c_int)] * 9
         L.hostsim_last_chunk_iters.restype = C.c_int
+        L.hostsim_last_chunk_dc_mismatch.restype = C.c_int
         _sim = L
     return _sim
 

@@ -29,7 +29,8 @@ struct VecSink {
 
 static const uint8_t kTpos[64] = JD_TPOS_INIT;
 static uint32_t kTposW[64];
-static int g_chunk_iters = 0;
+static int g_chunk_iters = 0, g_chunk_dc_mismatch = 0;
+extern "C" int hostsim_last_chunk_dc_mismatch(void) { return g_chunk_dc_mismatch; }
 extern "C" int hostsim_last_chunk_iters(void) { return g_chunk_iters; }
 
 struct Planes {
@@ -127,12 +128,13 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         sc.bpm = (uint32_t)info.bpm; sc.ncomp = (uint32_t)info.ncomp; sc.tsel = (uint32_t)info.tsel; sc.total_blocks = (uint32_t)nblk;
         const uint32_t nch = ((uint32_t)(size - info.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;
         std::vector<uint32_t> E(nch, JD_CS_PACK(0, 0, 0)), E2(nch), nst(nch, 0), pre(nch, 0);
+        std::vector<int32_t> dcs(nch * 3, 0);
         for (;;) {   /* fix point of the entry states */
             bool changed = false;
             E2[0] = E[0];
             for (uint32_t c = 0; c < nch; c++) {
                 uint32_t badc;
-                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], &nst[c], &badc);
+                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], &nst[c], &badc, &dcs[3 * c]);
                 if (c + 1 < nch) { E2[c + 1] = ex; if (ex != E[c + 1]) changed = true; }
             }
             E.swap(E2);
@@ -142,31 +144,27 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         }
         g_chunk_iters = chunk_iters;
         { uint32_t run = 0; for (uint32_t c = 0; c < nch; c++) { pre[c] = run; run += nst[c]; } }
+        /* DC predictors at each chunk's first block: prefix sums of the parse pass's per-chunk DC sums (jdk_chunk_prefix) */
+        std::vector<int32_t> pe(nch * 3, 0);
+        { int run[3] = {0, 0, 0}; for (uint32_t c = 0; c < nch; c++) for (int q = 0; q < 3; q++) { pe[c * 3 + q] = run[q]; run[q] += dcs[c * 3 + q]; } }
         std::vector<JDChunkOut> co(nch);
+        g_chunk_dc_mismatch = 0;
         for (uint32_t c = 0; c < nch; c++) {
             const uint32_t ri0 = JD_REC_INDEX((uint32_t)info.scan_offset + c * JD_CHUNK_BYTES, 1u + c);
             jd_chunk_emit(sc, lut.data(), kTposW, c, E[c], (c + 1 < nch) ? E[c + 1] : JD_CS_NONE, pre[c], hdr.data(), rec.data() + ri0, ri0,
-                          JD_REC_CAP(JD_CHUNK_BYTES), c, 0u, 0u, sink, co[c]);
+                          JD_REC_CAP(JD_CHUNK_BYTES), c, 0u, 0u, &pe[3 * c], sink, co[c]);
             if (co[c].status != JD_SEG_OK) bad = 1;
+            /* the parse pass and the emit pass must agree on the DC sums of every chunk whose blocks all lie inside the scan */
+            if (co[c].status == JD_SEG_OK && co[c].nown == nst[c])
+                for (int q = 0; q < 3; q++) if (co[c].dcsum[q] != dcs[c * 3 + q]) g_chunk_dc_mismatch++;
         }
-        /* stitch over chunks: true phase per chunk, DC predictor at each chunk entry */
+        /* stitch over chunks: true phase per chunk */
         phase_slot.assign(nch, 0);
-        std::vector<int> pe(nch * 3, 0);
-        { uint32_t cur = 0; int run[3] = {0, 0, 0};
+        { uint32_t cur = 0;
           for (uint32_t c = 0; c < nch; c++) {
               phase_slot[c] = cur;
               uint32_t j = (co[c].jmap >> (4 * cur)) & 15u; cur = (j >= 6) ? 0 : j;
-              for (int q = 0; q < 3; q++) { pe[c * 3 + q] = run[q]; run[q] += co[c].dcsum[q]; }
           } }
-        /* dc fix */
-        const uint32_t nl = (info.ncomp == 3) ? (uint32_t)info.bpm - 2 : (uint32_t)info.bpm;
-        for (uint32_t c = 0; c < nch; c++)
-            for (uint32_t bi = pre[c]; bi < pre[c] + co[c].nown; bi++) {
-                const uint32_t bim = bi % (uint32_t)info.bpm, comp = (bim < nl) ? 0u : bim - nl + 1u;
-                jd_u64 h = hdr[bi];
-                const int dc = JD_HDR_DC(h) + pe[c * 3 + comp];
-                hdr[bi] = (h & ~((jd_u64)0xFFFFu << 32)) | ((jd_u64)(uint16_t)(int16_t)dc << 32);
-            }
         jmap[0] = JD_JW_INIT;
     } else
     for (int sgi = 0; sgi < nseg; sgi++) {

@@ -40,6 +40,11 @@ ncu)
 bench)
   timeout 900 python bench.py --pipelined > $O/${tag}_bench_hd1024_1gpu.json 2> $O/${tag}_bench_hd1024.err; tail -c 600 $O/${tag}_bench_hd1024_1gpu.json
   timeout 600 python bench.py --workload uhd --no-cpu --pipelined > $O/${tag}_bench_uhd_1gpu.json 2> $O/${tag}_bench_uhd.err ;;
+norst)
+  B="python bench.py --no-cpu --no-e2e --steps 1 --warmup 1 --unique 16"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/${tag}_launches_hd_norst.csv $B --workload hd_norst > $O/${tag}_ncu_launches_norst.log 2>&1
+  timeout 600 python bench.py --workload hd_norst --no-cpu --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_hd_norst_1gpu.json 2> $O/${tag}_bench_hd_norst.err
+  tail -c 900 $O/${tag}_bench_hd_norst_1gpu.json; echo ;;
 others)
   for wl in uhd_quarter uhd_eighth dither dither444 hd_norst; do
     timeout 600 python bench.py --workload $wl --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_${wl}_1gpu.json 2> $O/${tag}_bench_${wl}.err
@@ -53,6 +58,13 @@ multi)
   timeout 1500 $TR bench.py --gpus $N --workload uhd10k --steps 3 --warmup 3 --no-cpu > $O/${tag}_bench_uhd10k_${N}gpu.json 2> $O/${tag}_bench_uhd10k_${N}gpu.err; tail -c 1200 $O/${tag}_bench_uhd10k_${N}gpu.json
   timeout 900 $TR bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > $O/${tag}_bench_hd1024_${N}gpu.json 2> $O/${tag}_bench_hd1024_${N}gpu.err; tail -c 900 $O/${tag}_bench_hd1024_${N}gpu.json
   if [ -n "$NOBIND" ]; then JPEGDEC_B200_NO_BIND=1 timeout 900 $TR bench.py --gpus $N --steps 3 --warmup 3 --no-cpu > $O/${tag}_bench_hd1024_${N}gpu_nobind.json 2> $O/${tag}_bench_hd1024_${N}gpu_nobind.err; fi ;;
+probe)
+  N=${NGPUS:-4}
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513"
+  nvidia-smi topo -m > $O/${tag}_topo.txt 2>&1
+  timeout 600 $TR tools/d2h_probe.py --out $O/${tag}_probe_bind > $O/${tag}_probe_bind.log 2>&1; cat $O/${tag}_probe_bind.rank* 
+  JPEGDEC_B200_NO_BIND=1 timeout 600 $TR tools/d2h_probe.py --out $O/${tag}_probe_nobind > $O/${tag}_probe_nobind.log 2>&1; cat $O/${tag}_probe_nobind.rank*
+  timeout 900 $TR bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > $O/${tag}_bench_hd1024_${N}gpu.json 2> $O/${tag}_bench_hd1024_${N}gpu.err; tail -c 900 $O/${tag}_bench_hd1024_${N}gpu.json ;;
 uhd10k)
   timeout 1200 python bench.py --workload uhd10k --no-cpu --steps 3 --warmup 3 > $O/${tag}_bench_uhd10k_1gpu.json 2> $O/${tag}_bench_uhd10k.err; tail -c 1500 $O/${tag}_bench_uhd10k_1gpu.json; tail -5 $O/${tag}_bench_uhd10k.err ;;
 refarm)
