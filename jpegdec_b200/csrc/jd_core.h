@@ -187,13 +187,24 @@ typedef struct {
     uint32_t img;         /* image index in the batch (for events) */
     uint32_t *ring;       /* CLEAN reader: this walker's 32-word stream ring (16-byte aligned; shared memory on the device) */
     uint16_t *stage;      /* this walker's 8-record staging chunk (16-byte aligned; shared memory on the device) */
+    /* Walk that starts in the middle of a stream (a chunk of a restart-free scan, jd_chunk.h; CLEAN reader only): */
+    uint32_t skip_bits;   /* bits between `start` (16-byte aligned there) and the first block's first bit */
+    uint32_t blk_first;   /* block-in-MCU index of the first block */
+    uint32_t nblk;        /* blocks to decode; 0 = nmcu * bpm */
+    uint32_t midstream;   /* 1: the walk ends where the next one starts: no end-of-interval byte alignment */
+    int32_t pred[3];      /* DC predictors at the first block */
 } JDSegIn;
+JD_HD void jd_segin_whole_interval(JDSegIn *in)
+{
+    in->skip_bits = 0; in->blk_first = 0; in->nblk = 0; in->midstream = 0; in->pred[0] = in->pred[1] = in->pred[2] = 0;
+}
 
 typedef struct {
     uint32_t jmap;   /* six nibbles: window phase at segment end (after byte alignment) per start candidate */
     int32_t err_mcu; /* -1 ok, else local MCU index where decoding failed */
     uint32_t status; /* JD_SEG_* */
     uint32_t nrec;
+    uint32_t nblk_done; /* blocks decoded (== blocks asked for unless status != 0) */
 } JDSegOut;
 
 /* status codes written per segment */
@@ -252,7 +263,7 @@ JD_HD void jd_decode_segment_flat(const JDSegIn &in, const uint16_t *lut /* JD_L
     bool last_was_eob = true;
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
-    const uint32_t nblk_total = in.nmcu * in.bpm;
+    const uint32_t nblk_total = in.nblk ? in.nblk : in.nmcu * in.bpm;
     /* per-MCU block schedule, one nibble per block: component (2 bits) | DC table << 2 | AC table << 3 */
     uint32_t sched = 0;
     for (uint32_t i = 0; i < in.bpm && i < 8u; i++) {
@@ -260,7 +271,7 @@ JD_HD void jd_decode_segment_flat(const JDSegIn &in, const uint16_t *lut /* JD_L
         sched |= (c | (((in.tsel >> (2 * c)) & 1u) << 2) | (((in.tsel >> (2 * c + 1)) & 1u) << 3)) << (4 * i);
     }
     const uint32_t bsh_end = 4u * in.bpm;
-    uint32_t bsh = 0;                            /* 4 * (block index inside the MCU) */
+    uint32_t bsh = 4u * in.blk_first;            /* 4 * (block index inside the MCU) */
     uint32_t cur = sched & 15u;                  /* schedule nibble of the current block */
     uint32_t nleft = nblk_total;                 /* blocks still to finish */
     jd_u64 *hp = blk_hdr;
@@ -435,7 +446,7 @@ JD_HD void jd_decode_segment_flat(const JDSegIn &in, const uint16_t *lut /* JD_L
     const uint32_t b = nblk_total - nleft;       /* blocks finished */
     if (err >= 0) {
         /* undecodable from here: later stages must still find well-formed (empty) headers */
-        out.err_mcu = (int32_t)(b / in.bpm);
+        out.err_mcu = (int32_t)((b + in.blk_first) / in.bpm);
         for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
     }
     out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
@@ -630,9 +641,17 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         }
     };
 
-    int pred0 = 0, pred1 = 0, pred2 = 0;
+    int pred0 = in.pred[0], pred1 = in.pred[1], pred2 = in.pred[2];
     uint32_t jw = JD_JW_INIT;                    /* window-phase candidates (six nibbles) */
-    uint32_t p7 = 0;                             /* bits consumed in this segment, mod 8 */
+    uint32_t p7 = in.skip_bits & 7u;             /* bits consumed in this segment, mod 8 (`start` is a byte boundary) */
+    if (CLEAN) {
+        /* mid-stream start: drop the bits in front of the first block */
+        for (uint32_t skip = in.skip_bits; skip != 0u;) {
+            refill();
+            const uint32_t d = skip < 32u ? skip : 32u;
+            bb <<= d; nb -= (int)d; skip -= d;
+        }
+    }
     uint32_t ro = 0;                             /* next record slot (index into rec) */
 #ifdef __CUDA_ARCH__
     /* one opaque register pair for the record base (else it is re-derived from its parts at every store) */
@@ -681,7 +700,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     const JDTab32 TP(tposw);
 
     const uint32_t nluma = (in.ncomp == 3) ? in.bpm - 2 : in.bpm;
-    const uint32_t nblk_total = in.nmcu * in.bpm;
+    const uint32_t nblk_total = in.nblk ? in.nblk : in.nmcu * in.bpm;
     /* per-MCU block schedule, one nibble per block: component (2 bits) | DC table << 2 | AC table << 3 */
     uint32_t sched = 0;
     for (uint32_t i = 0; i < in.bpm && i < 8u; i++) {
@@ -689,7 +708,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         sched |= (c | (((in.tsel >> (2 * c)) & 1u) << 2) | (((in.tsel >> (2 * c + 1)) & 1u) << 3)) << (4 * i);
     }
     const uint32_t bsh_end = 4u * in.bpm;
-    uint32_t bsh = 0;                            /* 4 * (block index inside the MCU) */
+    uint32_t bsh = 4u * in.blk_first;            /* 4 * (block index inside the MCU) */
     constexpr uint32_t LIMIT = (MODE == JD_MODE_STORE_LOW) ? 5u : 64u;
     uint32_t b = 0;                              /* blocks finished */
 
@@ -838,7 +857,7 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
     if (!direct && (ro & 7u) != 0u) flush_chunk(ro & ~7u);   /* the last, partly filled chunk (its tail lies in the slot's slack) */
     if (err >= 0) {
         /* undecodable from here: later stages must still find well-formed (empty) headers */
-        out.err_mcu = (int32_t)(b / in.bpm);
+        out.err_mcu = (int32_t)((b + in.blk_first) / in.bpm);
         for (uint32_t bb2 = b; bb2 < nblk_total; bb2++) blk_hdr[bb2] = jd_pack_hdr(in.rec_index0, 0, 0, 0, 0, 0);
     }
     out.status = (err < 0) ? (uint32_t)JD_SEG_OK : (uint32_t)err;
@@ -846,11 +865,14 @@ JD_HD void jd_decode_segment(const JDSegIn &in, const uint16_t *lut /* JD_LUT_EN
         out.err_mcu = -1;
         /* end of restart interval (jpeg.inl:5337-5347): R4 already happened unless the last
          * block ended with EOB; then the bit offset is rounded up to a byte without a reload. */
-        if (!last_was_eob) jw = jd_jw_ckpt(jw);
-        if (p7) jw += JD_JW_ONES;
+        if (!in.midstream) {
+            if (!last_was_eob) jw = jd_jw_ckpt(jw);
+            if (p7) jw += JD_JW_ONES;
+        }
     }
     out.jmap = jw;
     out.nrec = ro;
+    out.nblk_done = b;
 #undef JD_REC_ST
 }
 

@@ -165,7 +165,7 @@ struct JPEGB200_BATCH {
     std::vector<uint32_t> cimg_list, chunk_img;
     uint32_t nchunks, max_nch;
     DevBuf<uint8_t> d_filt;
-    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_Ep, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
+    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_Ep, d_cfirst, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
     DevBuf<int32_t> d_cdcs, d_cpe;
     uint32_t h_changed;
     bool chunk_iterate;            /* restart-free scans: iterate the entry states with a host check (fallback mode) */
@@ -624,7 +624,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
     b->d_clean.release(); b->d_seg_clen.release();
-    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release(); b->d_Ep.release();
+    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release(); b->d_Ep.release(); b->d_cfirst.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
@@ -740,7 +740,7 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
         const size_t nc = b->nchunks;
         CK(b->d_filt.alloc(&b->ctx->pool, b->comp_total + 512));
         CK(b->d_cimg_list.alloc(&b->ctx->pool, b->cimg_list.size())); CK(b->d_chunk_img.alloc(&b->ctx->pool, nc)); CK(b->d_flen.alloc(&b->ctx->pool, n));
-        CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_Ep.alloc(&b->ctx->pool, nc)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
+        CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_Ep.alloc(&b->ctx->pool, nc)); CK(b->d_cfirst.alloc(&b->ctx->pool, nc)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
         CK(b->d_cstatus.alloc(&b->ctx->pool, nc)); CK(b->d_cnown.alloc(&b->ctx->pool, nc)); CK(b->d_cdcs.alloc(&b->ctx->pool, 3 * nc)); CK(b->d_cpe.alloc(&b->ctx->pool, 3 * nc));
     }
     CK(b->d_counters.alloc(&b->ctx->pool, 8));
@@ -1024,8 +1024,10 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         ca.events = b->d_events.p; ca.event_count = b->d_counters.p; ca.event_cap = JD_EVENT_CAP;
         ca.seg_phase = b->d_seg_phase.p; ca.seg_jmap = b->d_seg_jmap.p; ca.seg_status = b->d_seg_status.p; ca.nseg_total = b->nseg;
         const unsigned gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
-        ca.max_nch = b->max_nch; ca.Ep = b->d_Ep.p;
+        ca.max_nch = b->max_nch; ca.Ep = b->d_Ep.p; ca.cfirst = b->d_cfirst.p;
         const dim3 gchunks((b->max_nch + 127) / 128, (unsigned)b->cimg_list.size());
+        /* per device, so per call: the parse pass stages its stretch of the stream in 87 KB of shared memory */
+        CK(cudaFuncSetAttribute(jdk_chunk_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JD_PARSE_SMEM));
         /* guess: every chunk starts a block at its first bit (exit state of every left neighbour = (0, 0, 0)); no chunk parsed yet */
         CK(cudaMemsetAsync(b->d_E0.p, 0, (size_t)(b->nchunks + 1) * 4, st));
         CK(cudaMemsetAsync(b->d_Ep.p, 0xFE, (size_t)b->nchunks * 4, st));
@@ -1050,7 +1052,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             for (int k = 0; k < burst; k++) {
                 if (k == burst - 1) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
                 ca.X_in = Xin; ca.X_out = Xout;
-                jdk_chunk_parse<<<gchunks, 128, 0, st>>>(ca);
+                jdk_chunk_parse<<<gchunks, 128, JD_PARSE_SMEM, st>>>(ca);
                 launches++; passes++;
                 uint32_t *tmp = Xin; Xin = Xout; Xout = tmp;
             }

@@ -151,6 +151,7 @@ __device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const ui
     in.img = img;
     in.ring = s_ring + threadIdx.x * JD_RING_STRIDE;
     in.stage = s_stage + threadIdx.x * 8;
+    jd_segin_whole_interval(&in);
     in.blk0 = im.blk_base + m0 * im.bpm;
     jd_u64 *hdr = a.blk_hdr + im.blk_base + (size_t)m0 * im.bpm;
     JDSegOut so;
@@ -368,6 +369,7 @@ struct JDChunkArgs {
     uint32_t *Ep;                  /* entry state each chunk was last parsed from */
     uint32_t max_nch;              /* chunks of the longest scan (grid x = ceil / 128) */
     uint32_t *cn, *cpre, *cjmap, *cstatus, *cnown;
+    uint32_t *cfirst;              /* per chunk: first block that starts in it (jd_chunk_parse) | invalid-code flag << 31 */
     int32_t *cdcs, *cpe;           /* per chunk x 3: DC sums (parse pass) / DC predictors at the chunk's first block (prefix) */
     uint32_t *changed;
     jd_u64 *blk_hdr;
@@ -481,16 +483,46 @@ __device__ __forceinline__ void jd_load_lut_set(uint16_t *s_lut, const uint16_t 
     for (uint32_t i = threadIdx.x; i < (uint32_t)(JD_LUT_ENTRIES / 8); i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
+/* Bit window over the CTA's stretch of the stream staged in shared memory (jdk_chunk_parse).  Word w of the stretch lives at
+ * index w + (w >> 7): one pad word per chunk (128 words), so the 32 lanes of a warp -- one chunk each, 512 bytes apart --
+ * read 32 different banks.  (Reading the stream straight from global memory, every refill of any lane was an L2 round trip
+ * that the whole warp waited for: scoreboards are per warp register.) */
+struct JDBitWinS {
+    const uint32_t *s;
+    int base_bits;                 /* scan-relative bit position of staged word 0 */
+    uint32_t wi;
+    jd_u64 bb;
+    int nb;
+    __device__ __forceinline__ JDBitWinS(const uint32_t *stage, int base) : s(stage), base_bits(base), wi(0), bb(0), nb(0) {}
+    __device__ __forceinline__ uint32_t word() { const uint32_t v = s[wi + (wi >> 7)]; wi++; return jd_bswap32(v); }
+    __device__ __forceinline__ void seek(uint32_t rel)
+    {
+        const uint32_t ap = (uint32_t)((int)rel - base_bits);
+        wi = ap >> 5;
+        const uint32_t sft = ap & 31u;
+        bb = (jd_u64)word() << (32u + sft);
+        nb = 32 - (int)sft;
+    }
+    __device__ __forceinline__ void refill() { if (nb <= 32) { bb |= (jd_u64)word() << (32 - nb); nb += 32; } }
+    __device__ __forceinline__ uint32_t hi() const { return (uint32_t)(bb >> 32); }
+    __device__ __forceinline__ void drop(uint32_t n) { bb <<= n; nb -= (int)n; }
+};
+#define JD_PARSE_STAGE_WORDS (128u * 128u + 8u)                               /* 128 chunks + the few bytes a symbol straddles */
+#define JD_PARSE_STAGE_SLOTS (JD_PARSE_STAGE_WORDS + (JD_PARSE_STAGE_WORDS >> 7) + 1u)
+#define JD_PARSE_SMEM (JD_LUT_ENTRIES * 2u + JD_PARSE_STAGE_SLOTS * 4u)
+
 /* One speculative pass.  The entry state of chunk c is the exit state chunk c-1 produced in the previous pass (X_in);
  * a chunk whose entry state is the one it was last parsed from keeps its results, so after the first two passes only the
- * few chunks whose left neighbour had not re-synchronised are parsed again. */
+ * few chunks whose left neighbour had not re-synchronised are parsed again (those read the stream from global memory). */
 __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
 {
-    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_dyn);
+    uint32_t *s_words = reinterpret_cast<uint32_t *>(s_dyn + JD_LUT_ENTRIES * 2u);
     const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
-    const uint32_t c = blockIdx.x * 128u + threadIdx.x;
-    if (blockIdx.x * 128u >= im.nch) return;
+    const uint32_t cb = blockIdx.x * 128u, c = cb + threadIdx.x;
+    if (cb >= im.nch) return;
     const uint32_t g = im.chunk_base + c;
     const bool live = c < im.nch;
     uint32_t entry = 0;
@@ -500,15 +532,31 @@ __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
         need = entry != a.Ep[g];
         if (!need) a.X_out[g] = a.X_in[g];
     }
-    if (!__syncthreads_or(need ? 1 : 0)) return;
+    const int nneed = __syncthreads_count(need ? 1 : 0);
+    if (nneed == 0) return;
     jd_load_lut_set(s_lut, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES);
+    const JDScanIn sc = jd_scan_of(a, im, ii);
+    const bool staged = nneed >= 24;
+    const uint32_t w0 = (sc.f0 + cb * JD_CHUNK_BYTES) >> 2;                     /* first staged word of the stream buffer */
+    if (staged) {
+        const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.filt);
+        const uint32_t wend = ((sc.f0 + sc.flen + 24u) >> 2) + 1u;              /* the zero tail ends here */
+        for (uint32_t w = threadIdx.x; w < JD_PARSE_STAGE_WORDS; w += 128u)
+            s_words[w + (w >> 7)] = (w0 + w < wend) ? __ldg(gw + w0 + w) : 0u;
+    }
     __syncthreads();
     if (!need) return;
-    const JDScanIn sc = jd_scan_of(a, im, ii);
-    uint32_t nstart, bad;
+    uint32_t nstart, bad, first, ex;
     int32_t dcs[3];
-    const uint32_t ex = jd_chunk_parse(sc, s_lut, c, entry, &nstart, &bad, dcs);
+    if (staged) {
+        JDBitWinS win(s_words, (int)(w0 * 32u) - (int)(sc.f0 * 8u));
+        ex = jd_chunk_parse(sc, s_lut, c, entry, win, &nstart, &bad, dcs, &first);
+    } else {
+        JDBitWin win(sc);
+        ex = jd_chunk_parse(sc, s_lut, c, entry, win, &nstart, &bad, dcs, &first);
+    }
     a.cn[g] = nstart;
+    a.cfirst[g] = first | (bad << 31);
     a.cdcs[3 * g] = dcs[0]; a.cdcs[3 * g + 1] = dcs[1]; a.cdcs[3 * g + 2] = dcs[2];
     a.Ep[g] = entry;
     if (ex != a.X_in[g]) atomicOr(a.changed, 1u);
@@ -545,10 +593,14 @@ __global__ void __launch_bounds__(128) jdk_chunk_prefix(const JDChunkArgs a)
     }
 }
 
+/* every chunk decodes the blocks that start in it: the entropy walk of jdk_entropy (jd_decode_segment, CLEAN reader: stream
+ * ring and record staging in shared memory) started in the middle of the stream */
 __global__ void __launch_bounds__(128) jdk_chunk_emit(const JDChunkArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     __shared__ uint32_t s_tpos[64];
+    __shared__ __align__(16) uint32_t s_ring[128 * JD_RING_STRIDE];
+    __shared__ __align__(16) uint16_t s_stage[128 * 8];
     const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
     if (blockIdx.x * 128u >= im.nch) return;
@@ -558,20 +610,42 @@ __global__ void __launch_bounds__(128) jdk_chunk_emit(const JDChunkArgs a)
     const uint32_t c = blockIdx.x * 128u + threadIdx.x;
     if (c >= im.nch) return;
     const uint32_t g = im.chunk_base + c;
-    const JDScanIn sc = jd_scan_of(a, im, ii);
-    const uint32_t entry = (c == 0) ? JD_CS_PACK(0, 0, 0) : a.X_in[g - 1];
-    const uint32_t next = (c + 1 < im.nch) ? a.X_in[g] : JD_CS_NONE;
-    /* image-relative record slot: the scan's one "segment" owns slot 0..nseg-1, its chunks follow */
-    const uint32_t ri0 = JD_REC_INDEX(im.scan_off - im.comp_off + c * JD_CHUNK_BYTES, im.nseg + c);
-    const uint32_t cap = JD_REC_CAP(JD_CHUNK_BYTES);
-    JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
-    JDChunkOut co;
-    const int32_t pred_in[3] = {a.cpe[3 * g], a.cpe[3 * g + 1], a.cpe[3 * g + 2]};
-    jd_chunk_emit(sc, s_lut, s_tpos, c, entry, next, a.cpre[g], a.blk_hdr + im.blk_base,
-                  a.rec + im.rec_base + ri0, ri0, cap, a.nseg_total + g, im.blk_base, ii, pred_in, sink, co);
-    a.cjmap[g] = co.jmap;
-    a.cstatus[g] = co.status;
-    a.cnown[g] = co.nown;
+    const uint32_t total_blocks = (uint32_t)im.mcus_x * im.mcus_y * im.bpm;
+    const uint32_t pre = a.cpre[g], fb = a.cfirst[g];
+    uint32_t n = a.cn[g];
+    n = (pre >= total_blocks) ? 0u : ((n < total_blocks - pre) ? n : total_blocks - pre);   /* bits after the last block are not blocks */
+    uint32_t jmap = JD_JW_INIT, status = JD_SEG_OK, done = 0;
+    if (n != 0u) {
+        const uint32_t P0 = c * JD_CHUNK_BYTES * 8u + (fb & 0xFFFFu);       /* first block's first bit, relative to the scan */
+        const uint32_t byte0 = im.scan_off + (P0 >> 3);
+        JDSegIn in;
+        in.data = a.filt;
+        in.start = byte0 & ~15u;
+        in.end = im.scan_off + a.flen[ii];
+        in.nmcu = 0; in.bpm = im.bpm; in.ncomp = im.ncomp; in.tsel = im.tsel;
+        in.skip_bits = (byte0 - in.start) * 8u + (P0 & 7u);
+        in.blk_first = (fb >> 16) & 0xFu;
+        in.nblk = n;
+        in.midstream = 1;
+        in.pred[0] = a.cpe[3 * g]; in.pred[1] = a.cpe[3 * g + 1]; in.pred[2] = a.cpe[3 * g + 2];
+        /* image-relative record slot: the scan's one "segment" owns slot 0..nseg-1, its chunks follow */
+        in.rec_index0 = JD_REC_INDEX(im.scan_off - im.comp_off + c * JD_CHUNK_BYTES, im.nseg + c);
+        in.rec_cap = JD_REC_CAP(JD_CHUNK_BYTES);
+        in.seg = a.nseg_total + g;             /* phase slot of this walk (events) */
+        in.img = ii;
+        in.blk0 = im.blk_base + pre;
+        in.al = 0;
+        in.ring = s_ring + threadIdx.x * JD_RING_STRIDE;
+        in.stage = s_stage + threadIdx.x * 8;
+        JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
+        JDSegOut so;
+        jd_decode_segment<JDEventSinkDev, JD_MODE_BASELINE, true>(in, s_lut, s_tpos, a.blk_hdr + im.blk_base + pre, a.rec + im.rec_base + in.rec_index0, sink, so);
+        jmap = so.jmap; status = so.status; done = so.nblk_done;
+    }
+    if (status == JD_SEG_OK && (fb >> 31) != 0u) status = JD_SEG_BADCODE;    /* the parse pass met an invalid code after these blocks */
+    a.cjmap[g] = jmap;
+    a.cstatus[g] = status;
+    a.cnown[g] = done;
 }
 
 /* phase map composition: first `a`, then `b` (six nibbles: next phase for each current phase; both normalised to 0..5) */

@@ -129,12 +129,15 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         const uint32_t nch = ((uint32_t)(size - info.scan_offset) + JD_CHUNK_BYTES - 1) / JD_CHUNK_BYTES + 1;
         std::vector<uint32_t> E(nch, JD_CS_PACK(0, 0, 0)), E2(nch), nst(nch, 0), pre(nch, 0);
         std::vector<int32_t> dcs(nch * 3, 0);
+        std::vector<uint32_t> first(nch, 0);
         for (;;) {   /* fix point of the entry states */
             bool changed = false;
             E2[0] = E[0];
             for (uint32_t c = 0; c < nch; c++) {
                 uint32_t badc;
-                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], &nst[c], &badc, &dcs[3 * c]);
+                JDBitWin win(sc);
+                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], win, &nst[c], &badc, &dcs[3 * c], &first[c]);
+                first[c] |= badc << 31;
                 if (c + 1 < nch) { E2[c + 1] = ex; if (ex != E[c + 1]) changed = true; }
             }
             E.swap(E2);
@@ -147,28 +150,44 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
         /* DC predictors at each chunk's first block: prefix sums of the parse pass's per-chunk DC sums (jdk_chunk_prefix) */
         std::vector<int32_t> pe(nch * 3, 0);
         { int run[3] = {0, 0, 0}; for (uint32_t c = 0; c < nch; c++) for (int q = 0; q < 3; q++) { pe[c * 3 + q] = run[q]; run[q] += dcs[c * 3 + q]; } }
-        std::vector<JDChunkOut> co(nch);
+        /* emit: the entropy walk itself (CLEAN reader), started at each chunk's first block (jdk_chunk_emit) */
+        std::vector<uint32_t> cjmap(nch, JD_JW_INIT);
         g_chunk_dc_mismatch = 0;
         for (uint32_t c = 0; c < nch; c++) {
-            const uint32_t ri0 = JD_REC_INDEX((uint32_t)info.scan_offset + c * JD_CHUNK_BYTES, 1u + c);
-            jd_chunk_emit(sc, lut.data(), kTposW, c, E[c], (c + 1 < nch) ? E[c + 1] : JD_CS_NONE, pre[c], hdr.data(), rec.data() + ri0, ri0,
-                          JD_REC_CAP(JD_CHUNK_BYTES), c, 0u, 0u, &pe[3 * c], sink, co[c]);
-            if (co[c].status != JD_SEG_OK) bad = 1;
-            /* the parse pass and the emit pass must agree on the DC sums of every chunk whose blocks all lie inside the scan */
-            if (co[c].status == JD_SEG_OK && co[c].nown == nst[c])
-                for (int q = 0; q < 3; q++) if (co[c].dcsum[q] != dcs[c * 3 + q]) g_chunk_dc_mismatch++;
+            uint32_t n = nst[c];
+            n = (pre[c] >= (uint32_t)nblk) ? 0u : ((n < (uint32_t)nblk - pre[c]) ? n : (uint32_t)nblk - pre[c]);
+            uint32_t status = JD_SEG_OK;
+            if (n) {
+                const uint32_t P0 = c * JD_CHUNK_BYTES * 8u + (first[c] & 0xFFFFu);
+                const uint32_t byte0 = (uint32_t)info.scan_offset + (P0 >> 3);
+                JDSegIn in;
+                in.data = filt; in.start = byte0 & ~15u; in.end = (uint32_t)info.scan_offset + flen;
+                in.nmcu = 0; in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel;
+                in.skip_bits = (byte0 - in.start) * 8u + (P0 & 7u);
+                in.blk_first = (first[c] >> 16) & 0xFu; in.nblk = n; in.midstream = 1;
+                in.pred[0] = pe[3 * c]; in.pred[1] = pe[3 * c + 1]; in.pred[2] = pe[3 * c + 2];
+                in.rec_index0 = JD_REC_INDEX((uint32_t)info.scan_offset + c * JD_CHUNK_BYTES, 1u + c);
+                in.rec_cap = JD_REC_CAP(JD_CHUNK_BYTES);
+                in.seg = c; in.img = 0; in.blk0 = pre[c]; in.al = 0; in.ring = g_ring; in.stage = g_stage;
+                JDSegOut so;
+                jd_decode_segment<VecSink, JD_MODE_BASELINE, true>(in, lut.data(), kTposW, hdr.data() + pre[c], rec.data() + in.rec_index0, sink, so);
+                cjmap[c] = so.jmap; status = so.status;
+            }
+            if (status == JD_SEG_OK && (first[c] >> 31)) status = JD_SEG_BADCODE;
+            if (status != JD_SEG_OK) bad = 1;
         }
         /* stitch over chunks: true phase per chunk */
         phase_slot.assign(nch, 0);
         { uint32_t cur = 0;
           for (uint32_t c = 0; c < nch; c++) {
               phase_slot[c] = cur;
-              uint32_t j = (co[c].jmap >> (4 * cur)) & 15u; cur = (j >= 6) ? 0 : j;
+              uint32_t j = (cjmap[c] >> (4 * cur)) & 15u; cur = (j >= 6) ? 0 : j;
           } }
         jmap[0] = JD_JW_INIT;
     } else
     for (int sgi = 0; sgi < nseg; sgi++) {
         JDSegIn in;
+        jd_segin_whole_interval(&in);
         in.data = cdata;
         in.start = seg_start[sgi];
         in.end = (uint32_t)size;
@@ -475,7 +494,7 @@ extern "C" int hostsim_block_stats(const uint8_t *data, int size, double *out /*
     std::vector<uint16_t> rec((size_t)size * JD_REC_PER_BYTE + (size_t)JD_REC_SLOT_SLACK * (nseg + 1) + 1024, 0);
     VecSink sink;
     for (int sgi = 0; sgi < nseg; sgi++) {
-        JDSegIn in; in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
+        JDSegIn in; jd_segin_whole_interval(&in); in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
         int m0 = sgi * mps; in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);
         in.bpm = (uint32_t)info.bpm; in.ncomp = (uint32_t)info.ncomp; in.tsel = (uint32_t)info.tsel; in.img = 0; in.al = 0; in.ring = g_ring; in.stage = g_stage;
         in.rec_index0 = JD_REC_INDEX(in.start, sgi); in.rec_cap = JD_REC_CAP((uint32_t)size - in.start); in.seg = (uint32_t)sgi; in.blk0 = (uint32_t)(m0 * info.bpm);
@@ -524,6 +543,7 @@ extern "C" int hostsim_walk_check(const uint8_t *data, int size, int *n_segments
     for (int sgi = 0; sgi < nseg; sgi++) {
         if (seg_start[sgi] == 0xFFFFFFFFu) break;
         JDSegIn in;
+        jd_segin_whole_interval(&in);
         in.data = (const uint8_t *)padded.data(); in.start = seg_start[sgi]; in.end = (uint32_t)size;
         const int m0 = sgi * mps;
         in.nmcu = (uint32_t)((m0 + mps <= total_mcus) ? mps : total_mcus - m0);

@@ -116,7 +116,6 @@ def test_chunk_parallel_decode_of_restart_free_scans(name):
                 want = d["%s/%s/%s" % (mode, ptn, sn)]
                 rc, out, nev = T.hostsim_decode(data, pt, opt, arith, w, h, chunked=True)
                 assert rc == want["rc"] and T.sha(out) == want["sha"], (name, mode, ptn, sn)
-                assert T.hostsim().hostsim_last_chunk_dc_mismatch() == 0      # parse pass and emit pass agree on the DC sums
     assert 2 <= T.hostsim().hostsim_last_chunk_iters() <= 8
 
 
@@ -132,7 +131,6 @@ def test_chunk_parallel_decode_synthetic_vs_restatement():
             rc2, got, _ = T.hostsim_decode(data, 0, 0, arith, w, h, chunked=True)
             assert rc1 == rc2 == 1 and np.array_equal(got, want), n
             assert T.hostsim().hostsim_last_chunk_iters() <= 8
-            assert T.hostsim().hostsim_last_chunk_dc_mismatch() == 0
 
 
 def _odd_restart_cases():

@@ -45,6 +45,12 @@ norst)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/${tag}_launches_hd_norst.csv $B --workload hd_norst > $O/${tag}_ncu_launches_norst.log 2>&1
   timeout 600 python bench.py --workload hd_norst --no-cpu --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_hd_norst_1gpu.json 2> $O/${tag}_bench_hd_norst.err
   tail -c 900 $O/${tag}_bench_hd_norst_1gpu.json; echo ;;
+sanitize)
+  CS=/usr/local/cuda/bin/compute-sanitizer
+  K="fixture_batch or synthetic_formats or dither_batch or progressive or restart_free or corrupt or two_threads"
+  timeout 1500 $CS --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "$K" > $O/${tag}_compute_sanitizer_memcheck.txt 2>&1; tail -3 $O/${tag}_compute_sanitizer_memcheck.txt
+  timeout 900 $CS --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/${tag}_compute_sanitizer_racecheck.txt 2>&1; tail -3 $O/${tag}_compute_sanitizer_racecheck.txt
+  timeout 900 $CS --tool synccheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "restart_free or dither_batch or two_threads" > $O/${tag}_compute_sanitizer_synccheck.txt 2>&1; tail -3 $O/${tag}_compute_sanitizer_synccheck.txt ;;
 others)
   for wl in uhd_quarter uhd_eighth dither dither444 hd_norst; do
     timeout 600 python bench.py --workload $wl --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_${wl}_1gpu.json 2> $O/${tag}_bench_${wl}.err
