@@ -40,21 +40,18 @@ typedef struct {
 /* Bit window over the un-stuffed scan: 64-bit register buffer, MSB first, one aligned 32-bit word fetched per 32 bits
  * consumed (the first version fetched two words per SYMBOL, which made the L1 the bound of every pass). */
 struct JDBitWin {
-    const uint32_t *words;
-    uint32_t f0bits;
-    uint32_t wi;
+    const uint32_t *wp;            /* next word to fetch */
     jd_u64 bb;
     int nb;
-    JD_HDM JDBitWin(const JDScanIn &sc) : words((const uint32_t *)sc.filt), f0bits(sc.f0 * 8u), wi(0), bb(0), nb(0) {}
-    JD_HDM void seek(uint32_t rel)                                     /* rel = bit position relative to the scan start */
+    JD_HDM void seek(const JDScanIn &sc, uint32_t rel)                 /* rel = bit position relative to the scan start */
     {
-        const uint32_t ap = f0bits + rel;
-        wi = ap >> 5;
+        const uint32_t ap = sc.f0 * 8u + rel;
+        wp = (const uint32_t *)sc.filt + (ap >> 5);
         const uint32_t sft = ap & 31u;
-        bb = (jd_u64)jd_bswap32(words[wi++]) << (32u + sft);
+        bb = (jd_u64)jd_bswap32(*wp++) << (32u + sft);
         nb = 32 - (int)sft;
     }
-    JD_HDM void refill() { if (nb <= 32) { bb |= (jd_u64)jd_bswap32(words[wi++]) << (32 - nb); nb += 32; } }
+    JD_HDM void refill() { if (nb <= 32) { bb |= (jd_u64)jd_bswap32(*wp++) << (32 - nb); nb += 32; } }
     JD_HDM uint32_t hi() const { return (uint32_t)(bb >> 32); }       /* the next 32 bits (>= 33 valid after refill) */
     JD_HDM void drop(uint32_t n) { bb <<= n; nb -= (int)n; }
 };
@@ -85,9 +82,11 @@ JD_HD uint32_t jd_ac_entry(const T16 &T, const T32 &TF, uint32_t actab, uint32_t
 
 /* Pass 1: parse chunk `ci` from `entry`; returns the state at which the first symbol of chunk ci+1 starts
  * (JD_CS_NONE if the stream ends before) and counts the DC symbols (= block starts) inside this chunk.
- * `lut` = the image's table set (on the device: in the CTA's shared memory). */
-template <typename Win /* JDBitWin, or the kernel's shared-memory staged window */>
-JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t ci, uint32_t entry, Win &w, uint32_t *nstart, uint32_t *bad,
+ * `lut` = the image's table set (on the device: in the CTA's shared memory).
+ * Organised like jd_decode_segment: a loop over blocks (DC symbol, then the block's AC symbols), so that the lanes of a warp
+ * -- one chunk each -- run the DC code once per block together instead of nearly every symbol for one lane in eight (the
+ * flat one-symbol-per-iteration form of this loop issued ~85 instructions per symbol, half of them the DC path). */
+JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t ci, uint32_t entry, uint32_t *nstart, uint32_t *bad,
                                int32_t *dcs /* [3]: per component, sum of the DC differences of the blocks that start here */,
                                uint32_t *first /* first block that starts here: bit offset from the chunk start | block-in-MCU index << 16 */)
 {
@@ -97,47 +96,66 @@ JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t 
     const uint32_t c0 = ci * JD_CHUNK_BYTES * 8u, c1 = c0 + JD_CHUNK_BYTES * 8u, endbits = sc.flen * 8u;
     uint32_t rel = c0 + JD_CS_BIT(entry), k = JD_CS_K(entry);
     if (c0 >= endbits) return JD_CS_NONE;
+    const uint32_t stop = (c1 < endbits) ? c1 : endbits;   /* no symbol starts at or after this bit */
     const JDTab16 T(lut);
     const JDTab32 TF((const uint32_t *)lut);
     const uint32_t sched = jd_block_schedule(sc.tsel, sc.bpm, sc.ncomp), bsh_end = 4u * sc.bpm;
     uint32_t bsh = 4u * JD_CS_BIM(entry);
-    w.seek(rel);
-    uint32_t n = 0;
+    JDBitWin w;
+    w.seek(sc, rel);
+    uint32_t n = 0, fst = 0;
     int d0 = 0, d1 = 0, d2 = 0;
-    while (rel < c1) {
-        if (rel >= endbits) { *nstart = n; dcs[0] = d0; dcs[1] = d1; dcs[2] = d2; return JD_CS_NONE; }
-        w.refill();
-        const uint32_t hi = w.hi(), cur = (sched >> bsh) & 15u;
-        uint32_t adv;
+    bool invalid = false;
+    while (rel < stop) {
+        const uint32_t cur = (sched >> bsh) & 15u;
         if (k == 0) {
-            const uint32_t w16 = hi >> 16;
+            /* ---- the block's DC symbol ---- */
+            w.refill();
+            const uint32_t hi = w.hi(), w16 = hi >> 16;
             const uint32_t e = T.at(JD_LUT_DC((cur >> 2) & 1u) + ((w16 >= 0xF800u) ? (1024u + ((w16 >> 4) & 0x7Fu)) : (w16 >> 6)));
-            if (e == 0u) { *bad = 1; *nstart = n; return JD_CS_PACK(0, 0, 0); }
+            if (e == 0u) { invalid = true; break; }
             const uint32_t len = e >> 8, s = e & 15u;
             const int v = jd_extend_top(hi << len, s);
             const uint32_t comp = cur & 3u;
             d0 += (comp == 0u) ? v : 0; d1 += (comp == 1u) ? v : 0; d2 += (comp >= 2u) ? v : 0;
-            adv = len + s;
-            if (n == 0u) *first = (rel - c0) | ((bsh >> 2) << 16);
+            if (n == 0u) fst = (rel - c0) | ((bsh >> 2) << 16);
             n++; k = 1;
-        } else {
-            const uint32_t e = jd_ac_entry(T, TF, cur >> 3, hi);
-            /* an invalid code under a guessed entry state only says the guess was wrong: let the right neighbour keep
-             * speculating from its own first bit (a truly corrupt stream is reported by jd_chunk_emit) */
-            if (e == 0u) { *bad = 1; *nstart = n; return JD_CS_PACK(0, 0, 0); }
-            adv = e & 0x1Fu;
-            k += e >> 24;                        /* run + 1; 128 for EOB */
+            w.drop(len + s);
+            rel += len + s;
         }
-        w.drop(adv);
-        rel += adv;
+        /* ---- its AC symbols, as far as they start inside the chunk ---- */
+        const uint32_t tacf = JD_LUT_ACF(cur >> 3) >> 1;
+        while (rel < stop) {
+            w.refill();
+            const uint32_t hi = w.hi();
+            uint32_t e = TF.at(tacf + (hi >> 22));
+            if (e == 0u) {
+                const uint32_t e16 = (hi >= 0xFC000000u) ? T.at(JD_LUT_AC(cur >> 3) + 1024u + ((hi >> 16) & 0x3FFu)) : 0u;
+                if (e16 == 0u) { invalid = true; break; }
+                e = JD_ACF_PACK(e16 >> 8, e16 & 0xFFu);
+            }
+            const uint32_t adv = e & 0x1Fu;
+            w.drop(adv);
+            rel += adv;
+            k += e >> 24;                        /* run + 1; 128 for EOB */
+            if (k >= 64u) break;
+        }
+        if (invalid) break;
         if (k >= 64u) {
             k = 0;
             bsh += 4u;
             if (bsh == bsh_end) bsh = 0;
         }
     }
-    *nstart = n;
+    *nstart = n; *first = fst;
+    if (invalid) {
+        /* an invalid code under a guessed entry state only says the guess was wrong: let the right neighbour keep
+         * speculating from its own first bit (a truly corrupt stream is reported through the flag in `bad`) */
+        *bad = 1;
+        return JD_CS_PACK(0, 0, 0);
+    }
     dcs[0] = d0; dcs[1] = d1; dcs[2] = d2;
+    if (rel >= endbits && rel < c1) return JD_CS_NONE;   /* the stream ends inside this chunk */
     return JD_CS_PACK(rel - c1, k, bsh >> 2);
 }
 

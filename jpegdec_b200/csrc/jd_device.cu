@@ -1026,8 +1026,6 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         const unsigned gi = ((unsigned)b->cimg_list.size() * 32 + 127) / 128;
         ca.max_nch = b->max_nch; ca.Ep = b->d_Ep.p; ca.cfirst = b->d_cfirst.p;
         const dim3 gchunks((b->max_nch + 127) / 128, (unsigned)b->cimg_list.size());
-        /* per device, so per call: the parse pass stages its stretch of the stream in 87 KB of shared memory */
-        CK(cudaFuncSetAttribute(jdk_chunk_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JD_PARSE_SMEM));
         /* guess: every chunk starts a block at its first bit (exit state of every left neighbour = (0, 0, 0)); no chunk parsed yet */
         CK(cudaMemsetAsync(b->d_E0.p, 0, (size_t)(b->nchunks + 1) * 4, st));
         CK(cudaMemsetAsync(b->d_Ep.p, 0xFE, (size_t)b->nchunks * 4, st));
@@ -1052,7 +1050,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             for (int k = 0; k < burst; k++) {
                 if (k == burst - 1) CK(cudaMemsetAsync(b->d_counters.p + 2, 0, 4, st));
                 ca.X_in = Xin; ca.X_out = Xout;
-                jdk_chunk_parse<<<gchunks, 128, JD_PARSE_SMEM, st>>>(ca);
+                jdk_chunk_parse<<<gchunks, 128, 0, st>>>(ca);
                 launches++; passes++;
                 uint32_t *tmp = Xin; Xin = Xout; Xout = tmp;
             }

@@ -390,29 +390,44 @@ template <bool WRITE>
 __device__ __forceinline__ uint32_t jd_unstuff_piece(const uint8_t *__restrict__ src, uint32_t len, uint32_t p0, uint32_t p1, uint8_t *dst,
                                                      uint32_t base, bool &stopped, uint32_t lane)
 {
+    /* 128 bytes per iteration, one ALIGNED 32-bit word per lane: the walk runs over word addresses, so the first word of a
+     * piece may begin up to 3 bytes before p0 (those bytes belong to the piece on the left and are masked off), and pieces
+     * end on the same grid.  Neighbour bytes come from the neighbour lanes. */
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(src - mis);
+    /* piece [p0, p1) in scan offsets = word-grid offsets [g0, g1) where offset = scan offset + mis; the grid cut between two
+     * pieces is the multiple of 4 at or below the piece boundary + mis */
+    const uint32_t g0 = (p0 == 0u) ? 0u : ((p0 + mis) & ~3u), g1 = (p1 >= len) ? (len + mis) : ((p1 + mis) & ~3u);
     uint32_t kept = 0;
     stopped = false;
-    for (uint32_t q0 = p0; q0 < p1 && !stopped; q0 += 128) {
-        const uint32_t p = q0 + lane * 4;
-        uint32_t b[6]; /* b[0] = byte before, b[1..4] = mine, b[5] = byte after */
-#pragma unroll
-        for (int i = 0; i < 6; i++) {
-            const int q = (int)p + i - 1;
-            b[i] = (q >= 0 && (uint32_t)q < len) ? (uint32_t)__ldg(src + q) : ((uint32_t)q >= len && q >= 0 ? 0xD9u : 0u);
-        }
+    for (uint32_t q0 = g0; q0 < g1 && !stopped; q0 += 128) {
+        const uint32_t gq = q0 + lane * 4;                         /* grid offset of this lane's word */
+        const bool in = gq < g1;
+        const uint32_t w = in ? __ldg(wsrc + (gq >> 2)) : 0u;
+        /* byte before / after this word */
+        uint32_t before = __shfl_up_sync(0xffffffffu, w >> 24, 1), after = __shfl_down_sync(0xffffffffu, w & 0xFFu, 1);
+        if (lane == 0) before = (gq > mis) ? (uint32_t)__ldg(src + (gq - mis) - 1u) : 0u;
+        if (lane == 31 || gq + 4u >= g1) after = (gq + 4u < len + mis) ? (uint32_t)__ldg(src + (gq + 4u - mis)) : 0xD9u;
         uint32_t keep = 0, endpos = 0xFFFFFFFFu;
+        uint32_t prev = before;
 #pragma unroll
-        for (int i = 1; i <= 4; i++) {
-            const uint32_t q = p + (uint32_t)i - 1u;
-            if (q >= len) { if (endpos == 0xFFFFFFFFu) endpos = q; continue; }
-            if (b[i] == 0xFFu) { if (b[i + 1] == 0u) keep |= 1u << (i - 1); else if (endpos == 0xFFFFFFFFu) endpos = q; }
-            else if (!(b[i] == 0u && b[i - 1] == 0xFFu)) keep |= 1u << (i - 1);
+        for (int i = 0; i < 4; i++) {
+            const uint32_t go = gq + (uint32_t)i;                  /* grid offset of byte i */
+            const uint32_t cur = (w >> (8 * i)) & 0xFFu;
+            const uint32_t nxt = (i < 3) ? ((w >> (8 * (i + 1))) & 0xFFu) : after;
+            const bool mine = in && go >= mis && go >= g0 && go < g1;      /* inside the scan and inside this piece */
+            if (mine) {
+                if (go - mis >= len) { if (endpos == 0xFFFFFFFFu) endpos = go; }
+                else if (cur == 0xFFu) { if (nxt == 0u && go + 1u - mis < len) keep |= 1u << i; else if (endpos == 0xFFFFFFFFu) endpos = go; }
+                else if (!(cur == 0u && prev == 0xFFu && go > mis)) keep |= 1u << i;
+            }
+            prev = cur;
         }
         const uint32_t stop = __reduce_min_sync(0xffffffffu, endpos);
         if (stop != 0xFFFFFFFFu) {
             stopped = true;
 #pragma unroll
-            for (int i = 0; i < 4; i++) if (p + (uint32_t)i >= stop) keep &= ~(1u << i);
+            for (int i = 0; i < 4; i++) if (gq + (uint32_t)i >= stop) keep &= ~(1u << i);
         }
         const uint32_t cnt = __popc(keep);
         uint32_t x = cnt;
@@ -421,7 +436,7 @@ __device__ __forceinline__ uint32_t jd_unstuff_piece(const uint8_t *__restrict__
         if (WRITE) {
             uint32_t o = base + kept + x - cnt;
 #pragma unroll
-            for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)b[i + 1];
+            for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)(w >> (8 * i));
         }
         kept += __shfl_sync(0xffffffffu, x, 31);
     }
@@ -483,42 +498,14 @@ __device__ __forceinline__ void jd_load_lut_set(uint16_t *s_lut, const uint16_t 
     for (uint32_t i = threadIdx.x; i < (uint32_t)(JD_LUT_ENTRIES / 8); i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
-/* Bit window over the CTA's stretch of the stream staged in shared memory (jdk_chunk_parse).  Word w of the stretch lives at
- * index w + (w >> 7): one pad word per chunk (128 words), so the 32 lanes of a warp -- one chunk each, 512 bytes apart --
- * read 32 different banks.  (Reading the stream straight from global memory, every refill of any lane was an L2 round trip
- * that the whole warp waited for: scoreboards are per warp register.) */
-struct JDBitWinS {
-    const uint32_t *s;
-    int base_bits;                 /* scan-relative bit position of staged word 0 */
-    uint32_t wi;
-    jd_u64 bb;
-    int nb;
-    __device__ __forceinline__ JDBitWinS(const uint32_t *stage, int base) : s(stage), base_bits(base), wi(0), bb(0), nb(0) {}
-    __device__ __forceinline__ uint32_t word() { const uint32_t v = s[wi + (wi >> 7)]; wi++; return jd_bswap32(v); }
-    __device__ __forceinline__ void seek(uint32_t rel)
-    {
-        const uint32_t ap = (uint32_t)((int)rel - base_bits);
-        wi = ap >> 5;
-        const uint32_t sft = ap & 31u;
-        bb = (jd_u64)word() << (32u + sft);
-        nb = 32 - (int)sft;
-    }
-    __device__ __forceinline__ void refill() { if (nb <= 32) { bb |= (jd_u64)word() << (32 - nb); nb += 32; } }
-    __device__ __forceinline__ uint32_t hi() const { return (uint32_t)(bb >> 32); }
-    __device__ __forceinline__ void drop(uint32_t n) { bb <<= n; nb -= (int)n; }
-};
-#define JD_PARSE_STAGE_WORDS (128u * 128u + 8u)                               /* 128 chunks + the few bytes a symbol straddles */
-#define JD_PARSE_STAGE_SLOTS (JD_PARSE_STAGE_WORDS + (JD_PARSE_STAGE_WORDS >> 7) + 1u)
-#define JD_PARSE_SMEM (JD_LUT_ENTRIES * 2u + JD_PARSE_STAGE_SLOTS * 4u)
-
 /* One speculative pass.  The entry state of chunk c is the exit state chunk c-1 produced in the previous pass (X_in);
  * a chunk whose entry state is the one it was last parsed from keeps its results, so after the first two passes only the
- * few chunks whose left neighbour had not re-synchronised are parsed again (those read the stream from global memory). */
+ * few chunks whose left neighbour had not re-synchronised are parsed again.
+ * (Measured and dropped: staging the CTA's 64 KB of stream in shared memory -- 8 resident warps per SM instead of 40, and
+ * the pass went from 1.84 to 3.95 ms: the loop is issue-bound, not latency-bound.) */
 __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_dyn);
-    uint32_t *s_words = reinterpret_cast<uint32_t *>(s_dyn + JD_LUT_ENTRIES * 2u);
+    __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
     const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
     const uint32_t cb = blockIdx.x * 128u, c = cb + threadIdx.x;
@@ -532,29 +519,14 @@ __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
         need = entry != a.Ep[g];
         if (!need) a.X_out[g] = a.X_in[g];
     }
-    const int nneed = __syncthreads_count(need ? 1 : 0);
-    if (nneed == 0) return;
+    if (!__syncthreads_or(need ? 1 : 0)) return;
     jd_load_lut_set(s_lut, a.luts + (size_t)im.lutset * JD_LUT_ENTRIES);
-    const JDScanIn sc = jd_scan_of(a, im, ii);
-    const bool staged = nneed >= 24;
-    const uint32_t w0 = (sc.f0 + cb * JD_CHUNK_BYTES) >> 2;                     /* first staged word of the stream buffer */
-    if (staged) {
-        const uint32_t *gw = reinterpret_cast<const uint32_t *>(a.filt);
-        const uint32_t wend = ((sc.f0 + sc.flen + 24u) >> 2) + 1u;              /* the zero tail ends here */
-        for (uint32_t w = threadIdx.x; w < JD_PARSE_STAGE_WORDS; w += 128u)
-            s_words[w + (w >> 7)] = (w0 + w < wend) ? __ldg(gw + w0 + w) : 0u;
-    }
     __syncthreads();
     if (!need) return;
-    uint32_t nstart, bad, first, ex;
+    const JDScanIn sc = jd_scan_of(a, im, ii);
+    uint32_t nstart, bad, first;
     int32_t dcs[3];
-    if (staged) {
-        JDBitWinS win(s_words, (int)(w0 * 32u) - (int)(sc.f0 * 8u));
-        ex = jd_chunk_parse(sc, s_lut, c, entry, win, &nstart, &bad, dcs, &first);
-    } else {
-        JDBitWin win(sc);
-        ex = jd_chunk_parse(sc, s_lut, c, entry, win, &nstart, &bad, dcs, &first);
-    }
+    const uint32_t ex = jd_chunk_parse(sc, s_lut, c, entry, &nstart, &bad, dcs, &first);
     a.cn[g] = nstart;
     a.cfirst[g] = first | (bad << 31);
     a.cdcs[3 * g] = dcs[0]; a.cdcs[3 * g + 1] = dcs[1]; a.cdcs[3 * g + 2] = dcs[2];
