@@ -26,6 +26,7 @@
 #ifndef JD_ENTROPY_THREADS
 #define JD_ENTROPY_THREADS 128
 #endif
+#define JD_PRING_STRIDE 20   /* words between two parsers' rings (jdk_chunk_parse): 16 + 4 */
 #define JD_RING_STRIDE 36   /* words between two walkers' rings: 32 + 4 keeps 16-byte alignment and spreads the banks */
 
 __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
@@ -386,60 +387,82 @@ struct JDChunkArgs {
  * the counts to its left and writes its kept bytes there.  (The first version walked a whole scan with one warp: 1.9 ms per
  * 1024 HD images, all of it latency.) */
 #define JD_UNSTUFF_PIECE 4096u
+/* 0x80 in every byte of the result where the byte of x is zero (exact per byte) */
+__device__ __forceinline__ uint32_t jd_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); }
+/* flags (0x80 per byte) for bytes [lo, hi) of a word, 0 <= lo, hi <= 4 */
+__device__ __forceinline__ uint32_t jd_byte_range(uint32_t lo, uint32_t hi)
+{
+    const uint32_t below_hi = (hi >= 4u) ? 0x80808080u : (0x80808080u & ((1u << (8u * hi)) - 1u));
+    const uint32_t below_lo = (lo >= 4u) ? 0x80808080u : (0x80808080u & ((1u << (8u * lo)) - 1u));
+    return below_hi & ~below_lo;
+}
+
 template <bool WRITE>
 __device__ __forceinline__ uint32_t jd_unstuff_piece(const uint8_t *__restrict__ src, uint32_t len, uint32_t p0, uint32_t p1, uint8_t *dst,
                                                      uint32_t base, bool &stopped, uint32_t lane)
 {
-    /* 128 bytes per iteration, one ALIGNED 32-bit word per lane: the walk runs over word addresses, so the first word of a
-     * piece may begin up to 3 bytes before p0 (those bytes belong to the piece on the left and are masked off), and pieces
-     * end on the same grid.  Neighbour bytes come from the neighbour lanes. */
+    /* 128 bytes per iteration, one ALIGNED 32-bit word per lane, classified four bytes at a time with byte-flag words: the walk
+     * runs over word addresses, so the first word of a piece may begin up to 3 bytes before p0 (those bytes belong to the piece
+     * on the left and are masked off), and pieces end on the same grid.  The byte before / after a word comes from the
+     * neighbour lane; across iterations from the previous iteration's lane 31 / the next iteration's word, loaded one
+     * iteration ahead. */
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
     const uint32_t *wsrc = reinterpret_cast<const uint32_t *>(src - mis);
-    /* piece [p0, p1) in scan offsets = word-grid offsets [g0, g1) where offset = scan offset + mis; the grid cut between two
-     * pieces is the multiple of 4 at or below the piece boundary + mis */
+    /* piece [p0, p1) in scan offsets = word-grid offsets [g0, g1) where grid offset = scan offset + mis */
     const uint32_t g0 = (p0 == 0u) ? 0u : ((p0 + mis) & ~3u), g1 = (p1 >= len) ? (len + mis) : ((p1 + mis) & ~3u);
+    const uint32_t vlo = (g0 > mis) ? g0 : mis;                     /* this piece's bytes of the scan: grid offsets [vlo, g1) */
+    const uint32_t wlimit = (len + mis + 3u) >> 2;                  /* words that hold scan bytes */
     uint32_t kept = 0;
     stopped = false;
+    if (g0 >= g1) return 0u;
+    uint32_t carry = (g0 > mis) ? (uint32_t)__ldg(src + (g0 - mis) - 1u) : 0u;    /* byte before the piece */
+    uint32_t wn = ((g0 >> 2) + lane < wlimit) ? __ldg(wsrc + (g0 >> 2) + lane) : 0xD9D9D9D9u;
     for (uint32_t q0 = g0; q0 < g1 && !stopped; q0 += 128) {
         const uint32_t gq = q0 + lane * 4;                         /* grid offset of this lane's word */
-        const bool in = gq < g1;
-        const uint32_t w = in ? __ldg(wsrc + (gq >> 2)) : 0u;
-        /* byte before / after this word */
+        const uint32_t w = wn;
+        { const uint32_t wi = ((q0 + 128u) >> 2) + lane; wn = (q0 + 128u < g1 + 4u && wi < wlimit) ? __ldg(wsrc + wi) : 0xD9D9D9D9u; }
         uint32_t before = __shfl_up_sync(0xffffffffu, w >> 24, 1), after = __shfl_down_sync(0xffffffffu, w & 0xFFu, 1);
-        if (lane == 0) before = (gq > mis) ? (uint32_t)__ldg(src + (gq - mis) - 1u) : 0u;
-        if (lane == 31 || gq + 4u >= g1) after = (gq + 4u < len + mis) ? (uint32_t)__ldg(src + (gq + 4u - mis)) : 0xD9u;
-        uint32_t keep = 0, endpos = 0xFFFFFFFFu;
-        uint32_t prev = before;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t go = gq + (uint32_t)i;                  /* grid offset of byte i */
-            const uint32_t cur = (w >> (8 * i)) & 0xFFu;
-            const uint32_t nxt = (i < 3) ? ((w >> (8 * (i + 1))) & 0xFFu) : after;
-            const bool mine = in && go >= mis && go >= g0 && go < g1;      /* inside the scan and inside this piece */
-            if (mine) {
-                if (go - mis >= len) { if (endpos == 0xFFFFFFFFu) endpos = go; }
-                else if (cur == 0xFFu) { if (nxt == 0u && go + 1u - mis < len) keep |= 1u << i; else if (endpos == 0xFFFFFFFFu) endpos = go; }
-                else if (!(cur == 0u && prev == 0xFFu && go > mis)) keep |= 1u << i;
-            }
-            prev = cur;
-        }
-        const uint32_t stop = __reduce_min_sync(0xffffffffu, endpos);
-        if (stop != 0xFFFFFFFFu) {
+        const uint32_t first_next = __shfl_sync(0xffffffffu, wn & 0xFFu, 0);
+        if (lane == 0) before = carry;
+        if (lane == 31) after = first_next;
+        carry = __shfl_sync(0xffffffffu, w >> 24, 31);
+        /* byte flags */
+        const uint32_t ff = jd_zero_bytes(~w), zz = jd_zero_bytes(w);
+        const uint32_t prev_ff = (ff << 8) | ((before == 0xFFu) ? 0x80u : 0u);
+        const uint32_t next_zz = (zz >> 8) | ((after == 0u) ? 0x80000000u : 0u);
+        const uint32_t lo = (vlo > gq) ? ((vlo - gq < 4u) ? vlo - gq : 4u) : 0u;
+        const uint32_t hi = (g1 > gq) ? ((g1 - gq < 4u) ? g1 - gq : 4u) : 0u;
+        const uint32_t mine = jd_byte_range(lo, hi);
+        /* the first byte of the scan has no byte before it */
+        const uint32_t noprev = (gq <= mis && mis < gq + 4u) ? (0x80u << (8u * (mis - gq))) : 0u;
+        uint32_t keep = mine & ~(zz & prev_ff & ~noprev);           /* everything but the zero that follows an FF */
+        const uint32_t mk = mine & ff & ~next_zz;                   /* FF followed by something else: a marker ends the scan */
+        const uint32_t anymk = __ballot_sync(0xffffffffu, mk != 0u);
+        if (anymk) {
             stopped = true;
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (gq + (uint32_t)i >= stop) keep &= ~(1u << i);
+            const uint32_t fl = (uint32_t)__ffs((int)anymk) - 1u;  /* first lane with a marker */
+            if (lane > fl) keep = 0u;
+            else if (lane == fl) keep &= ((mk & (0u - mk)) - 1u);   /* bytes below its first marker byte */
         }
         const uint32_t cnt = __popc(keep);
-        uint32_t x = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
         if (WRITE) {
-            uint32_t o = base + kept + x - cnt;
+            uint32_t x = cnt;
 #pragma unroll
-            for (int i = 0; i < 4; i++) if (keep & (1u << i)) dst[o++] = (uint8_t)(w >> (8 * i));
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+            uint8_t *o = dst + base + kept + x - cnt;
+            /* kept bytes to the front, in order */
+            uint32_t v = w, m = keep;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (m & 0x80u) *o++ = (uint8_t)v;
+                v >>= 8; m >>= 8;
+            }
+            kept += __shfl_sync(0xffffffffu, x, 31);
+        } else {
+            kept += cnt;                                            /* per lane; summed after the loop */
         }
-        kept += __shfl_sync(0xffffffffu, x, 31);
     }
+    if (!WRITE) kept = __reduce_add_sync(0xffffffffu, kept);
     return kept;
 }
 
@@ -506,6 +529,7 @@ __device__ __forceinline__ void jd_load_lut_set(uint16_t *s_lut, const uint16_t 
 __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
+    __shared__ __align__(16) uint32_t s_pring[128 * JD_PRING_STRIDE];       /* per-parser stream rings (jd_chunk.h JDBitWin) */
     const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
     const uint32_t cb = blockIdx.x * 128u, c = cb + threadIdx.x;
@@ -526,7 +550,7 @@ __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
     const JDScanIn sc = jd_scan_of(a, im, ii);
     uint32_t nstart, bad, first;
     int32_t dcs[3];
-    const uint32_t ex = jd_chunk_parse(sc, s_lut, c, entry, &nstart, &bad, dcs, &first);
+    const uint32_t ex = jd_chunk_parse(sc, s_lut, s_pring + threadIdx.x * JD_PRING_STRIDE, c, entry, &nstart, &bad, dcs, &first);
     a.cn[g] = nstart;
     a.cfirst[g] = first | (bad << 31);
     a.cdcs[3 * g] = dcs[0]; a.cdcs[3 * g + 1] = dcs[1]; a.cdcs[3 * g + 2] = dcs[2];
