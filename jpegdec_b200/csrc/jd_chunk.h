@@ -37,67 +37,21 @@ typedef struct {
     uint32_t total_blocks; /* blocks in the scan */
 } JDScanIn;
 
-/* Bit window over the un-stuffed scan: 64-bit register buffer, MSB first, fed from a 16-word ring per parser (shared memory on
- * the device) that is topped up 16 bytes at a time where the warp is converged -- the top of every block -- exactly like the
- * stream ring of jd_decode_segment: each parser first parks the 16 bytes it requested one block earlier, then requests the
- * next 16 if there is room.  (Fetching the words straight from global memory, any lane's refill was an L2 round trip the
- * whole warp waited for -- scoreboards are per warp register -- and 55 % of the pass's instructions were refill code.) */
-#define JD_PRING_WORDS 16u
+/* Bit window over the un-stuffed scan: 64-bit register buffer, MSB first, one aligned 32-bit word fetched per 32 bits
+ * consumed (the first version fetched two words per SYMBOL, which made the L1 the bound of every pass). */
 struct JDBitWin {
-    uint32_t *ring;                /* JD_PRING_WORDS words, 16-byte aligned */
-    const uint8_t *cbase;          /* 16-byte aligned start of the chunks this window reads */
-    uint32_t nchunk;               /* 16-byte chunks that exist from cbase on (zeros beyond) */
-    uint32_t rd, wr, gi;           /* words read / written so far; next chunk to request */
-    jd_u128 pa;
-    bool pend;
+    const uint32_t *wp;            /* next word to fetch */
     jd_u64 bb;
     int nb;
-    JD_HDM jd_u128 chunk(uint32_t i) const
+    JD_HDM void seek(const JDScanIn &sc, uint32_t rel)                 /* rel = bit position relative to the scan start */
     {
-        const jd_u128 z = {0u, 0u, 0u, 0u};
-        return (i < nchunk) ? jd_ld128(cbase + 16u * i) : z;
+        const uint32_t ap = sc.f0 * 8u + rel;
+        wp = (const uint32_t *)sc.filt + (ap >> 5);
+        const uint32_t sft = ap & 31u;
+        bb = (jd_u64)jd_bswap32(*wp++) << (32u + sft);
+        nb = 32 - (int)sft;
     }
-    JD_HDM void put(uint32_t at, const jd_u128 &v)
-    {
-#ifdef __CUDA_ARCH__
-        *reinterpret_cast<uint4 *>(ring + at) = make_uint4(v.x, v.y, v.z, v.w);
-#else
-        ring[at] = v.x; ring[at + 1] = v.y; ring[at + 2] = v.z; ring[at + 3] = v.w;
-#endif
-    }
-    JD_HDM void topup()
-    {
-        if (pend) { put(wr & (JD_PRING_WORDS - 1u), pa); wr += 4u; }
-        pend = (JD_PRING_WORDS - (wr - rd)) >= 4u;
-        if (pend) { pa = chunk(gi); gi++; }
-    }
-    JD_HDM void seek(const JDScanIn &sc, uint32_t *ring_, uint32_t rel)   /* rel = bit position relative to the scan start */
-    {
-        const uint32_t byte0 = sc.f0 + (rel >> 3), a0 = byte0 & ~15u;
-        ring = ring_;
-        cbase = sc.filt + a0;
-        nchunk = (sc.f0 + sc.flen + 24u + 15u - a0) >> 4;           /* the zero tail after the stream ends here */
-        for (uint32_t i = 0; i < 3u; i++) put(4u * i, chunk(i));
-        rd = 0; wr = 12u; gi = 3u; pend = false;
-        topup();
-        bb = 0; nb = 0;
-        for (uint32_t skip = (byte0 - a0) * 8u + (rel & 7u);;) {       /* drop the bits in front of `rel` */
-            refill();
-            if (skip == 0u) break;
-            const uint32_t d = skip < 32u ? skip : 32u;
-            bb <<= d; nb -= (int)d; skip -= d;
-        }
-    }
-    JD_HDM void refill()
-    {
-        if (nb <= 32) {
-            while (rd == wr) topup();            /* ring ran dry inside one block (rare) */
-            const uint32_t v = ring[rd & (JD_PRING_WORDS - 1u)];
-            rd++;
-            bb |= (jd_u64)jd_bswap32(v) << (32 - nb);
-            nb += 32;
-        }
-    }
+    JD_HDM void refill() { if (nb <= 32) { bb |= (jd_u64)jd_bswap32(*wp++) << (32 - nb); nb += 32; } }
     JD_HDM uint32_t hi() const { return (uint32_t)(bb >> 32); }       /* the next 32 bits (>= 33 valid after refill) */
     JD_HDM void drop(uint32_t n) { bb <<= n; nb -= (int)n; }
 };
@@ -132,8 +86,7 @@ JD_HD uint32_t jd_ac_entry(const T16 &T, const T32 &TF, uint32_t actab, uint32_t
  * Organised like jd_decode_segment: a loop over blocks (DC symbol, then the block's AC symbols), so that the lanes of a warp
  * -- one chunk each -- run the DC code once per block together instead of nearly every symbol for one lane in eight (the
  * flat one-symbol-per-iteration form of this loop issued ~85 instructions per symbol, half of them the DC path). */
-JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t *ring /* JD_PRING_WORDS, this parser's */, uint32_t ci, uint32_t entry,
-                               uint32_t *nstart, uint32_t *bad,
+JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t ci, uint32_t entry, uint32_t *nstart, uint32_t *bad,
                                int32_t *dcs /* [3]: per component, sum of the DC differences of the blocks that start here */,
                                uint32_t *first /* first block that starts here: bit offset from the chunk start | block-in-MCU index << 16 */)
 {
@@ -149,13 +102,12 @@ JD_HD uint32_t jd_chunk_parse(const JDScanIn &sc, const uint16_t *lut, uint32_t 
     const uint32_t sched = jd_block_schedule(sc.tsel, sc.bpm, sc.ncomp), bsh_end = 4u * sc.bpm;
     uint32_t bsh = 4u * JD_CS_BIM(entry);
     JDBitWin w;
-    w.seek(sc, ring, rel);
+    w.seek(sc, rel);
     uint32_t n = 0, fst = 0;
     int d0 = 0, d1 = 0, d2 = 0;
     bool invalid = false;
     while (rel < stop) {
         const uint32_t cur = (sched >> bsh) & 15u;
-        w.topup();                               /* the warp is converged here */
         if (k == 0) {
             /* ---- the block's DC symbol ---- */
             w.refill();

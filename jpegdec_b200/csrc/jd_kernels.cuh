@@ -26,7 +26,6 @@
 #ifndef JD_ENTROPY_THREADS
 #define JD_ENTROPY_THREADS 128
 #endif
-#define JD_PRING_STRIDE 20   /* words between two parsers' rings (jdk_chunk_parse): 16 + 4 */
 #define JD_RING_STRIDE 36   /* words between two walkers' rings: 32 + 4 keeps 16-byte alignment and spreads the banks */
 
 __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
@@ -524,12 +523,12 @@ __device__ __forceinline__ void jd_load_lut_set(uint16_t *s_lut, const uint16_t 
 /* One speculative pass.  The entry state of chunk c is the exit state chunk c-1 produced in the previous pass (X_in);
  * a chunk whose entry state is the one it was last parsed from keeps its results, so after the first two passes only the
  * few chunks whose left neighbour had not re-synchronised are parsed again.
- * (Measured and dropped: staging the CTA's 64 KB of stream in shared memory -- 8 resident warps per SM instead of 40, and
- * the pass went from 1.84 to 3.95 ms: the loop is issue-bound, not latency-bound.) */
+ * (Measured and dropped: staging the CTA's 64 KB of stream in shared memory -- 8 resident warps per SM instead of 40, 1.84 ->
+ * 3.95 ms -- and a 16-word stream ring per parser topped up at block starts like jdk_entropy's -- 28 warps, 1.44 -> 1.50 ms:
+ * with 40 resident warps the loads straight from global memory are hidden well enough.) */
 __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
 {
     __shared__ __align__(16) uint16_t s_lut[JD_LUT_ENTRIES];
-    __shared__ __align__(16) uint32_t s_pring[128 * JD_PRING_STRIDE];       /* per-parser stream rings (jd_chunk.h JDBitWin) */
     const uint32_t ii = a.cimg_list[blockIdx.y];
     const JDImageDesc &im = a.imgs[ii];
     const uint32_t cb = blockIdx.x * 128u, c = cb + threadIdx.x;
@@ -550,7 +549,7 @@ __global__ void __launch_bounds__(128) jdk_chunk_parse(const JDChunkArgs a)
     const JDScanIn sc = jd_scan_of(a, im, ii);
     uint32_t nstart, bad, first;
     int32_t dcs[3];
-    const uint32_t ex = jd_chunk_parse(sc, s_lut, s_pring + threadIdx.x * JD_PRING_STRIDE, c, entry, &nstart, &bad, dcs, &first);
+    const uint32_t ex = jd_chunk_parse(sc, s_lut, c, entry, &nstart, &bad, dcs, &first);
     a.cn[g] = nstart;
     a.cfirst[g] = first | (bad << 31);
     a.cdcs[3 * g] = dcs[0]; a.cdcs[3 * g + 1] = dcs[1]; a.cdcs[3 * g + 2] = dcs[2];

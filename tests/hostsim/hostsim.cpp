@@ -135,7 +135,7 @@ extern "C" int hostsim_decode(const uint8_t *data, int size, int pixel_type, int
             E2[0] = E[0];
             for (uint32_t c = 0; c < nch; c++) {
                 uint32_t badc;
-                uint32_t ex = jd_chunk_parse(sc, lut.data(), g_ring, c, E[c], &nst[c], &badc, &dcs[3 * c], &first[c]);
+                uint32_t ex = jd_chunk_parse(sc, lut.data(), c, E[c], &nst[c], &badc, &dcs[3 * c], &first[c]);
                 first[c] |= badc << 31;
                 if (c + 1 < nch) { E2[c + 1] = ex; if (ex != E[c + 1]) changed = true; }
             }
