@@ -162,10 +162,10 @@ struct JPEGB200_BATCH {
     DevBuf<JDEvent> d_events;
     std::vector<uint64_t> arena_off; /* per-image offset inside d_out */
     /* restart-free scans decoded chunk-parallel (jd_chunk.h) */
-    std::vector<uint32_t> cimg_list, chunk_img;
+    std::vector<uint32_t> cimg_list;
     uint32_t nchunks, max_nch;
     DevBuf<uint8_t> d_filt;
-    DevBuf<uint32_t> d_cimg_list, d_chunk_img, d_flen, d_E0, d_E1, d_Ep, d_cfirst, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
+    DevBuf<uint32_t> d_cimg_list, d_flen, d_E0, d_E1, d_Ep, d_cfirst, d_cn, d_cpre, d_cjmap, d_cstatus, d_cnown;
     DevBuf<int32_t> d_cdcs, d_cpe;
     uint32_t h_changed;
     bool chunk_iterate;            /* restart-free scans: iterate the entry states with a host check (fallback mode) */
@@ -563,7 +563,6 @@ extern "C" JPEGB200_BATCH *JPEGB200_batchCreate(JPEGB200_CTX *ctx, const uint8_t
             b->nchunks += d.nch;
             if (d.nch > b->max_nch) b->max_nch = d.nch;
             b->cimg_list.push_back((uint32_t)i);
-            for (uint32_t cc = 0; cc < d.nch; cc++) b->chunk_img.push_back((uint32_t)i);
         }
         d.seg_base = seg;
         d.blk_base = (uint32_t)blk;
@@ -624,7 +623,7 @@ extern "C" void JPEGB200_batchDestroy(JPEGB200_BATCH *b)
     b->d_comp.release(); b->d_out.release(); b->d_gray.release(); b->d_errline.release();
     b->d_gray_off.release(); b->d_err_off.release(); b->d_dprog.release(); b->d_dbands.release();
     b->d_clean.release(); b->d_seg_clen.release();
-    b->d_filt.release(); b->d_cimg_list.release(); b->d_chunk_img.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release(); b->d_Ep.release(); b->d_cfirst.release();
+    b->d_filt.release(); b->d_cimg_list.release(); b->d_flen.release(); b->d_E0.release(); b->d_E1.release(); b->d_Ep.release(); b->d_cfirst.release();
     b->d_cn.release(); b->d_cpre.release(); b->d_cjmap.release(); b->d_cstatus.release(); b->d_cnown.release(); b->d_cdcs.release(); b->d_cpe.release();
     b->d_descs.release(); b->d_quant.release(); b->d_luts.release(); b->d_rec.release();
     b->d_work.release(); b->d_cta_lut.release(); b->d_seg_img.release(); b->d_seg_start.release();
@@ -739,7 +738,7 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
     if (b->nchunks) {
         const size_t nc = b->nchunks;
         CK(b->d_filt.alloc(&b->ctx->pool, b->comp_total + 512));
-        CK(b->d_cimg_list.alloc(&b->ctx->pool, b->cimg_list.size())); CK(b->d_chunk_img.alloc(&b->ctx->pool, nc)); CK(b->d_flen.alloc(&b->ctx->pool, n));
+        CK(b->d_cimg_list.alloc(&b->ctx->pool, b->cimg_list.size())); CK(b->d_flen.alloc(&b->ctx->pool, n));
         CK(b->d_E0.alloc(&b->ctx->pool, nc + 1)); CK(b->d_E1.alloc(&b->ctx->pool, nc + 1)); CK(b->d_Ep.alloc(&b->ctx->pool, nc)); CK(b->d_cfirst.alloc(&b->ctx->pool, nc)); CK(b->d_cn.alloc(&b->ctx->pool, nc)); CK(b->d_cpre.alloc(&b->ctx->pool, nc)); CK(b->d_cjmap.alloc(&b->ctx->pool, nc));
         CK(b->d_cstatus.alloc(&b->ctx->pool, nc)); CK(b->d_cnown.alloc(&b->ctx->pool, nc)); CK(b->d_cdcs.alloc(&b->ctx->pool, 3 * nc)); CK(b->d_cpe.alloc(&b->ctx->pool, 3 * nc));
     }
@@ -765,7 +764,6 @@ extern "C" int JPEGB200_batchUpload(JPEGB200_BATCH *b)
     CK(cudaMemcpyAsync(b->d_seg_img.p, b->seg_img.data(), b->seg_img.size() * 4, cudaMemcpyHostToDevice, st));
     if (b->nchunks) {
         CK(cudaMemcpyAsync(b->d_cimg_list.p, b->cimg_list.data(), b->cimg_list.size() * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->d_chunk_img.p, b->chunk_img.data(), b->chunk_img.size() * 4, cudaMemcpyHostToDevice, st));
     }
     CK(cudaEventRecord(b->ev[1], st));
     b->uploaded = true;
@@ -1017,7 +1015,7 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
         JDChunkArgs ca;
         ca.comp = b->d_comp.p; ca.filt = b->d_filt.p; ca.imgs = b->d_descs.p; ca.luts = b->d_luts.p;
         ca.cimg_list = b->d_cimg_list.p; ca.ncimg = (uint32_t)b->cimg_list.size(); ca.flen = b->d_flen.p;
-        ca.chunk_img = b->d_chunk_img.p; ca.nchunks = b->nchunks;
+        ca.nchunks = b->nchunks;
         ca.cn = b->d_cn.p; ca.cpre = b->d_cpre.p; ca.cjmap = b->d_cjmap.p; ca.cstatus = b->d_cstatus.p; ca.cnown = b->d_cnown.p;
         ca.cdcs = b->d_cdcs.p; ca.cpe = b->d_cpe.p; ca.changed = b->d_counters.p + 2;
         ca.blk_hdr = b->d_blk_hdr.p; ca.rec = b->d_rec.p;

@@ -33,6 +33,13 @@ __constant__ uint8_t c_tpos[64] = JD_TPOS_INIT;
 /* ------------------------------------------------------------------------------------ */
 /* prescan                                                                                */
 /* ------------------------------------------------------------------------------------ */
+/* 0x80 in every byte of the result where the byte of x is zero (exact per byte) */
+__device__ __forceinline__ uint32_t jd_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); }
+
+/* One CTA per image walks its scan 16 KB at a time: 64 contiguous bytes per thread (four 16-byte loads in flight), RSTn
+ * markers (FF D0..D7) found four bytes at a time with byte-flag words, then a block-wide scan of the counts gives every
+ * marker its index.  (4 KB per iteration with byte compares: 0.23 ms per 1024 HD files, 0.71 ms per 512 UHD files, all of it
+ * the latency of ~70 / ~270 dependent iterations.) */
 __global__ void __launch_bounds__(256) jdk_prescan(const uint8_t *__restrict__ data, const JDImageDesc *__restrict__ imgs,
                                                     uint32_t *__restrict__ seg_start)
 {
@@ -48,23 +55,31 @@ __global__ void __launch_bounds__(256) jdk_prescan(const uint8_t *__restrict__ d
     const uint32_t lo = im.scan_off, hi = im.scan_end;
     uint32_t found = 0; /* markers found so far (block-uniform) */
     int buf = 0;
-    for (uint32_t p0 = lo & ~15u; p0 < hi && found + 1 < nseg; p0 += 256 * 16) {
-        const uint32_t p = p0 + tid * 16;
-        uint32_t m = 0;
+    for (uint32_t p0 = lo & ~15u; p0 < hi && found + 1 < nseg; p0 += 256 * 64) {
+        const uint32_t p = p0 + tid * 64;
+        unsigned long long m = 0;
         if (p < hi) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(data + p);
-            const uint32_t nxt = (p + 16 < hi) ? data[p + 16] : 0u;
-            const uint32_t w[5] = {v.x, v.y, v.z, v.w, nxt};
+            uint32_t w[17];
+            const uint4 zero4 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = (p + 16u * j < hi) ? *reinterpret_cast<const uint4 *>(data + p + 16 * j) : zero4;
+                w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+            }
+            w[16] = (p + 64 < hi) ? (uint32_t)data[p + 64] : 0u;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const uint32_t b0 = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
-                const uint32_t b1 = (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFFu;
-                if (b0 == 0xFFu && (b1 & 0xF8u) == 0xD0u && p + i >= lo && p + i + 1 < hi) m |= 1u << i;
+                const uint32_t nx = __funnelshift_r(w[i], w[i + 1], 8);                       /* the four bytes one further */
+                const uint32_t f = jd_zero_bytes(~w[i]) & jd_zero_bytes((nx & 0xF8F8F8F8u) ^ 0xD0D0D0D0u);
+                m |= (unsigned long long)((((f >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * i);
             }
+            /* only markers whose two bytes lie inside [lo, hi) */
+            if (p < lo) m &= ~0ull << (lo - p);
+            if (p + 64 >= hi) { const uint32_t nvalid = hi - 1u - p; m &= (nvalid >= 64u) ? ~0ull : ((1ull << nvalid) - 1ull); }
         }
-        if (!__syncthreads_or(m != 0)) continue;
+        if (!__syncthreads_or(m != 0ull)) continue;
         /* block-wide exclusive scan of popc(m) */
-        const uint32_t cnt = __popc(m);
+        const uint32_t cnt = (uint32_t)__popcll(m);
         uint32_t x = cnt;
         const uint32_t lane = tid & 31, wid = tid >> 5;
 #pragma unroll
@@ -76,7 +91,7 @@ __global__ void __launch_bounds__(256) jdk_prescan(const uint8_t *__restrict__ d
         for (int w2 = 0; w2 < 8; w2++) { uint32_t t = s_wtot[buf][w2]; if ((uint32_t)w2 < wid) wbase += t; tot += t; }
         uint32_t k = found + wbase + x - cnt; /* index of this thread's first marker */
         while (m) {
-            const int bit = __ffs(m) - 1;
+            const int bit = __ffsll((long long)m) - 1;
             m &= m - 1;
             if (k + 1 < nseg) seg_start[base + k + 1] = p + bit + 2;
             k++;
@@ -363,7 +378,6 @@ struct JDChunkArgs {
     const uint32_t *cimg_list;     /* indices of the chunked images */
     uint32_t ncimg;
     uint32_t *flen;                /* per image: un-stuffed scan length */
-    const uint32_t *chunk_img;     /* per chunk: image index */
     uint32_t nchunks;
     uint32_t *X_in, *X_out;        /* exit state of every chunk = entry state of its right neighbour (double buffered across passes) */
     uint32_t *Ep;                  /* entry state each chunk was last parsed from */
@@ -386,8 +400,6 @@ struct JDChunkArgs {
  * the counts to its left and writes its kept bytes there.  (The first version walked a whole scan with one warp: 1.9 ms per
  * 1024 HD images, all of it latency.) */
 #define JD_UNSTUFF_PIECE 4096u
-/* 0x80 in every byte of the result where the byte of x is zero (exact per byte) */
-__device__ __forceinline__ uint32_t jd_zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu); }
 /* flags (0x80 per byte) for bytes [lo, hi) of a word, 0 <= lo, hi <= 4 */
 __device__ __forceinline__ uint32_t jd_byte_range(uint32_t lo, uint32_t hi)
 {

@@ -289,7 +289,13 @@ def test_restart_free_scans_chunk_parallel(ctxs):
              "uhd": (synth.synth_jpeg(3840, 2160, 3, 85, restart_rows=0), 3840, 2160),
              "gray": (synth.synth_jpeg(2048, 1536, 1, 75, gray=True, restart_rows=0), 2048, 1536),
              "s444": (synth.synth_jpeg(1024, 768, 2, 96, subsampling="4:4:4", restart_rows=0), 1024, 768),
-             "q98": (synth.synth_jpeg(512, 512, 5, 98, restart_rows=0), 512, 512)}
+             "q98": (synth.synth_jpeg(512, 512, 5, 98, restart_rows=0), 512, 512),
+             # 4 blocks per MCU: chunks whose first block is not the first block of an MCU
+             "s422": (synth.synth_jpeg(1000, 700, 4, 85, subsampling="4:2:2", restart_rows=0), 1000, 700)}
+    import cv2
+    ok, enc = cv2.imencode(".jpg", synth.synth_pixels(999, 701, 6),
+                           [cv2.IMWRITE_JPEG_QUALITY, 70, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440])
+    cases["s440"] = (enc.tobytes(), 999, 701)
     names = list(cases)
     for arith in (0, 1):
         for pt in (0, 3):
