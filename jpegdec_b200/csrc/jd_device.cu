@@ -1469,7 +1469,11 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     /* the line entry S[j] is written by the band above at its step j + 95; lane 0 is about to read entries < `upto` */
     auto wait_for = [&](int upto) {
         if (prev) {
-            if (lane == 0) { const uint32_t need = (uint32_t)(upto + 96); while (jd_ld_acquire(prev) < need) __nanosleep(64); }
+            if (lane == 0) {
+                const uint32_t need = (uint32_t)(upto + 96);
+                uint32_t ns = 32;                   /* back off: a band that starts together with the one above waits a long time once */
+                while (jd_ld_acquire(prev) < need) { __nanosleep(ns); if (ns < 1024u) ns *= 2u; }
+            }
             __syncwarp();
         }
     };
@@ -1552,9 +1556,11 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
                 enext = (lane == 0 && m + 1 < nchunks) ? __ldcg(reinterpret_cast<const uint4 *>(S + 16 * (m + 1))) : zero4;
             }
             /* tb + 16 steps done (the shuffles ordered the warp's stores before lane 31's release) */
-            if (lane == 31) { __threadfence(); jd_st_release(mine, (uint32_t)(tb + 16)); }
+            /* lane 31 wrote every line entry the band below reads, so its own release store orders them (no fence for the
+             * whole warp); every 32 steps is often enough for a follower that stays 96 steps behind */
+            if (lane == 31 && (tb & 16)) jd_st_release(mine, (uint32_t)(tb + 16));
         }
         __syncwarp();
-        if (lane == 31) { __threadfence(); jd_st_release(mine, 0x7FFFFFFFu); }
+        if (lane == 31) jd_st_release(mine, 0x7FFFFFFFu);
     }
 }

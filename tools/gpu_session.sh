@@ -52,7 +52,7 @@ sanitize)
   timeout 900 $CS --tool racecheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/${tag}_compute_sanitizer_racecheck.txt 2>&1; tail -3 $O/${tag}_compute_sanitizer_racecheck.txt
   timeout 900 $CS --tool synccheck --print-limit 20 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "restart_free or dither_batch or two_threads" > $O/${tag}_compute_sanitizer_synccheck.txt 2>&1; tail -3 $O/${tag}_compute_sanitizer_synccheck.txt ;;
 onecall)
-  for mb in ${ONECALL_MB:-32 64 128 192}; do JPEGDEC_B200_JOB_MB=$mb timeout 600 python tools/onecall_probe.py 625 >> $O/${tag}_onecall.txt 2>&1; done
+  for mb in ${ONECALL_MB:-32 64 128 192}; do JPEGDEC_B200_JOB_MB=$mb timeout 600 python tools/onecall_probe.py ${ONECALL_N:-625} >> $O/${tag}_onecall.txt 2>&1; done
   cat $O/${tag}_onecall.txt ;;
 others)
   for wl in uhd_quarter uhd_eighth dither dither444 hd_norst; do
