@@ -886,8 +886,9 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
     return 1;
 }
 
+template <int BITS>
 __global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift,
+                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
                            const uint4 *bands, uint32_t nbands, uint32_t *progress);
 
 extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
@@ -1132,9 +1133,13 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
     CK(cudaEventRecord(b->ev[6], st));
     if (b->dither_bits) {
         if (!b->dbands.empty()) {
-            jdk_dither<<<((unsigned)b->dbands.size() * 32 + 127) / 128, 128, 0, st>>>(b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p,
-                                                                                  b->d_err_off.p, out_base, (uint32_t)b->dither_bits, (uint32_t)b->sshift,
-                                                                                  b->d_dbands.p, (uint32_t)b->dbands.size(), b->d_dprog.p);
+            const unsigned dgrid = ((unsigned)b->dbands.size() * 32 + 127) / 128;
+#define JD_DITHER_ARGS b->d_descs.p, (uint32_t)n, b->d_gray.p, b->d_gray_off.p, b->d_errline.p, b->d_err_off.p, out_base, (uint32_t)b->sshift, \
+                       b->d_dbands.p, (uint32_t)b->dbands.size(), b->d_dprog.p
+            if (b->dither_bits == 1) jdk_dither<1><<<dgrid, 128, 0, st>>>(JD_DITHER_ARGS);
+            else if (b->dither_bits == 2) jdk_dither<2><<<dgrid, 128, 0, st>>>(JD_DITHER_ARGS);
+            else jdk_dither<4><<<dgrid, 128, 0, st>>>(JD_DITHER_ARGS);
+#undef JD_DITHER_ARGS
             launches++;
         }
     }
@@ -1428,11 +1433,13 @@ __device__ __forceinline__ void jd_st_release(uint32_t *p, uint32_t v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+template <int BITS /* output bits per pixel: 1, 2, 4 */>
 __global__ void __launch_bounds__(128)
 jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t bits, uint32_t sshift,
+           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
            const uint4 *bands, uint32_t nbands, uint32_t *progress)
 {
+    constexpr uint32_t bits = BITS;
     /* Bands are handed out through a ticket counter (progress[nbands]) in the order in which warps START, not by warp index:
      * the list is band-major (band k of every image before band k + 1), so the band a warp waits on was always claimed by a
      * warp that is already running -- forward progress does not depend on the order in which the hardware schedules CTAs. */
@@ -1471,7 +1478,9 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         if (prev) {
             if (lane == 0) {
                 const uint32_t need = (uint32_t)(upto + 96);
-                uint32_t ns = 32;                   /* back off: a band that starts together with the one above waits a long time once */
+                /* a band that started together with the one above follows it in lock step and waits here nearly every time: sleep
+                 * about a step's worth rather than poll (the polling loop was 29 % of the kernel's issued instructions) */
+                uint32_t ns = 256;
                 while (jd_ld_acquire(prev) < need) { __nanosleep(ns); if (ns < 1024u) ns *= 2u; }
             }
             __syncwarp();

@@ -55,7 +55,7 @@ onecall)
   for mb in ${ONECALL_MB:-32 64 128 192}; do JPEGDEC_B200_JOB_MB=$mb timeout 600 python tools/onecall_probe.py ${ONECALL_N:-625} >> $O/${tag}_onecall.txt 2>&1; done
   cat $O/${tag}_onecall.txt ;;
 others)
-  for wl in uhd_quarter uhd_eighth dither dither444 hd_norst; do
+  for wl in ${OTHERS:-uhd_quarter uhd_eighth dither dither444 hd_norst}; do
     timeout 600 python bench.py --workload $wl --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 > $O/${tag}_bench_${wl}_1gpu.json 2> $O/${tag}_bench_${wl}.err
     tail -c 300 $O/${tag}_bench_${wl}_1gpu.json; echo
   done ;;
