@@ -33,6 +33,9 @@ WORKLOADS = {
                 desc="512 x 3840x2160 4:2:0 q85 -> RGB565 per GPU (BASELINE.json configs[2] shape, per-GPU slice)"),
     "dither": dict(n=256, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=2, gray=True,
                    desc="256 x 2048x1536 1-component q75 -> 1-bpp Floyd-Steinberg (BASELINE.json configs[4] shape)"),
+    "dither1024": dict(n=1024, w=2048, h=1536, q=75, pt="ONE_BIT_DITHERED", bpp_out=0.125, coef_bpp=2, gray=True,
+                       desc="1024 x 2048x1536 1-component q75 -> 1-bpp Floyd-Steinberg (configs[4] shape at the batch size of configs[1]: below ~512 images "
+                            "jdk_dither is bound by one image's row-to-row dependency chain, not by throughput)"),
     "hd_norst": dict(n=1024, w=1920, h=1080, q=75, pt="RGB8888", bpp_out=4, coef_bpp=3, restart_rows=0,
                      desc="1024 x 1920x1080 4:2:0 q75 WITHOUT restart markers -> RGB8888 (SURVEY 8(f)2: chunk-parallel entropy decode)"),
     "uhd_quarter": dict(n=512, w=3840, h=2160, q=85, pt="RGB565_LITTLE_ENDIAN", bpp_out=2.0 / 16, coef_bpp=0.1875, opt=4, kernel="jdk_scaled",
@@ -243,6 +246,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="hd1024")
     ap.add_argument("--unique", type=int, default=64, help="unique synthetic images per rank (cycled to the batch size)")
+    ap.add_argument("--images", type=int, default=0, help="development aid: override the workload's images per GPU (the line's config says so)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--pipelined", action="store_true", help="also time the steps with two resident batches in flight")
@@ -255,7 +259,7 @@ def main():
     K = max(args.steps, 1)
     cpu_facts = host_cpu_facts()
     threads = cpu_facts["usable"]
-    n_img = wl["n"]
+    n_img = args.images if args.images > 0 else wl["n"]
     if "unique" in wl:
         args.unique = wl["unique"]
     mp_per_step_rank = n_img * wl["w"] * wl["h"] / 1e6
