@@ -1,17 +1,24 @@
 /*
  * jd_kernels.cuh -- hand-written sm_100a kernels of the decode pipeline.
  *
- *   jdk_prescan     one CTA per image: finds RSTn markers, writes per-segment byte offsets
- *   jdk_entropy     one thread per restart segment: Huffman decode in registers, LUTs in
- *                   shared memory, writes compact coefficient records + per-block headers
- *   jdk_stitch      one thread per image: resolves the reference's bit-window phase across
- *                   segments and folds per-segment status into the image status
- *   jdk_patch       one thread per truncation event: rewrites the affected record
- *   jdk_idct_color  fused record-expand + dequant + 8x8 integer IDCT + colour conversion,
- *                   8 lanes per block, coefficient tiles and pixel planes staged in shared
- *                   memory, 128-bit coalesced scanline stores
- *   jdk_scaled      1/4 and 1/8 decode (DC / 2x2 butterfly), one thread per MCU
- *   jdk_dither      Floyd-Steinberg 1/2/4-bpp, one warp-lane per image row wavefront
+ *   jdk_prescan       one CTA per image: finds RSTn markers, writes per-segment byte offsets
+ *   jdk_unstuff_segs  one warp per restart segment: FF00 -> FF into 16-byte aligned clean streams
+ *   jdk_entropy       one thread per restart segment: Huffman walk (jd_core.h jd_decode_segment), tables + a stream ring
+ *                     + a record staging chunk per walker in shared memory; compact coefficient records + block headers
+ *   jdk_stitch        one thread per image: resolves the reference's bit-window phase across segments and folds the
+ *                     per-segment status into the image status
+ *   jdk_patch         one thread per truncation event: rewrites the affected record
+ *   jdk_unstuff<count/write>, jdk_chunk_parse / _prefix / _emit / _stitch
+ *                     scans without restart markers: chunk-parallel entropy decode (jd_chunk.h)
+ *   jdk_idct_tb       fused record-expand + dequant + 8x8 integer IDCT + colour conversion for 4:2:0 colour at full size:
+ *                     blocks binned by class, one thread per block for the common classes, planes staged in shared
+ *                     memory, 128-bit coalesced scanline stores
+ *   jdk_idct_p        the same for every other sampling / pixel type / half scale (SSE2-build arithmetic): one thread per
+ *                     block, two columns per register
+ *   jdk_idct_color    those cases in scalar-build arithmetic: 8 lanes per block
+ *   jdk_scaled        1/4 and 1/8 decode (DC / 2x2 butterfly), one thread per MCU
+ *   jdk_dither        (jd_device.cu) Floyd-Steinberg 1/2/4-bpp, one warp-lane per image row wavefront
+ *   jdk_digest        (jd_device.cu) 64-bit digest of device-resident pixels (verification aid)
  *
  * No tensor cores: this is integer, byte-granular, HBM-bound work.
  */
