@@ -138,13 +138,14 @@ struct JPEGB200_BATCH {
     std::vector<uint64_t> comp_off; /* offset of each file in the device blob */
     std::vector<void *> outs;
     std::vector<int64_t> pitches;
-    std::vector<uint8_t> errinit;   /* dither: initial error line per image (reference quirk) */
+    std::vector<uint16_t> errinit;  /* dither: initial error line per image (reference quirk), value | 0xFF00 (tag of "the band above band 0") */
     size_t comp_total, out_total, gray_total;
     uint32_t nseg, nlut;
     uint64_t nblk;
     bool contiguous_in;
     bool uploaded, out_device, arena_owned;
-    DevBuf<uint8_t> d_comp, d_out, d_gray, d_errline;
+    DevBuf<uint8_t> d_comp, d_out, d_gray;
+    DevBuf<uint16_t> d_errline;
     DevBuf<uint64_t> d_gray_off; /* [0,n): gray-stage offsets, [n,2n): packed output offsets */
     DevBuf<uint32_t> d_err_off, d_dprog;
     DevBuf<uint8_t> d_clean;       /* un-stuffed restart segments (jdk_unstuff_segs) */
@@ -886,9 +887,12 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
     return 1;
 }
 
+#ifndef JD_DITHER_MINB
+#define JD_DITHER_MINB 9
+#endif
 template <int BITS>
 __global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-                           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
+                           uint16_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
                            const uint4 *bands, uint32_t nbands, uint32_t *progress);
 
 extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
@@ -946,14 +950,14 @@ extern "C" int JPEGB200_batchDecode(JPEGB200_BATCH *b, int flags)
             go += (((size_t)pw * ph) + 255) & ~(size_t)255;
             /* initial error line = the reference's DHT scratch bytes (they share usPixels, jpeg.inl:843 / :4881) */
             const size_t el = ((size_t)pw + 16 + 15) & ~(size_t)15;
-            b->errinit.resize(eo + el, 0);
+            b->errinit.resize(eo + el, (uint16_t)0xFF00u);
             /* device line S[x] = errors[x + 2] */
             const size_t cp = (el + 2 < JD_HUFFVALS_BYTES) ? el : JD_HUFFVALS_BYTES - 2;
-            memcpy(&b->errinit[eo], inf.p.huffvals + 2, cp);
+            for (size_t q = 0; q < cp; q++) b->errinit[eo + q] = (uint16_t)(0xFF00u | inf.p.huffvals[q + 2]);
             eo += el;
         }
         CK(b->d_errline.alloc(&b->ctx->pool, eo + 16));
-        CK(cudaMemcpyAsync(b->d_errline.p, b->errinit.data(), eo, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->d_errline.p, b->errinit.data(), eo * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
         CK(b->d_gray_off.alloc(&b->ctx->pool, 2 * (size_t)n)); CK(b->d_err_off.alloc(&b->ctx->pool, n));
         /* pageable sources: the runtime stages them before returning, so the vectors may go out of scope */
         CK(cudaMemcpyAsync(b->d_gray_off.p, gray_off.data(), (size_t)n * 16, cudaMemcpyHostToDevice, st));
@@ -1434,9 +1438,9 @@ __device__ __forceinline__ void jd_st_release(uint32_t *p, uint32_t v)
 }
 
 template <int BITS /* output bits per pixel: 1, 2, 4 */>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, JD_DITHER_MINB)
 jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
-           uint8_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
+           uint16_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
            const uint4 *bands, uint32_t nbands, uint32_t *progress)
 {
     constexpr uint32_t bits = BITS;
@@ -1456,8 +1460,12 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     const int W = (int)((uint32_t)im.mcus_x * ((hs * 8) >> sshift)); /* padded width = pitch of the gray stage (multiple of 8) */
     const uint32_t rows = im.out_h;
     const uint8_t *src = gray + gray_off[i];
-    /* S[x] = error flowing from the row above into pixel x+1 (the reference's errors[x + 2]); 16-byte aligned */
-    uint8_t *S = errlines + err_off[i];
+    /* S[x] = error flowing from the row above into pixel x+1 (the reference's errors[x + 2]) in the low byte, and in the high
+     * byte the number (mod 256) of the band that wrote it: the band below polls the entries themselves until they carry the
+     * tag of the band above it.  Value and tag travel in one 16-bit store, so no fence and no progress counter is needed (a
+     * release store per 16-32 steps cost 2.2 us each on the critical path of an image). */
+    uint16_t *S = errlines + err_off[i];
+    const uint32_t tag_mine = (bi & 0xFFu) << 8, tag_above = ((bi - 1u) & 0xFFu) * 0x01000100u;
     uint8_t *o = out + gray_off[nimg + i];
     const uint32_t dpitch = ((uint32_t)W * bits + 7) / 8;
     const int mask = (bits == 4) ? 0xF0 : (bits == 2 ? 0xC0 : 0x80);
@@ -1471,20 +1479,21 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     const uint32_t mo = (uint32_t)((16 - (skew & 15)) & 15);   /* byte offset of the window inside the aligned pair */
     const int jsh = (skew + 15) >> 4;                           /* aligned chunk index of window m = m - jsh */
     const int nchunks = W >> 4;
-    const uint32_t *prev = (bi > 0) ? progress + bd.z : nullptr;     /* steps the band above has completed */
-    uint32_t *mine = progress + wg;
-    /* the line entry S[j] is written by the band above at its step j + 95; lane 0 is about to read entries < `upto` */
-    auto wait_for = [&](int upto) {
-        if (prev) {
-            if (lane == 0) {
-                const uint32_t need = (uint32_t)(upto + 96);
-                /* a band that started together with the one above follows it in lock step and waits here nearly every time: sleep
-                 * about a step's worth rather than poll (the polling loop was 29 % of the kernel's issued instructions) */
-                uint32_t ns = 256;
-                while (jd_ld_acquire(prev) < need) { __nanosleep(ns); if (ns < 1024u) ns *= 2u; }
-            }
-            __syncwarp();
-        }
+    /* 16 line entries starting at entry 16 * m (two 16-byte loads that bypass L1 and are never hoisted) */
+    auto line_load = [&](int m, uint4 &lo, uint4 &hi) {
+        const uint16_t *q = S + 16 * m;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(q) : "memory");
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(q + 8) : "memory");
+    };
+    auto line_ok = [&](const uint4 &lo, const uint4 &hi) {
+        const uint32_t bad = ((lo.x ^ tag_above) | (lo.y ^ tag_above) | (lo.z ^ tag_above) | (lo.w ^ tag_above) |
+                              (hi.x ^ tag_above) | (hi.y ^ tag_above) | (hi.z ^ tag_above) | (hi.w ^ tag_above)) & 0xFF00FF00u;
+        return bad == 0u;
+    };
+    /* lane 0: make (lo, hi) the entries of window m as the band above left them */
+    auto line_settle = [&](int m, uint4 &lo, uint4 &hi) {
+        uint32_t ns = 128;
+        while (!line_ok(lo, hi)) { __nanosleep(ns); if (ns < 1024u) ns *= 2u; line_load(m, lo, hi); }
     };
     {
         const uint32_t band = bi * 32u;
@@ -1500,18 +1509,26 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         uint32_t from_above = 0;     /* D[x+1] of the row above, delivered by the previous step's shuffle */
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         /* aligned chunks A0 = chunk(m - jsh), A1 = chunk(m - jsh + 1), A2 = prefetch of chunk(m - jsh + 2) */
-        uint4 A0 = zero4, A1 = zero4, A2 = zero4, win = zero4, ewin = zero4, enext = zero4;
+        uint4 A0 = zero4, A1 = zero4, A2 = zero4, win = zero4;
+        uint4 ewin = zero4;                    /* lane 0: the 16 error values of this window (the entries' low bytes) */
+        uint4 nlo = zero4, nhi = zero4;        /* lane 0: the 16 line entries of the next window as last read */
+        auto line_values = [](const uint4 &lo, const uint4 &hi) {
+            return make_uint4(__byte_perm(lo.x, lo.y, 0x6420), __byte_perm(lo.z, lo.w, 0x6420), __byte_perm(hi.x, hi.y, 0x6420), __byte_perm(hi.z, hi.w, 0x6420));
+        };
         auto chunk = [&](int j) -> uint4 {
             return (live && j >= 0 && j < nchunks) ? *reinterpret_cast<const uint4 *>(p + 16 * j) : zero4;
         };
         if (vec) {
             A0 = chunk(-jsh); A1 = chunk(1 - jsh); A2 = chunk(2 - jsh);
-            wait_for(32);
-            if (lane == 0) { ewin = __ldcg(reinterpret_cast<const uint4 *>(S)); enext = (1 < nchunks) ? __ldcg(reinterpret_cast<const uint4 *>(S + 16)) : zero4; }
+            if (lane == 0) {
+                line_load(0, nlo, nhi);
+                line_settle(0, nlo, nhi);
+                ewin = line_values(nlo, nhi);
+                if (1 < nchunks) line_load(1, nlo, nhi);
+            }
             win = jd_window16(A0, A1, mo);
-        } else {
-            wait_for(W + 2);         /* unusual widths: the band above finishes first */
         }
+        const bool parks = live && (lane == 31 || y + 1 == rows);
         const int nsteps = W + 3 * 31 + 2;
         for (int tb = 0; tb < nsteps; tb += 16) {
 #pragma unroll
@@ -1521,14 +1538,23 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
             const bool inrow = live && x >= 0 && x < W;
             uint32_t pix, inc = from_above;
             if (vec) {
-                /* warp-uniform: byte t of every lane's skewed row, and (lane 0) byte t of the error line */
+                /* warp-uniform: byte t of every lane's skewed row, and (lane 0) entry t of the error line */
                 const uint32_t ww = (k < 4) ? win.x : (k < 8) ? win.y : (k < 12) ? win.z : win.w;
                 const uint32_t ee = (k < 4) ? ewin.x : (k < 8) ? ewin.y : (k < 12) ? ewin.z : ewin.w;
                 pix = (ww >> (8 * (k & 3))) & 0xFFu;
                 if (lane == 0) inc = (ee >> (8 * (k & 3))) & 0xFFu;
             } else {
                 pix = inrow ? p[x] : 0u;
-                if (lane == 0 && inrow) inc = __ldcg(S + x);
+                if (lane == 0 && inrow) {
+                    /* unusual widths: entry by entry */
+                    uint32_t v, ns = 128;
+                    for (;;) {
+                        asm volatile("ld.volatile.global.u16 %0, [%1];" : "=r"(v) : "l"(S + x) : "memory");
+                        if (((v ^ tag_above) & 0xFF00u) == 0u) break;
+                        __nanosleep(ns); if (ns < 1024u) ns *= 2u;
+                    }
+                    inc = v & 0xFFu;
+                }
             }
             uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
             if (inrow) {
@@ -1550,26 +1576,29 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
             } else if (live && x == W) {
                 dcomplete = (uint32_t)down_m1 & 0xFFu;           /* D[W-1] = e2(W-2) + e3(W-1) (no right neighbour) */
             }
-            /* the last row of the band parks what it sends down: D[x-1] feeds pixel x-1 of the next band's first row = S[x-2] */
-            if (live && (lane == 31 || y + 1 == rows) && x >= 2 && x <= W) S[x - 2] = (uint8_t)dcomplete;
+            /* the last row of the band parks what it sends down: D[x-1] feeds pixel x-1 of the next band's first row = S[x-2].
+             * One entry more than anybody consumes (x = W + 1 -> S[W-1], value 0): the band below waits for the tags of whole
+             * windows. */
+            if (parks && x >= 2 && x <= W + 1) {
+                const uint16_t ev = (uint16_t)(dcomplete | tag_mine);
+                asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(S + (x - 2)), "h"(ev) : "memory");
+            }
             /* next step lane l+1 handles pixel x-2 and needs D[x-1] of this row */
             from_above = __shfl_up_sync(0xffffffffu, dcomplete, 1);
         }
-            /* ---- every 16 steps: next windows, and publish progress ---- */
+            /* ---- every 16 steps: next windows ---- */
             if (vec) {
                 const int m = (tb >> 4) + 1;               /* next window index */
                 A0 = A1; A1 = A2; A2 = chunk(m - jsh + 2);
                 win = jd_window16(A0, A1, mo);
-                ewin = enext;
-                if (m + 1 < nchunks) wait_for(16 * (m + 2));
-                enext = (lane == 0 && m + 1 < nchunks) ? __ldcg(reinterpret_cast<const uint4 *>(S + 16 * (m + 1))) : zero4;
+                if (lane == 0 && m < nchunks) {
+                    /* the entries requested 16 steps ago; usually the band above wrote them long before (it runs >= 95 + 16 steps
+                     * ahead), else ask again until they carry its tag */
+                    line_settle(m, nlo, nhi);
+                    ewin = line_values(nlo, nhi);
+                    if (m + 1 < nchunks) line_load(m + 1, nlo, nhi);
+                }
             }
-            /* tb + 16 steps done (the shuffles ordered the warp's stores before lane 31's release) */
-            /* lane 31 wrote every line entry the band below reads, so its own release store orders them (no fence for the
-             * whole warp); every 32 steps is often enough for a follower that stays 96 steps behind */
-            if (lane == 31 && (tb & 16)) jd_st_release(mine, (uint32_t)(tb + 16));
         }
-        __syncwarp();
-        if (lane == 31) jd_st_release(mine, 0x7FFFFFFFu);
     }
 }

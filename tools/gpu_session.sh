@@ -55,7 +55,7 @@ onecall)
   for mb in ${ONECALL_MB:-32 64 128 192}; do JPEGDEC_B200_JOB_MB=$mb timeout 600 python tools/onecall_probe.py ${ONECALL_N:-625} >> $O/${tag}_onecall.txt 2>&1; done
   cat $O/${tag}_onecall.txt ;;
 scale_n)
-  for nimg in 64 256 1024; do timeout 600 python bench.py --workload ${SCALE_WL:-dither} --images $nimg --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 2>/dev/null | tail -1 | python -c "
+  for nimg in ${SCALE_NS:-64 256 1024}; do timeout 600 python bench.py --workload ${SCALE_WL:-dither} --images $nimg --no-cpu --no-e2e --steps 5 --warmup 3 --unique 32 2>/dev/null | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); print('$nimg images', round(d['value']), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['stages_ms'].items()})" >> $O/${tag}_scale_n.txt 2>&1; done; cat $O/${tag}_scale_n.txt ;;
 others)
