@@ -890,6 +890,10 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
 #ifndef JD_DITHER_MINB
 #define JD_DITHER_MINB 9
 #endif
+#ifndef JD_DITHER_SKEW
+#define JD_DITHER_SKEW 3   /* pixels by which a row trails the row above: 3 = the error from above is folded into the NEXT pixel's
+                             forward error (one step of slack for the shuffle); 2 = it is added to the current pixel */
+#endif
 template <int BITS>
 __global__ void jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const uint64_t *gray_off,
                            uint16_t *errlines, const uint32_t *err_off, uint8_t *out, uint32_t sshift,
@@ -1475,7 +1479,7 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
      * register that other lanes are still consuming would serialise the whole warp on the scoreboard), each lane reads
      * its row through a pointer skewed by 3l bytes: at step t every lane needs byte t of its skewed row, so all lanes
      * cross 16-byte boundaries together.  The skewed 16 bytes are cut out of two aligned chunks (jd_window16). */
-    const int skew = 3 * (int)lane;
+    const int skew = JD_DITHER_SKEW * (int)lane;
     const uint32_t mo = (uint32_t)((16 - (skew & 15)) & 15);   /* byte offset of the window inside the aligned pair */
     const int jsh = (skew + 15) >> 4;                           /* aligned chunk index of window m = m - jsh */
     const int nchunks = W >> 4;
@@ -1509,27 +1513,35 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         uint32_t from_above = 0;     /* D[x+1] of the row above, delivered by the previous step's shuffle */
         const uint4 zero4 = make_uint4(0, 0, 0, 0);
         /* aligned chunks A0 = chunk(m - jsh), A1 = chunk(m - jsh + 1), A2 = prefetch of chunk(m - jsh + 2) */
-        uint4 A0 = zero4, A1 = zero4, A2 = zero4, win = zero4;
+        uint4 A0 = zero4, A1 = zero4, win = zero4;
         uint4 ewin = zero4;                    /* lane 0: the 16 error values of this window (the entries' low bytes) */
-        uint4 nlo = zero4, nhi = zero4;        /* lane 0: the 16 line entries of the next window as last read */
         auto line_values = [](const uint4 &lo, const uint4 &hi) {
             return make_uint4(__byte_perm(lo.x, lo.y, 0x6420), __byte_perm(lo.z, lo.w, 0x6420), __byte_perm(hi.x, hi.y, 0x6420), __byte_perm(hi.z, hi.w, 0x6420));
         };
         auto chunk = [&](int j) -> uint4 {
             return (live && j >= 0 && j < nchunks) ? *reinterpret_cast<const uint4 *>(p + 16 * j) : zero4;
         };
+        /* what the next window switch will load is requested one window ahead with prefetches (no registers held across the
+         * 16 unrolled steps): the pixel chunk into L1, the line entries -- written by another SM -- into L2 */
+        auto prefetch_next = [&](int m) {
+            const int j = m - jsh + 1;
+            if (live && j >= 0 && j < nchunks) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 16 * j));
+            if (lane == 0 && m < nchunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + 16 * m));
+        };
         if (vec) {
-            A0 = chunk(-jsh); A1 = chunk(1 - jsh); A2 = chunk(2 - jsh);
+            A0 = chunk(-jsh); A1 = chunk(1 - jsh);
             if (lane == 0) {
-                line_load(0, nlo, nhi);
-                line_settle(0, nlo, nhi);
-                ewin = line_values(nlo, nhi);
-                if (1 < nchunks) line_load(1, nlo, nhi);
+                uint4 lo, hi;
+                line_load(0, lo, hi);
+                line_settle(0, lo, hi);
+                ewin = line_values(lo, hi);
             }
             win = jd_window16(A0, A1, mo);
+            prefetch_next(1);
         }
         const bool parks = live && (lane == 31 || y + 1 == rows);
-        const int nsteps = W + 3 * 31 + 2;
+        const int nsteps = W + JD_DITHER_SKEW * 31 + 2;
+        uint32_t line_prev = 0;     /* lane 0, skew 2: the line entry of the previous step (= error into the current pixel) */
         for (int tb = 0; tb < nsteps; tb += 16) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {                    /* unrolled: byte k of the 16-byte windows is a constant extract */
@@ -1542,14 +1554,18 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
                 const uint32_t ww = (k < 4) ? win.x : (k < 8) ? win.y : (k < 12) ? win.z : win.w;
                 const uint32_t ee = (k < 4) ? ewin.x : (k < 8) ? ewin.y : (k < 12) ? ewin.z : ewin.w;
                 pix = (ww >> (8 * (k & 3))) & 0xFFu;
-                if (lane == 0) inc = (ee >> (8 * (k & 3))) & 0xFFu;
+                if (lane == 0) {
+                    const uint32_t line_now = (ee >> (8 * (k & 3))) & 0xFFu;   /* S[t] = error into pixel t + 1 */
+                    inc = (JD_DITHER_SKEW == 3) ? line_now : line_prev;
+                    line_prev = line_now;
+                }
             } else {
                 pix = inrow ? p[x] : 0u;
-                if (lane == 0 && inrow) {
+                if (lane == 0 && inrow && (JD_DITHER_SKEW == 3 || x >= 1)) {
                     /* unusual widths: entry by entry */
                     uint32_t v, ns = 128;
                     for (;;) {
-                        asm volatile("ld.volatile.global.u16 %0, [%1];" : "=r"(v) : "l"(S + x) : "memory");
+                        asm volatile("ld.volatile.global.u16 %0, [%1];" : "=r"(v) : "l"(S + (JD_DITHER_SKEW == 3 ? x : x - 1)) : "memory");
                         if (((v ^ tag_above) & 0xFF00u) == 0u) break;
                         __nanosleep(ns); if (ns < 1024u) ns *= 2u;
                     }
@@ -1559,6 +1575,13 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
             uint32_t dcomplete = 0;   /* outgoing error for pixel x-1, complete after this step */
             if (inrow) {
                 int c = (int)pix + fwd;
+                if (JD_DITHER_SKEW == 2) {
+                    /* error arriving at THIS pixel from the row above: none at pixel 0, and pixel 1's slot (errors[2]) is cleared at
+                     * the first row of every MCU row */
+                    uint32_t upc = inc & 0xFFu;
+                    if (x == 0 || (mcu_first && x == 1)) upc = 0;
+                    c += (int)upc;
+                }
                 if (c > 255) c = 255;
                 acc = ((acc << bits) | ((uint32_t)c >> (8 - bits))) & 0xFFu;
                 if (((uint32_t)x & xmask) == xmask) { *d++ = (uint8_t)acc; acc = 0; }
@@ -1569,7 +1592,7 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
                  * every MCU row, and nothing ever reaches pixel 0 from above (lFErr starts at 0) */
                 uint32_t up = inc & 0xFFu;
                 if (mcu_first && x == 0) up = 0;
-                fwd = e1 + (int)up;
+                fwd = (JD_DITHER_SKEW == 3) ? e1 + (int)up : e1;
                 dcomplete = (uint32_t)(down_m1 + e4) & 0xFFu;   /* D[x-1] = e2(x-2) + e3(x-1) + e4(x) */
                 down_m1 = e2_prev + e3;                          /* becomes D[x] once e4(x+1) arrives */
                 e2_prev = e2;
@@ -1589,15 +1612,17 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
             /* ---- every 16 steps: next windows ---- */
             if (vec) {
                 const int m = (tb >> 4) + 1;               /* next window index */
-                A0 = A1; A1 = A2; A2 = chunk(m - jsh + 2);
+                A0 = A1; A1 = chunk(m - jsh + 1);
                 win = jd_window16(A0, A1, mo);
                 if (lane == 0 && m < nchunks) {
-                    /* the entries requested 16 steps ago; usually the band above wrote them long before (it runs >= 95 + 16 steps
-                     * ahead), else ask again until they carry its tag */
-                    line_settle(m, nlo, nhi);
-                    ewin = line_values(nlo, nhi);
-                    if (m + 1 < nchunks) line_load(m + 1, nlo, nhi);
+                    /* usually the band above wrote these entries long before (it runs >= 95 + 16 steps ahead), else ask again until
+                     * they carry its tag */
+                    uint4 lo, hi;
+                    line_load(m, lo, hi);
+                    line_settle(m, lo, hi);
+                    ewin = line_values(lo, hi);
                 }
+                prefetch_next(m + 1);
             }
         }
     }
