@@ -891,7 +891,7 @@ static int launch_idct_geo(const JDIdctArgs &a, uint32_t mcus_x, uint32_t mcus_y
 #define JD_DITHER_MINB 9
 #endif
 #ifndef JD_DITHER_SKEW
-#define JD_DITHER_SKEW 3   /* pixels by which a row trails the row above: 3 = the error from above is folded into the NEXT pixel's
+#define JD_DITHER_SKEW 2   /* pixels by which a row trails the row above: 3 = the error from above is folded into the NEXT pixel's
                              forward error (one step of slack for the shuffle); 2 = it is added to the current pixel */
 #endif
 template <int BITS>
@@ -1515,6 +1515,7 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         /* aligned chunks A0 = chunk(m - jsh), A1 = chunk(m - jsh + 1), A2 = prefetch of chunk(m - jsh + 2) */
         uint4 A0 = zero4, A1 = zero4, win = zero4;
         uint4 ewin = zero4;                    /* lane 0: the 16 error values of this window (the entries' low bytes) */
+        uint4 nlo = zero4, nhi = zero4;        /* lane 0: the next window's 16 line entries as read one window ahead */
         auto line_values = [](const uint4 &lo, const uint4 &hi) {
             return make_uint4(__byte_perm(lo.x, lo.y, 0x6420), __byte_perm(lo.z, lo.w, 0x6420), __byte_perm(hi.x, hi.y, 0x6420), __byte_perm(hi.z, hi.w, 0x6420));
         };
@@ -1526,15 +1527,14 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         auto prefetch_next = [&](int m) {
             const int j = m - jsh + 1;
             if (live && j >= 0 && j < nchunks) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 16 * j));
-            if (lane == 0 && m < nchunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + 16 * m));
         };
         if (vec) {
             A0 = chunk(-jsh); A1 = chunk(1 - jsh);
             if (lane == 0) {
-                uint4 lo, hi;
-                line_load(0, lo, hi);
-                line_settle(0, lo, hi);
-                ewin = line_values(lo, hi);
+                line_load(0, nlo, nhi);
+                line_settle(0, nlo, nhi);
+                ewin = line_values(nlo, nhi);
+                if (1 < nchunks) line_load(1, nlo, nhi);
             }
             win = jd_window16(A0, A1, mo);
             prefetch_next(1);
@@ -1617,10 +1617,9 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
                 if (lane == 0 && m < nchunks) {
                     /* usually the band above wrote these entries long before (it runs >= 95 + 16 steps ahead), else ask again until
                      * they carry its tag */
-                    uint4 lo, hi;
-                    line_load(m, lo, hi);
-                    line_settle(m, lo, hi);
-                    ewin = line_values(lo, hi);
+                    line_settle(m, nlo, nhi);          /* read 16 steps ago */
+                    ewin = line_values(nlo, nhi);
+                    if (m + 1 < nchunks) line_load(m + 1, nlo, nhi);
                 }
                 prefetch_next(m + 1);
             }
