@@ -1400,18 +1400,21 @@ extern "C" int JPEGB200_lastCallCounters(JPEGB200_CTX *ctx, int64_t *counters)
 /* Floyd-Steinberg dither (reference JPEGDither src/jpeg.inl:4871-4940).                    */
 /*                                                                                          */
 /* One warp per band of 32 rows, a wavefront inside the warp and a second one across the warps  */
-/* of an image.  Inside: lane l works on row (band*32 + l) and trails lane l-1 by three pixels,*/
-/* which is exactly when the error that row l-1 sends down to a pixel (e2 of its left          */
-/* neighbour + e3 + e4 of its right neighbour, summed in uint8 like the reference's error      */
-/* line) is complete; it travels to the next lane with one shuffle per step.  Across: the last */
-/* lane's outgoing errors go through an error line in global memory to the next band -- the    */
-/* same line the reference keeps in usPixels: it persists across MCU rows, only entries 0..2   */
-/* are cleared per MCU row (:4881), and before the first row it holds the DHT scratch bytes    */
-/* (the host uploads them, see batchDecode).  Band b+1 runs concurrently, JD_DITHER_LAG steps  */
-/* behind band b: every 16 steps a band publishes how many steps it has completed and checks   */
-/* its predecessor's count before it reads the next 16 bytes of the line.  Each entry of the   */
-/* line is read by band b+1 before band b+1 overwrites it (95 steps later) and after band b    */
-/* wrote it, so one line per image serves all bands, as in the reference.                      */
+/* of an image.  Inside: lane l works on row (band*32 + l) and trails lane l-1 by two pixels:    */
+/* the error row l-1 sends down to a pixel (e2 of its left neighbour + e3 + e4 of its right     */
+/* neighbour, summed in uint8 like the reference's error line) is complete one step before the  */
+/* pixel is due and travels to the next lane with one shuffle per step.  Across: the last       */
+/* lane's outgoing errors go through an error line in global memory to the next band -- the     */
+/* same line the reference keeps in usPixels: it persists across MCU rows, only entries 0..2    */
+/* are cleared per MCU row (:4881), and before the first row it holds the DHT scratch bytes     */
+/* (the host uploads them, see batchDecode).  Band b+1 runs concurrently about 80 steps behind  */
+/* band b.  Every entry of the line is 16 bits: the error and the number (mod 256) of the band  */
+/* that wrote it; band b+1 reads 16 entries at a time and asks again until all of them carry    */
+/* band b's number, so value and "ready" arrive in one store and the bands need no counters or  */
+/* fences between them.  Each entry is read by band b+1 before band b+1 overwrites it (64 steps */
+/* later), so one line per image serves all bands, as in the reference.  An image is a chain of  */
+/* ~(bands x 80 + width) dependent steps whatever the batch size; with fewer than ~500 images    */
+/* that chain, not throughput, sets the kernel's time.                     */
 /* ------------------------------------------------------------------------------------ */
 /* 16 bytes starting at byte offset `mo` (0..15) of the 32-byte pair (a, b) */
 __device__ __forceinline__ uint4 jd_window16(const uint4 a, const uint4 b, uint32_t mo)
@@ -1475,9 +1478,9 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
     const int mask = (bits == 4) ? 0xF0 : (bits == 2 ? 0xC0 : 0x80);
     const uint32_t xmask = (bits == 4) ? 1u : (bits == 2 ? 3u : 7u);
     const bool vec = ((W & 15) == 0);
-    /* Lane l works on pixel x = t - 3l at step t.  To keep every global load at a warp-uniform step (a load into a
+    /* Lane l works on pixel x = t - JD_DITHER_SKEW * l at step t.  To keep every global load at a warp-uniform step (a load into a
      * register that other lanes are still consuming would serialise the whole warp on the scoreboard), each lane reads
-     * its row through a pointer skewed by 3l bytes: at step t every lane needs byte t of its skewed row, so all lanes
+     * its row through a pointer skewed by that many bytes: at step t every lane needs byte t of its skewed row, so all lanes
      * cross 16-byte boundaries together.  The skewed 16 bytes are cut out of two aligned chunks (jd_window16). */
     const int skew = JD_DITHER_SKEW * (int)lane;
     const uint32_t mo = (uint32_t)((16 - (skew & 15)) & 15);   /* byte offset of the window inside the aligned pair */
@@ -1515,7 +1518,6 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         /* aligned chunks A0 = chunk(m - jsh), A1 = chunk(m - jsh + 1), A2 = prefetch of chunk(m - jsh + 2) */
         uint4 A0 = zero4, A1 = zero4, win = zero4;
         uint4 ewin = zero4;                    /* lane 0: the 16 error values of this window (the entries' low bytes) */
-        uint4 nlo = zero4, nhi = zero4;        /* lane 0: the next window's 16 line entries as read one window ahead */
         auto line_values = [](const uint4 &lo, const uint4 &hi) {
             return make_uint4(__byte_perm(lo.x, lo.y, 0x6420), __byte_perm(lo.z, lo.w, 0x6420), __byte_perm(hi.x, hi.y, 0x6420), __byte_perm(hi.z, hi.w, 0x6420));
         };
@@ -1527,14 +1529,15 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
         auto prefetch_next = [&](int m) {
             const int j = m - jsh + 1;
             if (live && j >= 0 && j < nchunks) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 16 * j));
+            if (lane == 0 && m < nchunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + 16 * m));
         };
         if (vec) {
             A0 = chunk(-jsh); A1 = chunk(1 - jsh);
             if (lane == 0) {
-                line_load(0, nlo, nhi);
-                line_settle(0, nlo, nhi);
-                ewin = line_values(nlo, nhi);
-                if (1 < nchunks) line_load(1, nlo, nhi);
+                uint4 lo, hi;
+                line_load(0, lo, hi);
+                line_settle(0, lo, hi);
+                ewin = line_values(lo, hi);
             }
             win = jd_window16(A0, A1, mo);
             prefetch_next(1);
@@ -1617,9 +1620,12 @@ jdk_dither(const JDImageDesc *imgs, uint32_t nimg, const uint8_t *gray, const ui
                 if (lane == 0 && m < nchunks) {
                     /* usually the band above wrote these entries long before (it runs >= 95 + 16 steps ahead), else ask again until
                      * they carry its tag */
-                    line_settle(m, nlo, nhi);          /* read 16 steps ago */
-                    ewin = line_values(nlo, nhi);
-                    if (m + 1 < nchunks) line_load(m + 1, nlo, nhi);
+                    /* read now, not a window ahead: a band that follows the one above in lock step would mostly have read
+                     * entries that were not written yet (measured: 2.92 vs 2.49 ms per 256 images) */
+                    uint4 lo, hi;
+                    line_load(m, lo, hi);
+                    line_settle(m, lo, hi);
+                    ewin = line_values(lo, hi);
                 }
                 prefetch_next(m + 1);
             }
