@@ -33,7 +33,7 @@ ncu)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$2 -s 1 -c 1 -f -o $O/${tag}_$1 $B --workload $3 > $O/${tag}_ncu_$1.log 2>&1
     python tools/ncu_summary.py $O/${tag}_$1.ncu-rep $O/${tag}_$1_summary.txt > /dev/null 2>&1
     sz=$(stat -c %s $O/${tag}_$1.ncu-rep 2>/dev/null || echo 0); [ "$sz" -gt 14000000 ] && rm -f $O/${tag}_$1.ncu-rep; }
-  for spec in ${NCUSPECS:-entropy_hd1024:jdk_entropy:hd1024 idct_p_hd1024:jdk_idct_p:hd1024 idct_p_uhd:jdk_idct_p:uhd}; do
+  for spec in ${NCUSPECS:-entropy_hd1024:jdk_entropy:hd1024 idct_tb_hd1024:jdk_idct_tb:hd1024 idct_tb_uhd:jdk_idct_tb:uhd}; do
     IFS=: read n rx w <<< "$spec"; prof $n $rx $w
   done
   ls -la $O | tail -20 ;;
