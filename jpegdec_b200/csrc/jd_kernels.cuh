@@ -198,17 +198,10 @@ __device__ __forceinline__ void jd_entropy_body(const JDEntropyArgs &a, const ui
     }
     JDEventSinkDev sink{a.events, a.event_count, a.event_cap};
     in.al = (im.prog >> 8) & 15u;
-#ifdef JD_ENTROPY_V1
-    if (im.prog & 1u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_DC_SCAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
-    else if (a.dc_output == 1u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_PARSE_AC>(in, s_lut, s_tpos, hdr, rec, sink, so);
-    else if (a.dc_output == 2u) jd_decode_segment_flat<JDEventSinkDev, JD_MODE_STORE_LOW>(in, s_lut, s_tpos, hdr, rec, sink, so);
-    else jd_decode_segment_flat<JDEventSinkDev, JD_MODE_BASELINE>(in, s_lut, s_tpos, hdr, rec, sink, so);
-#else
     if (im.prog & 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_DC_SCAN, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
     else if (a.dc_output == 1u) jd_decode_segment<JDEventSinkDev, JD_MODE_PARSE_AC, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
     else if (a.dc_output == 2u) jd_decode_segment<JDEventSinkDev, JD_MODE_STORE_LOW, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
     else jd_decode_segment<JDEventSinkDev, JD_MODE_BASELINE, CLEAN>(in, s_lut, s_tpos, hdr, rec, sink, so);
-#endif
     a.seg_jmap[seg] = so.jmap;
     a.seg_status[seg] = (so.err_mcu < 0) ? 0u : (((uint32_t)so.status << 28) | ((uint32_t)so.err_mcu & 0x0FFFFFFFu));
     a.seg_nrec[seg] = so.nrec;

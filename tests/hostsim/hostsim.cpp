@@ -17,6 +17,7 @@
 
 #include "../../jpegdec_b200/csrc/jd_core.h"
 #include "../../jpegdec_b200/csrc/jd_chunk.h"
+#include "jd_flat_walk.h"
 #include "../../jpegdec_b200/csrc/jd_internal.h"
 
 static uint32_t g_ring[64];
