@@ -133,6 +133,25 @@ def test_chunk_parallel_decode_synthetic_vs_restatement():
             assert T.hostsim().hostsim_last_chunk_iters() <= 8
 
 
+def test_chunk_parallel_random_sweep_vs_restatement():
+    """Seeded random restart-free files (size, quality 15..100, sampling, gray): the chunk-parallel path -- speculative parse
+    passes, then jd_decode_segment started in the middle of the stream at each chunk's first block, whatever its position in the
+    MCU -- against the sequential C restatement, pixel for pixel."""
+    from tests import synth
+    rng = np.random.default_rng(1234)
+    for case in range(28):
+        w, h = int(rng.integers(16, 360)), int(rng.integers(16, 260))
+        q = int(rng.integers(15, 101))
+        gray = bool(rng.integers(0, 5) == 0)
+        sub = ["4:2:0", "4:2:2", "4:4:4", "4:2:0"][int(rng.integers(0, 4))]
+        data = synth.synth_jpeg(w, h, 7000 + case, q, subsampling=sub, gray=gray, restart_rows=0)
+        pt = 3 if gray else int(rng.integers(0, 3)) * (1 if rng.integers(0, 2) else 0)   # GRAY8 for gray files, else RGB565 LE / BE / RGB8888
+        arith = int(rng.integers(0, 2))
+        rc1, want = T.oracle_decode(data, pt, 0, arith, w, h)
+        rc2, got, _ = T.hostsim_decode(data, pt, 0, arith, w, h, chunked=True)
+        assert rc1 == rc2 == 1 and np.array_equal(got, want), (case, w, h, q, sub, gray, pt, arith, len(data))
+
+
 def _odd_restart_cases():
     import io
     from PIL import Image
