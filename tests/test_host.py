@@ -176,3 +176,24 @@ def test_delivery_schedule_equals_the_reference_callback_sequence():
                         with_crop_scaled += int(crop is not None and (opt & 14) != 0)
         j.close()
     assert checked > 1500 and with_crop_scaled > 300
+
+
+def test_bench_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the reference's own CPU path on the host cores) needs no GPU: run one step here and check
+    the JSON line the driver parses."""
+    import json, subprocess, sys
+    r = subprocess.run([sys.executable, os.path.join(T.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                       # ONE JSON line
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mpixels/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert "workload" in d["config"] and d["steps"] == 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and abs(cb["value"] - d["value"]) < 1e-6 * d["value"] + 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0 and e["unit"] == d["unit"] and abs(e["value"] - d["value"]) < 1e-6 * d["value"] + 1e-9
